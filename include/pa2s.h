@@ -1,0 +1,115 @@
+/* pa2s.h -- C ABI of libpa2s.so, the sm_100a kernel library behind piano-a2s's data-parallel hot path.
+ *
+ * The reference (wei-zeng98/piano-a2s @ ca8bc59) has NO native/FFI interface: its hot path is the Python class
+ * `models.ScoreTranscription` (models.py:14-51) executed through stock PyTorch library calls, and its front end
+ * is `utilities.get_VQT` (utilities.py:240-254) executed through librosa on the CPU.  The entry points below are
+ * what a binding for that path attaches to; each cites the reference lines whose computation it replaces.  The
+ * reference-side binding (a ctypes stub inside models.py) is shown in INTEGRATION.md.
+ *
+ * Conventions: every pointer is a DEVICE pointer to densely packed fp32 data unless stated otherwise; `stream` is a
+ * cudaStream_t; every function only enqueues work on `stream` and returns 0 or a cudaError_t value (or -1 for an
+ * unsupported shape).  No torch types cross this boundary.  Activations are channels-last: (B, T, F, C).
+ */
+#ifndef PA2S_H
+#define PA2S_H
+#ifdef __cplusplus
+#define PA2S_API extern "C"
+#else
+#define PA2S_API
+#endif
+
+/* Number of kernels this library has launched in this process (bench.py `gpu_launches`). */
+PA2S_API unsigned long long pa2s_launch_count(void);
+
+/* ---- dense contractions ------------------------------------------------------------------------------------
+ * C[b] = op(A[b]) op(B[b]) (+bias) (+C[b]);  op(A)(m,k) = transA ? A[k*lda+m] : A[m*lda+k];
+ * op(B)(k,n) = transB ? B[n*ldb+k] : B[k*ldb+n].  `atomic`/`splitk>1` accumulate into C with atomicAdd (C must hold
+ * the value to add to).  If t_scale != NULL one operand (B if t_on_b else A; it must be the non-transposed-A /
+ * non-transposed-B form whose contiguous index is k resp. n) is read as relu?(x*t_scale[i%t_period]+t_shift[i%t_period]).
+ * Replaces: F.linear of ConvStack.out (models.py:504,539), the nn.GRU input projections (models.py:63-67,117,353),
+ * the encoder half of AttentionLayer.attn (models.py:444,458), the MLP heads (models.py:123-132), torch.bmm context
+ * gradients, and every weight-gradient contraction autograd derives from them.  With lda = hop it is also the VQT
+ * filterbank contraction over overlapping audio frames (utilities.py:246). */
+PA2S_API int pa2s_gemm_f32(void* stream, int transA, int transB, int M, int N, int K,
+                           const float* A, long long lda, const float* B, long long ldb, float* C, long long ldc,
+                           const float* bias, int accumulate, int atomic,
+                           int batch, long long strideA, long long strideB, long long strideC,
+                           const float* t_scale, const float* t_shift, int t_period, int t_relu, int t_on_b,
+                           int splitk);
+
+/* ---- VQT front end (utilities.py:246-253) -------------------------------------------------------------------
+ * C: (nclips*rows_per_clip, 2*nb) filterbank responses (re,im interleaved).  Writes
+ * out = amplitude_to_db(|V|, ref=max over the clip, amin=1e-5, top_db=80)/80 + 1 as (nclips, rows_per_clip, nb). */
+PA2S_API int pa2s_vqt_post(void* stream, const float* C, float* out, unsigned int* clip_max, int nclips, int rows_per_clip, int nb);
+
+/* ---- ConvStack (models.py:463-543) ---------------------------------------------------------------------------
+ * mode 0: Y = conv3x3(relu?(X*in_scale+in_shift)) (in_scale NULL = identity), Wpacked = W.permute(2,3,1,0);
+ *         partial (if not NULL) gets one [sum y, sum y^2] row per CTA (pa2s_conv3x3_num_partials rows).
+ * mode 1: data gradient (conv2d backward wrt input): X = dL/d(relu out) of the layer, the BatchNorm+ReLU backward
+ *         transform k1*(g-k2-xhat*k3) is applied on load; Wpacked = W.flip(2,3).permute(2,3,0,1). */
+PA2S_API int pa2s_conv3x3_num_partials(int B, int T, int F, int ntile);
+PA2S_API int pa2s_conv3x3(void* stream, int mode, int B, int T, int F, int Cin, int Cout, const float* X, const float* Wpacked,
+                          float* Y, float* partial, int ntile,
+                          const float* in_scale, const float* in_shift, int in_relu,
+                          const float* Yraw, const float* zs, const float* zb, const float* mean, const float* invstd,
+                          const float* k1, const float* k2, const float* k3);
+/* conv2d backward wrt weight; partial is [nctas][Cout*Cin*9] in torch (Cout,Cin,3,3) order. */
+PA2S_API int pa2s_conv3x3_wgrad(void* stream, int B, int T, int F, int Cin, int Cout, const float* Xin, const float* G,
+                                float* partial, int nctas, const float* in_scale, const float* in_shift, int in_relu,
+                                const float* Yraw, const float* zs, const float* zb, const float* mean, const float* invstd,
+                                const float* k1, const float* k2, const float* k3);
+/* out[n] (=|+=) sum_r partial[r][n], accumulated in fp64. */
+PA2S_API int pa2s_reduce_rows(void* stream, const float* partial, int R, int N, double* out64, float* out32, int accumulate);
+/* per-channel sums over (npix, C): mode 0 [sum x, sum x^2]; mode 1 [sum g, sum g*xhat] (BatchNorm backward). */
+PA2S_API int pa2s_colstats(void* stream, int mode, const float* X, const float* G, const float* mask, long long npix, int C,
+                           const float* zs, const float* zb, const float* mean, const float* invstd, float* partial, int nctas);
+/* nn.BatchNorm{1,2}d (models.py:499-505) train-mode statistics -> affine, running buffers updated in place. */
+PA2S_API int pa2s_bn_finalize(void* stream, const double* sums, double count, int C, const float* gamma, const float* beta,
+                              float eps, float momentum, float* running_mean, float* running_var,
+                              float* scale, float* shift, float* mean, float* invstd);
+PA2S_API int pa2s_bn_eval_affine(void* stream, int C, const float* gamma, const float* beta, const float* rm, const float* rv,
+                                 float eps, float* scale, float* shift, float* mean, float* invstd);
+PA2S_API int pa2s_bn_bwd_finalize(void* stream, const double* sums, double count, int C, const float* gamma, const float* invstd,
+                                  float* dgamma, float* dbeta, float* k1, float* k2, float* k3);
+/* out = relu(Z*scale+shift)*mask : out_bn + ReLU + dropout(0.2) (models.py:539-541). */
+PA2S_API int pa2s_bn_relu_mask(void* stream, const float* Z, const float* scale, const float* shift, const float* mask,
+                               float* out, long long npix, int C);
+PA2S_API int pa2s_bn_bwd_apply(void* stream, const float* G, const float* Yraw, const float* mask, long long npix, int C,
+                               const float* zs, const float* zb, const float* mean, const float* invstd,
+                               const float* k1, const float* k2, const float* k3, float* out);
+
+/* ---- Encoder BiGRU recurrence (models.py:63-67,77): gi = x W_ih^T + b_ih for all directions, H = 256 ----------- */
+PA2S_API int pa2s_gru_seq_max_bg(void);
+PA2S_API int pa2s_gru_seq_fwd(void* stream, int B, int T, int ND, int H, int bg, const float* gi, const float* Whh, const float* bhh,
+                              float* out, float* gates, float* hN);
+PA2S_API int pa2s_gru_seq_bwd(void* stream, int B, int T, int ND, int H, int bg, const float* Whh, const float* out, const float* gates,
+                              const float* dOut, const float* dhN, float* dgi, float* dgh);
+/* ---- staff summariser: note_emb -> packed BiGRU(16->32) -> h_n (models.py:107-111,164-189) -------------------- */
+PA2S_API int pa2s_staff_gru_fwd(void* stream, int B, int L, int I, int H, const long long* tokens, const long long* lengths,
+                                const float* emb, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                                float* hN, float* hs, float* gates);
+PA2S_API int pa2s_staff_gru_bwd(void* stream, int B, int L, int I, int H, const long long* tokens, const long long* lengths,
+                                const float* emb, const float* w_ih, const float* w_hh, const float* hs, const float* gates,
+                                const float* dhN, float* d_emb, float* d_w_ih, float* d_w_hh, float* d_b_ih, float* d_b_hh);
+/* ---- gate non-linearity of one GRU cell (bar-level GRU, models.py:117-120,247) --------------------------------- */
+PA2S_API int pa2s_gru_gates_fwd(void* stream, int B, int H, const float* gi, const float* gh, const float* hprev, float* hnew, float* save);
+PA2S_API int pa2s_gru_gates_bwd(void* stream, int B, int H, const float* dh, const float* save, const float* hprev,
+                                float* dgi, float* dgh, float* dhprev);
+
+/* ---- note-level attention decoder (models.py:366-420, 452-461) ------------------------------------------------
+ * `args` points to a HOST struct DecArgs (layout in piano_a2s_b200/csrc/decoder.cu, mirrored by ctypes in
+ * piano_a2s_b200/_lib.py; pa2s_dec_args_size() lets the binding verify the layout). */
+PA2S_API int pa2s_dec_args_size(void);
+PA2S_API int pa2s_note_decoder_fwd(void* stream, const void* args, int sos_id, int eos_id);
+PA2S_API int pa2s_note_decoder_bwd(void* stream, const void* args);
+PA2S_API int pa2s_attn_step_fwd(void* stream, const void* args);
+PA2S_API int pa2s_attn_step_bwd(void* stream, const void* args);
+
+/* ---- loss and optimiser (pretrain.py:56-93, 125-128; pretrain.yaml:44-55) -------------------------------------- */
+PA2S_API int pa2s_nll_fwd(void* stream, const float* logp, const long long* tgt, long long rows, int V, long long ignore, float* acc2);
+PA2S_API int pa2s_nll_bwd(void* stream, float* grad, const long long* tgt, long long rows, int V, long long ignore,
+                          const float* acc2, const float* gout);
+PA2S_API int pa2s_sumsq(void* stream, const float* g, long long n, double* out, int zero_first);
+PA2S_API int pa2s_adadelta(void* stream, float* p, const float* g, float* sq, float* acc, long long n, const double* sumsq,
+                           float max_norm, float lr, float rho, float eps, float* norm_out);
+#endif

@@ -1,0 +1,100 @@
+"""ctypes binding of libpa2s.so.  Signatures are taken from include/pa2s.h so header, library and binding cannot drift.
+
+There is NO fallback: if the library is missing or a call returns non-zero this raises."""
+import ctypes
+import os
+import re
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libpa2s.so")
+HEADER = os.path.join(os.path.dirname(HERE), "include", "pa2s.h")
+
+_SCALARS = {"int": ctypes.c_int, "long long": ctypes.c_longlong, "float": ctypes.c_float, "double": ctypes.c_double,
+            "unsigned long long": ctypes.c_ulonglong}
+
+
+def parse_header(path=HEADER):
+    """-> {name: (restype, [argtypes])} for every PA2S_API prototype in the header."""
+    src = open(path).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"PA2S_API\s+([\w\s]+?)\s*(\w+)\s*\(([^)]*)\)\s*;", src):
+        ret, name, args = m.group(1).strip(), m.group(2), m.group(3).strip()
+        argtypes = []
+        if args and args != "void":
+            for a in args.split(","):
+                a = a.strip()
+                if "*" in a:
+                    argtypes.append(ctypes.c_void_p)
+                else:
+                    ty = " ".join(a.split()[:-1]).replace("const ", "").strip()
+                    argtypes.append(_SCALARS[ty])
+        protos[name] = (_SCALARS[ret], argtypes)
+    return protos
+
+
+class _Lib:
+    def __init__(self):
+        self._dll = None
+
+    def load(self):
+        if self._dll is None:
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -m piano_a2s_b200.build` "
+                                   "(there is no CPU / PyTorch fallback for the hot path)")
+            dll = ctypes.CDLL(LIB_PATH)
+            for name, (ret, argtypes) in parse_header().items():
+                fn = getattr(dll, name)
+                fn.restype = ret
+                fn.argtypes = argtypes
+            self._dll = dll
+        return self._dll
+
+    def __getattr__(self, name):
+        fn = getattr(self.load(), name)
+        if name in ("pa2s_launch_count", "pa2s_dec_args_size", "pa2s_gru_seq_max_bg", "pa2s_conv3x3_num_partials"):
+            return fn
+
+        def call(*args):
+            rc = fn(*args)
+            if rc != 0:
+                raise RuntimeError(f"{name} failed with code {rc}")
+        return call
+
+
+lib = _Lib()
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    if t is None:
+        return None
+    assert t.is_cuda, "libpa2s only takes device tensors"
+    return ctypes.c_void_p(t.data_ptr())
+
+
+class DecArgs(ctypes.Structure):
+    """Mirror of `struct DecArgs` in csrc/decoder.cu (field order and types must match exactly)."""
+    _ints = ["B", "T", "V", "VP", "S", "max_steps", "NS", "tile", "inference", "save"]
+    _ptrs = ["enc", "Ep", "Wattn", "v", "emb", "W_ih", "W_hh", "b_ih", "b_hh", "W_out", "b_out",
+             "W_outT", "W_hT", "W_ihT", "W_hhT", "gt", "use_gt", "mask", "logp", "lengths", "eos", "counters",
+             "hs", "ctxs", "attn", "gates", "qs", "xtok", "toks", "xbuf", "hc", "logits", "pm", "pl", "pc", "tickets",
+             "dlogp", "dlogits_all", "dgi_all", "dgh_all", "dq_all", "dctx_all", "dxtok_all", "dEp", "dv_part",
+             "d_hc", "dhq", "dx", "dq_part", "dh_carry", "dh_last"]
+    _fields_ = [(n, ctypes.c_int) for n in _ints] + [(n, ctypes.c_void_p) for n in _ptrs]
+
+
+def make_dec_args(**kw):
+    a = DecArgs()
+    for k, v in kw.items():
+        if k in DecArgs._ints:
+            setattr(a, k, int(v))
+        else:
+            assert k in DecArgs._ptrs, k
+            setattr(a, k, None if v is None else v.data_ptr())
+    return a

@@ -1,0 +1,215 @@
+// Exact-fp32 GEMM on the FFMA pipe: C = op(A) * op(B) (+bias) (+C), batched / split-K, with an optional fused
+// per-column affine(+ReLU) transform on one operand (BatchNorm-apply fused into the consumer's operand load).
+//
+// This is the fp32 reference-precision contraction of the library (the `out` Linear of ConvStack
+// (models.py:504,539), GRU input projections (models.py:63-67), the attention encoder projection
+// (models.py:444,458) and every weight-gradient contraction).  The tcgen05 path in tc_gemm.cu replaces it
+// where a split-bf16 tensor-core contraction meets the parity tolerance.
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 16, NT = 256, PAD = 4;
+
+struct GemmArgs {
+    const float* A; const float* B; float* C; const float* bias;
+    int M, N, K;
+    long long lda, ldb, ldc;
+    long long sA, sB, sC;     // batch strides (elements)
+    int batch, splitk, kchunk;
+    int accumulate, atomic;
+    // operand transform: x' = relu?(x*scale[col % period] + shift[col % period]) on the operand's contiguous index
+    const float* t_scale; const float* t_shift; int t_period; int t_relu; int t_on_b;
+    int vecA, vecB;
+};
+
+__device__ __forceinline__ float xform(float x, long long col, const GemmArgs& g) {
+    int c = (int)(col % g.t_period);
+    float y = fmaf(x, __ldg(g.t_scale + c), __ldg(g.t_shift + c));
+    return g.t_relu ? fmaxf(y, 0.f) : y;
+}
+
+// Load a (BMN x BK) operand tile into registers.
+//  KC=true : memory is [mn][k] (k contiguous, leading dim ld);  KC=false: memory is [k][mn] (mn contiguous).
+template <bool KC>
+__device__ __forceinline__ void load_tile(const float* __restrict__ P, long long ld, int mn0, int k0, int MN, int kend,
+                                          bool vec, bool tf, const GemmArgs& g, float4 (&r)[2]) {
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        int f = tid + i * NT;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (KC) {
+            int row = f >> 2, kq = (f & 3) * 4;
+            int m = mn0 + row, k = k0 + kq;
+            if (m < MN) {
+                const float* p = P + (long long)m * ld + k;
+                if (vec && k + 3 < kend) {
+                    v = __ldg(reinterpret_cast<const float4*>(p));
+                } else {
+                    if (k + 0 < kend) v.x = __ldg(p + 0);
+                    if (k + 1 < kend) v.y = __ldg(p + 1);
+                    if (k + 2 < kend) v.z = __ldg(p + 2);
+                    if (k + 3 < kend) v.w = __ldg(p + 3);
+                }
+                if (tf) {   // transform keyed on the contiguous (k) index
+                    if (k + 0 < kend) v.x = xform(v.x, k + 0, g);
+                    if (k + 1 < kend) v.y = xform(v.y, k + 1, g);
+                    if (k + 2 < kend) v.z = xform(v.z, k + 2, g);
+                    if (k + 3 < kend) v.w = xform(v.w, k + 3, g);
+                }
+            }
+        } else {
+            int kk = f >> 5, mq = (f & 31) * 4;
+            int k = k0 + kk, m = mn0 + mq;
+            if (k < kend) {
+                const float* p = P + (long long)k * ld + m;
+                if (vec && m + 3 < MN) {
+                    v = __ldg(reinterpret_cast<const float4*>(p));
+                } else {
+                    if (m + 0 < MN) v.x = __ldg(p + 0);
+                    if (m + 1 < MN) v.y = __ldg(p + 1);
+                    if (m + 2 < MN) v.z = __ldg(p + 2);
+                    if (m + 3 < MN) v.w = __ldg(p + 3);
+                }
+                if (tf) {   // transform keyed on the contiguous (mn) index
+                    if (m + 0 < MN) v.x = xform(v.x, m + 0, g);
+                    if (m + 1 < MN) v.y = xform(v.y, m + 1, g);
+                    if (m + 2 < MN) v.z = xform(v.z, m + 2, g);
+                    if (m + 3 < MN) v.w = xform(v.w, m + 3, g);
+                }
+            }
+        }
+        r[i] = v;
+    }
+}
+
+template <bool KC>
+__device__ __forceinline__ void store_tile(float (*S)[BM + PAD], const float4 (&r)[2]) {
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        int f = tid + i * NT;
+        if (KC) {
+            int row = f >> 2, kq = (f & 3) * 4;
+            S[kq + 0][row] = r[i].x; S[kq + 1][row] = r[i].y; S[kq + 2][row] = r[i].z; S[kq + 3][row] = r[i].w;
+        } else {
+            int kk = f >> 5, mq = (f & 31) * 4;
+            *reinterpret_cast<float4*>(&S[kk][mq]) = r[i];
+        }
+    }
+}
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(NT) gemm_f32_kernel(GemmArgs g) {
+    __shared__ __align__(16) float As[2][BK][BM + PAD];
+    __shared__ __align__(16) float Bs[2][BK][BN + PAD];
+    const int z = blockIdx.z;
+    const int bz = z / g.splitk, sk = z % g.splitk;
+    const float* A = g.A + (long long)bz * g.sA;
+    const float* B = g.B + (long long)bz * g.sB;
+    float* C = g.C + (long long)bz * g.sC;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int kbeg = sk * g.kchunk;
+    const int kend = min(g.K, kbeg + g.kchunk);
+    const bool tfA = g.t_scale != nullptr && !g.t_on_b;
+    const bool tfB = g.t_scale != nullptr && g.t_on_b;
+
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    float4 ra[2], rb[2];
+    // A is [m][k] when !TA (k contiguous); B is [n][k] when TB (k contiguous).
+    load_tile<!TA>(A, g.lda, m0, kbeg, g.M, kend, g.vecA, tfA, g, ra);
+    load_tile<TB>(B, g.ldb, n0, kbeg, g.N, kend, g.vecB, tfB, g, rb);
+    store_tile<!TA>(As[0], ra);
+    store_tile<TB>(Bs[0], rb);
+    __syncthreads();
+    int buf = 0;
+    for (int k0 = kbeg; k0 < kend; k0 += BK) {
+        const bool more = k0 + BK < kend;
+        if (more) {
+            load_tile<!TA>(A, g.lda, m0, k0 + BK, g.M, kend, g.vecA, tfA, g, ra);
+            load_tile<TB>(B, g.ldb, n0, k0 + BK, g.N, kend, g.vecB, tfB, g, rb);
+        }
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+            float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][64 + ty * 4]);
+            float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+            float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 + tx * 4]);
+            float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        if (more) {
+            store_tile<!TA>(As[buf ^ 1], ra);
+            store_tile<TB>(Bs[buf ^ 1], rb);
+        }
+        __syncthreads();
+        buf ^= 1;
+    }
+
+    const bool use_atomic = g.atomic || g.splitk > 1;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+        if (m >= g.M) continue;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+            if (n >= g.N) continue;
+            float v = acc[i][j];
+            if (g.bias != nullptr && sk == 0) v += __ldg(g.bias + n);
+            float* c = C + (long long)m * g.ldc + n;
+            if (use_atomic) atomicAdd(c, v);
+            else if (g.accumulate) *c += v;
+            else *c = v;
+        }
+    }
+}
+
+}  // namespace
+
+unsigned long long g_pa2s_launches = 0;
+
+PA2S_API unsigned long long pa2s_launch_count(void) { return g_pa2s_launches; }
+
+// See include/pa2s.h for the argument contract.
+PA2S_API int pa2s_gemm_f32(void* stream, int transA, int transB, int M, int N, int K,
+                           const float* A, long long lda, const float* B, long long ldb, float* C, long long ldc,
+                           const float* bias, int accumulate, int atomic,
+                           int batch, long long strideA, long long strideB, long long strideC,
+                           const float* t_scale, const float* t_shift, int t_period, int t_relu, int t_on_b,
+                           int splitk) {
+    if (M <= 0 || N <= 0 || batch <= 0) return 0;
+    GemmArgs g;
+    g.A = A; g.B = B; g.C = C; g.bias = bias;
+    g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldb = ldb; g.ldc = ldc;
+    g.sA = strideA; g.sB = strideB; g.sC = strideC;
+    g.batch = batch;
+    if (splitk < 1) splitk = 1;
+    int kchunk = ceil_div(ceil_div(K, splitk), BK) * BK;
+    if (kchunk < BK) kchunk = BK;
+    splitk = ceil_div(K > 0 ? K : 1, kchunk);
+    g.splitk = splitk; g.kchunk = kchunk;
+    g.accumulate = accumulate; g.atomic = atomic;
+    g.t_scale = t_scale; g.t_shift = t_shift; g.t_period = t_period > 0 ? t_period : 1; g.t_relu = t_relu; g.t_on_b = t_on_b;
+    g.vecA = (lda % 4 == 0) && (strideA % 4 == 0) && ((uintptr_t)A % 16 == 0);
+    g.vecB = (ldb % 4 == 0) && (strideB % 4 == 0) && ((uintptr_t)B % 16 == 0);
+    dim3 grid(ceil_div(N, BN), ceil_div(M, BM), batch * splitk);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!transA && !transB) gemm_f32_kernel<false, false><<<grid, NT, 0, st>>>(g);
+    else if (!transA && transB) gemm_f32_kernel<false, true><<<grid, NT, 0, st>>>(g);
+    else if (transA && !transB) gemm_f32_kernel<true, false><<<grid, NT, 0, st>>>(g);
+    else gemm_f32_kernel<true, true><<<grid, NT, 0, st>>>(g);
+    PA2S_CHECK_LAST();
+    return 0;
+}

@@ -1,0 +1,481 @@
+// GRU recurrences.
+//  * encoder BiGRU (models.py:63-67,77): persistent thread-block-cluster kernels.  One cluster of 8 CTAs per
+//    (direction, batch group); every CTA keeps its 96x256 slice of W_hh in REGISTERS for the whole sequence, the
+//    hidden state lives in shared memory and is exchanged through distributed shared memory with one cluster
+//    barrier per time step.  The input projections (x W_ih^T + b_ih) are one GEMM outside.
+//  * staff summariser BiGRU(16->32) over packed token sequences (models.py:107-111,164-189): one CTA per
+//    (sample, direction), weights in registers, embedding gather / scatter-add fused.
+//  * the gate non-linearity of a single GRU cell (bar-level GRU, models.py:117-120,247), forward and backward.
+// Gate order is torch's (r, z, n):  r = s(gi_r+gh_r), z = s(gi_z+gh_z), n = tanh(gi_n + r*gh_n), h' = (1-z) n + z h.
+#include "common.cuh"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int EH = 256;          // encoder hidden size per direction
+constexpr int ECL = 8;           // CTAs per cluster
+constexpr int EU = EH / ECL;     // units per CTA (32)
+constexpr int ENT = 256;         // threads per CTA = EU * 8 k-slices
+
+struct GruSeqArgs {
+    const float* gi;      // (B,T,ND*3H)  x W_ih^T + b_ih, both directions
+    const float* Whh;     // (ND,3H,H)
+    const float* bhh;     // (ND,3H)
+    float* out;           // (B,T,ND*H)
+    float* gates;         // (B,T,ND,4H): r, z, n, hn_lin (= W_hn h + b_hn)
+    float* hN;            // (ND,B,H)
+    // backward
+    const float* dOut;    // (B,T,ND*H)
+    const float* dhN;     // (ND,B,H) or null
+    float* dgi;           // (B,T,ND*3H)
+    float* dgh;           // (B,T,ND*3H)
+    int B, T, ND, G;
+};
+
+template <int BG>
+__device__ __forceinline__ float pick(const float (&v)[BG], int s) {
+    float r = v[0];
+#pragma unroll
+    for (int i = 1; i < BG; ++i) r = (s == i) ? v[i] : r;
+    return r;
+}
+
+template <int BG>
+__global__ void __launch_bounds__(ENT, 1) gru_seq_fwd_kernel(GruSeqArgs a) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int cid = blockIdx.x / ECL;
+    const int dir = cid / a.G, grp = cid % a.G;
+    const int b0 = grp * BG;
+    const int tid = threadIdx.x, u = tid >> 3, s = tid & 7;
+    const int j = rank * EU + u;
+    const int H = EH, T = a.T, ND = a.ND;
+
+    __shared__ __align__(16) float hbuf[2][BG][EH];
+    float* remote[ECL];
+#pragma unroll
+    for (int c = 0; c < ECL; ++c) remote[c] = cluster.map_shared_rank(&hbuf[0][0][0], c);
+
+    // W_hh slice in registers: rows (g*H + j), columns (kk*8+s)*4 + i
+    float w[3][32];
+#pragma unroll
+    for (int g = 0; g < 3; ++g)
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+            float4 v = __ldg(reinterpret_cast<const float4*>(a.Whh + ((size_t)dir * 3 * H + g * H + j) * H + (kk * 8 + s) * 4));
+            w[g][kk * 4 + 0] = v.x; w[g][kk * 4 + 1] = v.y; w[g][kk * 4 + 2] = v.z; w[g][kk * 4 + 3] = v.w;
+        }
+    const float bhr = a.bhh[dir * 3 * H + j], bhz = a.bhh[dir * 3 * H + H + j], bhn = a.bhh[dir * 3 * H + 2 * H + j];
+    for (int i = tid; i < 2 * BG * EH; i += ENT) (&hbuf[0][0][0])[i] = 0.f;
+    cluster.sync();
+
+    const int b = b0 + s;
+    const bool gate_thread = (s < BG) && (b < a.B);
+    int p = 0;
+    for (int step = 0; step < T; ++step) {
+        const int t = dir == 0 ? step : T - 1 - step;
+        float gir = 0.f, giz = 0.f, gin = 0.f;
+        if (gate_thread) {
+            const float* gp = a.gi + ((size_t)b * T + t) * ND * 3 * H + dir * 3 * H + j;
+            gir = __ldg(gp); giz = __ldg(gp + H); gin = __ldg(gp + 2 * H);
+        }
+        float acc[3][BG];
+#pragma unroll
+        for (int g = 0; g < 3; ++g)
+#pragma unroll
+            for (int bb = 0; bb < BG; ++bb) acc[g][bb] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+#pragma unroll
+            for (int bb = 0; bb < BG; ++bb) {
+                float4 hv = *reinterpret_cast<const float4*>(&hbuf[p][bb][(kk * 8 + s) * 4]);
+#pragma unroll
+                for (int g = 0; g < 3; ++g) {
+                    acc[g][bb] = fmaf(w[g][kk * 4 + 0], hv.x, acc[g][bb]);
+                    acc[g][bb] = fmaf(w[g][kk * 4 + 1], hv.y, acc[g][bb]);
+                    acc[g][bb] = fmaf(w[g][kk * 4 + 2], hv.z, acc[g][bb]);
+                    acc[g][bb] = fmaf(w[g][kk * 4 + 3], hv.w, acc[g][bb]);
+                }
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < 3; ++g)
+#pragma unroll
+            for (int bb = 0; bb < BG; ++bb) {
+                float v = acc[g][bb];
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                v += __shfl_xor_sync(0xffffffffu, v, 4);
+                acc[g][bb] = v;
+            }
+        if (gate_thread) {
+            float ghr = pick<BG>(acc[0], s) + bhr, ghz = pick<BG>(acc[1], s) + bhz, ghn = pick<BG>(acc[2], s) + bhn;
+            float r = sigmoidf_(gir + ghr), z = sigmoidf_(giz + ghz);
+            float n = tanhf(gin + r * ghn);
+            float hp = hbuf[p][s][j];
+            float hn = (1.f - z) * n + z * hp;
+            a.out[((size_t)b * T + t) * ND * H + dir * H + j] = hn;
+            if (a.gates != nullptr) {
+                float* gs = a.gates + (((size_t)b * T + t) * ND + dir) * 4 * H + j;
+                gs[0] = r; gs[H] = z; gs[2 * H] = n; gs[3 * H] = ghn;
+            }
+            if (step == T - 1) a.hN[((size_t)dir * a.B + b) * H + j] = hn;
+            const int off = ((p ^ 1) * BG + s) * EH + j;
+#pragma unroll
+            for (int c = 0; c < ECL; ++c) remote[c][off] = hn;
+        }
+        cluster.sync();
+        p ^= 1;
+    }
+}
+
+template <int BG>
+__global__ void __launch_bounds__(ENT, 1) gru_seq_bwd_kernel(GruSeqArgs a) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int cid = blockIdx.x / ECL;
+    const int dir = cid / a.G, grp = cid % a.G;
+    const int b0 = grp * BG;
+    const int tid = threadIdx.x, u = tid >> 3, s = tid & 7;
+    const int j = rank * EU + u;
+    const int H = EH, T = a.T, ND = a.ND;
+
+    __shared__ __align__(16) float dbuf[2][BG][3 * EH];
+    float* remote[ECL];
+#pragma unroll
+    for (int c = 0; c < ECL; ++c) remote[c] = cluster.map_shared_rank(&dbuf[0][0][0], c);
+
+    // W_hh^T slice in registers: column j, rows (kk*8+s)*4 + i  (kk < 24)
+    float w[96];
+#pragma unroll
+    for (int kk = 0; kk < 24; ++kk)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            w[kk * 4 + i] = __ldg(a.Whh + ((size_t)dir * 3 * H + (kk * 8 + s) * 4 + i) * H + j);
+
+    const int b = b0 + s;
+    const bool gate_thread = (s < BG) && (b < a.B);
+    float dhc = 0.f;
+    if (gate_thread && a.dhN != nullptr) dhc = a.dhN[((size_t)dir * a.B + b) * H + j];
+    for (int i = tid; i < 2 * BG * 3 * EH; i += ENT) (&dbuf[0][0][0])[i] = 0.f;
+    cluster.sync();
+
+    int p = 0;
+    for (int step = T - 1; step >= 0; --step) {
+        const int t = dir == 0 ? step : T - 1 - step;
+        float dh_direct = 0.f;
+        if (gate_thread) {
+            const size_t bt = (size_t)b * T + t;
+            const float* gs = a.gates + (bt * ND + dir) * 4 * H + j;
+            float r = gs[0], z = gs[H], n = gs[2 * H], hnl = gs[3 * H];
+            float hp = 0.f;
+            if (step > 0) {
+                const int tp = dir == 0 ? t - 1 : t + 1;
+                hp = a.out[((size_t)b * T + tp) * ND * H + dir * H + j];
+            }
+            float dh = a.dOut[bt * ND * H + dir * H + j] + dhc;
+            float dn = dh * (1.f - z), dzv = dh * (hp - n);
+            float dn_pre = dn * (1.f - n * n);
+            float dr_pre = dn_pre * hnl * r * (1.f - r);
+            float dhn_lin = dn_pre * r;
+            float dz_pre = dzv * z * (1.f - z);
+            dh_direct = dh * z;
+            float* gi = a.dgi + bt * ND * 3 * H + dir * 3 * H + j;
+            gi[0] = dr_pre; gi[H] = dz_pre; gi[2 * H] = dn_pre;
+            float* gh = a.dgh + bt * ND * 3 * H + dir * 3 * H + j;
+            gh[0] = dr_pre; gh[H] = dz_pre; gh[2 * H] = dhn_lin;
+            const int off = (p * BG + s) * 3 * EH + j;
+#pragma unroll
+            for (int c = 0; c < ECL; ++c) {
+                remote[c][off] = dr_pre; remote[c][off + H] = dz_pre; remote[c][off + 2 * H] = dhn_lin;
+            }
+        }
+        cluster.sync();
+        float acc[BG];
+#pragma unroll
+        for (int bb = 0; bb < BG; ++bb) acc[bb] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < 24; ++kk) {
+#pragma unroll
+            for (int bb = 0; bb < BG; ++bb) {
+                float4 dv = *reinterpret_cast<const float4*>(&dbuf[p][bb][(kk * 8 + s) * 4]);
+                acc[bb] = fmaf(w[kk * 4 + 0], dv.x, acc[bb]);
+                acc[bb] = fmaf(w[kk * 4 + 1], dv.y, acc[bb]);
+                acc[bb] = fmaf(w[kk * 4 + 2], dv.z, acc[bb]);
+                acc[bb] = fmaf(w[kk * 4 + 3], dv.w, acc[bb]);
+            }
+        }
+#pragma unroll
+        for (int bb = 0; bb < BG; ++bb) {
+            float v = acc[bb];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            acc[bb] = v;
+        }
+        if (gate_thread) dhc = dh_direct + pick<BG>(acc, s);
+        p ^= 1;
+    }
+}
+
+template <typename K>
+int launch_cluster(K kernel, cudaStream_t st, int nblocks, GruSeqArgs a) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(nblocks);
+    cfg.blockDim = dim3(ENT);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = ECL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    PA2S_TRY(cudaLaunchKernelEx(&cfg, kernel, a));
+    PA2S_COUNT_LAUNCH();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Staff summariser BiGRU (input 16, hidden 32) over packed sequences
+// ---------------------------------------------------------------------------------------------------------
+constexpr int SH = 32, SI = 16, SR = 3 * SH;
+
+struct StaffArgs {
+    const long long* tokens;   // (B, L)
+    const long long* lengths;  // (B)
+    const float* emb;          // (V, SI)
+    const float* w_ih;         // (2, 96, SI)
+    const float* w_hh;         // (2, 96, SH)
+    const float* b_ih;         // (2, 96)
+    const float* b_hh;         // (2, 96)
+    float* hN;                 // (B, 2*SH)
+    float* hs;                 // (B, 2, L, SH)   h after each executed step
+    float* gates;              // (B, 2, L, 4*SH) r, z, n, hn_lin
+    // backward
+    const float* dhN;          // (B, 2*SH)
+    float* d_emb;              // (V, SI)           atomically accumulated
+    float* d_w_ih; float* d_w_hh; float* d_b_ih; float* d_b_hh;
+    int B, L;
+};
+
+__global__ void __launch_bounds__(SR) staff_gru_fwd_kernel(StaffArgs a) {
+    const int b = blockIdx.x, dir = blockIdx.y, row = threadIdx.x;
+    __shared__ float xs[SI], hsm[SH], gis[SR], ghs[SR];
+    float wi[SI], wh[SH];
+#pragma unroll
+    for (int i = 0; i < SI; ++i) wi[i] = a.w_ih[((size_t)dir * SR + row) * SI + i];
+#pragma unroll
+    for (int k = 0; k < SH; ++k) wh[k] = a.w_hh[((size_t)dir * SR + row) * SH + k];
+    const float bi = a.b_ih[dir * SR + row], bh = a.b_hh[dir * SR + row];
+    long long len = a.lengths[b];
+    if (len > a.L) len = a.L;
+    if (len < 0) len = 0;
+    if (row < SH) hsm[row] = 0.f;
+    __syncthreads();
+    for (int step = 0; step < (int)len; ++step) {
+        const int t = dir == 0 ? step : (int)len - 1 - step;
+        if (row < SI) xs[row] = a.emb[a.tokens[(size_t)b * a.L + t] * SI + row];
+        __syncthreads();
+        float gi = bi, gh = bh;
+#pragma unroll
+        for (int i = 0; i < SI; ++i) gi = fmaf(wi[i], xs[i], gi);
+#pragma unroll
+        for (int k = 0; k < SH; ++k) gh = fmaf(wh[k], hsm[k], gh);
+        gis[row] = gi; ghs[row] = gh;
+        __syncthreads();
+        if (row < SH) {
+            float r = sigmoidf_(gis[row] + ghs[row]);
+            float z = sigmoidf_(gis[SH + row] + ghs[SH + row]);
+            float hnl = ghs[2 * SH + row];
+            float n = tanhf(gis[2 * SH + row] + r * hnl);
+            float hn = (1.f - z) * n + z * hsm[row];
+            hsm[row] = hn;
+            if (a.hs != nullptr) {
+                size_t o = (((size_t)b * 2 + dir) * a.L + t);
+                a.hs[o * SH + row] = hn;
+                float* gs = a.gates + o * 4 * SH + row;
+                gs[0] = r; gs[SH] = z; gs[2 * SH] = n; gs[3 * SH] = hnl;
+            }
+        }
+        __syncthreads();
+    }
+    if (row < SH) a.hN[(size_t)b * 2 * SH + dir * SH + row] = hsm[row];
+}
+
+__global__ void __launch_bounds__(SR) staff_gru_bwd_kernel(StaffArgs a) {
+    const int b = blockIdx.x, dir = blockIdx.y, row = threadIdx.x;
+    __shared__ float xs[SI], hps[SH], dgi[SR], dgh[SR];
+    __shared__ float wis[SR][SI + 1], whs[SR][SH + 1];
+#pragma unroll
+    for (int i = 0; i < SI; ++i) wis[row][i] = a.w_ih[((size_t)dir * SR + row) * SI + i];
+#pragma unroll
+    for (int k = 0; k < SH; ++k) whs[row][k] = a.w_hh[((size_t)dir * SR + row) * SH + k];
+    float dwi[SI], dwh[SH], dbi = 0.f, dbh = 0.f;
+#pragma unroll
+    for (int i = 0; i < SI; ++i) dwi[i] = 0.f;
+#pragma unroll
+    for (int k = 0; k < SH; ++k) dwh[k] = 0.f;
+    long long len = a.lengths[b];
+    if (len > a.L) len = a.L;
+    if (len < 0) len = 0;
+    float dh = (row < SH) ? a.dhN[(size_t)b * 2 * SH + dir * SH + row] : 0.f;
+    __syncthreads();
+    for (int step = (int)len - 1; step >= 0; --step) {
+        const int t = dir == 0 ? step : (int)len - 1 - step;
+        const long long tok = a.tokens[(size_t)b * a.L + t];
+        if (row < SI) xs[row] = a.emb[tok * SI + row];
+        float dh_direct = 0.f;
+        if (row < SH) {
+            size_t o = (((size_t)b * 2 + dir) * a.L + t);
+            const float* gs = a.gates + o * 4 * SH + row;
+            float r = gs[0], z = gs[SH], n = gs[2 * SH], hnl = gs[3 * SH];
+            float hp = 0.f;
+            if (step > 0) {
+                const int tp = dir == 0 ? t - 1 : t + 1;
+                hp = a.hs[(((size_t)b * 2 + dir) * a.L + tp) * SH + row];
+            }
+            hps[row] = hp;
+            float dn = dh * (1.f - z), dzv = dh * (hp - n);
+            float dn_pre = dn * (1.f - n * n);
+            float dr_pre = dn_pre * hnl * r * (1.f - r);
+            float dz_pre = dzv * z * (1.f - z);
+            dgi[row] = dr_pre; dgi[SH + row] = dz_pre; dgi[2 * SH + row] = dn_pre;
+            dgh[row] = dr_pre; dgh[SH + row] = dz_pre; dgh[2 * SH + row] = dn_pre * r;
+            dh_direct = dh * z;
+        }
+        __syncthreads();
+        {
+            const float gi = dgi[row], gh = dgh[row];
+            dbi += gi; dbh += gh;
+#pragma unroll
+            for (int i = 0; i < SI; ++i) dwi[i] = fmaf(gi, xs[i], dwi[i]);
+#pragma unroll
+            for (int k = 0; k < SH; ++k) dwh[k] = fmaf(gh, hps[k], dwh[k]);
+        }
+        if (row < SH) {
+            float acc = dh_direct;
+            for (int r2 = 0; r2 < SR; ++r2) acc = fmaf(whs[r2][row], dgh[r2], acc);
+            dh = acc;
+        } else if (row < SH + SI) {
+            const int i = row - SH;
+            float acc = 0.f;
+            for (int r2 = 0; r2 < SR; ++r2) acc = fmaf(wis[r2][i], dgi[r2], acc);
+            atomicAdd(a.d_emb + tok * SI + i, acc);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < SI; ++i) atomicAdd(a.d_w_ih + ((size_t)dir * SR + row) * SI + i, dwi[i]);
+#pragma unroll
+    for (int k = 0; k < SH; ++k) atomicAdd(a.d_w_hh + ((size_t)dir * SR + row) * SH + k, dwh[k]);
+    atomicAdd(a.d_b_ih + dir * SR + row, dbi);
+    atomicAdd(a.d_b_hh + dir * SR + row, dbh);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Single GRU cell gate math (bar-level GRU): gi, gh are full pre-activations (biases included).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void gru_gates_fwd_kernel(const float* __restrict__ gi, const float* __restrict__ gh, const float* __restrict__ hprev,
+                                     float* __restrict__ hnew, float* __restrict__ save, int B, int H) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * H) return;
+    int b = i / H, j = i % H;
+    const float* pi = gi + (size_t)b * 3 * H + j;
+    const float* ph = gh + (size_t)b * 3 * H + j;
+    float r = sigmoidf_(pi[0] + ph[0]), z = sigmoidf_(pi[H] + ph[H]);
+    float hnl = ph[2 * H];
+    float n = tanhf(pi[2 * H] + r * hnl);
+    hnew[i] = (1.f - z) * n + z * hprev[i];
+    float* s = save + (size_t)b * 4 * H + j;
+    s[0] = r; s[H] = z; s[2 * H] = n; s[3 * H] = hnl;
+}
+
+__global__ void gru_gates_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ save, const float* __restrict__ hprev,
+                                     float* __restrict__ dgi, float* __restrict__ dgh, float* __restrict__ dhprev, int B, int H) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * H) return;
+    int b = i / H, j = i % H;
+    const float* s = save + (size_t)b * 4 * H + j;
+    float r = s[0], z = s[H], n = s[2 * H], hnl = s[3 * H];
+    float d = dh[i], hp = hprev[i];
+    float dn_pre = d * (1.f - z) * (1.f - n * n);
+    float dr_pre = dn_pre * hnl * r * (1.f - r);
+    float dz_pre = d * (hp - n) * z * (1.f - z);
+    float* pi = dgi + (size_t)b * 3 * H + j;
+    float* ph = dgh + (size_t)b * 3 * H + j;
+    pi[0] = dr_pre; pi[H] = dz_pre; pi[2 * H] = dn_pre;
+    ph[0] = dr_pre; ph[H] = dz_pre; ph[2 * H] = dn_pre * r;
+    dhprev[i] = d * z;
+}
+
+}  // namespace
+
+PA2S_API int pa2s_gru_seq_max_bg(void) { return 4; }
+
+// Encoder recurrence forward.  H must be 256.  `bg` in {1,2,4} = samples per cluster.
+PA2S_API int pa2s_gru_seq_fwd(void* stream, int B, int T, int ND, int H, int bg, const float* gi, const float* Whh, const float* bhh,
+                              float* out, float* gates, float* hN) {
+    if (H != EH) return -1;
+    GruSeqArgs a = {};
+    a.gi = gi; a.Whh = Whh; a.bhh = bhh; a.out = out; a.gates = gates; a.hN = hN; a.B = B; a.T = T; a.ND = ND;
+    a.G = ceil_div(B, bg);
+    int nblocks = ND * a.G * ECL;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (bg == 1) return launch_cluster(gru_seq_fwd_kernel<1>, st, nblocks, a);
+    if (bg == 2) return launch_cluster(gru_seq_fwd_kernel<2>, st, nblocks, a);
+    if (bg == 4) return launch_cluster(gru_seq_fwd_kernel<4>, st, nblocks, a);
+    return -1;
+}
+
+PA2S_API int pa2s_gru_seq_bwd(void* stream, int B, int T, int ND, int H, int bg, const float* Whh, const float* out, const float* gates,
+                              const float* dOut, const float* dhN, float* dgi, float* dgh) {
+    if (H != EH) return -1;
+    GruSeqArgs a = {};
+    a.Whh = Whh; a.out = const_cast<float*>(out); a.gates = const_cast<float*>(gates); a.dOut = dOut; a.dhN = dhN; a.dgi = dgi; a.dgh = dgh;
+    a.B = B; a.T = T; a.ND = ND;
+    a.G = ceil_div(B, bg);
+    int nblocks = ND * a.G * ECL;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (bg == 1) return launch_cluster(gru_seq_bwd_kernel<1>, st, nblocks, a);
+    if (bg == 2) return launch_cluster(gru_seq_bwd_kernel<2>, st, nblocks, a);
+    if (bg == 4) return launch_cluster(gru_seq_bwd_kernel<4>, st, nblocks, a);
+    return -1;
+}
+
+PA2S_API int pa2s_staff_gru_fwd(void* stream, int B, int L, int I, int H, const long long* tokens, const long long* lengths,
+                                const float* emb, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                                float* hN, float* hs, float* gates) {
+    if (I != SI || H != SH) return -1;
+    StaffArgs a = {};
+    a.tokens = tokens; a.lengths = lengths; a.emb = emb; a.w_ih = w_ih; a.w_hh = w_hh; a.b_ih = b_ih; a.b_hh = b_hh;
+    a.hN = hN; a.hs = hs; a.gates = gates; a.B = B; a.L = L;
+    staff_gru_fwd_kernel<<<dim3(B, 2), SR, 0, (cudaStream_t)stream>>>(a);
+    PA2S_CHECK_LAST();
+    return 0;
+}
+
+PA2S_API int pa2s_staff_gru_bwd(void* stream, int B, int L, int I, int H, const long long* tokens, const long long* lengths,
+                                const float* emb, const float* w_ih, const float* w_hh, const float* hs, const float* gates,
+                                const float* dhN, float* d_emb, float* d_w_ih, float* d_w_hh, float* d_b_ih, float* d_b_hh) {
+    if (I != SI || H != SH) return -1;
+    StaffArgs a = {};
+    a.tokens = tokens; a.lengths = lengths; a.emb = emb; a.w_ih = w_ih; a.w_hh = w_hh;
+    a.hs = const_cast<float*>(hs); a.gates = const_cast<float*>(gates); a.dhN = dhN;
+    a.d_emb = d_emb; a.d_w_ih = d_w_ih; a.d_w_hh = d_w_hh; a.d_b_ih = d_b_ih; a.d_b_hh = d_b_hh; a.B = B; a.L = L;
+    staff_gru_bwd_kernel<<<dim3(B, 2), SR, 0, (cudaStream_t)stream>>>(a);
+    PA2S_CHECK_LAST();
+    return 0;
+}
+
+PA2S_API int pa2s_gru_gates_fwd(void* stream, int B, int H, const float* gi, const float* gh, const float* hprev, float* hnew, float* save) {
+    gru_gates_fwd_kernel<<<ceil_div(B * H, 256), 256, 0, (cudaStream_t)stream>>>(gi, gh, hprev, hnew, save, B, H);
+    PA2S_CHECK_LAST();
+    return 0;
+}
+
+PA2S_API int pa2s_gru_gates_bwd(void* stream, int B, int H, const float* dh, const float* save, const float* hprev,
+                                float* dgi, float* dgh, float* dhprev) {
+    gru_gates_bwd_kernel<<<ceil_div(B * H, 256), 256, 0, (cudaStream_t)stream>>>(dh, save, hprev, dgi, dgh, dhprev, B, H);
+    PA2S_CHECK_LAST();
+    return 0;
+}

@@ -1,0 +1,150 @@
+// VQT epilogue (utilities.py:246-253), NLL losses (pretrain.py:56-93) and the clip + Adadelta update
+// (pretrain.py:125-128, pretrain.yaml:44-47).
+#include "common.cuh"
+#include <math.h>
+
+namespace {
+
+// C: (rows, 2*nb) filterbank responses, (re, im) interleaved per bin.  mag: (rows, nb).  One clip = rows_per_clip rows.
+__global__ void vqt_mag_kernel(const float2* __restrict__ C, float* __restrict__ mag, unsigned int* __restrict__ clip_max,
+                               long long n, int nb, int rows_per_clip) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    float m = 0.f;
+    int clip = 0;
+    if (i < n) {
+        float2 v = __ldg(C + i);
+        m = sqrtf(v.x * v.x + v.y * v.y);
+        mag[i] = m;
+        clip = (int)((i / nb) / rows_per_clip);
+    }
+    // a warp may straddle two clips only at a clip boundary; reduce when uniform, else fall back to per-lane atomics
+    int clip0 = __shfl_sync(0xffffffffu, clip, 0);
+    bool uniform = __all_sync(0xffffffffu, (i >= n) || clip == clip0);
+    if (uniform) {
+        float wm = warp_max(m);
+        if ((threadIdx.x & 31) == 0 && wm > 0.f) atomicMax(clip_max + clip0, __float_as_uint(wm));
+    } else if (i < n && m > 0.f) {
+        atomicMax(clip_max + clip, __float_as_uint(m));
+    }
+}
+
+// librosa.amplitude_to_db(|V|, ref=max, amin=1e-5, top_db=80)/80 + 1
+__global__ void vqt_logscale_kernel(float* __restrict__ mag, const unsigned int* __restrict__ clip_max, long long n, int nb,
+                                    int rows_per_clip) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int clip = (int)((i / nb) / rows_per_clip);
+    const float amin = 1e-5f;
+    float ref = fmaxf(amin, __uint_as_float(clip_max[clip]));
+    float db = 20.f * log10f(fmaxf(amin, mag[i])) - 20.f * log10f(ref);
+    float top = 20.f * log10f(fmaxf(amin, __uint_as_float(clip_max[clip]))) - 20.f * log10f(ref);   // log_spec.max() (= 0)
+    db = fmaxf(db, top - 80.f);
+    mag[i] = db * (1.f / 80.f) + 1.f;
+}
+
+// acc[0] += sum over rows (target != ignore) of logp[row, target]; acc[1] += count
+__global__ void nll_fwd_kernel(const float* __restrict__ logp, const long long* __restrict__ tgt, long long rows, int V,
+                               long long ignore, float* __restrict__ acc) {
+    long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    float s = 0.f, c = 0.f;
+    if (r < rows) {
+        long long t = tgt[r];
+        if (t != ignore) { s = __ldg(logp + r * V + t); c = 1.f; }
+    }
+    s = warp_sum(s); c = warp_sum(c);
+    if ((threadIdx.x & 31) == 0 && c > 0.f) { atomicAdd(acc, s); atomicAdd(acc + 1, c); }
+}
+// grad[row, target] = -gout / count   (grad pre-zeroed)
+__global__ void nll_bwd_kernel(float* __restrict__ grad, const long long* __restrict__ tgt, long long rows, int V, long long ignore,
+                               const float* __restrict__ acc, const float* __restrict__ gout) {
+    long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    long long t = tgt[r];
+    if (t != ignore) grad[r * V + t] = -gout[0] / acc[1];
+}
+
+__global__ void sumsq_kernel(const float4* __restrict__ g, long long n4, const float* __restrict__ tail, int ntail, double* __restrict__ out) {
+    double s = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 v = __ldg(g + i);
+        s += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+    }
+    if (blockIdx.x == 0 && (int)threadIdx.x < ntail) s += (double)tail[threadIdx.x] * tail[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    __shared__ double ws[32];
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += ws[i];
+        atomicAdd(out, t);
+    }
+}
+
+// clip_grad_norm_(max_norm) + Adadelta.  sumsq[0] = sum g^2 (after any all-reduce averaging).  Skips the update when the
+// norm is not finite (speechbrain check_gradients semantics).
+__global__ void adadelta_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ sq, float* __restrict__ acc,
+                                long long n, const double* __restrict__ sumsq, float max_norm, float lr, float rho, float eps,
+                                float* __restrict__ norm_out) {
+    double nrm = sqrt(sumsq[0]);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && norm_out != nullptr) norm_out[0] = (float)nrm;
+    if (!isfinite(nrm)) return;
+    float coef = fminf(1.f, max_norm / ((float)nrm + 1e-6f));
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float gi = g[i] * coef;
+        float s = rho * sq[i] + (1.f - rho) * gi * gi;
+        float d = sqrtf(acc[i] + eps) / sqrtf(s + eps) * gi;
+        acc[i] = rho * acc[i] + (1.f - rho) * d * d;
+        sq[i] = s;
+        p[i] -= lr * d;
+    }
+}
+
+}  // namespace
+
+PA2S_API int pa2s_vqt_post(void* stream, const float* C, float* out, unsigned int* clip_max, int nclips, int rows_per_clip, int nb) {
+    cudaStream_t st = (cudaStream_t)stream;
+    long long n = (long long)nclips * rows_per_clip * nb;
+    PA2S_TRY(cudaMemsetAsync(clip_max, 0, sizeof(unsigned int) * nclips, st));
+    vqt_mag_kernel<<<ceil_div(n, 256), 256, 0, st>>>((const float2*)C, out, clip_max, n, nb, rows_per_clip);
+    PA2S_CHECK_LAST();
+    vqt_logscale_kernel<<<ceil_div(n, 256), 256, 0, st>>>(out, clip_max, n, nb, rows_per_clip);
+    PA2S_CHECK_LAST();
+    return 0;
+}
+
+PA2S_API int pa2s_nll_fwd(void* stream, const float* logp, const long long* tgt, long long rows, int V, long long ignore, float* acc2) {
+    cudaStream_t st = (cudaStream_t)stream;
+    PA2S_TRY(cudaMemsetAsync(acc2, 0, 2 * sizeof(float), st));
+    nll_fwd_kernel<<<ceil_div(rows, 256), 256, 0, st>>>(logp, tgt, rows, V, ignore, acc2);
+    PA2S_CHECK_LAST();
+    return 0;
+}
+
+PA2S_API int pa2s_nll_bwd(void* stream, float* grad, const long long* tgt, long long rows, int V, long long ignore,
+                          const float* acc2, const float* gout) {
+    cudaStream_t st = (cudaStream_t)stream;
+    PA2S_TRY(cudaMemsetAsync(grad, 0, sizeof(float) * rows * V, st));
+    nll_bwd_kernel<<<ceil_div(rows, 256), 256, 0, st>>>(grad, tgt, rows, V, ignore, acc2, gout);
+    PA2S_CHECK_LAST();
+    return 0;
+}
+
+PA2S_API int pa2s_sumsq(void* stream, const float* g, long long n, double* out, int zero_first) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (zero_first) PA2S_TRY(cudaMemsetAsync(out, 0, sizeof(double), st));
+    long long n4 = ((uintptr_t)g % 16 == 0) ? n / 4 : 0;
+    int ntail = (int)(n - n4 * 4);
+    if (ntail > 256) { n4 = 0; ntail = 0; return -1; }
+    sumsq_kernel<<<592, 256, 0, st>>>((const float4*)g, n4, g + n4 * 4, ntail, out);
+    PA2S_CHECK_LAST();
+    return 0;
+}
+
+PA2S_API int pa2s_adadelta(void* stream, float* p, const float* g, float* sq, float* acc, long long n, const double* sumsq,
+                           float max_norm, float lr, float rho, float eps, float* norm_out) {
+    adadelta_kernel<<<592, 256, 0, (cudaStream_t)stream>>>(p, g, sq, acc, n, sumsq, max_norm, lr, rho, eps, norm_out);
+    PA2S_CHECK_LAST();
+    return 0;
+}

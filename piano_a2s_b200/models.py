@@ -1,0 +1,412 @@
+"""Drop-in replacement for the reference's `models.py` (wei-zeng98/piano-a2s @ ca8bc59), B200-native.
+
+Same public names, constructor arguments (hparams/pretrain.yaml:84-96 == finetune.yaml), forward signatures and
+state_dict keys as /root/reference/models.py, so `!new:models.ScoreTranscription` and checkpoints keep working.
+The nn.Module children are *parameter holders* created in the reference's order with the reference's initialisers
+(identical weights under the same torch seed); every forward dispatches to libpa2s kernels (piano_a2s_b200.ops).
+There is no CPU path: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import hashlib
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops, rng
+
+# ---------------------------------------------------------------------------------------------------------------
+# Vocabulary (data_processing/humdrum.py:70-131 `LabelsMultiple(extended=True)`): 148 + 25 = 173 symbols.
+# ---------------------------------------------------------------------------------------------------------------
+def _pitches(letters, n):
+    return [l * n + acc for l in letters for acc in ("-", "", "#")]
+
+
+class LabelsMultiple:
+    def __init__(self, extended=False):
+        durations = ["1", "1.", "2", "2.", "4", "4.", "8", "8.", "16", "16.", "32", "32.", "64", "64.", "3", "6", "12", "24", "48", "96"]
+        low = ["BBB#"] + _pitches("CDEFGAB", 2)[1:]                       # "CC-" only exists in the extended set
+        mid = _pitches("CDEFGAB", 1) + _pitches("cdefgab", 1) + _pitches("cdefgab", 2) + _pitches("cdefgab", 3)
+        top = _pitches("cdef", 4)[:-1]                                     # ... "ffff-", "ffff"
+        control = ["r", ".", "[", "_", "]", ";", "\t", "\n", "<b>", "<sos>", "<eos>", "<pad>"]
+        self.labels = durations + low + mid + top + control
+        if extended:
+            self.labels += ["128", "20", "40", "176", "112"] + _pitches("CDEFGAB", 3)[1:-1] + ["CC-"]
+        self.labels_map = {c: i for i, c in enumerate(self.labels)}
+        self.labels_map_inv = {i: c for i, c in enumerate(self.labels)}
+
+    def decode(self, tokens):
+        decoded = list(filter(None, [self.labels_map_inv.get(t) for t in tokens]))
+        return [i if i != "<b>" else " " for i in decoded]
+
+    def checksum(self):
+        return hashlib.sha256("\x00".join(self.labels).encode()).hexdigest()
+
+
+labels = LabelsMultiple(extended=True)
+SOS = labels.labels_map["<sos>"]
+EOS = labels.labels_map["<eos>"]
+PAD = labels.labels_map["<pad>"]
+vocab_size = len(labels.labels_map)
+
+
+def _dev(device):
+    d = torch.device(device)
+    if d.type != "cuda":
+        raise RuntimeError("piano_a2s_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
+    return d
+
+
+class ScoreTranscription(nn.Module):
+    def __init__(self, in_channels=1, freq_bins=480, conv_feature_size=256, hidden_size=256, max_bars=5, num_time_sig=7,
+                 num_keys=14, max_length=(437, 129), note_emb_size=16, staff_emb_size=32, time_sig_emb_size=5, key_emb_size=8):
+        super().__init__()
+        self.convstack = ConvStack(in_channels, freq_bins, conv_feature_size)
+        self.encoder = Encoder(conv_feature_size, hidden_size)
+        self.decoder = HierarchicalDecoder(max_bars, num_time_sig, num_keys, hidden_size, max_length, note_emb_size,
+                                           staff_emb_size, time_sig_emb_size, key_emb_size)
+
+    def forward(self, spectrogram, inference=True, ground_truth=None, teacher_forcing_ratio=0.,
+                device=torch.device("cuda" if torch.cuda.is_available() else "cpu")):
+        self.device = device
+        conv_outputs = self.convstack(spectrogram)                       # (B, T, conv_feature_size)
+        encoder_outputs, hidden = self.encoder(conv_outputs)             # (B, T, 2H), (1, B, 2H)
+        return self.decoder(encoder_outputs, hidden, inference, ground_truth, teacher_forcing_ratio, device)
+
+
+class Encoder(nn.Module):
+    def __init__(self, input_size=200, hidden_size=200):
+        super().__init__()
+        self.gru = nn.GRU(input_size=input_size, hidden_size=hidden_size, num_layers=2, batch_first=True, bidirectional=True)
+        self.fc = nn.Linear(hidden_size * 2, hidden_size)
+        self.init_weight()
+
+    def init_weight(self):
+        init_gru(self.gru)
+        init_layer(self.fc)
+
+    def forward(self, x):
+        g = self.gru
+        B = x.shape[0]
+        bg = 4 if B >= 4 else (2 if B >= 2 else 1)
+        hs = []
+        for layer in range(g.num_layers):
+            p = [getattr(g, f"{n}_l{layer}{sfx}") for sfx in ("", "_reverse") for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
+            x, hN = ops.BiGRULayerFn.apply(x, *p, bg)
+            hs.append(hN)
+        hidden1 = torch.tanh(ops.linear(torch.cat((hs[0][0], hs[0][1]), dim=1), self.fc.weight, self.fc.bias))
+        hidden2 = torch.tanh(ops.linear(torch.cat((hs[1][0], hs[1][1]), dim=1), self.fc.weight, self.fc.bias))
+        hidden = torch.cat((hidden1, hidden2), dim=1).unsqueeze(0)       # (1, B, 2H)
+        return x, hidden
+
+
+class HierarchicalDecoder(nn.Module):
+    def __init__(self, max_bars=8, num_time_sig=9, num_keys=14, hidden_size=200, max_length=(437, 129), note_emb_size=16,
+                 staff_emb_size=16, time_sig_emb_size=8, key_emb_size=8):
+        super().__init__()
+        self.max_bars = max_bars
+        self.num_time_sig = num_time_sig
+        self.time_sig_SOS = num_time_sig
+        self.num_keys = num_keys
+        self.key_SOS = num_keys
+        self.hidden_size = hidden_size
+        self.max_length = max_length
+        self.note_emb_size = note_emb_size
+        self.staff_emb_size = staff_emb_size
+        self.time_sig_emb_size = time_sig_emb_size
+        self.key_emb_size = key_emb_size
+
+        self.note_emb = nn.Embedding(vocab_size, note_emb_size)
+        self.time_sig_emb = nn.Embedding(num_time_sig + 1, time_sig_emb_size)
+        self.key_emb = nn.Embedding(num_keys + 1, key_emb_size)
+        self.staff_emb = nn.GRU(note_emb_size, staff_emb_size, num_layers=1, batch_first=True, bidirectional=True)
+
+        self.upper_decoder = NoteDecoder(max_length[0], note_emb_size, hidden_size)
+        self.lower_decoder = NoteDecoder(max_length[1], note_emb_size, hidden_size)
+        self.attn = AttentionLayer(hidden_size)
+        self.gru = nn.GRU(staff_emb_size * 4 + time_sig_emb_size + key_emb_size + hidden_size * 2, hidden_size * 2,
+                          num_layers=1, batch_first=True)
+        self.time_sig_out = nn.Sequential(nn.Linear(hidden_size * 4, hidden_size * 4), nn.ReLU(),
+                                          nn.Linear(hidden_size * 4, hidden_size * 2), nn.ReLU(),
+                                          nn.Linear(hidden_size * 2, num_time_sig))
+        self.key_out = nn.Sequential(nn.Linear(hidden_size * 4, hidden_size * 4), nn.ReLU(),
+                                     nn.Linear(hidden_size * 4, hidden_size * 2), nn.ReLU(),
+                                     nn.Linear(hidden_size * 2, num_keys))
+        self.consume_python_rng = True      # keep the reference's python-`random` consumption count in inference too
+        self.init_weight()
+
+    def init_weight(self):
+        init_gru(self.gru)
+
+    # -- staff summariser ---------------------------------------------------------------------------------------
+    def _staff_summary(self, tokens, lengths):
+        g = self.staff_emb
+        p = [getattr(g, f"{n}_l0{sfx}") for sfx in ("", "_reverse") for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
+        return ops.StaffGRUFn.apply(tokens, lengths, self.note_emb.weight, *p)          # (B, 2*staff_emb)
+
+    def get_SOS_token(self, batch_size):
+        dev = self.note_emb.weight.device
+        se = torch.tensor([[SOS, EOS]], device=dev, dtype=torch.long).repeat(batch_size, 1)
+        staff_token = self._staff_summary(se, torch.full((batch_size,), 2, device=dev, dtype=torch.long)).unsqueeze(1)
+        bar_token = torch.cat([staff_token, staff_token], dim=-1)
+        ts = self.time_sig_emb(torch.full((batch_size, 1), self.time_sig_SOS, device=dev, dtype=torch.long))
+        ky = self.key_emb(torch.full((batch_size, 1), self.key_SOS, device=dev, dtype=torch.long))
+        return torch.cat([bar_token, ts, ky], dim=-1), staff_token
+
+    def get_staff_token_from_probs(self, score_probs, lengths):
+        return self._staff_summary(torch.argmax(score_probs, dim=-1), lengths).unsqueeze(1)
+
+    def get_staff_token_from_gt(self, score_gt, lengths):
+        return self._staff_summary(score_gt, lengths).unsqueeze(1)
+
+    @staticmethod
+    def _steps_from_gt(gt_staff):
+        """(B, bars, L) -> (bars,) executed steps: the reference leaves the loop once every clip's GT row has shown
+        <eos> (models.py:389,412-415), i.e. after max_b(first eos index)+1 steps, or never (L steps)."""
+        L = gt_staff.shape[-1]
+        is_eos = gt_staff == EOS
+        first = torch.where(is_eos.any(-1), is_eos.int().argmax(-1), torch.full_like(gt_staff[..., 0], L - 1))
+        return first.max(0).values + 1
+
+    def _heads(self, seq, x):
+        x = F.relu(ops.linear(x, seq[0].weight, seq[0].bias))
+        x = F.relu(ops.linear(x, seq[2].weight, seq[2].bias))
+        return F.log_softmax(ops.linear(x, seq[4].weight, seq[4].bias), dim=-1)
+
+    def decode_bars(self, encoder_outputs, hidden, inference=True, ground_truth=None, teacher_forcing_ratio=0):
+        enc = encoder_outputs
+        B, T, D = enc.shape
+        dev = enc.device
+        training = self.training
+        src = rng.source()
+        if inference:
+            assert teacher_forcing_ratio == 0
+            assert ground_truth is None
+        have_gt = ground_truth is not None
+        if have_gt:
+            time_sig_gt, key_gt, upper_gt, upper_len_gt, lower_gt, lower_len_gt = ground_truth
+            steps = torch.stack([self._steps_from_gt(upper_gt), self._steps_from_gt(lower_gt)]).cpu().tolist()   # one sync
+        else:
+            steps = [[self.max_length[0]] * self.max_bars, [self.max_length[1]] * self.max_bars]
+
+        # step-invariant encoder half of the three attention layers (models.py:458): Ep = enc W_e^T + b
+        enc2 = enc.reshape(B * T, D)
+        def ep(att):
+            return ops.linear(enc2, att.attn.weight[:, D:], att.attn.bias).view(B, T, -1)
+        Ep_bar, Ep_up, Ep_lo = ep(self.attn), ep(self.upper_decoder.attn), ep(self.lower_decoder.attn)
+
+        token = self.get_SOS_token(B)[0].squeeze(1)                      # (B, 4*staff+ts+key)
+        h = hidden[0]
+        ts_outs, key_outs, up_outs, lo_outs, counters = [], [], [], [], []
+        for bar in range(self.max_bars):
+            if training:
+                token = token * src.dropout_mask((B, 1, token.shape[-1]), 0.1, dev, "bar_token").view(B, -1)
+            q = ops.linear(h, self.attn.attn.weight[:, :D], None)
+            context = ops.AttnStepFn.apply(q, Ep_bar, enc, self.attn.v.weight)
+            g = self.gru
+            h = ops.gru_cell(torch.cat([token, context], dim=1), h, g.weight_ih_l0, g.weight_hh_l0, g.bias_ih_l0, g.bias_hh_l0)
+            bar_summary = h
+            res = []
+            for si, (dec, Ep) in enumerate(((self.upper_decoder, Ep_up), (self.lower_decoder, Ep_lo))):
+                gt_staff = (upper_gt, lower_gt)[si][:, bar, :] if have_gt else None
+                tf_in = teacher_forcing_ratio if have_gt else 0.
+                res.append(dec._decode(enc, Ep, bar_summary, inference, gt_staff, tf_in, steps[si][bar], src))
+            (up_p, up_len, up_cnt), (lo_p, lo_len, lo_cnt) = res
+            counters += [up_cnt, lo_cnt]
+            up_outs.append(up_p)
+            lo_outs.append(lo_p)
+            head_in = torch.cat([bar_summary, context], dim=1)
+            ts_lp = self._heads(self.time_sig_out, head_in)
+            key_lp = self._heads(self.key_out, head_in)
+            ts_outs.append(ts_lp)
+            key_outs.append(key_lp)
+            teacher_force = src.coin() < teacher_forcing_ratio
+            if teacher_force and not inference and have_gt:
+                us = self._staff_summary(upper_gt[:, bar, :], upper_len_gt[:, bar])
+                ls = self._staff_summary(lower_gt[:, bar, :], lower_len_gt[:, bar])
+                tst = self.time_sig_emb(time_sig_gt[:, bar])
+                kyt = self.key_emb(key_gt[:, bar])
+            else:
+                us = self._staff_summary(torch.argmax(up_p, dim=-1), up_len)
+                ls = self._staff_summary(torch.argmax(lo_p, dim=-1), lo_len)
+                tst = self.time_sig_emb(torch.argmax(ts_lp, dim=-1))
+                kyt = self.key_emb(torch.argmax(key_lp, dim=-1))
+            token = torch.cat([us, ls, tst, kyt], dim=-1)
+        if not have_gt and self.consume_python_rng:
+            # the reference draws one coin per executed note step (models.py:404); only the count matters here
+            src.coins(int(torch.stack(counters)[:, 1].sum().item()))
+        self.last_step_counters = counters
+        return (torch.stack(ts_outs, 1), torch.stack(key_outs, 1), torch.stack(up_outs, 1), torch.stack(lo_outs, 1))
+
+    def forward(self, encoder_outputs, hidden, inference=True, ground_truth=None, teacher_forcing_ratio=0,
+                device=torch.device("cuda" if torch.cuda.is_available() else "cpu")):
+        self.device = device
+        if inference:
+            assert teacher_forcing_ratio == 0
+            assert ground_truth is None
+            return self.decode_bars(encoder_outputs, hidden, True, None, 0.)
+        return self.decode_bars(encoder_outputs, hidden, False, ground_truth, teacher_forcing_ratio)
+
+
+class NoteDecoder(nn.Module):
+    def __init__(self, max_steps=25, note_emb_size=128, hidden_size=400):
+        super().__init__()
+        self.max_steps = max_steps
+        self.note_emb_size = note_emb_size
+        self.hidden_size = hidden_size
+        self.embedding = nn.Embedding(vocab_size, note_emb_size)
+        self.attn = AttentionLayer(hidden_size)
+        self.gru = nn.GRU(note_emb_size + hidden_size * 2, hidden_size * 2, num_layers=1, batch_first=True)
+        self.out = nn.Linear(hidden_size * 4, vocab_size)
+        self.init_weight()
+
+    def init_weight(self):
+        init_gru(self.gru)
+        init_layer(self.out)
+
+    def _decode(self, enc, Ep, h0, inference, gt, tf_ratio, S, src):
+        """All steps of one (bar, staff).  Coins/masks are pre-drawn in the reference's order (models.py:391,404)."""
+        B = enc.shape[0]
+        dev = enc.device
+        training = self.training
+        have_gt = gt is not None
+        use_gt = mask = None
+        if have_gt:
+            coins = src.coins(S)
+            if not inference:
+                use_gt = torch.tensor([1 if c < tf_ratio else 0 for c in coins], dtype=torch.int32).to(dev, non_blocking=True)
+        if training:
+            mask = src.dropout_mask((S, B, self.note_emb_size), 0.1, dev, "note_steps").contiguous()
+        cfg = dict(S=S, max_steps=self.max_steps, inference=inference or not have_gt, gt=gt.contiguous() if have_gt else None,
+                   use_gt=use_gt, mask=mask, sos=SOS, eos=EOS)
+        g = self.gru
+        return ops.NoteDecoderFn.apply(enc, Ep, h0, self.attn.attn.weight, self.attn.v.weight, self.embedding.weight,
+                                       g.weight_ih_l0, g.weight_hh_l0, g.bias_ih_l0, g.bias_hh_l0, self.out.weight, self.out.bias, cfg)
+
+    def decode_notes(self, encoder_outputs, hidden, inference=True, ground_truth=None, teacher_forcing_ratio=0):
+        if inference:
+            assert teacher_forcing_ratio == 0
+            assert ground_truth is None
+        enc = encoder_outputs
+        B, T, D = enc.shape
+        Ep = ops.linear(enc.reshape(B * T, D), self.attn.attn.weight[:, D:], self.attn.attn.bias).view(B, T, -1)
+        src = rng.source()
+        if ground_truth is not None:
+            S = int(HierarchicalDecoder._steps_from_gt(ground_truth.unsqueeze(1))[0].item())
+        else:
+            S = self.max_steps
+        logp, lengths, counters = self._decode(enc, Ep, hidden[0], inference, ground_truth, teacher_forcing_ratio, S, src)
+        if ground_truth is None:
+            src.coins(int(counters[1].item()))
+        return logp, lengths.cpu()
+
+    def forward(self, encoder_outputs, hidden, inference=True, ground_truth=None, teacher_forcing_ratio=0,
+                device=torch.device("cuda" if torch.cuda.is_available() else "cpu")):
+        self.device = device
+        if inference:
+            assert teacher_forcing_ratio == 0
+            assert ground_truth is None
+            return self.decode_notes(encoder_outputs, hidden, True, None, 0.)
+        return self.decode_notes(encoder_outputs, hidden, False, ground_truth, teacher_forcing_ratio)
+
+
+class AttentionLayer(nn.Module):
+    def __init__(self, hidden_size):
+        super().__init__()
+        self.attn = nn.Linear(hidden_size * 4, hidden_size)
+        self.v = nn.Linear(hidden_size, 1, bias=False)
+        self.init_weight()
+
+    def init_weight(self):
+        init_layer(self.attn)
+        init_layer(self.v)
+
+    def forward(self, hidden, encoder_output):
+        """(1,B,2H), (B,T,2H) -> softmax attention weights (B,T) (models.py:452-461)."""
+        B, T, D = encoder_output.shape
+        Ep = ops.linear(encoder_output.reshape(B * T, D), self.attn.weight[:, D:], self.attn.bias).view(B, T, -1)
+        q = ops.linear(hidden[0], self.attn.weight[:, :D], None)
+        energy = torch.tanh(q.unsqueeze(1) + Ep)
+        return F.softmax(ops.linear(energy, self.v.weight, None).squeeze(2), dim=1)
+
+
+class ConvStack(nn.Module):
+    def __init__(self, in_channels=1, freq_bins=480, output_size=200):
+        super().__init__()
+        self.conv1 = nn.Conv2d(in_channels, 20, kernel_size=(3, 3), stride=(1, 1), padding=(1, 1), bias=False)
+        self.conv2 = nn.Conv2d(20, 20, kernel_size=(3, 3), stride=(1, 1), padding=(1, 1), bias=False)
+        self.conv3 = nn.Conv2d(20, 40, kernel_size=(3, 3), stride=(1, 1), padding=(1, 1), bias=False)
+        self.conv4 = nn.Conv2d(40, 40, kernel_size=(3, 3), stride=(1, 1), padding=(1, 1), bias=False)
+        self.bn1 = nn.BatchNorm2d(20)
+        self.bn2 = nn.BatchNorm2d(20)
+        self.bn3 = nn.BatchNorm2d(40)
+        self.bn4 = nn.BatchNorm2d(40)
+        self.out = nn.Linear(freq_bins * 40, output_size, bias=False)
+        self.out_bn = nn.BatchNorm1d(output_size)
+        self.init_weight()
+
+    def init_weight(self):
+        for c in (self.conv1, self.conv2, self.conv3, self.conv4):
+            init_layer(c)
+        for b in (self.bn1, self.bn2, self.bn3, self.bn4):
+            init_bn(b)
+        init_layer(self.out)
+        init_bn(self.out_bn)
+
+    def forward(self, x):
+        _dev(x.device)
+        B, _, T, _ = x.shape
+        bns = (self.bn1, self.bn2, self.bn3, self.bn4, self.out_bn)
+        training = self.training
+        mask = None
+        if training:
+            mask = rng.source().dropout_mask((B, T, self.out.weight.shape[0]), 0.2, x.device, "conv")
+        # speechbrain wraps the model with SyncBatchNorm.convert_sync_batchnorm under DDP: honour cross-rank statistics
+        sync = isinstance(self.bn1, nn.SyncBatchNorm) or getattr(self, "sync_batchnorm", False)
+        bufs = [(b.running_mean, b.running_var) for b in bns]
+        params = []
+        for c, b in zip((self.conv1, self.conv2, self.conv3, self.conv4), bns[:4]):
+            params += [c.weight, b.weight, b.bias]
+        params += [self.out.weight, self.out_bn.weight, self.out_bn.bias]
+        y = ops.ConvStackFn.apply(x, mask, bufs, training, sync, float(self.bn1.eps), float(self.bn1.momentum), *params)
+        if training:
+            with torch.no_grad():
+                for b in bns:
+                    b.num_batches_tracked += 1
+        return y
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Initialisers (models.py:548-585)
+# ---------------------------------------------------------------------------------------------------------------
+def init_layer(layer):
+    """Xavier-uniform weight, zero bias."""
+    nn.init.xavier_uniform_(layer.weight)
+    if hasattr(layer, "bias") and layer.bias is not None:
+        layer.bias.data.fill_(0.)
+
+
+def init_bn(bn):
+    bn.bias.data.fill_(0.)
+    bn.weight.data.fill_(1.)
+
+
+def init_gru(rnn):
+    """Per-gate uniform(+-sqrt(3/fan_in)) for W_ih and the r,z blocks of W_hh, orthogonal n block, zero biases.
+    (Like the reference, only the forward-direction parameters of each layer are touched.)"""
+    def _blocks(tensor, fns):
+        n = tensor.shape[0] // len(fns)
+        for i, fn in enumerate(fns):
+            fn(tensor[i * n:(i + 1) * n, :])
+
+    def _uniform(t):
+        fan_in = nn.init._calculate_correct_fan(t, "fan_in")
+        nn.init.uniform_(t, -math.sqrt(3 / fan_in), math.sqrt(3 / fan_in))
+
+    for i in range(rnn.num_layers):
+        _blocks(getattr(rnn, f"weight_ih_l{i}"), [_uniform, _uniform, _uniform])
+        torch.nn.init.constant_(getattr(rnn, f"bias_ih_l{i}"), 0)
+        _blocks(getattr(rnn, f"weight_hh_l{i}"), [_uniform, _uniform, nn.init.orthogonal_])
+        torch.nn.init.constant_(getattr(rnn, f"bias_hh_l{i}"), 0)

@@ -1,0 +1,598 @@
+"""Host-side operators: torch.autograd.Functions whose forward AND backward are libpa2s kernels.
+
+PyTorch here is plumbing only (device memory, streams, autograd bookkeeping between fused groups).  Every function
+raises if its inputs are not CUDA tensors -- there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from ._lib import lib, ptr, stream, make_dec_args
+
+F32 = torch.float32
+N_SM = 148
+
+
+def _f(t: torch.Tensor) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError("piano_a2s_b200 operators run on CUDA (sm_100a) only; got a CPU tensor")
+    if t.dtype != F32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _dist_on() -> bool:
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# GEMM wrapper
+# ----------------------------------------------------------------------------------------------------------------
+def gemm(A, B, C, M, N, K, *, transA=False, transB=False, lda=None, ldb=None, ldc=None, bias=None, accumulate=False,
+         atomic=False, batch=1, strideA=0, strideB=0, strideC=0, t_scale=None, t_shift=None, t_period=1, t_relu=False,
+         t_on_b=False, splitk=1, a_off=0, b_off=0, c_off=0):
+    """C = op(A) op(B); A/B/C are tensors used as raw storage (+ element offsets), see include/pa2s.h."""
+    es = 4
+    pa = ctypes.c_void_p(A.data_ptr() + a_off * es)
+    pb = ctypes.c_void_p(B.data_ptr() + b_off * es)
+    pc = ctypes.c_void_p(C.data_ptr() + c_off * es)
+    lib.pa2s_gemm_f32(stream(), int(transA), int(transB), M, N, K, pa, lda, pb, ldb, pc, ldc, ptr(bias), int(accumulate),
+                      int(atomic), batch, strideA, strideB, strideC, ptr(t_scale), ptr(t_shift), t_period, int(t_relu),
+                      int(t_on_b), splitk)
+    return C
+
+
+def _auto_splitk(M, N, K):
+    tiles = ((M + 127) // 128) * ((N + 127) // 128)
+    if tiles >= N_SM or K < 2048:
+        return 1
+    return max(1, min(K // 512, (2 * N_SM) // tiles))
+
+
+def colsum(X2d: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate=False) -> torch.Tensor:
+    """Column sums of a (R, N) fp32 matrix (fp64 accumulation)."""
+    R, N = X2d.shape
+    if out is None:
+        out = torch.empty(N, device=X2d.device, dtype=F32)
+    lib.pa2s_reduce_rows(stream(), ptr(X2d), R, N, None, ptr(out), int(accumulate))
+    return out
+
+
+class LinearFn(torch.autograd.Function):
+    """y = x W^T + b (F.linear).  W may be a column-sliced view (stride(1) == 1)."""
+
+    @staticmethod
+    def forward(ctx, x, W, b):
+        x2 = _f(x).reshape(-1, x.shape[-1])
+        assert W.stride(1) == 1 and W.dtype == F32
+        M, K = x2.shape
+        N = W.shape[0]
+        y = torch.empty(M, N, device=x.device, dtype=F32)
+        gemm(x2, W, y, M, N, K, transB=True, lda=K, ldb=W.stride(0), ldc=N, bias=b)
+        ctx.save_for_backward(x2, W)
+        ctx.has_bias = b is not None
+        ctx.xshape = x.shape
+        return y.reshape(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, W = ctx.saved_tensors
+        M, K = x2.shape
+        N = W.shape[0]
+        dy2 = _f(dy).reshape(M, N)
+        dx = dW = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(M, K, device=dy.device, dtype=F32)
+            gemm(dy2, W, dx, M, K, N, lda=N, ldb=W.stride(0), ldc=K)
+            dx = dx.reshape(ctx.xshape)
+        if ctx.needs_input_grad[1]:
+            sk = _auto_splitk(N, K, M)
+            dW = (torch.zeros if sk > 1 else torch.empty)(N, K, device=dy.device, dtype=F32)
+            gemm(dy2, x2, dW, N, K, M, transA=True, lda=N, ldb=K, ldc=K, splitk=sk)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = colsum(dy2)
+        return dx, dW, db
+
+
+def linear(x, W, b=None):
+    return LinearFn.apply(x, W, b)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# ConvStack (models.py:463-543) as one fused group
+# ----------------------------------------------------------------------------------------------------------------
+def _bn_sums(partial, C):
+    sums = torch.empty(2 * C, device=partial.device, dtype=torch.float64)
+    lib.pa2s_reduce_rows(stream(), ptr(partial), partial.shape[0], 2 * C, ptr(sums), None, 0)
+    return sums
+
+
+class ConvStackFn(torch.autograd.Function):
+    """spectrogram (B,1,T,F) -> relu(out_bn(out(flatten(relu(bn4(conv4(...)))))))*mask  (B,T,O).
+
+    Argument order: spec, mask(or None), then for i=1..4: conv_i.weight, bn_i.weight, bn_i.bias, then out.weight,
+    out_bn.weight, out_bn.bias; `bufs` = list of 5 (running_mean, running_var) pairs (updated in place when training);
+    `training`, `sync` (cross-rank BatchNorm statistics, SyncBatchNorm semantics), eps, momentum."""
+
+    @staticmethod
+    def forward(ctx, spec, mask, bufs, training, sync, eps, momentum, *params):
+        spec = _f(spec)
+        B, Cin0, T, Fq = spec.shape
+        assert Cin0 == 1, "in_channels must be 1 (pretrain.yaml:85)"
+        dev = spec.device
+        st = stream()
+        conv_w = [params[3 * i] for i in range(4)]
+        gam = [params[3 * i + 1] for i in range(4)] + [params[13]]
+        bet = [params[3 * i + 2] for i in range(4)] + [params[14]]
+        Wout = params[12]
+        O = Wout.shape[0]
+        world = dist.get_world_size() if (sync and _dist_on()) else 1
+        ntile = 4
+        ys, affs = [], []
+        xin, in_scale, in_shift = spec, None, None           # (B,1,T,F) == (B,T,F,1) channels-last
+        for i in range(4):
+            W = conv_w[i]
+            Cout, Cin = W.shape[0], W.shape[1]
+            Wp = W.detach().permute(2, 3, 1, 0).contiguous()
+            y = torch.empty(B, T, Fq, Cout, device=dev, dtype=F32)
+            nparts = lib.pa2s_conv3x3_num_partials(B, T, Fq, ntile)
+            partial = torch.empty(nparts, 2 * Cout, device=dev, dtype=F32) if training else None
+            lib.pa2s_conv3x3(st, 0, B, T, Fq, Cin, Cout, ptr(xin), ptr(Wp), ptr(y), ptr(partial), ntile,
+                             ptr(in_scale), ptr(in_shift), 1, None, None, None, None, None, None, None, None)
+            aff = torch.empty(4, Cout, device=dev, dtype=F32)      # scale, shift, mean, invstd
+            if training:
+                sums = _bn_sums(partial, Cout)
+                if world > 1:
+                    dist.all_reduce(sums)
+                rm, rv = bufs[i]
+                lib.pa2s_bn_finalize(st, ptr(sums), float(B * T * Fq * world), Cout, ptr(gam[i]), ptr(bet[i]), eps, momentum,
+                                     ptr(rm), ptr(rv), ptr(aff[0]), ptr(aff[1]), ptr(aff[2]), ptr(aff[3]))
+            else:
+                rm, rv = bufs[i]
+                lib.pa2s_bn_eval_affine(st, Cout, ptr(gam[i]), ptr(bet[i]), ptr(rm), ptr(rv), eps,
+                                        ptr(aff[0]), ptr(aff[1]), ptr(aff[2]), ptr(aff[3]))
+            ys.append(y)
+            affs.append(aff)
+            xin, in_scale, in_shift = y, aff[0], aff[1]
+        C4 = conv_w[3].shape[0]
+        Kf = Fq * C4
+        # reference feature index is c*F+f (models.py:537); ours is f*C+c
+        Wp_out = Wout.detach().view(O, C4, Fq).permute(0, 2, 1).reshape(O, Kf).contiguous()
+        M = B * T
+        z = torch.empty(M, O, device=dev, dtype=F32)
+        gemm(ys[3], Wp_out, z, M, O, Kf, transB=True, lda=Kf, ldb=Kf, ldc=O,
+             t_scale=affs[3][0], t_shift=affs[3][1], t_period=C4, t_relu=True)
+        aff5 = torch.empty(4, O, device=dev, dtype=F32)
+        if training:
+            nct = 4 * N_SM
+            partial = torch.empty(nct, 2 * O, device=dev, dtype=F32)
+            lib.pa2s_colstats(st, 0, ptr(z), None, None, M, O, None, None, None, None, ptr(partial), nct)
+            sums = _bn_sums(partial, O)
+            if world > 1:
+                dist.all_reduce(sums)
+            rm, rv = bufs[4]
+            lib.pa2s_bn_finalize(st, ptr(sums), float(M * world), O, ptr(gam[4]), ptr(bet[4]), eps, momentum,
+                                 ptr(rm), ptr(rv), ptr(aff5[0]), ptr(aff5[1]), ptr(aff5[2]), ptr(aff5[3]))
+        else:
+            rm, rv = bufs[4]
+            lib.pa2s_bn_eval_affine(st, O, ptr(gam[4]), ptr(bet[4]), ptr(rm), ptr(rv), eps,
+                                    ptr(aff5[0]), ptr(aff5[1]), ptr(aff5[2]), ptr(aff5[3]))
+        out = torch.empty(B, T, O, device=dev, dtype=F32)
+        mk = _f(mask) if mask is not None else None
+        lib.pa2s_bn_relu_mask(st, ptr(z), ptr(aff5[0]), ptr(aff5[1]), ptr(mk), ptr(out), M, O)
+        ctx.save_for_backward(spec, mk, z, aff5, Wp_out, *ys, *affs, *conv_w, *gam)
+        ctx.dims = (B, T, Fq, O, world, training)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        sv = ctx.saved_tensors
+        spec, mk, z, aff5, Wp_out = sv[:5]
+        ys, affs, conv_w, gam = sv[5:9], sv[9:13], sv[13:17], sv[17:22]
+        B, T, Fq, O, world, training = ctx.dims
+        assert training, "backward through ConvStack requires train-mode BatchNorm statistics"
+        dev = dout.device
+        st = stream()
+        dout = _f(dout)
+        M = B * T
+        nct = 4 * N_SM
+        grads = [None] * 15
+
+        def bn_bwd_consts(Y, G, mask, aff, gamma, npix, C):
+            partial = torch.empty(nct, 2 * C, device=dev, dtype=F32)
+            lib.pa2s_colstats(st, 1, ptr(Y), ptr(G), ptr(mask), npix, C, ptr(aff[0]), ptr(aff[1]), ptr(aff[2]), ptr(aff[3]),
+                              ptr(partial), nct)
+            sums = _bn_sums(partial, C)
+            if world > 1:
+                dist.all_reduce(sums)
+            dg = torch.zeros(C, device=dev, dtype=F32)
+            db = torch.zeros(C, device=dev, dtype=F32)
+            k = torch.empty(3, C, device=dev, dtype=F32)
+            lib.pa2s_bn_bwd_finalize(st, ptr(sums), float(npix * world), C, ptr(gamma), ptr(aff[3]), ptr(dg), ptr(db),
+                                     ptr(k[0]), ptr(k[1]), ptr(k[2]))
+            if world > 1:      # DDP averages parameter gradients afterwards; local grads must be the local sums
+                pass
+            return dg, db, k
+
+        # out_bn + relu + dropout backward
+        dg5, db5, k5 = bn_bwd_consts(z, dout, mk, aff5, gam[4], M, O)
+        if world > 1:
+            dg5, db5 = _local_bn_param_grads(z, dout, mk, aff5, M, O, nct, dev)
+        grads[13], grads[14] = dg5, db5
+        dz = torch.empty(M, O, device=dev, dtype=F32)
+        lib.pa2s_bn_bwd_apply(st, ptr(dout), ptr(z), ptr(mk), M, O, ptr(aff5[0]), ptr(aff5[1]), ptr(aff5[2]), ptr(aff5[3]),
+                              ptr(k5[0]), ptr(k5[1]), ptr(k5[2]), ptr(dz))
+        C4 = conv_w[3].shape[0]
+        Kf = Fq * C4
+        # dW_out[n,k] = sum_m dz[m,n] * relu(bn4(y4))[m,k]
+        dWp = torch.zeros(O, Kf, device=dev, dtype=F32)
+        gemm(dz, ys[3], dWp, O, Kf, M, transA=True, lda=O, ldb=Kf, ldc=Kf,
+             t_scale=affs[3][0], t_shift=affs[3][1], t_period=C4, t_relu=True, t_on_b=True, splitk=_auto_splitk(O, Kf, M))
+        grads[12] = dWp.view(O, Fq, C4).permute(0, 2, 1).reshape(O, Kf).contiguous()
+        # G4 = dL/d relu(bn4(y4))
+        G = torch.empty(B, T, Fq, C4, device=dev, dtype=F32)
+        gemm(dz, Wp_out, G, M, Kf, O, lda=O, ldb=Kf, ldc=Kf)
+        nw = 2 * N_SM
+        for i in (3, 2, 1, 0):
+            W = conv_w[i]
+            Cout, Cin = W.shape[0], W.shape[1]
+            y, aff = ys[i], affs[i]
+            npix = B * T * Fq
+            dg, db, k = bn_bwd_consts(y, G, None, aff, gam[i], npix, Cout)
+            if world > 1:
+                dg, db = _local_bn_param_grads(y, G, None, aff, npix, Cout, nct, dev)
+            grads[3 * i + 1], grads[3 * i + 2] = dg, db
+            xin = ys[i - 1] if i > 0 else spec
+            isc = affs[i - 1][0] if i > 0 else None
+            ish = affs[i - 1][1] if i > 0 else None
+            partial = torch.empty(nw, Cout * Cin * 9, device=dev, dtype=F32)
+            lib.pa2s_conv3x3_wgrad(st, B, T, Fq, Cin, Cout, ptr(xin), ptr(G), ptr(partial), nw, ptr(isc), ptr(ish), 1,
+                                   ptr(y), ptr(aff[0]), ptr(aff[1]), ptr(aff[2]), ptr(aff[3]), ptr(k[0]), ptr(k[1]), ptr(k[2]))
+            dW = torch.empty(Cout, Cin, 3, 3, device=dev, dtype=F32)
+            lib.pa2s_reduce_rows(st, ptr(partial), nw, Cout * Cin * 9, None, ptr(dW), 0)
+            grads[3 * i] = dW
+            if i > 0:
+                W2 = W.detach().flip(2, 3).permute(2, 3, 0, 1).contiguous()        # [tap][co][ci]
+                Gp = torch.empty(B, T, Fq, Cin, device=dev, dtype=F32)
+                lib.pa2s_conv3x3(st, 1, B, T, Fq, Cout, Cin, ptr(G), ptr(W2), ptr(Gp), None, 4, None, None, 1,
+                                 ptr(y), ptr(aff[0]), ptr(aff[1]), ptr(aff[2]), ptr(aff[3]), ptr(k[0]), ptr(k[1]), ptr(k[2]))
+                G = Gp
+        return (None, None, None, None, None, None, None, *grads)
+
+
+def _local_bn_param_grads(Y, G, mask, aff, npix, C, nct, dev):
+    """SyncBatchNorm: dgamma/dbeta are LOCAL sums (DDP averages them later), while the input gradient uses the global sums."""
+    partial = torch.empty(nct, 2 * C, device=dev, dtype=F32)
+    lib.pa2s_colstats(stream(), 1, ptr(Y), ptr(G), ptr(mask), npix, C, ptr(aff[0]), ptr(aff[1]), ptr(aff[2]), ptr(aff[3]),
+                      ptr(partial), nct)
+    s = _bn_sums(partial, C).float()
+    return s[C:].contiguous(), s[:C].contiguous()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Encoder BiGRU layer (models.py:63-67,77)
+# ----------------------------------------------------------------------------------------------------------------
+class BiGRULayerFn(torch.autograd.Function):
+    """One bidirectional GRU layer over (B,T,I): returns out (B,T,2H) and h_n (2,B,H)."""
+
+    @staticmethod
+    def forward(ctx, x, w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_b, w_hh_b, b_ih_b, b_hh_b, bg):
+        x = _f(x)
+        B, T, I = x.shape
+        H = w_hh_f.shape[1]
+        dev = x.device
+        Wih = torch.cat([w_ih_f, w_ih_b], 0).detach().contiguous()       # (6H, I)
+        bih = torch.cat([b_ih_f, b_ih_b], 0).detach().contiguous()
+        Whh = torch.stack([w_hh_f, w_hh_b], 0).detach().contiguous()     # (2,3H,H)
+        bhh = torch.stack([b_hh_f, b_hh_b], 0).detach().contiguous()
+        gi = torch.empty(B * T, 6 * H, device=dev, dtype=F32)
+        gemm(x, Wih, gi, B * T, 6 * H, I, transB=True, lda=I, ldb=I, ldc=6 * H, bias=bih)
+        out = torch.empty(B, T, 2 * H, device=dev, dtype=F32)
+        need = any(ctx.needs_input_grad)
+        gates = torch.empty(B, T, 2, 4 * H, device=dev, dtype=F32) if need else None
+        hN = torch.empty(2, B, H, device=dev, dtype=F32)
+        lib.pa2s_gru_seq_fwd(stream(), B, T, 2, H, bg, ptr(gi), ptr(Whh), ptr(bhh), ptr(out), ptr(gates), ptr(hN))
+        if need:
+            ctx.save_for_backward(x, Wih, Whh, out, gates)
+        ctx.bg = bg
+        return out, hN
+
+    @staticmethod
+    def backward(ctx, dout, dhN):
+        x, Wih, Whh, out, gates = ctx.saved_tensors
+        B, T, I = x.shape
+        H = Whh.shape[2]
+        dev = x.device
+        dout = _f(dout) if dout is not None else torch.zeros_like(out)
+        dhN = _f(dhN) if dhN is not None else None
+        dgi = torch.empty(B, T, 6 * H, device=dev, dtype=F32)
+        dgh = torch.empty(B, T, 6 * H, device=dev, dtype=F32)
+        lib.pa2s_gru_seq_bwd(stream(), B, T, 2, H, ctx.bg, ptr(Whh), ptr(out), ptr(gates), ptr(dout), ptr(dhN), ptr(dgi), ptr(dgh))
+        M = B * T
+        dx = torch.empty(B, T, I, device=dev, dtype=F32)
+        gemm(dgi, Wih, dx, M, I, 6 * H, lda=6 * H, ldb=I, ldc=I)
+        dWih = torch.zeros(6 * H, I, device=dev, dtype=F32)
+        gemm(dgi, x, dWih, 6 * H, I, M, transA=True, lda=6 * H, ldb=I, ldc=I, splitk=_auto_splitk(6 * H, I, M))
+        dbih = colsum(dgi.view(M, 6 * H))
+        dbhh = colsum(dgh.view(M, 6 * H))
+        # dW_hh[dir] = sum_{b,t} dgh[b,t,dir]^T h_prev[b,t,dir];  h_prev = out at the previous step of that direction
+        dWhh = torch.zeros(2, 3 * H, H, device=dev, dtype=F32)
+        if T > 1:
+            gemm(dgh, out, dWhh, 3 * H, H, T - 1, transA=True, lda=6 * H, ldb=2 * H, ldc=H, atomic=True, batch=B,
+                 strideA=T * 6 * H, strideB=T * 2 * H, strideC=0, a_off=6 * H, b_off=0, c_off=0)
+            gemm(dgh, out, dWhh, 3 * H, H, T - 1, transA=True, lda=6 * H, ldb=2 * H, ldc=H, atomic=True, batch=B,
+                 strideA=T * 6 * H, strideB=T * 2 * H, strideC=0, a_off=3 * H, b_off=2 * H + H, c_off=3 * H * H)
+        return (dx, dWih[:3 * H], dWhh[0], dbih[:3 * H], dbhh[:3 * H], dWih[3 * H:], dWhh[1], dbih[3 * H:], dbhh[3 * H:], None)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Staff summariser (models.py:164-189)
+# ----------------------------------------------------------------------------------------------------------------
+class StaffGRUFn(torch.autograd.Function):
+    """tokens (B,L) int64, lengths (B) int64 -> (B, 2*S) = [h_n forward | h_n reverse] of the packed BiGRU."""
+
+    @staticmethod
+    def forward(ctx, tokens, lengths, emb, w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_b, w_hh_b, b_ih_b, b_hh_b):
+        tokens = tokens.contiguous()
+        lengths = lengths.to(device=tokens.device, dtype=torch.int64).contiguous()
+        B, L = tokens.shape
+        dev = tokens.device
+        H, I = w_hh_f.shape[1], w_ih_f.shape[1]
+        wih = torch.stack([w_ih_f, w_ih_b]).detach().contiguous()
+        whh = torch.stack([w_hh_f, w_hh_b]).detach().contiguous()
+        bih = torch.stack([b_ih_f, b_ih_b]).detach().contiguous()
+        bhh = torch.stack([b_hh_f, b_hh_b]).detach().contiguous()
+        need = any(ctx.needs_input_grad)
+        hN = torch.empty(B, 2 * H, device=dev, dtype=F32)
+        hs = torch.empty(B, 2, L, H, device=dev, dtype=F32) if need else None
+        gates = torch.empty(B, 2, L, 4 * H, device=dev, dtype=F32) if need else None
+        lib.pa2s_staff_gru_fwd(stream(), B, L, I, H, ptr(tokens), ptr(lengths), ptr(emb), ptr(wih), ptr(whh), ptr(bih), ptr(bhh),
+                               ptr(hN), ptr(hs), ptr(gates))
+        if need:
+            ctx.save_for_backward(tokens, lengths, emb, wih, whh, hs, gates)
+        return hN
+
+    @staticmethod
+    def backward(ctx, dhN):
+        tokens, lengths, emb, wih, whh, hs, gates = ctx.saved_tensors
+        B, L = tokens.shape
+        H, I = whh.shape[2], wih.shape[2]
+        dev = tokens.device
+        d_emb = torch.zeros_like(emb)
+        dwih = torch.zeros_like(wih)
+        dwhh = torch.zeros_like(whh)
+        dbih = torch.zeros(2, 3 * H, device=dev, dtype=F32)
+        dbhh = torch.zeros(2, 3 * H, device=dev, dtype=F32)
+        lib.pa2s_staff_gru_bwd(stream(), B, L, I, H, ptr(tokens), ptr(lengths), ptr(emb), ptr(wih), ptr(whh), ptr(hs), ptr(gates),
+                               ptr(_f(dhN)), ptr(d_emb), ptr(dwih), ptr(dwhh), ptr(dbih), ptr(dbhh))
+        return (None, None, d_emb, dwih[0], dwhh[0], dbih[0], dbhh[0], dwih[1], dwhh[1], dbih[1], dbhh[1])
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# GRU cell gates (bar-level GRU)
+# ----------------------------------------------------------------------------------------------------------------
+class GRUGatesFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, gi, gh, hprev):
+        gi, gh, hprev = _f(gi), _f(gh), _f(hprev)
+        B, H = hprev.shape
+        hnew = torch.empty_like(hprev)
+        save = torch.empty(B, 4 * H, device=gi.device, dtype=F32)
+        lib.pa2s_gru_gates_fwd(stream(), B, H, ptr(gi), ptr(gh), ptr(hprev), ptr(hnew), ptr(save))
+        ctx.save_for_backward(save, hprev)
+        return hnew
+
+    @staticmethod
+    def backward(ctx, dh):
+        save, hprev = ctx.saved_tensors
+        B, H = hprev.shape
+        dgi = torch.empty(B, 3 * H, device=dh.device, dtype=F32)
+        dgh = torch.empty(B, 3 * H, device=dh.device, dtype=F32)
+        dhp = torch.empty_like(hprev)
+        lib.pa2s_gru_gates_bwd(stream(), B, H, ptr(_f(dh)), ptr(save), ptr(hprev), ptr(dgi), ptr(dgh), ptr(dhp))
+        return dgi, dgh, dhp
+
+
+def gru_cell(x, h, w_ih, w_hh, b_ih, b_hh):
+    return GRUGatesFn.apply(linear(x, w_ih, b_ih), linear(h, w_hh, b_hh), h)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Attention (models.py:440-461) -- one step, used by the bar-level decoder
+# ----------------------------------------------------------------------------------------------------------------
+def attn_split(B, T):
+    ns = max(1, min(16, N_SM // max(B, 1)))
+    tile = (T + ns - 1) // ns
+    ns = (T + tile - 1) // tile
+    return ns, tile
+
+
+class AttnStepFn(torch.autograd.Function):
+    """context = softmax_T(v . tanh(q + Ep)) @ enc.   q (B,A) = W_h h;  Ep (B,T,A) = enc W_e^T + b."""
+
+    @staticmethod
+    def forward(ctx, q, Ep, enc, v):
+        q, Ep, enc = _f(q), _f(Ep), _f(enc)
+        vv = _f(v).reshape(-1)
+        B, T, D = enc.shape
+        A = Ep.shape[2]
+        assert D == 512 and A == 256, "attention kernels are specialised for hidden_size=256"
+        dev = q.device
+        NS, tile = attn_split(B, T)
+        z = lambda *s, dt=F32: torch.zeros(*s, device=dev, dtype=dt)
+        e = lambda *s, dt=F32: torch.empty(*s, device=dev, dtype=dt)
+        bufs = dict(attn=e(1, B, T), ctxs=e(1, B, D), xbuf=e(B, 16 + D), hc=e(B, 2 * D), pm=e(B, NS), pl=e(B, NS), pc=e(B, NS, D),
+                    tickets=z(B, dt=torch.int32), counters=z(2, dt=torch.int32))
+        qs = q.reshape(1, B, A).contiguous()
+        args = make_dec_args(B=B, T=T, V=0, VP=0, S=1, max_steps=1, NS=NS, tile=tile, inference=0, save=1, enc=enc, Ep=Ep, v=vv, qs=qs,
+                             **bufs)
+        lib.pa2s_attn_step_fwd(stream(), ctypes.byref(args))
+        ctx.save_for_backward(qs, Ep, enc, vv, bufs["attn"], bufs["ctxs"])
+        ctx.split = (NS, tile)
+        ctx.vshape = v.shape
+        return bufs["ctxs"].reshape(B, D)
+
+    @staticmethod
+    def backward(ctx, dctx):
+        qs, Ep, enc, vv, attn, ctxs = ctx.saved_tensors
+        B, T, D = enc.shape
+        A = Ep.shape[2]
+        dev = enc.device
+        NS, tile = ctx.split
+        d_hc = torch.zeros(B, 2 * D, device=dev, dtype=F32)
+        d_hc[:, D:] = dctx
+        dx = torch.zeros(B, 16 + D, device=dev, dtype=F32)
+        dEp = torch.zeros(B, T, A, device=dev, dtype=F32)
+        dq_part = torch.empty(B, NS, A, device=dev, dtype=F32)
+        dv_part = torch.zeros(B * NS, A, device=dev, dtype=F32)
+        dctx_all = torch.empty(1, B, D, device=dev, dtype=F32)
+        args = make_dec_args(B=B, T=T, V=0, VP=0, S=1, max_steps=1, NS=NS, tile=tile, inference=0, save=1, enc=enc, Ep=Ep, v=vv, qs=qs,
+                             attn=attn, ctxs=ctxs, d_hc=d_hc, dx=dx, dEp=dEp, dq_part=dq_part, dv_part=dv_part, dctx_all=dctx_all)
+        lib.pa2s_attn_step_bwd(stream(), ctypes.byref(args))
+        dq = dq_part.sum(1)
+        dv = colsum(dv_part).reshape(ctx.vshape)
+        denc = context_grad_enc(attn, dctx_all, B, T, D, 1)
+        return dq, dEp, denc, dv
+
+
+def context_grad_enc(attn, dctx_all, B, T, D, S):
+    """d_enc[b] = attn[:, b, :]^T (T x S) @ dctx_all[:, b, :] (S x D): the context read-out's gradient, one GEMM per clip."""
+    denc = torch.empty(B, T, D, device=attn.device, dtype=F32)
+    gemm(attn, dctx_all, denc, T, D, S, transA=True, lda=B * T, ldb=B * D, ldc=D, batch=B, strideA=T, strideB=D, strideC=T * D)
+    return denc
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Note decoder (models.py:366-420) -- all steps of one (bar, staff) in one call
+# ----------------------------------------------------------------------------------------------------------------
+class NoteDecoderFn(torch.autograd.Function):
+    """Returns (logp (B,max_steps,V), lengths (B) int64 device, counters (2) int32 device = [eos_count, steps])."""
+
+    @staticmethod
+    def forward(ctx, enc, Ep, h0, attn_w, attn_v, emb, W_ih, W_hh, b_ih, b_hh, W_out, b_out, cfg):
+        enc, Ep, h0 = _f(enc), _f(Ep), _f(h0)
+        B, T, D = enc.shape
+        A = Ep.shape[2]
+        V, E = emb.shape
+        assert D == 512 and A == 256 and E == 16 and V <= 256, "decoder kernels are specialised for hidden_size=256, note_emb_size=16"
+        dev = enc.device
+        S, max_steps = int(cfg["S"]), int(cfg["max_steps"])
+        inference = bool(cfg["inference"])
+        gt, use_gt, mask = cfg.get("gt"), cfg.get("use_gt"), cfg.get("mask")
+        save = any(ctx.needs_input_grad)
+        VP = (V + 3) // 4 * 4
+        NS, tile = attn_split(B, T)
+        z = lambda *s, dt=F32: torch.zeros(*s, device=dev, dtype=dt)
+        e = lambda *s, dt=F32: torch.empty(*s, device=dev, dtype=dt)
+        SS = S if save else 1
+        logp = z(B, max_steps, V)
+        lengths = torch.full((B,), max_steps, device=dev, dtype=torch.int64)
+        eos = z(B, dt=torch.int32)
+        counters = z(2, dt=torch.int32)
+        hs = e(SS + 1, B, D)
+        hs[0] = h0
+        sv = dict(hs=hs, ctxs=e(SS, B, D), attn=e(SS, B, T), gates=e(SS, B, 4 * D) if save else None, qs=e(SS + 1, B, A),
+                  xtok=e(SS + 1, B, E) if save else None, toks=e(SS + 1, B, dt=torch.int32) if save else None)
+        scratch = dict(xbuf=e(B, E + D), hc=e(B, 2 * D), logits=z(B, VP), pm=e(B, NS), pl=e(B, NS), pc=e(B, NS, D),
+                       tickets=z(B, dt=torch.int32))
+        if gt is not None:
+            gt = gt.contiguous()
+            assert gt.shape == (B, max_steps) and gt.dtype == torch.int64
+        wts = dict(Wattn=attn_w, v=_f(attn_v).reshape(-1), emb=emb, W_ih=W_ih, W_hh=W_hh, b_ih=b_ih, b_hh=b_hh, W_out=W_out, b_out=b_out)
+        for k, w in wts.items():
+            assert w.is_contiguous() and w.dtype == F32, k
+        args = make_dec_args(B=B, T=T, V=V, VP=VP, S=S, max_steps=max_steps, NS=NS, tile=tile, inference=int(inference), save=int(save),
+                             enc=enc, Ep=Ep, gt=gt, use_gt=use_gt, mask=mask, logp=logp, lengths=lengths, eos=eos, counters=counters,
+                             **wts, **sv, **scratch)
+        lib.pa2s_note_decoder_fwd(stream(), ctypes.byref(args), int(cfg["sos"]), int(cfg["eos"]))
+        ctx.mark_non_differentiable(lengths, counters)
+        if save:
+            ctx.save_for_backward(enc, Ep, attn_w, wts["v"], emb, W_ih, W_hh, W_out, logp, sv["hs"], sv["ctxs"], sv["attn"], sv["gates"],
+                                  sv["qs"], sv["xtok"], sv["toks"], mask if mask is not None else torch.empty(0, device=dev))
+            ctx.meta = (B, T, D, A, V, E, VP, S, max_steps, NS, tile, mask is not None, attn_v.shape)
+        return logp, lengths, counters
+
+    @staticmethod
+    def backward(ctx, dlogp, _dl, _dc):
+        (enc, Ep, attn_w, v, emb, W_ih, W_hh, W_out, logp, hs, ctxs, attn, gates, qs, xtok, toks, mask) = ctx.saved_tensors
+        B, T, D, A, V, E, VP, S, max_steps, NS, tile, has_mask, vshape = ctx.meta
+        dev = enc.device
+        st = stream()
+        dlogp = _f(dlogp)
+        X = E + D
+        z = lambda *s, dt=F32: torch.zeros(*s, device=dev, dtype=dt)
+        e = lambda *s, dt=F32: torch.empty(*s, device=dev, dtype=dt)
+        W_outT = z(2 * D, VP)
+        W_outT[:, :V] = W_out.detach().t()
+        W_hT = attn_w.detach()[:, :D].t().contiguous()
+        W_ihT = W_ih.detach().t().contiguous()
+        W_hhT = W_hh.detach().t().contiguous()
+        bw = dict(dlogits_all=e(S, B, VP), dgi_all=e(S, B, 3 * D), dgh_all=e(S, B, 3 * D), dq_all=z(S + 1, B, A), dctx_all=e(S, B, D),
+                  dxtok_all=e(S, B, E), dEp=z(B, T, A), dv_part=z(B * NS, A), d_hc=z(B, 2 * D), dhq=z(B, D), dx=z(B, X),
+                  dq_part=z(B, NS, A), dh_carry=z(2, B, D))
+        args = make_dec_args(B=B, T=T, V=V, VP=VP, S=S, max_steps=max_steps, NS=NS, tile=tile, inference=0, save=1,
+                             enc=enc, Ep=Ep, Wattn=attn_w, v=v, emb=emb, W_ih=W_ih, W_hh=W_hh, W_out=W_out,
+                             W_outT=W_outT, W_hT=W_hT, W_ihT=W_ihT, W_hhT=W_hhT, logp=logp, hs=hs, ctxs=ctxs, attn=attn, gates=gates, qs=qs,
+                             dlogp=dlogp, **bw)
+        lib.pa2s_note_decoder_bwd(st, ctypes.byref(args))
+        SB = S * B
+        # deferred weight gradients: contractions over all (step, clip) rows
+        dW_out = e(V, 2 * D)
+        gemm(bw["dlogits_all"], hs, dW_out, V, D, SB, transA=True, lda=VP, ldb=D, ldc=2 * D, b_off=B * D)          # h' part
+        gemm(bw["dlogits_all"], ctxs, dW_out, V, D, SB, transA=True, lda=VP, ldb=D, ldc=2 * D, c_off=D)             # ctx part
+        db_out = colsum(bw["dlogits_all"].view(SB, VP))[:V].contiguous()
+        dW_ih = e(3 * D, X)
+        gemm(bw["dgi_all"], xtok, dW_ih, 3 * D, E, SB, transA=True, lda=3 * D, ldb=E, ldc=X)
+        gemm(bw["dgi_all"], ctxs, dW_ih, 3 * D, D, SB, transA=True, lda=3 * D, ldb=D, ldc=X, c_off=E)
+        db_ih = colsum(bw["dgi_all"].view(SB, 3 * D))
+        dW_hh = e(3 * D, D)
+        gemm(bw["dgh_all"], hs, dW_hh, 3 * D, D, SB, transA=True, lda=3 * D, ldb=D, ldc=D)
+        db_hh = colsum(bw["dgh_all"].view(SB, 3 * D))
+        d_attn_w = z(A, 2 * D)
+        gemm(bw["dq_all"], hs, d_attn_w, A, D, SB, transA=True, lda=A, ldb=D, ldc=2 * D)                             # W_h half only
+        dv = colsum(bw["dv_part"]).reshape(vshape)
+        # embedding: scatter-add of the (masked) token-input gradients
+        dxt = bw["dxtok_all"]
+        if has_mask:
+            dxt = dxt * mask[:S]
+        d_emb = z(V, E)
+        d_emb.index_add_(0, toks[:S].reshape(-1).long(), dxt.reshape(SB, E))
+        denc = context_grad_enc(attn, bw["dctx_all"], B, T, D, S)
+        dh0 = bw["dh_carry"][0] + bw["dhq"]
+        return (denc, bw["dEp"], dh0, d_attn_w, dv, d_emb, dW_ih, dW_hh, db_ih, db_hh, dW_out, db_out, None)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Loss / optimiser (pretrain.py:56-93, 125-128)
+# ----------------------------------------------------------------------------------------------------------------
+class NLLFn(torch.autograd.Function):
+    """mean over rows with target != ignore of -logp[row, target] (torch.nn.NLLLoss)."""
+
+    @staticmethod
+    def forward(ctx, logp, target, ignore):
+        logp = _f(logp)
+        V = logp.shape[-1]
+        rows = logp.numel() // V
+        tgt = target.reshape(-1).contiguous()
+        assert tgt.numel() == rows and tgt.dtype == torch.int64
+        acc = torch.empty(2, device=logp.device, dtype=F32)
+        lib.pa2s_nll_fwd(stream(), ptr(logp), ptr(tgt), rows, V, ignore, ptr(acc))
+        ctx.save_for_backward(tgt, acc)
+        ctx.meta = (logp.shape, rows, V, ignore)
+        return -(acc[0] / acc[1])
+
+    @staticmethod
+    def backward(ctx, g):
+        tgt, acc = ctx.saved_tensors
+        shape, rows, V, ignore = ctx.meta
+        grad = torch.empty(shape, device=tgt.device, dtype=F32)
+        lib.pa2s_nll_bwd(stream(), ptr(grad), ptr(tgt), rows, V, ignore, ptr(acc), ptr(_f(g).reshape(1)))
+        return grad, None, None
+
+
+def nll_loss(logp, target, ignore_index=-100):
+    return NLLFn.apply(logp, target, int(ignore_index))

@@ -1,0 +1,96 @@
+"""Batched on-GPU variable-Q transform front end: drop-in for `utilities.get_VQT` (utilities.py:240-254).
+
+The reference calls `librosa.vqt(y, sr=16000, hop_length=160, fmin=A0, n_bins=480, bins_per_octave=60, gamma=20)`
+on the CPU, one clip at a time, offline.  Here the transform is evaluated in its direct (time-domain) form as ONE
+strided complex filterbank contraction over overlapping frames of the zero-padded clip
+(row stride = hop, so the frame matrix is never materialised), followed by a fused |.| / per-clip max / dB / scale
+epilogue.  Filter design (host, float64, once): librosa's wavelet definition -- see DESIGN.md "VQT".
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import ops
+from ._lib import lib, ptr, stream
+
+FMIN_A0 = 27.5     # librosa.note_to_hz('A0')
+WINDOW = 1024      # analysis window holding the longest filter (787 taps), centred on t*hop
+
+
+def design_filters(sample_rate=16000, bins_per_octave=60, n_octaves=8, gamma=20, window=WINDOW):
+    """-> (2*n_bins, K) float32 rows [re_0, im_0, re_1, ...] restricted to the K-column support, and the support offset.
+
+    b_k[o] = exp(2i*pi*f_k*o/sr) * hann_periodic(n)[o - o_min], o = arange(-N_k//2, N_k//2), L1-normalised, times
+    sqrt(N_k); N_k = Q*sr/(f_k + gamma/alpha), alpha = (2^(2/bpo)-1)/(2^(2/bpo)+1), Q = 1/alpha
+    (librosa filters.wavelet / wavelet_lengths with filter_scale=1, norm=1, window='hann'; vqt(scale=True))."""
+    n_bins = bins_per_octave * n_octaves
+    freqs = FMIN_A0 * 2.0 ** (np.arange(n_bins, dtype=np.float64) / bins_per_octave)
+    r = 2.0 ** (2.0 / bins_per_octave)
+    alpha = (r - 1.0) / (r + 1.0)
+    lengths = (1.0 / alpha) * sample_rate / (freqs + gamma / alpha)
+    G = np.zeros((n_bins, window), dtype=np.complex128)
+    for k in range(n_bins):
+        o = np.arange(-lengths[k] // 2, lengths[k] // 2, dtype=np.float64)
+        n = len(o)
+        sig = np.exp(2j * np.pi * freqs[k] * o / sample_rate) * (0.5 - 0.5 * np.cos(2.0 * np.pi * np.arange(n) / n))
+        sig /= np.abs(sig).sum()
+        j = (window // 2 - o).astype(np.int64)
+        if j.min() < 0 or j.max() >= window:
+            raise ValueError("filter longer than the analysis window")
+        G[k, j] = sig * np.sqrt(lengths[k])
+    nz = np.nonzero(np.abs(G).sum(0))[0]
+    j0 = (nz.min() // 4) * 4                               # keep 16-byte alignment of the frame rows
+    j1 = ((nz.max() + 1 + 15) // 16) * 16
+    j1 = min(max(j1, j0 + 16), window)
+    W = np.empty((2 * n_bins, j1 - j0), dtype=np.float32)
+    W[0::2] = G.real[:, j0:j1]
+    W[1::2] = G.imag[:, j0:j1]
+    return W, int(j0)
+
+
+class VQT(torch.nn.Module):
+    """audio (B, n_samples) float32 on CUDA -> (B, 1 + n_samples//hop, n_bins) float32 in [0, 1]."""
+
+    def __init__(self, sample_rate=16000, hop_length=160, bins_per_octave=60, n_octaves=8, gamma=20):
+        super().__init__()
+        self.hop = hop_length
+        self.n_bins = bins_per_octave * n_octaves
+        W, j0 = design_filters(sample_rate, bins_per_octave, n_octaves, gamma)
+        self.j0 = j0
+        self.register_buffer("filters", torch.from_numpy(W), persistent=False)
+
+    @torch.no_grad()
+    def forward(self, audio):
+        if not audio.is_cuda:
+            raise RuntimeError("VQT runs on CUDA only")
+        audio = audio.float()
+        B, n = audio.shape
+        T = 1 + n // self.hop
+        K = self.filters.shape[1]
+        half = WINDOW // 2
+        plen = ((half + n + half + self.hop + 3) // 4) * 4
+        ypad = torch.zeros(B, plen, device=audio.device, dtype=torch.float32)
+        ypad[:, half:half + n] = audio
+        C = torch.empty(B, T, 2 * self.n_bins, device=audio.device, dtype=torch.float32)
+        # frames[t, j] = ypad[t*hop + j0 + j]: overlapping rows, lda = hop
+        ops.gemm(ypad, self.filters, C, T, 2 * self.n_bins, K, transB=True, lda=self.hop, ldb=K, ldc=2 * self.n_bins,
+                 batch=B, strideA=plen, strideB=0, strideC=T * 2 * self.n_bins, a_off=self.j0)
+        out = torch.empty(B, T, self.n_bins, device=audio.device, dtype=torch.float32)
+        cmax = torch.empty(B, device=audio.device, dtype=torch.int32)
+        lib.pa2s_vqt_post(stream(), ptr(C), ptr(out), ptr(cmax), B, T, self.n_bins)
+        return out
+
+
+_CACHE = {}
+
+
+def get_VQT(audio_or_path, hparams):
+    """Same signature as utilities.get_VQT: (frames, n_bins) float32 numpy for one clip."""
+    if isinstance(audio_or_path, str):
+        raise NotImplementedError("file decoding/resampling (librosa.load) is outside the hot path; pass a 16 kHz mono array")
+    key = (hparams["sample_rate"], hparams["hop_length"], hparams["bins_per_octave"], hparams["n_octaves"], hparams["gamma"])
+    if key not in _CACHE:
+        _CACHE[key] = VQT(*key).cuda()
+    y = torch.as_tensor(np.asarray(audio_or_path), dtype=torch.float32).cuda().reshape(1, -1)
+    return _CACHE[key](y)[0].cpu().numpy()

@@ -1,0 +1,253 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Tolerances (fp32 path): activations 1e-4 relative (BASELINE north_star), gradients 2e-3 relative to the largest
+entry of each tensor (sums over 1e4..1e7 terms in a different order), greedy tokens bit-identical.
+"""
+import random
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import ReplayDeviceSource, make_ground_truth, rel_err, synth_state_dict
+from oracle import a2s_oracle as O
+from oracle import vqt_oracle as VO
+
+pytestmark = pytest.mark.gpu
+
+ACT_TOL = 1e-4
+GRAD_TOL = 2e-3
+
+
+def _model(cuda, **cfg):
+    import models
+    torch.manual_seed(1234)
+    m = models.ScoreTranscription(**cfg)
+    sd = synth_state_dict(m)
+    m.load_state_dict(sd)
+    return m.to(cuda), sd
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,K", [(1, 1, 1), (37, 53, 19), (128, 128, 16), (200, 173, 1024), (300, 40, 515)])
+def test_gemm_shapes(cuda, ta, tb, M, N, K):
+    from piano_a2s_b200 import ops
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    A = torch.randn((K, M) if ta else (M, K), generator=g)
+    Bm = torch.randn((N, K) if tb else (K, N), generator=g)
+    bias = torch.randn(N, generator=g)
+    ref = (A.t() if ta else A).double() @ (Bm.t() if tb else Bm).double() + bias.double()
+    C = torch.empty(M, N, device=cuda)
+    ops.gemm(A.to(cuda), Bm.to(cuda), C, M, N, K, transA=bool(ta), transB=bool(tb), lda=A.shape[1], ldb=Bm.shape[1], ldc=N,
+             bias=bias.to(cuda))
+    assert rel_err(C, ref) < 1e-5
+    # split-K / atomic accumulate on top of an existing C
+    C2 = torch.ones(M, N, device=cuda)
+    ops.gemm(A.to(cuda), Bm.to(cuda), C2, M, N, K, transA=bool(ta), transB=bool(tb), lda=A.shape[1], ldb=Bm.shape[1], ldc=N,
+             bias=bias.to(cuda), splitk=3)
+    assert rel_err(C2, ref + 1) < 1e-5
+
+
+def test_gemm_batched_transform_overlap(cuda):
+    from piano_a2s_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    # operand transform relu(x*s[c]+t[c]) with period 5 on A (k index) and on B (n index)
+    M, N, K, P = 70, 45, 60, 5
+    A = torch.randn(M, K, generator=g); Bm = torch.randn(N, K, generator=g)
+    s = torch.randn(P, generator=g); t = torch.randn(P, generator=g)
+    At = F.relu(A * s.repeat(K // P) + t.repeat(K // P))
+    C = torch.empty(M, N, device=cuda)
+    ops.gemm(A.to(cuda), Bm.to(cuda), C, M, N, K, transB=True, lda=K, ldb=K, ldc=N, t_scale=s.to(cuda), t_shift=t.to(cuda),
+             t_period=P, t_relu=True)
+    assert rel_err(C, At.double() @ Bm.double().t()) < 1e-5
+    Bn = torch.randn(K, N, generator=g)
+    Bt = F.relu(Bn * s.repeat(N // P) + t.repeat(N // P))
+    A2 = torch.randn(K, M, generator=g)
+    C = torch.empty(M, N, device=cuda)
+    ops.gemm(A2.to(cuda), Bn.to(cuda), C, M, N, K, transA=True, lda=M, ldb=N, ldc=N, t_scale=s.to(cuda), t_shift=t.to(cuda),
+             t_period=P, t_relu=True, t_on_b=True, splitk=2) if False else None
+    C = torch.zeros(M, N, device=cuda)
+    ops.gemm(A2.to(cuda), Bn.to(cuda), C, M, N, K, transA=True, lda=M, ldb=N, ldc=N, t_scale=s.to(cuda), t_shift=t.to(cuda),
+             t_period=P, t_relu=True, t_on_b=True, splitk=2)
+    assert rel_err(C, A2.double().t() @ Bt.double()) < 1e-5
+    # overlapping rows (lda < K), batched: the VQT frame matrix
+    y = torch.randn(2, 1000, generator=g)
+    W = torch.randn(12, 64, generator=g)
+    Tn, hop = 20, 16
+    C = torch.empty(2, Tn, 12, device=cuda)
+    ops.gemm(y.to(cuda), W.to(cuda), C, Tn, 12, 64, transB=True, lda=hop, ldb=64, ldc=12, batch=2, strideA=1000, strideB=0,
+             strideC=Tn * 12, a_off=8)
+    fr = torch.stack([torch.stack([y[b, 8 + t * hop: 8 + t * hop + 64] for t in range(Tn)]) for b in range(2)])
+    assert rel_err(C, fr.double() @ W.double().t()) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ VQT
+def test_vqt_matches_direct_form_oracle(cuda):
+    from piano_a2s_b200.vqt import VQT
+    rng_ = np.random.default_rng(0)
+    t = np.arange(192000) / 16000.0
+    clips = [np.clip(0.25 * rng_.standard_normal(192000), -1, 1),
+             0.4 * np.sin(2 * np.pi * 440 * t) + 0.2 * np.sin(2 * np.pi * 3520 * t * (1 + 0.01 * t)) + 0.001 * rng_.standard_normal(192000)]
+    y = torch.tensor(np.stack(clips), dtype=torch.float32)
+    out = VQT().to(cuda)(y.to(cuda)).cpu().numpy()
+    assert out.shape == (2, 1201, 480)
+    for i in range(2):
+        ref = VO.get_vqt(y[i].numpy())
+        err = np.abs(out[i] - ref)
+        print("vqt clip", i, "max abs err", err.max(), "mean", err.mean())
+        assert err.max() < 2e-4        # output is in [0,1] (dB/80+1); 2e-4 == 0.016 dB
+    # short / ragged clip: frames = 1 + n//hop, zero outside the clip
+    ys = y[:1, :16000 * 3 + 77]
+    o = VQT().to(cuda)(ys.to(cuda)).cpu().numpy()[0]
+    r = VO.get_vqt(ys[0].numpy())
+    assert o.shape == r.shape and np.abs(o - r).max() < 2e-4
+
+
+# ------------------------------------------------------------------------------------------------ ConvStack
+@pytest.mark.parametrize("B,T,Fq", [(2, 20, 32), (3, 21, 37)])
+def test_convstack_eval_train_backward(cuda, B, T, Fq):
+    import models
+    torch.manual_seed(0)
+    cs = models.ConvStack(1, Fq, 256)
+    sd = synth_state_dict(cs)
+    cs.load_state_dict(sd)
+    cs = cs.to(cuda)
+    sdo = {"convstack." + k: v.clone() for k, v in sd.items()}
+    x = torch.rand(B, 1, T, Fq, generator=torch.Generator().manual_seed(5))
+    # eval
+    cs.eval()
+    with torch.no_grad():
+        y = cs(x.to(cuda))
+        ref = O.conv_stack(x, sdo, False, O.RandomSource())
+    e = rel_err(y, ref)
+    print("convstack eval rel err", e)
+    assert e < ACT_TOL
+    # train forward + backward with a replayed dropout mask
+    rec = O.RecordingSource()
+    torch.manual_seed(11)
+    sdg = {k: v.clone().requires_grad_(v.dtype == torch.float32 and "running" not in k) for k, v in sdo.items()}
+    ns = {}
+    ref = O.conv_stack(x, sdg, True, rec, new_stats=ns)
+    w = torch.randn(ref.shape, generator=torch.Generator().manual_seed(6))
+    (ref * w).sum().backward()
+    from piano_a2s_b200 import rng
+    cs.train()
+    with rng.use_source(ReplayDeviceSource([], rec.masks)):
+        y = cs(x.to(cuda))
+    (y * w.to(cuda)).sum().backward()
+    e = rel_err(y, ref)
+    print("convstack train rel err", e)
+    assert e < ACT_TOL
+    for k, p in cs.named_parameters():
+        ge = rel_err(p.grad, sdg["convstack." + k].grad)
+        print("  grad", k, ge)
+        assert ge < GRAD_TOL, k
+    for k, v in ns.items():
+        got = cs.state_dict()[k[len("convstack."):]]
+        assert rel_err(got.float(), v.float()) < 1e-5, k
+
+
+# ------------------------------------------------------------------------------------------------ Encoder
+@pytest.mark.parametrize("B,T", [(1, 9), (3, 17), (5, 6)])
+def test_encoder_forward_backward(cuda, B, T):
+    import models
+    torch.manual_seed(0)
+    enc = models.Encoder(256, 256)
+    sd = synth_state_dict(enc)
+    enc.load_state_dict(sd)
+    enc = enc.to(cuda)
+    x = torch.randn(B, T, 256, generator=torch.Generator().manual_seed(2))
+    sdg = {"encoder." + k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    xo = x.clone().requires_grad_(True)
+    ro, rh = O.encoder(xo, sdg)
+    w1 = torch.randn(ro.shape, generator=torch.Generator().manual_seed(3))
+    w2 = torch.randn(rh.shape, generator=torch.Generator().manual_seed(4))
+    ((ro * w1).sum() + (rh * w2).sum()).backward()
+    xc = x.to(cuda).requires_grad_(True)
+    yo, yh = enc(xc)
+    ((yo * w1.to(cuda)).sum() + (yh * w2.to(cuda)).sum()).backward()
+    print("encoder out", rel_err(yo, ro), "hidden", rel_err(yh, rh), "dx", rel_err(xc.grad, xo.grad))
+    assert rel_err(yo, ro) < ACT_TOL and rel_err(yh, rh) < ACT_TOL
+    assert rel_err(xc.grad, xo.grad) < GRAD_TOL
+    for k, p in enc.named_parameters():
+        g = sdg["encoder." + k].grad
+        if g is None:
+            continue
+        ge = rel_err(p.grad, g)
+        print("  grad", k, ge)
+        assert ge < GRAD_TOL, k
+
+
+# ------------------------------------------------------------------------------------------------ full model
+SMALL = dict(freq_bins=32, max_bars=2, max_length=(14, 9))
+
+
+def test_model_greedy_inference_matches_oracle(cuda):
+    m, sd = _model(cuda, **SMALL)
+    m.eval()
+    B, T = 3, 24
+    x = torch.rand(B, 1, T, 32, generator=torch.Generator().manual_seed(9))
+    with torch.no_grad():
+        outs = m(x.to(cuda), device=cuda)
+        ref = O.score_transcription(sd, x, SMALL)
+    for name, a, b in zip(("time_sig", "key", "upper", "lower"), outs, ref):
+        print("greedy", name, rel_err(a, b))
+        assert rel_err(a, b) < 5e-4, name
+    assert O.greedy_tokens([o.cpu() for o in outs]) == O.greedy_tokens(ref)
+
+
+def test_model_training_forward_backward_matches_oracle(cuda):
+    from piano_a2s_b200 import rng
+    from piano_a2s_b200.train import compute_objectives
+    m, sd = _model(cuda, **SMALL)
+    m.train()
+    B, T = 3, 24
+    x = torch.rand(B, 1, T, 32, generator=torch.Generator().manual_seed(9))
+    gt = make_ground_truth(B, 2, 14, 9, seed=4, lo_up=(3, 13), lo_lo=(2, 9))
+    rec = O.RecordingSource()
+    torch.manual_seed(21)
+    random.seed(21)
+    sdg = {k: v.clone().requires_grad_(v.dtype == torch.float32 and "running" not in k) for k, v in sd.items()}
+    trace = []
+    ref = O.score_transcription(sdg, x, SMALL, False, gt, 0.6, True, rec, trace=trace)
+    ref_loss = O.training_loss(ref, gt)
+    ref_loss.backward()
+    with rng.use_source(ReplayDeviceSource(rec.coins, rec.masks)):
+        outs = m(x.to(cuda), inference=False, ground_truth=[g.to(cuda) for g in gt], teacher_forcing_ratio=0.6, device=cuda)
+    loss, _ = compute_objectives(outs, [g.to(cuda) for g in gt])
+    loss.backward()
+    print("steps", trace, "loss", loss.item(), ref_loss.item())
+    for name, a, b in zip(("time_sig", "key", "upper", "lower"), outs, ref):
+        print("train", name, rel_err(a, b))
+        assert rel_err(a, b) < 5e-4, name
+    assert abs(loss.item() - ref_loss.item()) < 1e-4 * abs(ref_loss.item())
+    bad = []
+    for k, p in m.named_parameters():
+        g = sdg[k].grad
+        if g is None or p.grad is None:
+            assert (g is None or g.abs().max() == 0) and (p.grad is None or p.grad.abs().max() == 0), k
+            continue
+        ge = rel_err(p.grad, g)
+        print("  grad %-50s %.2e  (|g|max %.2e)" % (k, ge, g.abs().max().item()))
+        if ge > GRAD_TOL:
+            bad.append((k, ge))
+    assert not bad, bad
+
+
+def test_adadelta_step_matches_oracle(cuda):
+    from piano_a2s_b200.train import FlatAdadelta
+    lin = torch.nn.Linear(37, 11).to(cuda)
+    opt = FlatAdadelta(lin)
+    params = {k: v.detach().cpu().clone() for k, v in lin.named_parameters()}
+    state = {k: (torch.zeros_like(v), torch.zeros_like(v)) for k, v in params.items()}
+    for it in range(3):
+        g = {k: torch.randn(v.shape, generator=torch.Generator().manual_seed(it)) * (30.0 if it == 1 else 0.1) for k, v in params.items()}
+        for k, p in lin.named_parameters():
+            p.grad.copy_(g[k].to(cuda))
+        n = opt.step()
+        n_ref = O.adadelta_step(params, g, state)
+        assert abs(n.item() - n_ref.item()) < 1e-4 * n_ref.item()
+        for k, p in lin.named_parameters():
+            assert rel_err(p, params[k]) < 1e-5, (it, k)
