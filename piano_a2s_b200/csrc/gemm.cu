@@ -196,6 +196,7 @@ PA2S_API int pa2s_gemm_f32(void* stream, int transA, int transB, int M, int N, i
     g.sA = strideA; g.sB = strideB; g.sC = strideC;
     g.batch = batch;
     if (splitk < 1) splitk = 1;
+    if (splitk > 1) atomic = 1;          // a split-K request always means "add into C", even if K is too small to split
     int kchunk = ceil_div(ceil_div(K, splitk), BK) * BK;
     if (kchunk < BK) kchunk = BK;
     splitk = ceil_div(K > 0 ? K : 1, kchunk);

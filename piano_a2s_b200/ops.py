@@ -25,6 +25,38 @@ def _f(t: torch.Tensor) -> torch.Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
 
+class KernelTimers:
+    """Optional CUDA-event brackets around named kernel launches (bench.py roofline leg).  Disabled by default."""
+    enabled = False
+    events = {}
+
+    @classmethod
+    def reset(cls, enabled):
+        cls.enabled = enabled
+        cls.events = {}
+
+    @classmethod
+    def summary(cls):
+        """-> {name: (launches, mean_ms)}; call after torch.cuda.synchronize()."""
+        return {k: (len(v), sum(a.elapsed_time(b) for a, b in v) / len(v)) for k, v in cls.events.items() if v}
+
+
+class ktime:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if KernelTimers.enabled:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+
+    def __exit__(self, *exc):
+        if KernelTimers.enabled:
+            b = torch.cuda.Event(enable_timing=True)
+            b.record()
+            KernelTimers.events.setdefault(self.name, []).append((self.a, b))
+
+
 def _dist_on() -> bool:
     return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
@@ -141,8 +173,9 @@ class ConvStackFn(torch.autograd.Function):
             y = torch.empty(B, T, Fq, Cout, device=dev, dtype=F32)
             nparts = lib.pa2s_conv3x3_num_partials(B, T, Fq, ntile)
             partial = torch.empty(nparts, 2 * Cout, device=dev, dtype=F32) if training else None
-            lib.pa2s_conv3x3(st, 0, B, T, Fq, Cin, Cout, ptr(xin), ptr(Wp), ptr(y), ptr(partial), ntile,
-                             ptr(in_scale), ptr(in_shift), 1, None, None, None, None, None, None, None, None)
+            with ktime(f"conv{i + 1}_fwd"):
+                lib.pa2s_conv3x3(st, 0, B, T, Fq, Cin, Cout, ptr(xin), ptr(Wp), ptr(y), ptr(partial), ntile,
+                                 ptr(in_scale), ptr(in_shift), 1, None, None, None, None, None, None, None, None)
             aff = torch.empty(4, Cout, device=dev, dtype=F32)      # scale, shift, mean, invstd
             if training:
                 sums = _bn_sums(partial, Cout)
@@ -164,8 +197,9 @@ class ConvStackFn(torch.autograd.Function):
         Wp_out = Wout.detach().view(O, C4, Fq).permute(0, 2, 1).reshape(O, Kf).contiguous()
         M = B * T
         z = torch.empty(M, O, device=dev, dtype=F32)
-        gemm(ys[3], Wp_out, z, M, O, Kf, transB=True, lda=Kf, ldb=Kf, ldc=O,
-             t_scale=affs[3][0], t_shift=affs[3][1], t_period=C4, t_relu=True)
+        with ktime("out_linear_fwd"):
+            gemm(ys[3], Wp_out, z, M, O, Kf, transB=True, lda=Kf, ldb=Kf, ldc=O,
+                 t_scale=affs[3][0], t_shift=affs[3][1], t_period=C4, t_relu=True)
         aff5 = torch.empty(4, O, device=dev, dtype=F32)
         if training:
             nct = 4 * N_SM
@@ -230,12 +264,14 @@ class ConvStackFn(torch.autograd.Function):
         Kf = Fq * C4
         # dW_out[n,k] = sum_m dz[m,n] * relu(bn4(y4))[m,k]
         dWp = torch.zeros(O, Kf, device=dev, dtype=F32)
-        gemm(dz, ys[3], dWp, O, Kf, M, transA=True, lda=O, ldb=Kf, ldc=Kf,
-             t_scale=affs[3][0], t_shift=affs[3][1], t_period=C4, t_relu=True, t_on_b=True, splitk=_auto_splitk(O, Kf, M))
+        with ktime("out_linear_wgrad"):
+            gemm(dz, ys[3], dWp, O, Kf, M, transA=True, lda=O, ldb=Kf, ldc=Kf,
+                 t_scale=affs[3][0], t_shift=affs[3][1], t_period=C4, t_relu=True, t_on_b=True, splitk=_auto_splitk(O, Kf, M))
         grads[12] = dWp.view(O, Fq, C4).permute(0, 2, 1).reshape(O, Kf).contiguous()
         # G4 = dL/d relu(bn4(y4))
         G = torch.empty(B, T, Fq, C4, device=dev, dtype=F32)
-        gemm(dz, Wp_out, G, M, Kf, O, lda=O, ldb=Kf, ldc=Kf)
+        with ktime("out_linear_dgrad"):
+            gemm(dz, Wp_out, G, M, Kf, O, lda=O, ldb=Kf, ldc=Kf)
         nw = 2 * N_SM
         for i in (3, 2, 1, 0):
             W = conv_w[i]
@@ -250,16 +286,18 @@ class ConvStackFn(torch.autograd.Function):
             isc = affs[i - 1][0] if i > 0 else None
             ish = affs[i - 1][1] if i > 0 else None
             partial = torch.empty(nw, Cout * Cin * 9, device=dev, dtype=F32)
-            lib.pa2s_conv3x3_wgrad(st, B, T, Fq, Cin, Cout, ptr(xin), ptr(G), ptr(partial), nw, ptr(isc), ptr(ish), 1,
-                                   ptr(y), ptr(aff[0]), ptr(aff[1]), ptr(aff[2]), ptr(aff[3]), ptr(k[0]), ptr(k[1]), ptr(k[2]))
+            with ktime(f"conv{i + 1}_wgrad"):
+                lib.pa2s_conv3x3_wgrad(st, B, T, Fq, Cin, Cout, ptr(xin), ptr(G), ptr(partial), nw, ptr(isc), ptr(ish), 1,
+                                       ptr(y), ptr(aff[0]), ptr(aff[1]), ptr(aff[2]), ptr(aff[3]), ptr(k[0]), ptr(k[1]), ptr(k[2]))
             dW = torch.empty(Cout, Cin, 3, 3, device=dev, dtype=F32)
             lib.pa2s_reduce_rows(st, ptr(partial), nw, Cout * Cin * 9, None, ptr(dW), 0)
             grads[3 * i] = dW
             if i > 0:
                 W2 = W.detach().flip(2, 3).permute(2, 3, 0, 1).contiguous()        # [tap][co][ci]
                 Gp = torch.empty(B, T, Fq, Cin, device=dev, dtype=F32)
-                lib.pa2s_conv3x3(st, 1, B, T, Fq, Cout, Cin, ptr(G), ptr(W2), ptr(Gp), None, 4, None, None, 1,
-                                 ptr(y), ptr(aff[0]), ptr(aff[1]), ptr(aff[2]), ptr(aff[3]), ptr(k[0]), ptr(k[1]), ptr(k[2]))
+                with ktime(f"conv{i + 1}_dgrad"):
+                    lib.pa2s_conv3x3(st, 1, B, T, Fq, Cout, Cin, ptr(G), ptr(W2), ptr(Gp), None, 4, None, None, 1,
+                                     ptr(y), ptr(aff[0]), ptr(aff[1]), ptr(aff[2]), ptr(aff[3]), ptr(k[0]), ptr(k[1]), ptr(k[2]))
                 G = Gp
         return (None, None, None, None, None, None, None, *grads)
 
@@ -295,7 +333,8 @@ class BiGRULayerFn(torch.autograd.Function):
         need = any(ctx.needs_input_grad)
         gates = torch.empty(B, T, 2, 4 * H, device=dev, dtype=F32) if need else None
         hN = torch.empty(2, B, H, device=dev, dtype=F32)
-        lib.pa2s_gru_seq_fwd(stream(), B, T, 2, H, bg, ptr(gi), ptr(Whh), ptr(bhh), ptr(out), ptr(gates), ptr(hN))
+        with ktime("encoder_gru_fwd"):
+            lib.pa2s_gru_seq_fwd(stream(), B, T, 2, H, bg, ptr(gi), ptr(Whh), ptr(bhh), ptr(out), ptr(gates), ptr(hN))
         if need:
             ctx.save_for_backward(x, Wih, Whh, out, gates)
         ctx.bg = bg
@@ -311,7 +350,8 @@ class BiGRULayerFn(torch.autograd.Function):
         dhN = _f(dhN) if dhN is not None else None
         dgi = torch.empty(B, T, 6 * H, device=dev, dtype=F32)
         dgh = torch.empty(B, T, 6 * H, device=dev, dtype=F32)
-        lib.pa2s_gru_seq_bwd(stream(), B, T, 2, H, ctx.bg, ptr(Whh), ptr(out), ptr(gates), ptr(dout), ptr(dhN), ptr(dgi), ptr(dgh))
+        with ktime("encoder_gru_bwd"):
+            lib.pa2s_gru_seq_bwd(stream(), B, T, 2, H, ctx.bg, ptr(Whh), ptr(out), ptr(gates), ptr(dout), ptr(dhN), ptr(dgi), ptr(dgh))
         M = B * T
         dx = torch.empty(B, T, I, device=dev, dtype=F32)
         gemm(dgi, Wih, dx, M, I, 6 * H, lda=6 * H, ldb=I, ldc=I)
@@ -504,11 +544,13 @@ class NoteDecoderFn(torch.autograd.Function):
             assert gt.shape == (B, max_steps) and gt.dtype == torch.int64
         wts = dict(Wattn=attn_w, v=_f(attn_v).reshape(-1), emb=emb, W_ih=W_ih, W_hh=W_hh, b_ih=b_ih, b_hh=b_hh, W_out=W_out, b_out=b_out)
         for k, w in wts.items():
-            assert w.is_contiguous() and w.dtype == F32, k
+            assert w.is_contiguous() and w.dtype == F32 and w.data_ptr() % 16 == 0, f"{k}: decoder weights must be contiguous, 16-byte aligned fp32"
+
         args = make_dec_args(B=B, T=T, V=V, VP=VP, S=S, max_steps=max_steps, NS=NS, tile=tile, inference=int(inference), save=int(save),
                              enc=enc, Ep=Ep, gt=gt, use_gt=use_gt, mask=mask, logp=logp, lengths=lengths, eos=eos, counters=counters,
                              **wts, **sv, **scratch)
-        lib.pa2s_note_decoder_fwd(stream(), ctypes.byref(args), int(cfg["sos"]), int(cfg["eos"]))
+        with ktime("note_decoder_fwd"):
+            lib.pa2s_note_decoder_fwd(stream(), ctypes.byref(args), int(cfg["sos"]), int(cfg["eos"]))
         ctx.mark_non_differentiable(lengths, counters)
         if save:
             ctx.save_for_backward(enc, Ep, attn_w, wts["v"], emb, W_ih, W_hh, W_out, logp, sv["hs"], sv["ctxs"], sv["attn"], sv["gates"],
@@ -538,7 +580,8 @@ class NoteDecoderFn(torch.autograd.Function):
                              enc=enc, Ep=Ep, Wattn=attn_w, v=v, emb=emb, W_ih=W_ih, W_hh=W_hh, W_out=W_out,
                              W_outT=W_outT, W_hT=W_hT, W_ihT=W_ihT, W_hhT=W_hhT, logp=logp, hs=hs, ctxs=ctxs, attn=attn, gates=gates, qs=qs,
                              dlogp=dlogp, **bw)
-        lib.pa2s_note_decoder_bwd(st, ctypes.byref(args))
+        with ktime("note_decoder_bwd"):
+            lib.pa2s_note_decoder_bwd(st, ctypes.byref(args))
         SB = S * B
         # deferred weight gradients: contractions over all (step, clip) rows
         dW_out = e(V, 2 * D)

@@ -31,9 +31,11 @@ class FlatAdadelta:
 
     def __init__(self, model, lr=1.0, rho=0.95, eps=1e-8, max_grad_norm=5.0):
         self.params = [p for p in model.parameters() if p.requires_grad]
-        n = sum(p.numel() for p in self.params)
+        # every parameter starts on a 256-byte boundary: the kernels read weight rows with 128-bit loads
+        al = lambda k: (k + 63) // 64 * 64
+        n = sum(al(p.numel()) for p in self.params)
         dev = self.params[0].device
-        self.flat = torch.empty(n, device=dev, dtype=torch.float32)
+        self.flat = torch.zeros(n, device=dev, dtype=torch.float32)
         self.grad = torch.zeros(n, device=dev, dtype=torch.float32)
         self.square_avg = torch.zeros(n, device=dev, dtype=torch.float32)
         self.acc_delta = torch.zeros(n, device=dev, dtype=torch.float32)
@@ -45,7 +47,7 @@ class FlatAdadelta:
             self.flat[off:off + k].copy_(p.data.reshape(-1))
             p.data = self.flat[off:off + k].view_as(p.data)
             p.grad = self.grad[off:off + k].view_as(p.data)
-            off += k
+            off += al(k)
         self.n = n
         self.lr, self.rho, self.eps, self.max_grad_norm = lr, rho, eps, max_grad_norm
 

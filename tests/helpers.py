@@ -5,27 +5,7 @@ import torch
 from oracle import a2s_oracle as O
 
 
-def make_ground_truth(B, bars, L_up, L_lo, seed=1, lo_up=(40, 80), lo_lo=(20, 50), n_ts=7, n_key=14):
-    """[time_sig (B,bars), key (B,bars), upper (B,bars,L_up), upper_len, lower (B,bars,L_lo), lower_len] (CPU int64).
-    tokens randint(0,144), <eos> at index len, <pad> after; lengths exclude <eos> (datasets/syn.py:60-74)."""
-    g = torch.Generator().manual_seed(seed)
-    ts = torch.randint(0, n_ts, (B, bars), generator=g)
-    key = torch.randint(0, n_key, (B, bars), generator=g)
-
-    def staff(L, lo, hi):
-        tok = torch.full((B, bars, L), O.PAD, dtype=torch.long)
-        ln = torch.zeros(B, bars, dtype=torch.long)
-        for b in range(B):
-            for k in range(bars):
-                n = int(torch.randint(min(lo, L - 1), min(hi, L), (1,), generator=g))
-                tok[b, k, :n] = torch.randint(0, 144, (n,), generator=g)
-                if n < L:
-                    tok[b, k, n] = O.EOS
-                ln[b, k] = n
-        return tok, ln
-    up, ul = staff(L_up, *lo_up)
-    lo, ll = staff(L_lo, *lo_lo)
-    return [ts, key, up, ul, lo, ll]
+from piano_a2s_b200.synthetic import make_ground_truth  # noqa: E402,F401  (same generator the bench uses)
 
 
 def synth_state_dict(model, seed=7):
@@ -54,6 +34,17 @@ def synth_state_dict(model, seed=7):
             t = (2 * u - 1) * a
         sd[k] = torch.from_numpy(t.astype(np.float32)).reshape(v.shape)
     return sd
+
+
+def lcg_uniform(shape, seed=1):
+    """Deterministic U[0,1) float32 tensor from integer arithmetic only (bit-exact on any machine)."""
+    n = int(np.prod(shape))
+    idx = np.arange(1, n + 1, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        x = (idx * np.uint64(6364136223846793005) + np.uint64(seed * 1000003 + 7)) ^ ((idx * np.uint64(1442695040888963407)) >> np.uint64(31))
+        x = x * np.uint64(2862933555777941757) + np.uint64(3037000493)
+    u = (x >> np.uint64(40)).astype(np.float64) / float(1 << 24)
+    return torch.from_numpy(u.astype(np.float32)).reshape(shape)
 
 
 class ReplayDeviceSource:
