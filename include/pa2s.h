@@ -37,6 +37,16 @@ PA2S_API int pa2s_gemm_f32(void* stream, int transA, int transB, int M, int N, i
                            const float* t_scale, const float* t_shift, int t_period, int t_relu, int t_on_b,
                            int splitk);
 
+/* Same contract on the tcgen05 tensor cores (tc_gemm.cu): fp32 operands are split on the fly into bf16 hi/lo and
+ * accumulated in TMEM as A_hi*B_hi + A_hi*B_lo + A_lo*B_hi (nsplit = 3, ~fp32 accuracy) or A_hi*B_hi (nsplit = 1). */
+PA2S_API int pa2s_gemm_tc_supported(int M, int N, int K, int batch);
+PA2S_API int pa2s_gemm_tc(void* stream, int transA, int transB, int M, int N, int K,
+                          const float* A, long long lda, const float* B, long long ldb, float* C, long long ldc,
+                          const float* bias, int accumulate, int atomic,
+                          int batch, long long strideA, long long strideB, long long strideC,
+                          const float* t_scale, const float* t_shift, int t_period, int t_relu, int t_on_b,
+                          int splitk, int nsplit);
+
 /* ---- VQT front end (utilities.py:246-253) -------------------------------------------------------------------
  * C: (nclips*rows_per_clip, 2*nb) filterbank responses (re,im interleaved).  Writes
  * out = amplitude_to_db(|V|, ref=max over the clip, amin=1e-5, top_db=80)/80 + 1 as (nclips, rows_per_clip, nb). */

@@ -64,14 +64,39 @@ def _dist_on() -> bool:
 # ----------------------------------------------------------------------------------------------------------------
 # GEMM wrapper
 # ----------------------------------------------------------------------------------------------------------------
+# Contraction precision: "fp32"   exact-fp32 FFMA kernel (gemm.cu);
+#                        "bf16x3" tcgen05, operands split into bf16 hi/lo, 3 MMAs per product (~fp32 accuracy);
+#                        "bf16"   tcgen05, bf16 operands, fp32 accumulation (BASELINE configs[2..3]).
+# Small contractions stay on the FFMA kernel (a 128-row UMMA tile would be mostly padding).
+PRECISION = {"train": "bf16x3", "eval": "fp32"}
+TC_MIN_FLOP = 2.0e8
+
+
+def set_precision(train=None, eval=None):
+    for k, v in (("train", train), ("eval", eval)):
+        if v is not None:
+            assert v in ("fp32", "bf16x3", "bf16")
+            PRECISION[k] = v
+
+
+def _precision():
+    return PRECISION["train" if torch.is_grad_enabled() else "eval"]
+
+
 def gemm(A, B, C, M, N, K, *, transA=False, transB=False, lda=None, ldb=None, ldc=None, bias=None, accumulate=False,
          atomic=False, batch=1, strideA=0, strideB=0, strideC=0, t_scale=None, t_shift=None, t_period=1, t_relu=False,
-         t_on_b=False, splitk=1, a_off=0, b_off=0, c_off=0):
+         t_on_b=False, splitk=1, a_off=0, b_off=0, c_off=0, precision=None):
     """C = op(A) op(B); A/B/C are tensors used as raw storage (+ element offsets), see include/pa2s.h."""
     es = 4
     pa = ctypes.c_void_p(A.data_ptr() + a_off * es)
     pb = ctypes.c_void_p(B.data_ptr() + b_off * es)
     pc = ctypes.c_void_p(C.data_ptr() + c_off * es)
+    prec = precision or _precision()
+    if prec != "fp32" and K > 0 and 2.0 * M * N * K * batch >= TC_MIN_FLOP:
+        lib.pa2s_gemm_tc(stream(), int(transA), int(transB), M, N, K, pa, lda, pb, ldb, pc, ldc, ptr(bias), int(accumulate),
+                         int(atomic), batch, strideA, strideB, strideC, ptr(t_scale), ptr(t_shift), t_period, int(t_relu),
+                         int(t_on_b), splitk, 3 if prec == "bf16x3" else 1)
+        return C
     lib.pa2s_gemm_f32(stream(), int(transA), int(transB), M, N, K, pa, lda, pb, ldb, pc, ldc, ptr(bias), int(accumulate),
                       int(atomic), batch, strideA, strideB, strideC, ptr(t_scale), ptr(t_shift), t_period, int(t_relu),
                       int(t_on_b), splitk)

@@ -1,0 +1,81 @@
+"""GPU: the tcgen05 tensor-core contraction (tc_gemm.cu) against float64 matmul, all four operand layouts."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def force_tensor_core_path():
+    """Route even tiny contractions through tc_gemm.cu (the product only does so above ops.TC_MIN_FLOP)."""
+    from piano_a2s_b200 import ops
+    old = ops.TC_MIN_FLOP
+    ops.TC_MIN_FLOP = 0.0
+    yield
+    ops.TC_MIN_FLOP = old
+
+
+@pytest.mark.parametrize("ta,tb", [(0, 1), (0, 0), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,K", [(128, 64, 32), (128, 256, 64), (300, 173, 515), (1000, 960, 800), (37, 40, 19)])
+def test_tc_gemm_bf16x3_matches_fp64(cuda, ta, tb, M, N, K):
+    from piano_a2s_b200 import ops
+    g = torch.Generator().manual_seed(M + 3 * N + 7 * K)
+    A = torch.randn((K, M) if ta else (M, K), generator=g)
+    Bm = torch.randn((N, K) if tb else (K, N), generator=g)
+    bias = torch.randn(N, generator=g)
+    ref = (A.t() if ta else A).double() @ (Bm.t() if tb else Bm).double() + bias.double()
+    C = torch.empty(M, N, device=cuda)
+    ops.gemm(A.to(cuda), Bm.to(cuda), C, M, N, K, transA=bool(ta), transB=bool(tb), lda=A.shape[1], ldb=Bm.shape[1], ldc=N,
+             bias=bias.to(cuda), precision="bf16x3")
+    e = rel_err(C, ref)
+    print(f"tc bf16x3 ta={ta} tb={tb} {M}x{N}x{K}: rel err {e:.2e}")
+    assert e < 2e-5
+    C1 = torch.empty(M, N, device=cuda)
+    ops.gemm(A.to(cuda), Bm.to(cuda), C1, M, N, K, transA=bool(ta), transB=bool(tb), lda=A.shape[1], ldb=Bm.shape[1], ldc=N,
+             bias=bias.to(cuda), precision="bf16")
+    e1 = rel_err(C1, ref)
+    print(f"tc bf16   rel err {e1:.2e}")
+    assert e1 < 2e-2
+
+
+def test_tc_gemm_batched_splitk_transform(cuda):
+    from piano_a2s_b200 import ops
+    ops_tc_min = ops.TC_MIN_FLOP
+    ops.TC_MIN_FLOP = 0.0
+    try:
+        g = torch.Generator().manual_seed(3)
+        M, N, K, P = 200, 96, 320, 40
+        A = torch.randn(M, K, generator=g); Bm = torch.randn(N, K, generator=g)
+        s = torch.randn(P, generator=g); t = torch.randn(P, generator=g)
+        At = F.relu(A * s.repeat(K // P) + t.repeat(K // P))
+        C = torch.zeros(M, N, device=cuda)
+        ops.gemm(A.to(cuda), Bm.to(cuda), C, M, N, K, transB=True, lda=K, ldb=K, ldc=N, t_scale=s.to(cuda), t_shift=t.to(cuda),
+                 t_period=P, t_relu=True, splitk=3, precision="bf16x3")
+        assert rel_err(C, At.double() @ Bm.double().t()) < 2e-5
+        # transform on a non-transposed B (weight-gradient form), transposed A
+        Bn = torch.randn(K, 80, generator=g)
+        Bt = F.relu(Bn * s.repeat(2) + t.repeat(2))
+        A2 = torch.randn(K, M, generator=g)
+        C = torch.empty(M, 80, device=cuda)
+        ops.gemm(A2.to(cuda), Bn.to(cuda), C, M, 80, K, transA=True, lda=M, ldb=80, ldc=80, t_scale=s.to(cuda), t_shift=t.to(cuda),
+                 t_period=P, t_relu=True, t_on_b=True, precision="bf16x3")
+        assert rel_err(C, A2.double().t() @ Bt.double()) < 2e-5
+        # batched, reduction over the batch with atomics (dW_hh form), overlapping rows (VQT form)
+        y = torch.randn(3, 4000, generator=g)
+        W = torch.randn(64, 512, generator=g)
+        Tn, hop = 20, 160
+        C = torch.empty(3, Tn, 64, device=cuda)
+        ops.gemm(y.to(cuda), W.to(cuda), C, Tn, 64, 512, transB=True, lda=hop, ldb=512, ldc=64, batch=3, strideA=4000, strideB=0,
+                 strideC=Tn * 64, a_off=8, precision="bf16x3")
+        fr = torch.stack([torch.stack([y[b, 8 + i * hop: 8 + i * hop + 512] for i in range(Tn)]) for b in range(3)])
+        assert rel_err(C, fr.double() @ W.double().t()) < 2e-5
+        X = torch.randn(4, 50, 96, generator=g); D = torch.randn(4, 50, 72, generator=g)
+        C = torch.zeros(72, 96, device=cuda)
+        ops.gemm(D.to(cuda), X.to(cuda), C, 72, 96, 50, transA=True, lda=72, ldb=96, ldc=96, atomic=True, batch=4, strideA=50 * 72,
+                 strideB=50 * 96, strideC=0, precision="bf16x3")
+        assert rel_err(C, torch.einsum("bkm,bkn->mn", D.double(), X.double())) < 2e-5
+    finally:
+        ops.TC_MIN_FLOP = ops_tc_min
