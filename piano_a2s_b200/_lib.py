@@ -80,7 +80,7 @@ def ptr(t):
 
 class DecArgs(ctypes.Structure):
     """Mirror of `struct DecArgs` in csrc/decoder.cu (field order and types must match exactly)."""
-    _ints = ["B", "T", "V", "VP", "S", "max_steps", "NS", "tile", "inference", "save"]
+    _ints = ["B", "T", "V", "VP", "S", "max_steps", "NS", "tile", "inference", "save", "tile_pad", "reserved_"]
     _ptrs = ["enc", "Ep", "Wattn", "v", "emb", "W_ih", "W_hh", "b_ih", "b_hh", "W_out", "b_out",
              "W_outT", "W_hT", "W_ihT", "W_hhT", "gt", "use_gt", "mask", "logp", "lengths", "eos", "counters",
              "hs", "ctxs", "attn", "gates", "qs", "xtok", "toks", "xbuf", "hc", "logits", "pm", "pl", "pc", "tickets",

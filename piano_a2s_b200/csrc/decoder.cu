@@ -23,6 +23,7 @@ constexpr int BT = 16;     // batch chunk held in registers by the row-dot kerne
 struct DecArgs {
     // problem
     int B, T, V, VP, S, max_steps, NS, tile, inference, save;
+    int tile_pad, reserved_;   // host-filled: tile rounded up to 4 floats
     // encoder memory and attention module
     const float* enc;      // (B,T,DD)
     const float* Ep;       // (B,T,DA)
@@ -82,6 +83,12 @@ __device__ __forceinline__ int slot(const DecArgs& a, int s) { return a.save ? s
 __device__ __forceinline__ int hslot(const DecArgs& a, int s) { return a.save ? s : (s & 1); }
 __device__ __forceinline__ bool all_done(const DecArgs& a) { return *((volatile int*)a.counters) >= a.B; }
 
+// tanh(x) = 1 - 2/(exp(2x)+1) on the SFU (ex2.approx + rcp.approx): absolute error ~1e-7, saturates correctly at +-1.
+__device__ __forceinline__ float tanh_fast(float x) {
+    const float e = __expf(2.f * x);
+    return 1.f - __fdividef(2.f, e + 1.f);
+}
+
 __device__ __forceinline__ float dot4(float4 a, float4 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w))); }
 
 // acc[b] += w[0..4*K4) . xs[b][0..4*K4) for b < nb; lanes stride over float4 columns.
@@ -90,11 +97,23 @@ __device__ __forceinline__ void warp_row_dot(const float* __restrict__ wrow, int
     const int lane = threadIdx.x & 31;
     const float4* w4 = reinterpret_cast<const float4*>(wrow);
     const float4* x4 = reinterpret_cast<const float4*>(xs);
-    for (int k = lane; k < K4; k += 32) {
-        const float4 w = __ldg(w4 + k);
+    constexpr int WB = 6;                       // weight float4s in flight per lane (covers K <= 768 per pass)
+    for (int k0 = lane; k0 < K4; k0 += 32 * WB) {
+        float4 w[WB];
 #pragma unroll
-        for (int b = 0; b < BT; ++b)
-            if (b < nb) acc[b] += dot4(w, x4[b * pitch4 + k]);
+        for (int j = 0; j < WB; ++j) {
+            const int k = k0 + 32 * j;
+            w[j] = k < K4 ? __ldg(w4 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < WB; ++j) {
+            const int k = k0 + 32 * j;
+            if (k < K4) {
+#pragma unroll
+                for (int b = 0; b < BT; ++b)
+                    if (b < nb) acc[b] += dot4(w[j], x4[b * pitch4 + k]);
+            }
+        }
     }
 }
 __device__ __forceinline__ void warp_reduce_all(float (&acc)[BT]) {
@@ -132,19 +151,30 @@ __global__ void __launch_bounds__(256) dec_attn_kernel(DecArgs a, int s) {
     qv[tid] = q[tid];
     vv[tid] = a.v[tid];
     __syncthreads();
-    // scores
+    // scores: 4 frames per warp iteration, all 8 128-bit loads issued before the tanh work
     {
         const float4 q0 = *reinterpret_cast<const float4*>(qv + lane * 4);
         const float4 q1 = *reinterpret_cast<const float4*>(qv + 128 + lane * 4);
         const float4 v0 = *reinterpret_cast<const float4*>(vv + lane * 4);
         const float4 v1 = *reinterpret_cast<const float4*>(vv + 128 + lane * 4);
-        for (int t = t0 + warp; t < t1; t += 8) {
-            const float4* ep = reinterpret_cast<const float4*>(a.Ep + ((size_t)b * T + t) * DA);
-            float4 e0 = __ldg(ep + lane), e1 = __ldg(ep + 32 + lane);
-            float e = v0.x * tanhf(q0.x + e0.x) + v0.y * tanhf(q0.y + e0.y) + v0.z * tanhf(q0.z + e0.z) + v0.w * tanhf(q0.w + e0.w)
-                    + v1.x * tanhf(q1.x + e1.x) + v1.y * tanhf(q1.y + e1.y) + v1.z * tanhf(q1.z + e1.z) + v1.w * tanhf(q1.w + e1.w);
-            e = warp_sum(e);
-            if (lane == 0) sc[t - t0] = e;
+        constexpr int FU = 4;
+        for (int tb = t0 + warp * FU; tb < t1; tb += 8 * FU) {
+            float4 e0[FU], e1[FU];
+#pragma unroll
+            for (int u = 0; u < FU; ++u) {
+                const int t = min(tb + u, t1 - 1);
+                const float4* ep = reinterpret_cast<const float4*>(a.Ep + ((size_t)b * T + t) * DA);
+                e0[u] = __ldg(ep + lane);
+                e1[u] = __ldg(ep + 32 + lane);
+            }
+#pragma unroll
+            for (int u = 0; u < FU; ++u) {
+                float e = v0.x * tanh_fast(q0.x + e0[u].x) + v0.y * tanh_fast(q0.y + e0[u].y) + v0.z * tanh_fast(q0.z + e0[u].z) +
+                          v0.w * tanh_fast(q0.w + e0[u].w) + v1.x * tanh_fast(q1.x + e1[u].x) + v1.y * tanh_fast(q1.y + e1[u].y) +
+                          v1.z * tanh_fast(q1.z + e1[u].z) + v1.w * tanh_fast(q1.w + e1[u].w);
+                e = warp_sum(e);
+                if (lane == 0 && tb + u < t1) sc[tb + u - t0] = e;
+            }
         }
     }
     __syncthreads();
@@ -173,16 +203,36 @@ __global__ void __launch_bounds__(256) dec_attn_kernel(DecArgs a, int s) {
     l = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) l += red[i];
-    // partial context: thread owns d = 2*tid, 2*tid+1
+    // partial context: warp w takes frames w, w+8, ...; lane owns d = 128*j + 4*lane .. +3 (j < 4); 2 frames in flight
     float c0 = 0.f, c1 = 0.f;
     {
-        const float2* e2 = reinterpret_cast<const float2*>(a.enc + ((size_t)b * T + t0) * DD) + tid;
-        for (int i = 0; i < n; ++i) {
-            float2 ev = __ldg(e2 + (size_t)i * (DD / 2));
-            float p = sc[i];
-            c0 = fmaf(p, ev.x, c0);
-            c1 = fmaf(p, ev.y, c1);
+        float4 cacc[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cacc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4* ebase = reinterpret_cast<const float4*>(a.enc + ((size_t)b * T + t0) * DD);
+        for (int i = warp; i < n; i += 16) {
+            const int i2 = i + 8;
+            const bool two = i2 < n;
+            float4 ea[4], eb[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ea[j] = __ldg(ebase + (size_t)i * (DD / 4) + j * 32 + lane);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) eb[j] = two ? __ldg(ebase + (size_t)i2 * (DD / 4) + j * 32 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float pa = sc[i], pb = two ? sc[i2] : 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                cacc[j].x = fmaf(pa, ea[j].x, fmaf(pb, eb[j].x, cacc[j].x));
+                cacc[j].y = fmaf(pa, ea[j].y, fmaf(pb, eb[j].y, cacc[j].y));
+                cacc[j].z = fmaf(pa, ea[j].z, fmaf(pb, eb[j].z, cacc[j].z));
+                cacc[j].w = fmaf(pa, ea[j].w, fmaf(pb, eb[j].w, cacc[j].w));
+            }
         }
+        float* part = sm + 2 * DA + a.tile_pad;          // 8 x DD per-warp partial rows (shared memory)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(part + warp * DD + j * 128 + lane * 4) = cacc[j];
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { c0 += part[w * DD + 2 * tid]; c1 += part[w * DD + 2 * tid + 1]; }
     }
     if (n <= 0) { m = -INFINITY; l = 0.f; }
     float* pc = a.pc + ((size_t)b * a.NS + js) * DD;
@@ -550,30 +600,46 @@ __global__ void __launch_bounds__(256) dec_bwd_attn_kernel(DecArgs a, int s) {
     const float4 v1 = *reinterpret_cast<const float4*>(vv + 128 + lane * 4);
     float dq[8] = {0, 0, 0, 0, 0, 0, 0, 0}, dv[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const float* at = a.attn + ((size_t)s * a.B + b) * T;
-    for (int t = t0 + warp; t < t1; t += 8) {
-        const float4* e4 = reinterpret_cast<const float4*>(a.enc + ((size_t)b * T + t) * DD);
-        float da = 0.f;
+    const float vk[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    const float qk[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+    constexpr int FU = 2;                     // frames in flight per warp: 2 x (4 enc + 2 Ep + 2 dEp) 128-bit loads
+    for (int tb = t0 + warp * FU; tb < t1; tb += 8 * FU) {
+        float4 en[FU][4], e0[FU], e1[FU], d0[FU], d1[FU];
+        float aw[FU];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) da += dot4(dcr[i], __ldg(e4 + i * 32 + lane));
-        da = warp_sum(da);
-        const float ds = at[t] * (da - c0);
-        float4* dep = reinterpret_cast<float4*>(a.dEp + ((size_t)b * T + t) * DA);
-        const float4* ep = reinterpret_cast<const float4*>(a.Ep + ((size_t)b * T + t) * DA);
-        float4 e0 = __ldg(ep + lane), e1 = __ldg(ep + 32 + lane);
-        float u[8] = {tanhf(q0.x + e0.x), tanhf(q0.y + e0.y), tanhf(q0.z + e0.z), tanhf(q0.w + e0.w),
-                      tanhf(q1.x + e1.x), tanhf(q1.y + e1.y), tanhf(q1.z + e1.z), tanhf(q1.w + e1.w)};
-        const float vk[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-        float dp[8];
+        for (int u = 0; u < FU; ++u) {
+            const int t = min(tb + u, t1 - 1);
+            const float4* e4 = reinterpret_cast<const float4*>(a.enc + ((size_t)b * T + t) * DD);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            dp[i] = ds * vk[i] * (1.f - u[i] * u[i]);
-            dq[i] += dp[i];
-            dv[i] = fmaf(ds, u[i], dv[i]);
+            for (int i = 0; i < 4; ++i) en[u][i] = __ldg(e4 + i * 32 + lane);
+            const float4* ep = reinterpret_cast<const float4*>(a.Ep + ((size_t)b * T + t) * DA);
+            e0[u] = __ldg(ep + lane); e1[u] = __ldg(ep + 32 + lane);
+            const float4* dep = reinterpret_cast<const float4*>(a.dEp + ((size_t)b * T + t) * DA);
+            d0[u] = dep[lane]; d1[u] = dep[32 + lane];
+            aw[u] = at[t];
         }
-        float4 d0 = dep[lane], d1 = dep[32 + lane];
-        d0.x += dp[0]; d0.y += dp[1]; d0.z += dp[2]; d0.w += dp[3];
-        d1.x += dp[4]; d1.y += dp[5]; d1.z += dp[6]; d1.w += dp[7];
-        dep[lane] = d0; dep[32 + lane] = d1;
+#pragma unroll
+        for (int u = 0; u < FU; ++u) {
+            const int t = tb + u;
+            float da = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) da += dot4(dcr[i], en[u][i]);
+            da = warp_sum(da);
+            if (t >= t1) continue;            // warp-uniform
+            const float ds = aw[u] * (da - c0);
+            const float ev[8] = {e0[u].x, e0[u].y, e0[u].z, e0[u].w, e1[u].x, e1[u].y, e1[u].z, e1[u].w};
+            float dp[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float uu = tanh_fast(qk[i] + ev[i]);
+                dp[i] = ds * vk[i] * (1.f - uu * uu);
+                dq[i] += dp[i];
+                dv[i] = fmaf(ds, uu, dv[i]);
+            }
+            float4* dep = reinterpret_cast<float4*>(a.dEp + ((size_t)b * T + t) * DA);
+            dep[lane] = make_float4(d0[u].x + dp[0], d0[u].y + dp[1], d0[u].z + dp[2], d0[u].w + dp[3]);
+            dep[32 + lane] = make_float4(d1[u].x + dp[4], d1[u].y + dp[5], d1[u].z + dp[6], d1[u].w + dp[7]);
+        }
     }
     // reduce dq, dv over the 8 warps
 #pragma unroll
@@ -612,7 +678,8 @@ PA2S_API int pa2s_note_decoder_fwd(void* stream, const void* args, int sos_id, i
     DecArgs a = *reinterpret_cast<const DecArgs*>(args);
     cudaStream_t st = (cudaStream_t)stream;
     if (a.B <= 0 || a.S <= 0) return 0;
-    const size_t sm_attn = (size_t)(2 * DA + a.tile) * sizeof(float);
+    a.tile_pad = (a.tile + 3) / 4 * 4;
+    const size_t sm_attn = (size_t)(2 * DA + a.tile_pad + 8 * DD) * sizeof(float);
     const size_t sm_gru = (size_t)BT * (DX + DD) * sizeof(float);
     const size_t sm_post = (size_t)BT * 2 * DD * sizeof(float);
     PA2S_TRY((cudaError_t)set_smem(dec_attn_kernel, sm_attn));
@@ -660,7 +727,8 @@ PA2S_API int pa2s_note_decoder_bwd(void* stream, const void* args) {
 // Stand-alone single attention step (bar-level attention, models.py:241-242): q must already be in a.qs slot 0.
 PA2S_API int pa2s_attn_step_fwd(void* stream, const void* args) {
     DecArgs a = *reinterpret_cast<const DecArgs*>(args);
-    const size_t sm_attn = (size_t)(2 * DA + a.tile) * sizeof(float);
+    a.tile_pad = (a.tile + 3) / 4 * 4;
+    const size_t sm_attn = (size_t)(2 * DA + a.tile_pad + 8 * DD) * sizeof(float);
     PA2S_TRY((cudaError_t)set_smem(dec_attn_kernel, sm_attn));
     dec_attn_kernel<<<dim3(a.NS, a.B), 256, sm_attn, (cudaStream_t)stream>>>(a, 0);
     PA2S_CHECK_LAST();

@@ -71,9 +71,10 @@ class ScoreTranscription(nn.Module):
     def forward(self, spectrogram, inference=True, ground_truth=None, teacher_forcing_ratio=0.,
                 device=torch.device("cuda" if torch.cuda.is_available() else "cpu")):
         self.device = device
-        conv_outputs = self.convstack(spectrogram)                       # (B, T, conv_feature_size)
-        encoder_outputs, hidden = self.encoder(conv_outputs)             # (B, T, 2H), (1, B, 2H)
-        return self.decoder(encoder_outputs, hidden, inference, ground_truth, teacher_forcing_ratio, device)
+        with ops.module_precision(self):
+            conv_outputs = self.convstack(spectrogram)                   # (B, T, conv_feature_size)
+            encoder_outputs, hidden = self.encoder(conv_outputs)         # (B, T, 2H), (1, B, 2H)
+            return self.decoder(encoder_outputs, hidden, inference, ground_truth, teacher_forcing_ratio, device)
 
 
 class Encoder(nn.Module):

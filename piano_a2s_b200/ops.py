@@ -70,17 +70,47 @@ def _dist_on() -> bool:
 # Small contractions stay on the FFMA kernel (a 128-row UMMA tile would be mostly padding).
 PRECISION = {"train": "bf16x3", "eval": "fp32"}
 TC_MIN_FLOP = 2.0e8
+_CURRENT = ["bf16x3"]
 
 
 def set_precision(train=None, eval=None):
+    """Contraction precision used by modules in train() / eval() mode."""
     for k, v in (("train", train), ("eval", eval)):
         if v is not None:
             assert v in ("fp32", "bf16x3", "bf16")
             PRECISION[k] = v
 
 
-def _precision():
-    return PRECISION["train" if torch.is_grad_enabled() else "eval"]
+def current_precision():
+    return _CURRENT[0]
+
+
+class use_precision:
+    """Scope set by the module forwards (`PRECISION["train" if module.training else "eval"]`); autograd Functions read it in
+    forward and remember it for their backward."""
+
+    def __init__(self, prec):
+        assert prec in ("fp32", "bf16x3", "bf16")
+        self.prec = prec
+
+    def __enter__(self):
+        self.old = _CURRENT[0]
+        _CURRENT[0] = self.prec
+
+    def __exit__(self, *exc):
+        _CURRENT[0] = self.old
+
+
+def _bwd_precision(fn):
+    """backward runs under the precision its forward ran with"""
+    def wrapper(ctx, *grads):
+        with use_precision(ctx.prec):
+            return fn(ctx, *grads)
+    return wrapper
+
+
+def module_precision(module):
+    return use_precision(PRECISION["train" if module.training else "eval"])
 
 
 def gemm(A, B, C, M, N, K, *, transA=False, transB=False, lda=None, ldb=None, ldc=None, bias=None, accumulate=False,
@@ -91,7 +121,7 @@ def gemm(A, B, C, M, N, K, *, transA=False, transB=False, lda=None, ldb=None, ld
     pa = ctypes.c_void_p(A.data_ptr() + a_off * es)
     pb = ctypes.c_void_p(B.data_ptr() + b_off * es)
     pc = ctypes.c_void_p(C.data_ptr() + c_off * es)
-    prec = precision or _precision()
+    prec = precision or current_precision()
     if prec != "fp32" and K > 0 and 2.0 * M * N * K * batch >= TC_MIN_FLOP:
         lib.pa2s_gemm_tc(stream(), int(transA), int(transB), M, N, K, pa, lda, pb, ldb, pc, ldc, ptr(bias), int(accumulate),
                          int(atomic), batch, strideA, strideB, strideC, ptr(t_scale), ptr(t_shift), t_period, int(t_relu),
@@ -124,6 +154,7 @@ class LinearFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, W, b):
+        ctx.prec = current_precision()
         x2 = _f(x).reshape(-1, x.shape[-1])
         assert W.stride(1) == 1 and W.dtype == F32
         M, K = x2.shape
@@ -136,6 +167,7 @@ class LinearFn(torch.autograd.Function):
         return y.reshape(*x.shape[:-1], N)
 
     @staticmethod
+    @_bwd_precision
     def backward(ctx, dy):
         x2, W = ctx.saved_tensors
         M, K = x2.shape
@@ -177,6 +209,7 @@ class ConvStackFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, spec, mask, bufs, training, sync, eps, momentum, *params):
+        ctx.prec = current_precision()
         spec = _f(spec)
         B, Cin0, T, Fq = spec.shape
         assert Cin0 == 1, "in_channels must be 1 (pretrain.yaml:85)"
@@ -248,6 +281,7 @@ class ConvStackFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_bwd_precision
     def backward(ctx, dout):
         sv = ctx.saved_tensors
         spec, mk, z, aff5, Wp_out = sv[:5]
@@ -344,6 +378,7 @@ class BiGRULayerFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_b, w_hh_b, b_ih_b, b_hh_b, bg):
+        ctx.prec = current_precision()
         x = _f(x)
         B, T, I = x.shape
         H = w_hh_f.shape[1]
@@ -366,6 +401,7 @@ class BiGRULayerFn(torch.autograd.Function):
         return out, hN
 
     @staticmethod
+    @_bwd_precision
     def backward(ctx, dout, dhN):
         x, Wih, Whh, out, gates = ctx.saved_tensors
         B, T, I = x.shape
@@ -481,6 +517,7 @@ class AttnStepFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, q, Ep, enc, v):
+        ctx.prec = current_precision()
         q, Ep, enc = _f(q), _f(Ep), _f(enc)
         vv = _f(v).reshape(-1)
         B, T, D = enc.shape
@@ -502,6 +539,7 @@ class AttnStepFn(torch.autograd.Function):
         return bufs["ctxs"].reshape(B, D)
 
     @staticmethod
+    @_bwd_precision
     def backward(ctx, dctx):
         qs, Ep, enc, vv, attn, ctxs = ctx.saved_tensors
         B, T, D = enc.shape
@@ -539,6 +577,7 @@ class NoteDecoderFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, enc, Ep, h0, attn_w, attn_v, emb, W_ih, W_hh, b_ih, b_hh, W_out, b_out, cfg):
+        ctx.prec = current_precision()
         enc, Ep, h0 = _f(enc), _f(Ep), _f(h0)
         B, T, D = enc.shape
         A = Ep.shape[2]
@@ -584,6 +623,7 @@ class NoteDecoderFn(torch.autograd.Function):
         return logp, lengths, counters
 
     @staticmethod
+    @_bwd_precision
     def backward(ctx, dlogp, _dl, _dc):
         (enc, Ep, attn_w, v, emb, W_ih, W_hh, W_out, logp, hs, ctxs, attn, gates, qs, xtok, toks, mask) = ctx.saved_tensors
         B, T, D, A, V, E, VP, S, max_steps, NS, tile, has_mask, vshape = ctx.meta

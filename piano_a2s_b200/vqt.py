@@ -59,6 +59,9 @@ class VQT(torch.nn.Module):
         W, j0 = design_filters(sample_rate, bins_per_octave, n_octaves, gamma)
         self.j0 = j0
         self.register_buffer("filters", torch.from_numpy(W), persistent=False)
+        # bins 80 dB below the clip maximum must keep ~1e-3 relative accuracy through the dB epilogue, which a bf16x3
+        # product (error ~5e-6 of the *dominant* terms) cannot give: the fp32 configuration contracts on the FFMA pipe.
+        self.precision = "fp32"
 
     @torch.no_grad()
     def forward(self, audio):
@@ -75,7 +78,7 @@ class VQT(torch.nn.Module):
         C = torch.empty(B, T, 2 * self.n_bins, device=audio.device, dtype=torch.float32)
         # frames[t, j] = ypad[t*hop + j0 + j]: overlapping rows, lda = hop
         ops.gemm(ypad, self.filters, C, T, 2 * self.n_bins, K, transB=True, lda=self.hop, ldb=K, ldc=2 * self.n_bins,
-                 batch=B, strideA=plen, strideB=0, strideC=T * 2 * self.n_bins, a_off=self.j0)
+                 batch=B, strideA=plen, strideB=0, strideC=T * 2 * self.n_bins, a_off=self.j0, precision=self.precision)
         out = torch.empty(B, T, self.n_bins, device=audio.device, dtype=torch.float32)
         cmax = torch.empty(B, device=audio.device, dtype=torch.int32)
         lib.pa2s_vqt_post(stream(), ptr(C), ptr(out), ptr(cmax), B, T, self.n_bins)
