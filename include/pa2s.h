@@ -63,6 +63,17 @@ PA2S_API int pa2s_conv3x3(void* stream, int mode, int B, int T, int F, int Cin, 
                           const float* in_scale, const float* in_shift, int in_relu,
                           const float* Yraw, const float* zs, const float* zb, const float* mean, const float* invstd,
                           const float* k1, const float* k2, const float* k3);
+/* The same two convolutions as an implicit GEMM on the tcgen05 tensor cores (tc_conv.cu; conv2..conv4 shapes).  Wpack is
+ * produced by pa2s_tc_conv_pack (dgrad = 0 forward filter, 1 = flipped/transposed filter of the data gradient) into a buffer
+ * of pa2s_tc_conv_pack_bytes(Kin, Nout) bytes; partial has pa2s_tc_conv_num_partials rows of [sum y, sum y^2]. */
+PA2S_API int pa2s_tc_conv_pack_bytes(int Kin, int Nout);
+PA2S_API int pa2s_tc_conv_pack(void* stream, const float* W, int Cout, int Cin, int dgrad, void* out);
+PA2S_API int pa2s_tc_conv_num_partials(int B, int T, int F);
+PA2S_API int pa2s_tc_conv3x3(void* stream, int mode, int B, int T, int F, int Cin, int Cout, const float* X, const void* Wpack,
+                             float* Y, float* partial, int nsplit,
+                             const float* in_scale, const float* in_shift, int in_relu,
+                             const float* Yraw, const float* zs, const float* zb, const float* mean, const float* invstd,
+                             const float* k1, const float* k2, const float* k3);
 /* conv2d backward wrt weight; partial is [nctas][Cout*Cin*9] in torch (Cout,Cin,3,3) order. */
 PA2S_API int pa2s_conv3x3_wgrad(void* stream, int B, int T, int F, int Cin, int Cout, const float* Xin, const float* G,
                                 float* partial, int nctas, const float* in_scale, const float* in_shift, int in_relu,

@@ -1,0 +1,372 @@
+// 3x3 convolution (ConvStack conv2..conv4, models.py:481-498, :526-534) as an implicit GEMM on the tcgen05 tensor cores,
+// forward and data-gradient, with the neighbouring BatchNorm/ReLU work fused into the operand load / epilogue.
+//
+// Formulation.  Activations are (B,T,F,C) fp32, channels innermost.  Per clip the output positions are linearised over a
+// width-padded grid q = t*(F+2) + (f+1); one tile = 128 consecutive q = the 128 rows (TMEM lanes) of a UMMA accumulator.
+// For tap (ky,kx) the A operand row i is the input pixel at q + (ky-1)*(F+2) + (kx-1): a constant shift of the row index.
+// The loader warps therefore stage, per tile, three "windows" (one per ky) of 130 consecutive positions as
+// bf16 planes [8-channel group][position][8 ch] at a 16-byte pitch.  In that no-swizzle K-major UMMA layout the row index
+// advances by exactly 16 bytes, so the three kx taps of a window are the SAME shared-memory bytes addressed with a
+// descriptor start address shifted by kx*16 bytes: 9 taps are fed from 3 staged windows, no im2col copy.
+// Halo positions (f = -1, F and t = -1, T) are staged as zeros and their output rows are simply not stored
+// (2 of every F+2 rows are wasted).
+//
+// Precision: fp32 activations/weights are split into bf16 hi + lo and accumulated in TMEM (fp32) as
+// hi*hi + hi*lo + lo*hi (nsplit = 3), or hi*hi only (nsplit = 1).
+//
+// Roles (416 threads, 1 CTA/SM, persistent over tiles): warps 0-3 epilogue (tcgen05.ld -> fp32 NHWC store + BatchNorm
+// batch-statistics partial sums), warp 4 TMEM alloc + single-thread MMA issue, warps 5-12 window loaders (LDG.128 ->
+// BatchNorm-apply+ReLU of the previous layer, or the BatchNorm/ReLU backward transform for the data gradient -> split -> STS.128).
+#include "tc_common.cuh"
+
+namespace {
+using namespace tc;
+
+constexpr int BM = 128;
+constexpr int WENT = 130;          // window entries used (128 rows + kx in {0,1,2})
+constexpr int WPIX = 137;          // plane pitch in 16-byte units (odd mod 8: conflict-free plane-strided stores)
+constexpr int NWIN = 4;            // window ring slots
+constexpr int N_EPI_WARPS = 4, N_LOAD_WARPS = 8;
+constexpr int NTHREADS = (N_EPI_WARPS + 1 + N_LOAD_WARPS) * 32;
+constexpr int N_LOAD_THREADS = N_LOAD_WARPS * 32;
+
+struct TcConvArgs {
+    const float* X;        // mode 0: raw input (B,T,F,CIN);  mode 1: G = dL/d(relu out) of this layer (B,T,F,CIN=channels of dy)
+    const uint4* Wpack;    // packed bf16 weights, see pa2s_tc_conv_pack
+    float* Y;              // (B,T,F,COUT)
+    float* partial;        // [gridDim.x*4][2*COUT] per-warp [sum y, sum y^2] or null
+    int B, T, F, nsplit;
+    // mode 0 operand transform (scale may be null = identity)
+    const float* scale; const float* shift; int relu;
+    // mode 1 operand transform: dy = k1*(g - k2 - xhat*k3), g = G*(z>0), z = y*zs+zb, xhat = (y-mean)*invstd
+    const float* Yraw; const float* zs; const float* zb; const float* mean; const float* invstd;
+    const float* k1; const float* k2; const float* k3;
+};
+
+__device__ __forceinline__ void split8v(const float (&x)[8], uint4& hi, uint4& lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * i]), h1 = __float2bfloat16_rn(x[2 * i + 1]);
+        __nv_bfloat16 l0 = __float2bfloat16_rn(x[2 * i] - __bfloat162float(h0));
+        __nv_bfloat16 l1 = __float2bfloat16_rn(x[2 * i + 1] - __bfloat162float(h1));
+        h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+template <int CIN, int COUT, int MODE>
+__global__ void __maxnreg__(152) tc_conv_kernel(TcConvArgs a) {
+    constexpr int CINP = (CIN + 15) / 16 * 16, COUTP = (COUT + 15) / 16 * 16;
+    constexpr int NG = CINP / 8, NGR = (CIN + 7) / 8, KS = CINP / 16;
+    constexpr int PLANE_BYTES = WPIX * 16;
+    constexpr int SLOT_BYTES = 2 * NG * PLANE_BYTES;                 // hi planes then lo planes
+    constexpr int WBLK_BYTES = 2 * COUTP * 16;                        // one (tap, ks, split) weight block: 2 k-groups x COUTP rows
+    constexpr int W_BYTES = 9 * KS * 2 * WBLK_BYTES;
+    constexpr int TM_COLS = 64;                                       // TMEM columns per accumulator buffer
+    static_assert(COUTP <= TM_COLS, "accumulator width");
+
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* wsm = smem;                                              // W_BYTES
+    uint8_t* win = smem + ((W_BYTES + 127) / 128) * 128;              // NWIN * SLOT_BYTES
+    __shared__ uint64_t full_bar[NWIN], empty_bar[NWIN], tfull_bar[2], tempty_bar[2];
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int T = a.T, F = a.F, PWD = F + 2;
+    const int tiles_per_clip = (T * PWD + BM - 1) / BM;
+    const long long ntiles = (long long)a.B * tiles_per_clip;
+
+    // weights -> smem (already bf16, already in UMMA layout); zero the window ring once (pad planes / pad entries stay zero)
+    for (int i = tid; i < W_BYTES / 16; i += NTHREADS) reinterpret_cast<uint4*>(wsm)[i] = __ldg(a.Wpack + i);
+    for (int i = tid; i < NWIN * SLOT_BYTES / 16; i += NTHREADS) reinterpret_cast<uint4*>(win)[i] = make_uint4(0, 0, 0, 0);
+    if (warp == N_EPI_WARPS) {
+        if (lane == 0) {
+            for (int s = 0; s < NWIN; ++s) { mbar_init(&full_bar[s], N_LOAD_THREADS); mbar_init(&empty_bar[s], 1); }
+            for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], N_EPI_WARPS * 32); }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        tmem_alloc(&tmem_base_s, 2 * TM_COLS);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp < N_EPI_WARPS) {
+        // ================================================================================= epilogue
+        float ssum[2] = {0.f, 0.f}, ssq[2] = {0.f, 0.f};              // lane c keeps channels c and c+32
+        uint32_t it = 0;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int b = (int)(tile / tiles_per_clip);
+            const int q = (int)(tile % tiles_per_clip) * BM + warp * 32 + lane;
+            const int t = q / PWD, fp = q - t * PWD;
+            const bool valid = (t < T) && (fp >= 1) && (fp <= F);
+            const int acc = it & 1;
+            mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
+            tc_fence_after();
+            float* yrow = a.Y + (((size_t)b * T + t) * F + (fp - 1)) * COUT;
+#pragma unroll
+            for (int c0 = 0; c0 < COUTP; c0 += 16) {
+                float v[16];
+                tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * TM_COLS + c0), v);
+                if (valid) {
+#pragma unroll
+                    for (int qd = 0; qd < 4; ++qd)
+                        if (c0 + 4 * qd < COUT)
+                            reinterpret_cast<float4*>(yrow + c0)[qd] = make_float4(v[4 * qd], v[4 * qd + 1], v[4 * qd + 2], v[4 * qd + 3]);
+                }
+                if (a.partial != nullptr) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int c = c0 + i;
+                        if (c < COUT) {
+                            const float x = valid ? v[i] : 0.f;
+                            const float s1 = warp_sum(x), s2 = warp_sum(x * x);
+                            if (lane == (c & 31)) { ssum[c >> 5] += s1; ssq[c >> 5] += s2; }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tempty_bar[acc]);
+        }
+        if (a.partial != nullptr) {
+            float* pr = a.partial + ((size_t)blockIdx.x * N_EPI_WARPS + warp) * 2 * COUT;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int c = lane + 32 * h;
+                if (c < COUT) { pr[c] = ssum[h]; pr[COUT + c] = ssq[h]; }
+            }
+        }
+    } else if (warp == N_EPI_WARPS) {
+        // ================================================================================= MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(BM, COUTP, 0, 0);
+            const uint32_t w_base = smem_u32(wsm), win_base = smem_u32(win);
+            uint32_t it = 0, wi = 0;
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                mbar_wait(&tempty_bar[acc], ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TM_COLS);
+                for (int ky = 0; ky < 3; ++ky, ++wi) {
+                    const int slot = wi % NWIN;
+                    mbar_wait(&full_bar[slot], (wi / NWIN) & 1);
+                    tc_fence_after();
+                    const uint32_t hi_base = win_base + slot * SLOT_BYTES, lo_base = hi_base + NG * PLANE_BYTES;
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll
+                        for (int ks = 0; ks < KS; ++ks) {
+                            const uint32_t aoff = (uint32_t)(2 * ks * PLANE_BYTES + kx * 16);
+                            const uint64_t dah = make_desc(hi_base + aoff, PLANE_BYTES, 128);
+                            const uint64_t dal = make_desc(lo_base + aoff, PLANE_BYTES, 128);
+                            const uint32_t wb = w_base + (uint32_t)((((ky * 3 + kx) * KS + ks) * 2) * WBLK_BYTES);
+                            const uint64_t dbh = make_desc(wb, COUTP * 16, 128);
+                            const uint64_t dbl = make_desc(wb + WBLK_BYTES, COUTP * 16, 128);
+                            tc_mma(d_tmem, dah, dbh, idesc, (ky | kx | ks) != 0);
+                            if (a.nsplit > 1) {
+                                tc_mma(d_tmem, dah, dbl, idesc, 1);
+                                tc_mma(d_tmem, dal, dbh, idesc, 1);
+                            }
+                        }
+                    }
+                    tc_commit(&empty_bar[slot]);
+                }
+                tc_commit(&tfull_bar[acc]);
+            }
+        }
+    } else {
+        // ================================================================================= window loaders
+        // Each thread owns NU units (position j, 8-channel group g) of every window.  The raw loads of window w+1 are
+        // issued before window w is converted, so the L2 latency overlaps the BatchNorm transform / bf16 split work.
+        const int ltid = tid - (N_EPI_WARPS + 1) * 32;
+        const bool want_lo = a.nsplit > 1;
+        constexpr int NU = (WENT * NGR + N_LOAD_THREADS - 1) / N_LOAD_THREADS;
+        constexpr int NV = MODE == 0 ? 2 : 4;          // float4 per unit: x (8 ch)  |  g (8 ch) + y (8 ch)
+        constexpr bool HALF_LAST = (CIN % 8) != 0;      // CIN = 20: the last real plane holds 4 channels only
+        struct Raw { float4 v[NU][NV]; bool ok[NU]; };
+        Raw cur, nxt;
+        auto issue = [&](Raw& r, long long tile, int ky) {
+            const int b = (int)(tile / tiles_per_clip);
+            const int q0 = (int)(tile % tiles_per_clip) * BM;
+            const int w0 = q0 + (ky - 1) * PWD - 1;                     // padded-linear position of window entry 0
+#pragma unroll
+            for (int i = 0; i < NU; ++i) {
+                const int u = ltid + i * N_LOAD_THREADS;
+                r.ok[i] = false;
+#pragma unroll
+                for (int k = 0; k < NV; ++k) r.v[i][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (u >= WENT * NGR) continue;
+                const int j = u / NGR, g = u - j * NGR;
+                const int w = w0 + j;
+                if (w < 0) continue;
+                const int t = w / PWD, fp = w - t * PWD;
+                if (t >= T || fp < 1 || fp > F) continue;
+                r.ok[i] = true;
+                const size_t base = (((size_t)b * T + t) * F + (fp - 1)) * CIN + 8 * g;
+                const bool half = HALF_LAST && (g == NGR - 1);
+                r.v[i][0] = __ldg(reinterpret_cast<const float4*>(a.X + base));
+                if (!half) r.v[i][1] = __ldg(reinterpret_cast<const float4*>(a.X + base) + 1);
+                if (MODE == 1) {
+                    r.v[i][NV - 2] = __ldg(reinterpret_cast<const float4*>(a.Yraw + base));
+                    if (!half) r.v[i][NV - 1] = __ldg(reinterpret_cast<const float4*>(a.Yraw + base) + 1);
+                }
+            }
+        };
+        auto convert_store = [&](const Raw& r, uint8_t* hi_base, uint8_t* lo_base) {
+#pragma unroll
+            for (int i = 0; i < NU; ++i) {
+                const int u = ltid + i * N_LOAD_THREADS;
+                if (u >= WENT * NGR) continue;
+                const int j = u / NGR, g = u - j * NGR;
+                float x[8] = {r.v[i][0].x, r.v[i][0].y, r.v[i][0].z, r.v[i][0].w, r.v[i][1].x, r.v[i][1].y, r.v[i][1].z, r.v[i][1].w};
+                if (r.ok[i]) {
+                    if (MODE == 0) {
+                        if (a.scale != nullptr) {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                const int c = 8 * g + e;
+                                if (c < CIN) {
+                                    float y = fmaf(x[e], __ldg(a.scale + c), __ldg(a.shift + c));
+                                    x[e] = a.relu ? fmaxf(y, 0.f) : y;
+                                }
+                            }
+                        }
+                    } else {
+                        const float yy[8] = {r.v[i][NV - 2].x, r.v[i][NV - 2].y, r.v[i][NV - 2].z, r.v[i][NV - 2].w,
+                                             r.v[i][NV - 1].x, r.v[i][NV - 1].y, r.v[i][NV - 1].z, r.v[i][NV - 1].w};
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const int c = 8 * g + e;
+                            if (c < CIN) {
+                                const float z = fmaf(yy[e], __ldg(a.zs + c), __ldg(a.zb + c));
+                                const float gi = z > 0.f ? x[e] : 0.f;
+                                const float xh = (yy[e] - __ldg(a.mean + c)) * __ldg(a.invstd + c);
+                                x[e] = __ldg(a.k1 + c) * (gi - __ldg(a.k2 + c) - xh * __ldg(a.k3 + c));
+                            } else {
+                                x[e] = 0.f;
+                            }
+                        }
+                    }
+                }
+                uint4 hi, lo;
+                split8v(x, hi, lo);
+                const int off = (g * WPIX + j) * 16;
+                *reinterpret_cast<uint4*>(hi_base + off) = hi;
+                if (want_lo) *reinterpret_cast<uint4*>(lo_base + off) = lo;
+            }
+        };
+        long long tile = blockIdx.x;
+        int ky = 0;
+        uint32_t wi = 0;
+        if (tile < ntiles) issue(cur, tile, 0);
+        while (tile < ntiles) {
+            long long ntile = tile; int nky = ky + 1;
+            if (nky == 3) { nky = 0; ntile += gridDim.x; }
+            if (ntile < ntiles) issue(nxt, ntile, nky);
+            const int slot = wi % NWIN;
+            mbar_wait(&empty_bar[slot], ((wi / NWIN) & 1) ^ 1);
+            uint8_t* hi_base = win + (size_t)slot * SLOT_BYTES;
+            convert_store(cur, hi_base, hi_base + NG * PLANE_BYTES);
+            fence_proxy_async();
+            mbar_arrive(&full_bar[slot]);
+            cur = nxt; tile = ntile; ky = nky; ++wi;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == N_EPI_WARPS) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 2 * TM_COLS);
+    }
+}
+
+// Pack fp32 conv weights (Cout,Cin,3,3) into the bf16 UMMA blocks the kernel expects:
+//   [tap][ks][split(hi,lo)][kgroup(2)][n (NOUTP)][8]   element k = ks*16 + kgroup*8 + e  (input channel), n = output channel.
+// transpose_flip = 0: forward  (n = co, k = ci, tap = ky*3+kx);
+// transpose_flip = 1: data gradient (n = ci, k = co, tap = (2-ky)*3 + (2-kx)):  conv of dy with the flipped, transposed filter.
+__global__ void tc_conv_pack_kernel(const float* __restrict__ W, int Cout, int Cin, int transpose_flip, __nv_bfloat16* __restrict__ out,
+                                    int KIN, int NOUT, int KS, int NOUTP) {
+    const int total = 9 * KS * 2 * 2 * NOUTP * 8;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        int e = idx % 8, r = idx / 8;
+        int n = r % NOUTP; r /= NOUTP;
+        int kg = r % 2; r /= 2;
+        int split = r % 2; r /= 2;
+        int ks = r % KS; int tap = r / KS;
+        int k = ks * 16 + kg * 8 + e;
+        float w = 0.f;
+        if (n < NOUT && k < KIN) {
+            int ky = tap / 3, kx = tap % 3;
+            if (!transpose_flip) w = W[((n * Cin + k) * 3 + ky) * 3 + kx];
+            else w = W[((k * Cin + n) * 3 + (2 - ky)) * 3 + (2 - kx)];
+        }
+        __nv_bfloat16 h = __float2bfloat16_rn(w);
+        out[idx] = split == 0 ? h : __float2bfloat16_rn(w - __bfloat162float(h));
+    }
+}
+
+template <int CIN, int COUT, int MODE>
+int launch_tc_conv(cudaStream_t st, const TcConvArgs& a) {
+    constexpr int CINP = (CIN + 15) / 16 * 16, COUTP = (COUT + 15) / 16 * 16;
+    constexpr int NG = CINP / 8, KS = CINP / 16;
+    constexpr int W_BYTES = 9 * KS * 2 * (2 * COUTP * 16);
+    constexpr int SMEM = ((W_BYTES + 127) / 128) * 128 + NWIN * (2 * NG * WPIX * 16) + 1024;
+    PA2S_TRY(cudaFuncSetAttribute(tc_conv_kernel<CIN, COUT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    const long long ntiles = (long long)a.B * ((a.T * (a.F + 2) + BM - 1) / BM);
+    const int grid = (int)(ntiles < 148 ? ntiles : 148);
+    tc_conv_kernel<CIN, COUT, MODE><<<grid, NTHREADS, SMEM, st>>>(a);
+    PA2S_CHECK_LAST();
+    return 0;
+}
+
+}  // namespace
+
+// bytes of the packed weight buffer for a (Kin -> Nout) 3x3 convolution
+PA2S_API int pa2s_tc_conv_pack_bytes(int Kin, int Nout) {
+    int KS = (Kin + 15) / 16, NOUTP = (Nout + 15) / 16 * 16;
+    return 9 * KS * 2 * 2 * NOUTP * 8 * 2;
+}
+// W: (Cout,Cin,3,3) fp32.  dgrad = 0 packs the forward filter (Kin = Cin, Nout = Cout); dgrad = 1 packs the flipped,
+// transposed filter of the data gradient (Kin = Cout, Nout = Cin).
+PA2S_API int pa2s_tc_conv_pack(void* stream, const float* W, int Cout, int Cin, int dgrad, void* out) {
+    int KIN = dgrad ? Cout : Cin, NOUT = dgrad ? Cin : Cout;
+    int KS = (KIN + 15) / 16, NOUTP = (NOUT + 15) / 16 * 16;
+    tc_conv_pack_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(W, Cout, Cin, dgrad, (__nv_bfloat16*)out, KIN, NOUT, KS, NOUTP);
+    PA2S_CHECK_LAST();
+    return 0;
+}
+// Rows of `partial` written by the forward kernel: 4 per CTA, 148 CTAs at most.
+PA2S_API int pa2s_tc_conv_num_partials(int B, int T, int F) {
+    long long ntiles = (long long)B * ((T * (F + 2) + BM - 1) / BM);
+    return (int)(ntiles < 148 ? ntiles : 148) * N_EPI_WARPS;
+}
+// mode 0 / 1 as pa2s_conv3x3 (Cin = channels of the tensor being convolved, Cout = channels produced).
+PA2S_API int pa2s_tc_conv3x3(void* stream, int mode, int B, int T, int F, int Cin, int Cout, const float* X, const void* Wpack,
+                             float* Y, float* partial, int nsplit,
+                             const float* in_scale, const float* in_shift, int in_relu,
+                             const float* Yraw, const float* zs, const float* zb, const float* mean, const float* invstd,
+                             const float* k1, const float* k2, const float* k3) {
+    TcConvArgs a;
+    a.X = X; a.Wpack = (const uint4*)Wpack; a.Y = Y; a.partial = partial; a.B = B; a.T = T; a.F = F; a.nsplit = nsplit >= 3 ? 3 : 1;
+    a.scale = in_scale; a.shift = in_shift; a.relu = in_relu;
+    a.Yraw = Yraw; a.zs = zs; a.zb = zb; a.mean = mean; a.invstd = invstd; a.k1 = k1; a.k2 = k2; a.k3 = k3;
+    if ((long long)T * (F + 2) + 2 * (F + 2) + 256 > 0x7fffffffLL) return -1;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mode == 0) {
+        if (Cin == 20 && Cout == 20) return launch_tc_conv<20, 20, 0>(st, a);
+        if (Cin == 20 && Cout == 40) return launch_tc_conv<20, 40, 0>(st, a);
+        if (Cin == 40 && Cout == 40) return launch_tc_conv<40, 40, 0>(st, a);
+    } else {
+        if (Cin == 20 && Cout == 20) return launch_tc_conv<20, 20, 1>(st, a);
+        if (Cin == 40 && Cout == 20) return launch_tc_conv<40, 20, 1>(st, a);
+        if (Cin == 40 && Cout == 40) return launch_tc_conv<40, 40, 1>(st, a);
+    }
+    return -1;
+}

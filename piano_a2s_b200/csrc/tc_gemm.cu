@@ -11,8 +11,7 @@
 //              in the UMMA no-swizzle canonical layout ("planes" of 8 contiguous elements at a 16-byte pitch), so
 //              a K-major source needs no transposition and an MN-major source is consumed as an MN-major operand.
 // Shared-memory ring of 4 stages (BK = 32), two TMEM accumulator buffers (epilogue of tile i overlaps MMAs of i+1).
-#include "common.cuh"
-#include <cuda_bf16.h>
+#include "tc_common.cuh"
 
 namespace {
 
@@ -39,155 +38,108 @@ struct TcArgs {
     int vecA, vecB, vecC;
 };
 
-// ------------------------------------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra.uni WAIT_DONE;\n\t"
-        "bra.uni WAIT_LOOP;\n\t"
-        "WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
+using namespace tc;
 
-// UMMA shared-memory descriptor, no swizzle (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
-// SBO>>4 [32,46), version=1 [46,48), layout_type=0 [61,64).
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-    d |= (uint64_t)1 << 46;
-    return d;
-}
-// Instruction descriptor (cute::UMMA::InstrDescriptor) for kind::f16, BF16 x BF16 -> F32.
-__device__ __forceinline__ uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
-    uint32_t d = 0;
-    d |= 1u << 4;                       // c_format = F32
-    d |= 1u << 7;                       // a_format = BF16
-    d |= 1u << 10;                      // b_format = BF16
-    d |= (uint32_t)a_mn_major << 15;
-    d |= (uint32_t)b_mn_major << 16;
-    d |= (uint32_t)(N >> 3) << 17;
-    d |= (uint32_t)(M >> 4) << 24;
-    return d;
-}
+// ---- operand staging ------------------------------------------------------------------------------------------
+// A loader thread owns, per pipeline stage, NIT "units" of one operand: 8 consecutive fp32 along the source's contiguous
+// index.  Loads of a whole stage (both operands) are issued before any of them is consumed, and the loads of stage s+1
+// are issued before stage s is converted, so the global/L2 latency overlaps the bf16 split work.
+//  KMAJ source P[mn][k]: unit (row r, k-group kg)      -> smem (kg*rows + r)*16      (UMMA K-major, LBO = rows*16, SBO = 128)
+//  MN   source P[k][mn]: unit (k row kk, mn-group mg)  -> smem (mg*BK + kk)*16       (UMMA MN-major, SBO = BK*16, LBO = 128)
+template <int NIT>
+struct Units {
+    float4 v[NIT][2];
+    int c0[NIT];            // contiguous-index of element 0 (transform key / guard), -1 = unit not loaded (zeros)
+    int off[NIT];           // smem byte offset, -1 = unit not owned in this stage
+};
 
-__device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo) {
-    uint32_t h[4], l[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * i]), h1 = __float2bfloat16_rn(x[2 * i + 1]);
-        __nv_bfloat16 l0 = __float2bfloat16_rn(x[2 * i] - __bfloat162float(h0));
-        __nv_bfloat16 l1 = __float2bfloat16_rn(x[2 * i + 1] - __bfloat162float(h1));
-        h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-        l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-    }
-    hi = make_uint4(h[0], h[1], h[2], h[3]);
-    lo = make_uint4(l[0], l[1], l[2], l[3]);
-}
-
-// Loads 8 consecutive fp32 at P[idx0 .. idx0+8) (guarded by `limit` on the contiguous index c0+i), applies the
-// optional affine/ReLU keyed on the contiguous index.
-__device__ __forceinline__ void load8(const float* __restrict__ P, bool row_ok, long long off, int c0, int limit, bool vec, bool tf,
-                                      const TcArgs& g, float (&x)[8]) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) x[i] = 0.f;
-    if (!row_ok) return;
-    if (vec && c0 + 7 < limit) {
-        float4 a = __ldg(reinterpret_cast<const float4*>(P + off));
-        float4 b = __ldg(reinterpret_cast<const float4*>(P + off) + 1);
-        x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
-    } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-            if (c0 + i < limit) x[i] = __ldg(P + off + i);
-    }
-    if (tf) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            if (c0 + i < limit) {
-                int c = (c0 + i) % g.t_period;
-                float y = fmaf(x[i], __ldg(g.t_scale + c), __ldg(g.t_shift + c));
-                x[i] = g.t_relu ? fmaxf(y, 0.f) : y;
-            }
-        }
-    }
-}
-
-// Fill one operand's hi/lo planes for one stage.
-//  KMAJ source: P[mn][k]   -> unit (mn row r, k-group kg): smem (kg*ROWS + r)*16
-//  MN   source: P[k][mn]   -> unit (k row kk, mn-group mg): smem (mg*BK + kk)*16
-template <bool KMAJ>
-__device__ __forceinline__ void load_operand(const float* __restrict__ P, long long ld, int mn0, int MN, int rows, int k0, int kend,
-                                             bool vec, bool tf, const TcArgs& g, uint8_t* hi_plane, uint8_t* lo_plane, int ltid,
-                                             bool want_lo) {
+template <bool KMAJ, int NIT>
+__device__ __forceinline__ void units_issue(Units<NIT>& u, const float* __restrict__ P, long long ld, int mn0, int MN, int rows, int k0,
+                                            int kend, bool vec, int ltid) {
     const int lane = ltid & 31, lw = ltid >> 5;
     const int i8 = lane & 7, g4 = lane >> 3;
-    if (KMAJ) {
-        // blocks of 8 rows x 4 k-groups per warp
-        for (int rb = lw; rb < rows / 8; rb += N_LOAD_WARPS) {
-            const int r = rb * 8 + i8, kg = g4;
-            const int m = mn0 + r, k = k0 + kg * 8;
-            float x[8];
-            load8(P, m < MN, (long long)m * ld + k, k, kend, vec, tf, g, x);
-            uint4 hi, lo;
-            split8(x, hi, lo);
-            const int off = (kg * rows + r) * 16;
-            *reinterpret_cast<uint4*>(hi_plane + off) = hi;
-            if (want_lo) *reinterpret_cast<uint4*>(lo_plane + off) = lo;
-        }
-    } else {
-        // blocks of 8 k-rows x 4 mn-groups per warp; (BK/8) * (rows/32) blocks
-        const int nblk = (BK / 8) * (rows / 32);
-        for (int blk = lw; blk < nblk; blk += N_LOAD_WARPS) {
+    const int nblk = KMAJ ? rows / 8 : (BK / 8) * (rows / 32);
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        const int blk = lw + it * N_LOAD_WARPS;
+        u.off[it] = -1; u.c0[it] = -1;
+        u.v[it][0] = make_float4(0.f, 0.f, 0.f, 0.f); u.v[it][1] = u.v[it][0];
+        if (blk >= nblk) continue;
+        int slow, fast0, limit;     // slow index (row of the source), first contiguous index, limit of the contiguous index
+        bool slow_ok;
+        if (KMAJ) {
+            const int r = blk * 8 + i8, kg = g4;
+            slow = mn0 + r; slow_ok = slow < MN; fast0 = k0 + kg * 8; limit = kend;
+            u.off[it] = (kg * rows + r) * 16;
+        } else {
             const int kb = blk % (BK / 8), mb = blk / (BK / 8);
             const int kk = kb * 8 + i8, mg = mb * 4 + g4;
-            const int k = k0 + kk, m = mn0 + mg * 8;
+            slow = k0 + kk; slow_ok = slow < kend; fast0 = mn0 + mg * 8; limit = MN;
+            u.off[it] = (mg * BK + kk) * 16;
+        }
+        if (!slow_ok || fast0 >= limit) continue;
+        u.c0[it] = fast0;
+        const float* p = P + (long long)slow * ld + fast0;
+        if (vec && fast0 + 7 < limit) {
+            u.v[it][0] = __ldg(reinterpret_cast<const float4*>(p));
+            u.v[it][1] = __ldg(reinterpret_cast<const float4*>(p) + 1);
+        } else {
             float x[8];
-            load8(P, k < kend, (long long)k * ld + m, m, MN, vec, tf, g, x);
-            uint4 hi, lo;
-            split8(x, hi, lo);
-            const int off = (mg * BK + kk) * 16;
-            *reinterpret_cast<uint4*>(hi_plane + off) = hi;
-            if (want_lo) *reinterpret_cast<uint4*>(lo_plane + off) = lo;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = (fast0 + i < limit) ? __ldg(p + i) : 0.f;
+            u.v[it][0] = make_float4(x[0], x[1], x[2], x[3]);
+            u.v[it][1] = make_float4(x[4], x[5], x[6], x[7]);
         }
     }
+}
+
+template <int NIT>
+__device__ __forceinline__ void units_store(const Units<NIT>& u, int limit, bool tf, const TcArgs& g, uint8_t* hi_plane, uint8_t* lo_plane,
+                                            bool want_lo) {
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        if (u.off[it] < 0) continue;
+        float x[8] = {u.v[it][0].x, u.v[it][0].y, u.v[it][0].z, u.v[it][0].w, u.v[it][1].x, u.v[it][1].y, u.v[it][1].z, u.v[it][1].w};
+        if (tf && u.c0[it] >= 0) {
+            int c = u.c0[it] % g.t_period;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (u.c0[it] + i < limit) {
+                    float y = fmaf(x[i], __ldg(g.t_scale + c), __ldg(g.t_shift + c));
+                    x[i] = g.t_relu ? fmaxf(y, 0.f) : y;
+                }
+                c = (c + 1 == g.t_period) ? 0 : c + 1;
+            }
+        }
+        uint4 hi, lo;
+        split8(x, hi, lo);
+        *reinterpret_cast<uint4*>(hi_plane + u.off[it]) = hi;
+        if (want_lo) *reinterpret_cast<uint4*>(lo_plane + u.off[it]) = lo;
+    }
+}
+
+// coordinates of one pipeline stage of this CTA's work list
+struct StageCoord {
+    long long tile; int kb, nkb, tm, tn, bz, kbeg, kend;
+    bool valid;
+};
+__device__ __forceinline__ void coord_set_tile(StageCoord& c, long long tile, long long ntiles, const TcArgs& g) {
+    c.tile = tile; c.valid = tile < ntiles; c.kb = 0;
+    if (!c.valid) return;
+    c.tn = (int)(tile % g.tiles_n);
+    c.tm = (int)((tile / g.tiles_n) % g.tiles_m);
+    const int z = (int)(tile / ((long long)g.tiles_n * g.tiles_m));
+    c.bz = z / g.splitk;
+    const int sk = z % g.splitk;
+    c.kbeg = sk * g.kchunk; c.kend = min(g.K, c.kbeg + g.kchunk);
+    c.nkb = (c.kend - c.kbeg + BK - 1) / BK;
+}
+__device__ __forceinline__ void coord_next(StageCoord& c, long long ntiles, const TcArgs& g) {
+    if (++c.kb >= c.nkb) coord_set_tile(c, c.tile + gridDim.x, ntiles, g);
 }
 
 template <bool A_KMAJ, bool B_KMAJ>
-__global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(TcArgs g) {
+__global__ void __maxnreg__(152) tc_gemm_kernel(TcArgs g) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t full_bar[NSTAGE], empty_bar[NSTAGE], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_s;
@@ -302,27 +254,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(TcArgs g) {
         const int ltid = tid - (N_EPI_WARPS + 1) * 32;
         const bool tfA = g.t_scale != nullptr && !g.t_on_b, tfB = g.t_scale != nullptr && g.t_on_b;
         const bool want_lo = g.nsplit > 1;
+        constexpr int NA = 2, NB = 4;                 // units per thread per stage (A: 128 rows, B: up to 256 rows)
+        Units<NA> ua, ua_n;
+        Units<NB> ub, ub_n;
+        StageCoord cur, nxt;
+        coord_set_tile(cur, blockIdx.x, ntiles, g);
+        auto issue = [&](const StageCoord& c, Units<NA>& xa, Units<NB>& xb) {
+            const float* A = g.A + (long long)c.bz * g.sA;
+            const float* B = g.B + (long long)c.bz * g.sB;
+            const int k0 = c.kbeg + c.kb * BK;
+            units_issue<A_KMAJ, NA>(xa, A, g.lda, c.tm * BM, g.M, BM, k0, c.kend, g.vecA, ltid);
+            units_issue<B_KMAJ, NB>(xb, B, g.ldb, c.tn * BN, g.N, BN, k0, c.kend, g.vecB, ltid);
+        };
+        if (cur.valid) issue(cur, ua, ub);
         uint32_t kit = 0;
-        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const int tn = (int)(tile % g.tiles_n);
-            const int tm = (int)((tile / g.tiles_n) % g.tiles_m);
-            const int z = (int)(tile / ((long long)g.tiles_n * g.tiles_m));
-            const int bz = z / g.splitk, sk = z % g.splitk;
-            const int kbeg = sk * g.kchunk, kend = min(g.K, kbeg + g.kchunk);
-            const int nkb = (kend - kbeg + BK - 1) / BK;
-            const float* A = g.A + (long long)bz * g.sA;
-            const float* B = g.B + (long long)bz * g.sB;
-            for (int kb = 0; kb < nkb; ++kb, ++kit) {
-                const int s = kit % NSTAGE;
-                mbar_wait(&empty_bar[s], ((kit / NSTAGE) & 1) ^ 1);
-                uint8_t* st = smem + (size_t)s * STAGE_BYTES;
-                const int k0 = kbeg + kb * BK;
-                load_operand<A_KMAJ>(A, g.lda, tm * BM, g.M, BM, k0, kend, g.vecA, tfA, g, st, st + A_PLANE_BYTES, ltid, want_lo);
-                load_operand<B_KMAJ>(B, g.ldb, tn * BN, g.N, BN, k0, kend, g.vecB, tfB, g, st + 2 * A_PLANE_BYTES,
-                                     st + 2 * A_PLANE_BYTES + B_PLANE_BYTES, ltid, want_lo);
-                fence_proxy_async();            // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-                mbar_arrive(&full_bar[s]);
-            }
+        while (cur.valid) {
+            nxt = cur;
+            coord_next(nxt, ntiles, g);
+            if (nxt.valid) issue(nxt, ua_n, ub_n);          // next stage's loads are in flight while this one is converted
+            const int s = kit % NSTAGE;
+            mbar_wait(&empty_bar[s], ((kit / NSTAGE) & 1) ^ 1);
+            uint8_t* st = smem + (size_t)s * STAGE_BYTES;
+            units_store<NA>(ua, A_KMAJ ? cur.kend : g.M, tfA, g, st, st + A_PLANE_BYTES, want_lo);
+            units_store<NB>(ub, B_KMAJ ? cur.kend : g.N, tfB, g, st + 2 * A_PLANE_BYTES, st + 2 * A_PLANE_BYTES + B_PLANE_BYTES, want_lo);
+            fence_proxy_async();            // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+            mbar_arrive(&full_bar[s]);
+            ua = ua_n; ub = ub_n; cur = nxt; ++kit;
         }
     }
 

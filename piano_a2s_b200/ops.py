@@ -194,6 +194,18 @@ def linear(x, W, b=None):
 # ----------------------------------------------------------------------------------------------------------------
 # ConvStack (models.py:463-543) as one fused group
 # ----------------------------------------------------------------------------------------------------------------
+def _nsplit(prec):
+    return 3 if prec == "bf16x3" else 1
+
+
+def _tc_pack(W, Cout, Cin, dgrad):
+    """fp32 (Cout,Cin,3,3) -> bf16 hi/lo UMMA weight blocks for tc_conv.cu"""
+    kin, nout = (Cout, Cin) if dgrad else (Cin, Cout)
+    buf = torch.empty(lib.pa2s_tc_conv_pack_bytes(kin, nout), device=W.device, dtype=torch.uint8)
+    lib.pa2s_tc_conv_pack(stream(), ptr(W.detach().contiguous()), Cout, Cin, dgrad, ptr(buf))
+    return buf
+
+
 def _bn_sums(partial, C):
     sums = torch.empty(2 * C, device=partial.device, dtype=torch.float64)
     lib.pa2s_reduce_rows(stream(), ptr(partial), partial.shape[0], 2 * C, ptr(sums), None, 0)
@@ -227,13 +239,22 @@ class ConvStackFn(torch.autograd.Function):
         for i in range(4):
             W = conv_w[i]
             Cout, Cin = W.shape[0], W.shape[1]
-            Wp = W.detach().permute(2, 3, 1, 0).contiguous()
             y = torch.empty(B, T, Fq, Cout, device=dev, dtype=F32)
-            nparts = lib.pa2s_conv3x3_num_partials(B, T, Fq, ntile)
-            partial = torch.empty(nparts, 2 * Cout, device=dev, dtype=F32) if training else None
-            with ktime(f"conv{i + 1}_fwd"):
-                lib.pa2s_conv3x3(st, 0, B, T, Fq, Cin, Cout, ptr(xin), ptr(Wp), ptr(y), ptr(partial), ntile,
-                                 ptr(in_scale), ptr(in_shift), 1, None, None, None, None, None, None, None, None)
+            use_tc = ctx.prec != "fp32" and Cin >= 16
+            if use_tc:
+                Wpk = _tc_pack(W, Cout, Cin, 0)
+                nparts = lib.pa2s_tc_conv_num_partials(B, T, Fq)
+                partial = torch.empty(nparts, 2 * Cout, device=dev, dtype=F32) if training else None
+                with ktime(f"conv{i + 1}_fwd"):
+                    lib.pa2s_tc_conv3x3(st, 0, B, T, Fq, Cin, Cout, ptr(xin), ptr(Wpk), ptr(y), ptr(partial), _nsplit(ctx.prec),
+                                        ptr(in_scale), ptr(in_shift), 1, None, None, None, None, None, None, None, None)
+            else:
+                Wp = W.detach().permute(2, 3, 1, 0).contiguous()
+                nparts = lib.pa2s_conv3x3_num_partials(B, T, Fq, ntile)
+                partial = torch.empty(nparts, 2 * Cout, device=dev, dtype=F32) if training else None
+                with ktime(f"conv{i + 1}_fwd"):
+                    lib.pa2s_conv3x3(st, 0, B, T, Fq, Cin, Cout, ptr(xin), ptr(Wp), ptr(y), ptr(partial), ntile,
+                                     ptr(in_scale), ptr(in_shift), 1, None, None, None, None, None, None, None, None)
             aff = torch.empty(4, Cout, device=dev, dtype=F32)      # scale, shift, mean, invstd
             if training:
                 sums = _bn_sums(partial, Cout)
@@ -352,11 +373,17 @@ class ConvStackFn(torch.autograd.Function):
             lib.pa2s_reduce_rows(st, ptr(partial), nw, Cout * Cin * 9, None, ptr(dW), 0)
             grads[3 * i] = dW
             if i > 0:
-                W2 = W.detach().flip(2, 3).permute(2, 3, 0, 1).contiguous()        # [tap][co][ci]
                 Gp = torch.empty(B, T, Fq, Cin, device=dev, dtype=F32)
-                with ktime(f"conv{i + 1}_dgrad"):
-                    lib.pa2s_conv3x3(st, 1, B, T, Fq, Cout, Cin, ptr(G), ptr(W2), ptr(Gp), None, 4, None, None, 1,
-                                     ptr(y), ptr(aff[0]), ptr(aff[1]), ptr(aff[2]), ptr(aff[3]), ptr(k[0]), ptr(k[1]), ptr(k[2]))
+                if ctx.prec != "fp32":
+                    W2 = _tc_pack(W, Cout, Cin, 1)
+                    with ktime(f"conv{i + 1}_dgrad"):
+                        lib.pa2s_tc_conv3x3(st, 1, B, T, Fq, Cout, Cin, ptr(G), ptr(W2), ptr(Gp), None, _nsplit(ctx.prec), None, None, 1,
+                                            ptr(y), ptr(aff[0]), ptr(aff[1]), ptr(aff[2]), ptr(aff[3]), ptr(k[0]), ptr(k[1]), ptr(k[2]))
+                else:
+                    W2 = W.detach().flip(2, 3).permute(2, 3, 0, 1).contiguous()        # [tap][co][ci]
+                    with ktime(f"conv{i + 1}_dgrad"):
+                        lib.pa2s_conv3x3(st, 1, B, T, Fq, Cout, Cin, ptr(G), ptr(W2), ptr(Gp), None, 4, None, None, 1,
+                                         ptr(y), ptr(aff[0]), ptr(aff[1]), ptr(aff[2]), ptr(aff[3]), ptr(k[0]), ptr(k[1]), ptr(k[2]))
                 G = Gp
         return (None, None, None, None, None, None, None, *grads)
 

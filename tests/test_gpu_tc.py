@@ -79,3 +79,50 @@ def test_tc_gemm_batched_splitk_transform(cuda):
         assert rel_err(C, torch.einsum("bkm,bkn->mn", D.double(), X.double())) < 2e-5
     finally:
         ops.TC_MIN_FLOP = ops_tc_min
+
+
+@pytest.mark.parametrize("Cin,Cout", [(20, 20), (20, 40), (40, 40)])
+@pytest.mark.parametrize("B,T,Fq", [(2, 9, 30), (1, 70, 481)])
+def test_tc_conv_forward_and_dgrad_match_torch(cuda, Cin, Cout, B, T, Fq):
+    """tc_conv.cu (mode 0 with the fused BatchNorm-apply+ReLU operand transform and batch-statistics epilogue; mode 1 with the
+    fused BatchNorm/ReLU backward transform) against float64 torch ops."""
+    from piano_a2s_b200 import ops
+    from piano_a2s_b200._lib import lib, ptr, stream
+    g = torch.Generator().manual_seed(Cin * 100 + Cout + T)
+    xraw = torch.randn(B, T, Fq, Cin, generator=g)
+    sc = torch.rand(Cin, generator=g) + 0.5
+    sh = torch.randn(Cin, generator=g) * 0.3
+    W = torch.randn(Cout, Cin, 3, 3, generator=g) * (1.0 / (3 * Cin ** 0.5))
+    a_in = F.relu(xraw.double() * sc.double() + sh.double())                                   # (B,T,F,Cin)
+    ref = F.conv2d(a_in.permute(0, 3, 1, 2), W.double(), None, 1, 1).permute(0, 2, 3, 1)     # (B,T,F,Cout)
+    xd, scd, shd, Wd = xraw.to(cuda), sc.to(cuda), sh.to(cuda), W.to(cuda)
+    Wpk = ops._tc_pack(Wd, Cout, Cin, 0)
+    y = torch.empty(B, T, Fq, Cout, device=cuda)
+    npart = lib.pa2s_tc_conv_num_partials(B, T, Fq)
+    partial = torch.zeros(npart, 2 * Cout, device=cuda)
+    lib.pa2s_tc_conv3x3(stream(), 0, B, T, Fq, Cin, Cout, ptr(xd), ptr(Wpk), ptr(y), ptr(partial), 3, ptr(scd), ptr(shd), 1,
+                        None, None, None, None, None, None, None, None)
+    e = rel_err(y, ref)
+    print(f"tc conv fwd {Cin}->{Cout} B{B} T{T} F{Fq}: rel err {e:.2e}")
+    assert e < 2e-5
+    sums = partial.double().sum(0).cpu()
+    assert rel_err(sums[:Cout], ref.sum((0, 1, 2))) < 1e-4 or ref.sum((0, 1, 2)).abs().max() < 1e-3
+    assert rel_err(sums[Cout:], (ref * ref).sum((0, 1, 2))) < 1e-4
+    # data gradient: dy = BN/ReLU backward transform of (G, yraw); d a_in = conv_transpose(dy, W)
+    yraw = ref.float()
+    G = torch.randn(B, T, Fq, Cout, generator=g)
+    zs = torch.rand(Cout, generator=g) + 0.5; zb = torch.randn(Cout, generator=g) * 0.2
+    mean = torch.randn(Cout, generator=g) * 0.1; invstd = torch.rand(Cout, generator=g) + 0.5
+    k1 = torch.rand(Cout, generator=g) + 0.5; k2 = torch.randn(Cout, generator=g) * 0.1; k3 = torch.randn(Cout, generator=g) * 0.1
+    z = yraw.double() * zs.double() + zb.double()
+    gg = torch.where(z > 0, G.double(), torch.zeros_like(z))
+    dy = k1.double() * (gg - k2.double() - (yraw.double() - mean.double()) * invstd.double() * k3.double())
+    ref_dx = F.conv_transpose2d(dy.permute(0, 3, 1, 2), W.double(), None, 1, 1).permute(0, 2, 3, 1)
+    W2 = ops._tc_pack(Wd, Cout, Cin, 1)
+    dx = torch.empty(B, T, Fq, Cin, device=cuda)
+    dev = lambda t: t.to(cuda)
+    cs = [dev(t) for t in (yraw, zs, zb, mean, invstd, k1, k2, k3)]
+    lib.pa2s_tc_conv3x3(stream(), 1, B, T, Fq, Cout, Cin, ptr(dev(G)), ptr(W2), ptr(dx), None, 3, None, None, 1, *[ptr(t) for t in cs])
+    e = rel_err(dx, ref_dx)
+    print(f"tc conv dgrad: rel err {e:.2e}")
+    assert e < 2e-5
