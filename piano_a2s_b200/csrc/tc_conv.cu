@@ -58,7 +58,7 @@ __device__ __forceinline__ void split8v(const float (&x)[8], uint4& hi, uint4& l
 }
 
 template <int CIN, int COUT, int MODE>
-__global__ void __maxnreg__(152) tc_conv_kernel(TcConvArgs a) {
+__global__ void __maxnreg__(144) tc_conv_kernel(TcConvArgs a) {
     constexpr int CINP = (CIN + 15) / 16 * 16, COUTP = (COUT + 15) / 16 * 16;
     constexpr int NG = CINP / 8, NGR = (CIN + 7) / 8, KS = CINP / 16;
     constexpr int PLANE_BYTES = WPIX * 16;
