@@ -74,6 +74,11 @@ PA2S_API int pa2s_tc_conv3x3(void* stream, int mode, int B, int T, int F, int Ci
                              const float* in_scale, const float* in_shift, int in_relu,
                              const float* Yraw, const float* zs, const float* zb, const float* mean, const float* invstd,
                              const float* k1, const float* k2, const float* k3);
+PA2S_API int pa2s_tc_conv_wgrad_num_partials(int B, int T, int F);
+PA2S_API int pa2s_tc_conv3x3_wgrad(void* stream, int B, int T, int F, int Cin, int Cout, const float* Xin, const float* G,
+                                   float* partial, int nsplit, const float* in_scale, const float* in_shift, int in_relu,
+                                   const float* Yraw, const float* zs, const float* zb, const float* mean, const float* invstd,
+                                   const float* k1, const float* k2, const float* k3);
 /* conv2d backward wrt weight; partial is [nctas][Cout*Cin*9] in torch (Cout,Cin,3,3) order. */
 PA2S_API int pa2s_conv3x3_wgrad(void* stream, int B, int T, int F, int Cin, int Cout, const float* Xin, const float* G,
                                 float* partial, int nctas, const float* in_scale, const float* in_shift, int in_relu,

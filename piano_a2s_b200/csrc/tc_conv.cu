@@ -58,7 +58,7 @@ __device__ __forceinline__ void split8v(const float (&x)[8], uint4& hi, uint4& l
 }
 
 template <int CIN, int COUT, int MODE>
-__global__ void __maxnreg__(144) tc_conv_kernel(TcConvArgs a) {
+__global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(TcConvArgs a) {
     constexpr int CINP = (CIN + 15) / 16 * 16, COUTP = (COUT + 15) / 16 * 16;
     constexpr int NG = CINP / 8, NGR = (CIN + 7) / 8, KS = CINP / 16;
     constexpr int PLANE_BYTES = WPIX * 16;
@@ -287,6 +287,267 @@ __global__ void __maxnreg__(144) tc_conv_kernel(TcConvArgs a) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Weight gradient on the tensor cores:  dW[co][ci][ky][kx] = sum_q dy[q][co] * a_in[q + (ky-1)(F+2) + (kx-1)][ci].
+// The reduction runs over pixels, so BOTH operands are MN-major UMMA operands (K = pixel index at a 16-byte pitch):
+//   A = dy  (M = 64 >= COUT channels)  staged per tile as planes [8-channel group][128 pixels][8 ch]
+//   B = a_in(N = CINP channels)        the forward kernel's three row-windows; tap kx = descriptor start + kx*16 bytes
+// Nine accumulators (one per tap, CINP columns each, 64 lanes) stay in TMEM for ALL tiles of the persistent CTA and are read
+// out once at the end into a per-CTA partial (summed by pa2s_reduce_rows).
+constexpr int APIX = 129;          // dy plane pitch in 16-byte units (odd: conflict-free plane-strided stores)
+constexpr int NASLOT = 2;
+
+struct TcWgradArgs {
+    const float* Xin;      // raw input of this layer (B,T,F,CIN)
+    const float* G;        // dL/d(relu out) of this layer (B,T,F,COUT)
+    float* partial;        // [gridDim.x][COUT*CIN*9]
+    int B, T, F, nsplit;
+    const float* scale; const float* shift; int relu;                                  // a_in = relu?(Xin*scale+shift)
+    const float* Yraw; const float* zs; const float* zb; const float* mean; const float* invstd;
+    const float* k1; const float* k2; const float* k3;                                 // dy transform
+};
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(NTHREADS, 1) tc_conv_wgrad_kernel(TcWgradArgs a) {
+    constexpr int CINP = (CIN + 15) / 16 * 16;
+    constexpr int NGB = CINP / 8, NGRB = (CIN + 7) / 8;          // a_in planes (padded / real)
+    constexpr int NGA = 8, NGRA = (COUT + 7) / 8;                 // dy planes: M = 64
+    constexpr int PLANE_BYTES = WPIX * 16, SLOT_BYTES = 2 * NGB * PLANE_BYTES;
+    constexpr int APLANE_BYTES = APIX * 16, ASLOT_BYTES = 2 * NGA * APLANE_BYTES;
+    constexpr int TM_COLS = 512;
+    static_assert(9 * CINP <= TM_COLS && COUT <= 64, "accumulators must fit TMEM");
+
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* win = smem;                                           // NWIN * SLOT_BYTES
+    uint8_t* asm_ = smem + NWIN * SLOT_BYTES;                      // NASLOT * ASLOT_BYTES
+    __shared__ uint64_t full_bar[NWIN], empty_bar[NWIN], afull_bar[NASLOT], aempty_bar[NASLOT], done_bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int T = a.T, F = a.F, PWD = F + 2;
+    const int tiles_per_clip = (T * PWD + BM - 1) / BM;
+    const long long ntiles = (long long)a.B * tiles_per_clip;
+
+    for (int i = tid; i < (NWIN * SLOT_BYTES + NASLOT * ASLOT_BYTES) / 16; i += NTHREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    if (warp == N_EPI_WARPS) {
+        if (lane == 0) {
+            for (int s = 0; s < NWIN; ++s) { mbar_init(&full_bar[s], N_LOAD_THREADS); mbar_init(&empty_bar[s], 1); }
+            for (int s = 0; s < NASLOT; ++s) { mbar_init(&afull_bar[s], N_LOAD_THREADS); mbar_init(&aempty_bar[s], 1); }
+            mbar_init(&done_bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        tmem_alloc(&tmem_base_s, TM_COLS);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp < N_EPI_WARPS) {
+        // ================================================================================= final read-out
+        mbar_wait(&done_bar, 0);
+        tc_fence_after();
+        const int co = 16 * warp + lane;                           // M = 64: row r lives in lane (r%16) + 32*(r/16)
+        float* out = a.partial + (size_t)blockIdx.x * COUT * CIN * 9;
+#pragma unroll 1
+        for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+            for (int c0 = 0; c0 < CINP; c0 += 16) {
+                float v[16];
+                tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(tap * CINP + c0), v);
+                if (lane < 16 && co < COUT) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (c0 + i < CIN) out[((size_t)co * CIN + c0 + i) * 9 + tap] = v[i];
+                }
+            }
+        }
+        tc_fence_before();
+    } else if (warp == N_EPI_WARPS) {
+        // ================================================================================= MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(64, CINP, 1, 1);
+            const uint32_t win_base = smem_u32(win), a_base0 = smem_u32(asm_);
+            uint32_t it = 0, wi = 0;
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                const int aslot = it % NASLOT;
+                mbar_wait(&afull_bar[aslot], (it / NASLOT) & 1);
+                tc_fence_after();
+                const uint32_t ahi = a_base0 + aslot * ASLOT_BYTES, alo = ahi + NGA * APLANE_BYTES;
+                for (int ky = 0; ky < 3; ++ky, ++wi) {
+                    const int slot = wi % NWIN;
+                    mbar_wait(&full_bar[slot], (wi / NWIN) & 1);
+                    tc_fence_after();
+                    const uint32_t bhi = win_base + slot * SLOT_BYTES, blo = bhi + NGB * PLANE_BYTES;
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const uint32_t d_tmem = tmem_base + (uint32_t)((ky * 3 + kx) * CINP);
+#pragma unroll
+                        for (int ks = 0; ks < BM / 16; ++ks) {
+                            const uint64_t dah = make_desc(ahi + ks * 256, 128, APLANE_BYTES);
+                            const uint64_t dal = make_desc(alo + ks * 256, 128, APLANE_BYTES);
+                            const uint64_t dbh = make_desc(bhi + (kx + 16 * ks) * 16, 128, PLANE_BYTES);
+                            const uint64_t dbl = make_desc(blo + (kx + 16 * ks) * 16, 128, PLANE_BYTES);
+                            tc_mma(d_tmem, dah, dbh, idesc, (it | (uint32_t)ks) != 0);
+                            if (a.nsplit > 1) {
+                                tc_mma(d_tmem, dah, dbl, idesc, 1);
+                                tc_mma(d_tmem, dal, dbh, idesc, 1);
+                            }
+                        }
+                    }
+                    tc_commit(&empty_bar[slot]);
+                }
+                tc_commit(&aempty_bar[aslot]);
+            }
+            tc_commit(&done_bar);
+        }
+    } else {
+        // ================================================================================= loaders (4 stages per tile)
+        const int ltid = tid - (N_EPI_WARPS + 1) * 32;
+        const bool want_lo = a.nsplit > 1;
+        constexpr int NUW = (WENT * NGRB + N_LOAD_THREADS - 1) / N_LOAD_THREADS;
+        constexpr int NUA = (BM * NGRA + N_LOAD_THREADS - 1) / N_LOAD_THREADS;
+        constexpr int NU = NUW > NUA ? NUW : NUA;
+        constexpr bool HALF_B = (CIN % 8) != 0, HALF_A = (COUT % 8) != 0;
+        struct Raw { float4 v[NU][4]; bool ok[NU]; };
+        Raw cur, nxt;
+        // stage st: 0 = dy tile (A operand), 1..3 = a_in window ky = st-1 (B operand)
+        auto issue = [&](Raw& r, long long tile, int st) {
+            const int b = (int)(tile / tiles_per_clip);
+            const int q0 = (int)(tile % tiles_per_clip) * BM;
+#pragma unroll
+            for (int i = 0; i < NU; ++i) {
+                r.ok[i] = false;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) r.v[i][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                const int u = ltid + i * N_LOAD_THREADS;
+                if (st == 0) {
+                    if (i >= NUA || u >= BM * NGRA) continue;
+                    const int j = u / NGRA, g = u - j * NGRA;
+                    const int q = q0 + j;
+                    const int t = q / PWD, fp = q - t * PWD;
+                    if (t >= T || fp < 1 || fp > F) continue;
+                    r.ok[i] = true;
+                    const size_t base = (((size_t)b * T + t) * F + (fp - 1)) * COUT + 8 * g;
+                    const bool half = HALF_A && (g == NGRA - 1);
+                    r.v[i][0] = __ldg(reinterpret_cast<const float4*>(a.G + base));
+                    r.v[i][2] = __ldg(reinterpret_cast<const float4*>(a.Yraw + base));
+                    if (!half) {
+                        r.v[i][1] = __ldg(reinterpret_cast<const float4*>(a.G + base) + 1);
+                        r.v[i][3] = __ldg(reinterpret_cast<const float4*>(a.Yraw + base) + 1);
+                    }
+                } else {
+                    if (i >= NUW || u >= WENT * NGRB) continue;
+                    const int j = u / NGRB, g = u - j * NGRB;
+                    const int w = q0 + (st - 2) * PWD - 1 + j;
+                    if (w < 0) continue;
+                    const int t = w / PWD, fp = w - t * PWD;
+                    if (t >= T || fp < 1 || fp > F) continue;
+                    r.ok[i] = true;
+                    const size_t base = (((size_t)b * T + t) * F + (fp - 1)) * CIN + 8 * g;
+                    const bool half = HALF_B && (g == NGRB - 1);
+                    r.v[i][0] = __ldg(reinterpret_cast<const float4*>(a.Xin + base));
+                    if (!half) r.v[i][1] = __ldg(reinterpret_cast<const float4*>(a.Xin + base) + 1);
+                }
+            }
+        };
+        auto convert_store = [&](const Raw& r, int st, uint8_t* hi_base, uint8_t* lo_base) {
+#pragma unroll
+            for (int i = 0; i < NU; ++i) {
+                const int u = ltid + i * N_LOAD_THREADS;
+                float x[8] = {r.v[i][0].x, r.v[i][0].y, r.v[i][0].z, r.v[i][0].w, r.v[i][1].x, r.v[i][1].y, r.v[i][1].z, r.v[i][1].w};
+                int off;
+                if (st == 0) {
+                    if (i >= NUA || u >= BM * NGRA) continue;
+                    const int j = u / NGRA, g = u - j * NGRA;
+                    off = (g * APIX + j) * 16;
+                    if (r.ok[i]) {
+                        const float yy[8] = {r.v[i][2].x, r.v[i][2].y, r.v[i][2].z, r.v[i][2].w, r.v[i][3].x, r.v[i][3].y, r.v[i][3].z, r.v[i][3].w};
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const int c = 8 * g + e;
+                            if (c < COUT) {
+                                const float z = fmaf(yy[e], __ldg(a.zs + c), __ldg(a.zb + c));
+                                const float gi = z > 0.f ? x[e] : 0.f;
+                                const float xh = (yy[e] - __ldg(a.mean + c)) * __ldg(a.invstd + c);
+                                x[e] = __ldg(a.k1 + c) * (gi - __ldg(a.k2 + c) - xh * __ldg(a.k3 + c));
+                            } else {
+                                x[e] = 0.f;
+                            }
+                        }
+                    }
+                } else {
+                    if (i >= NUW || u >= WENT * NGRB) continue;
+                    const int j = u / NGRB, g = u - j * NGRB;
+                    off = (g * WPIX + j) * 16;
+                    if (r.ok[i] && a.scale != nullptr) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const int c = 8 * g + e;
+                            if (c < CIN) {
+                                float y = fmaf(x[e], __ldg(a.scale + c), __ldg(a.shift + c));
+                                x[e] = a.relu ? fmaxf(y, 0.f) : y;
+                            }
+                        }
+                    }
+                }
+                uint4 hi, lo;
+                split8v(x, hi, lo);
+                *reinterpret_cast<uint4*>(hi_base + off) = hi;
+                if (want_lo) *reinterpret_cast<uint4*>(lo_base + off) = lo;
+            }
+        };
+        long long tile = blockIdx.x;
+        int st = 0;
+        uint32_t wi = 0, it = 0;
+        if (tile < ntiles) issue(cur, tile, 0);
+        while (tile < ntiles) {
+            long long ntile = tile; int nst = st + 1;
+            if (nst == 4) { nst = 0; ntile += gridDim.x; }
+            if (ntile < ntiles) issue(nxt, ntile, nst);
+            if (st == 0) {
+                const int aslot = it % NASLOT;
+                mbar_wait(&aempty_bar[aslot], ((it / NASLOT) & 1) ^ 1);
+                uint8_t* hb = asm_ + (size_t)aslot * ASLOT_BYTES;
+                convert_store(cur, 0, hb, hb + NGA * APLANE_BYTES);
+                fence_proxy_async();
+                mbar_arrive(&afull_bar[aslot]);
+                ++it;
+            } else {
+                const int slot = wi % NWIN;
+                mbar_wait(&empty_bar[slot], ((wi / NWIN) & 1) ^ 1);
+                uint8_t* hb = win + (size_t)slot * SLOT_BYTES;
+                convert_store(cur, st, hb, hb + NGB * PLANE_BYTES);
+                fence_proxy_async();
+                mbar_arrive(&full_bar[slot]);
+                ++wi;
+            }
+            cur = nxt; tile = ntile; st = nst;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == N_EPI_WARPS) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TM_COLS);
+    }
+}
+
+template <int CIN, int COUT>
+int launch_tc_wgrad(cudaStream_t st, const TcWgradArgs& a, int* grid_out) {
+    constexpr int CINP = (CIN + 15) / 16 * 16;
+    constexpr int SMEM = NWIN * (2 * (CINP / 8) * WPIX * 16) + NASLOT * (2 * 8 * APIX * 16) + 1024;
+    const long long ntiles = (long long)a.B * ((a.T * (a.F + 2) + BM - 1) / BM);
+    const int grid = (int)(ntiles < 148 ? ntiles : 148);
+    if (grid_out) *grid_out = grid;
+    PA2S_TRY(cudaFuncSetAttribute(tc_conv_wgrad_kernel<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    tc_conv_wgrad_kernel<CIN, COUT><<<grid, NTHREADS, SMEM, st>>>(a);
+    PA2S_CHECK_LAST();
+    return 0;
+}
+
 // Pack fp32 conv weights (Cout,Cin,3,3) into the bf16 UMMA blocks the kernel expects:
 //   [tap][ks][split(hi,lo)][kgroup(2)][n (NOUTP)][8]   element k = ks*16 + kgroup*8 + e  (input channel), n = output channel.
 // transpose_flip = 0: forward  (n = co, k = ci, tap = ky*3+kx);
@@ -346,6 +607,25 @@ PA2S_API int pa2s_tc_conv_pack(void* stream, const float* W, int Cout, int Cin, 
 PA2S_API int pa2s_tc_conv_num_partials(int B, int T, int F) {
     long long ntiles = (long long)B * ((T * (F + 2) + BM - 1) / BM);
     return (int)(ntiles < 148 ? ntiles : 148) * N_EPI_WARPS;
+}
+// conv2d backward wrt weight on the tensor cores; `partial` has pa2s_tc_conv_wgrad_num_partials rows of Cout*Cin*9.
+PA2S_API int pa2s_tc_conv_wgrad_num_partials(int B, int T, int F) {
+    long long ntiles = (long long)B * ((T * (F + 2) + BM - 1) / BM);
+    return (int)(ntiles < 148 ? ntiles : 148);
+}
+PA2S_API int pa2s_tc_conv3x3_wgrad(void* stream, int B, int T, int F, int Cin, int Cout, const float* Xin, const float* G,
+                                   float* partial, int nsplit, const float* in_scale, const float* in_shift, int in_relu,
+                                   const float* Yraw, const float* zs, const float* zb, const float* mean, const float* invstd,
+                                   const float* k1, const float* k2, const float* k3) {
+    TcWgradArgs a;
+    a.Xin = Xin; a.G = G; a.partial = partial; a.B = B; a.T = T; a.F = F; a.nsplit = nsplit >= 3 ? 3 : 1;
+    a.scale = in_scale; a.shift = in_shift; a.relu = in_relu;
+    a.Yraw = Yraw; a.zs = zs; a.zb = zb; a.mean = mean; a.invstd = invstd; a.k1 = k1; a.k2 = k2; a.k3 = k3;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (Cin == 20 && Cout == 20) return launch_tc_wgrad<20, 20>(st, a, nullptr);
+    if (Cin == 20 && Cout == 40) return launch_tc_wgrad<20, 40>(st, a, nullptr);
+    if (Cin == 40 && Cout == 40) return launch_tc_wgrad<40, 40>(st, a, nullptr);
+    return -1;
 }
 // mode 0 / 1 as pa2s_conv3x3 (Cin = channels of the tensor being convolved, Cout = channels produced).
 PA2S_API int pa2s_tc_conv3x3(void* stream, int mode, int B, int T, int F, int Cin, int Cout, const float* X, const void* Wpack,

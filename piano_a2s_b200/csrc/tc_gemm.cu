@@ -139,7 +139,7 @@ __device__ __forceinline__ void coord_next(StageCoord& c, long long ntiles, cons
 }
 
 template <bool A_KMAJ, bool B_KMAJ>
-__global__ void __maxnreg__(144) tc_gemm_kernel(TcArgs g) {
+__global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(TcArgs g) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t full_bar[NSTAGE], empty_bar[NSTAGE], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_s;

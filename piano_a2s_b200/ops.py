@@ -365,12 +365,20 @@ class ConvStackFn(torch.autograd.Function):
             xin = ys[i - 1] if i > 0 else spec
             isc = affs[i - 1][0] if i > 0 else None
             ish = affs[i - 1][1] if i > 0 else None
-            partial = torch.empty(nw, Cout * Cin * 9, device=dev, dtype=F32)
-            with ktime(f"conv{i + 1}_wgrad"):
-                lib.pa2s_conv3x3_wgrad(st, B, T, Fq, Cin, Cout, ptr(xin), ptr(G), ptr(partial), nw, ptr(isc), ptr(ish), 1,
-                                       ptr(y), ptr(aff[0]), ptr(aff[1]), ptr(aff[2]), ptr(aff[3]), ptr(k[0]), ptr(k[1]), ptr(k[2]))
+            if ctx.prec != "fp32" and Cin >= 16:
+                nwp = lib.pa2s_tc_conv_wgrad_num_partials(B, T, Fq)
+                partial = torch.empty(nwp, Cout * Cin * 9, device=dev, dtype=F32)
+                with ktime(f"conv{i + 1}_wgrad"):
+                    lib.pa2s_tc_conv3x3_wgrad(st, B, T, Fq, Cin, Cout, ptr(xin), ptr(G), ptr(partial), _nsplit(ctx.prec), ptr(isc), ptr(ish), 1,
+                                              ptr(y), ptr(aff[0]), ptr(aff[1]), ptr(aff[2]), ptr(aff[3]), ptr(k[0]), ptr(k[1]), ptr(k[2]))
+            else:
+                nwp = nw
+                partial = torch.empty(nw, Cout * Cin * 9, device=dev, dtype=F32)
+                with ktime(f"conv{i + 1}_wgrad"):
+                    lib.pa2s_conv3x3_wgrad(st, B, T, Fq, Cin, Cout, ptr(xin), ptr(G), ptr(partial), nw, ptr(isc), ptr(ish), 1,
+                                           ptr(y), ptr(aff[0]), ptr(aff[1]), ptr(aff[2]), ptr(aff[3]), ptr(k[0]), ptr(k[1]), ptr(k[2]))
             dW = torch.empty(Cout, Cin, 3, 3, device=dev, dtype=F32)
-            lib.pa2s_reduce_rows(st, ptr(partial), nw, Cout * Cin * 9, None, ptr(dW), 0)
+            lib.pa2s_reduce_rows(st, ptr(partial), nwp, Cout * Cin * 9, None, ptr(dW), 0)
             grads[3 * i] = dW
             if i > 0:
                 Gp = torch.empty(B, T, Fq, Cin, device=dev, dtype=F32)

@@ -1,0 +1,67 @@
+"""CPU, world_size 2, gloo: the host-side data-parallel logic (flat gradient averaging, SyncBatchNorm statistic reduction
+arithmetic, per-rank synthetic shards).  The CUDA kernels themselves are covered by the -m gpu tests."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from piano_a2s_b200.synthetic import make_ground_truth
+        from piano_a2s_b200.train import FlatAdadelta
+        torch.manual_seed(0)
+        lin = torch.nn.Sequential(torch.nn.Linear(7, 173), torch.nn.Linear(173, 3))       # 173-element bias: exercises the padding
+        opt = FlatAdadelta(lin)
+        assert all(p.data_ptr() % 256 == opt.flat.data_ptr() % 256 for p in lin.parameters())
+        for i, p in enumerate(lin.parameters()):
+            p.grad.fill_(float(rank + 1) * (i + 1))
+        opt.allreduce_mean()
+        ok = all(torch.allclose(p.grad, torch.full_like(p.grad, 1.5 * (i + 1))) for i, p in enumerate(lin.parameters()))
+        # SyncBatchNorm statistics: global mean/var from all-reduced fp64 (sum, sumsq) equals the statistics of the union
+        x = torch.randn(5 + rank, 4, dtype=torch.float64)
+        sums = torch.cat([x.sum(0), (x * x).sum(0), torch.tensor([float(x.shape[0])], dtype=torch.float64)])
+        dist.all_reduce(sums)
+        n = sums[-1]
+        mean, var = sums[:4] / n, sums[4:8] / n - (sums[:4] / n) ** 2
+        xs = [torch.zeros(5 + r, 4, dtype=torch.float64) for r in range(world)]
+        # gather the shards to check against the union directly
+        gathered = [torch.zeros(6, 4, dtype=torch.float64) for _ in range(world)]
+        pad = torch.zeros(6, 4, dtype=torch.float64)
+        pad[: x.shape[0]] = x
+        dist.all_gather(gathered, pad)
+        union = torch.cat([gathered[r][: 5 + r] for r in range(world)])
+        ok = ok and torch.allclose(mean, union.mean(0)) and torch.allclose(var, union.var(0, unbiased=False))
+        # per-rank synthetic shards differ (seed = base + rank, as bench.py does)
+        g = make_ground_truth(2, 2, 14, 9, seed=1234 + rank, lo_up=(3, 13), lo_lo=(2, 9))
+        tok = [torch.zeros_like(g[2]) for _ in range(world)]
+        dist.all_gather(tok, g[2])
+        ok = ok and not torch.equal(tok[0], tok[1])
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_flat_gradient_mean_and_syncbn_sums_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]

@@ -126,3 +126,12 @@ def test_tc_conv_forward_and_dgrad_match_torch(cuda, Cin, Cout, B, T, Fq):
     e = rel_err(dx, ref_dx)
     print(f"tc conv dgrad: rel err {e:.2e}")
     assert e < 2e-5
+    # weight gradient: dW = conv2d_weight(a_in, dy)
+    ref_dw = torch.nn.grad.conv2d_weight(a_in.permute(0, 3, 1, 2), W.shape, dy.permute(0, 3, 1, 2), 1, 1)
+    nwp = lib.pa2s_tc_conv_wgrad_num_partials(B, T, Fq)
+    part = torch.zeros(nwp, Cout * Cin * 9, device=cuda)
+    lib.pa2s_tc_conv3x3_wgrad(stream(), B, T, Fq, Cin, Cout, ptr(xd), ptr(dev(G)), ptr(part), 3, ptr(scd), ptr(shd), 1, *[ptr(t) for t in cs])
+    dW = part.double().sum(0).view(Cout, Cin, 3, 3)
+    e = rel_err(dW, ref_dw)
+    print(f"tc conv wgrad: rel err {e:.2e}")
+    assert e < 2e-5
