@@ -136,6 +136,8 @@ class HierarchicalDecoder(nn.Module):
                                      nn.Linear(hidden_size * 4, hidden_size * 2), nn.ReLU(),
                                      nn.Linear(hidden_size * 2, num_keys))
         self.consume_python_rng = True      # keep the reference's python-`random` consumption count in inference too
+        self.parallel_staves = True
+        self._side_stream = None
         self.init_weight()
 
     def init_weight(self):
@@ -209,11 +211,25 @@ class HierarchicalDecoder(nn.Module):
             g = self.gru
             h = ops.gru_cell(torch.cat([token, context], dim=1), h, g.weight_ih_l0, g.weight_hh_l0, g.bias_ih_l0, g.bias_hh_l0)
             bar_summary = h
+            # the two staves only depend on bar_summary (models.py:261-275): decode them concurrently on two streams
             res = []
+            main = torch.cuda.current_stream() if enc.is_cuda else None
             for si, (dec, Ep) in enumerate(((self.upper_decoder, Ep_up), (self.lower_decoder, Ep_lo))):
                 gt_staff = (upper_gt, lower_gt)[si][:, bar, :] if have_gt else None
                 tf_in = teacher_forcing_ratio if have_gt else 0.
-                res.append(dec._decode(enc, Ep, bar_summary, inference, gt_staff, tf_in, steps[si][bar], src))
+                if si == 1 and self.parallel_staves and main is not None:
+                    if self._side_stream is None:
+                        self._side_stream = torch.cuda.Stream()
+                    side = self._side_stream
+                    side.wait_stream(main)
+                    with torch.cuda.stream(side):
+                        out = dec._decode(enc, Ep, bar_summary, inference, gt_staff, tf_in, steps[si][bar], src)
+                    main.wait_stream(side)
+                    for t_ in out:
+                        t_.record_stream(main)
+                    res.append(out)
+                else:
+                    res.append(dec._decode(enc, Ep, bar_summary, inference, gt_staff, tf_in, steps[si][bar], src))
             (up_p, up_len, up_cnt), (lo_p, lo_len, lo_cnt) = res
             counters += [up_cnt, lo_cnt]
             up_outs.append(up_p)
