@@ -142,17 +142,20 @@ struct WgradArgs {
     XformFwd xf; XformBwd xb;
 };
 
-template <int CIN, int COUT, int COB, int NTHR>
+template <int CIN, int COUT, int COB, int NTHR, int PS = 1>
 __global__ void __launch_bounds__(NTHR) conv3x3_wgrad_kernel(WgradArgs a) {
     constexpr int CINP = (CIN % 2 == 0) ? CIN + 1 : CIN;
     constexpr int COUTP = COUT + 4;
-    constexpr int NCOMP = (COUT / COB) * CIN;         // compute threads
+    constexpr int NCOMP1 = (COUT / COB) * CIN;        // compute threads per pixel slice
+    constexpr int NCOMP = NCOMP1 * PS;                // PS pixel slices (for tiny channel counts) are reduced at the end
     static_assert(NCOMP <= NTHR, "thread budget");
+    __shared__ float red[PS > 1 ? COUT * CIN * 9 : 1];
     extern __shared__ __align__(16) float smem[];
     float* Ps = smem;                                 // PH*PW*CINP
     float* Ds = smem + ((PH * PW * CINP + 3) / 4) * 4; // TH*TW*COUTP (16B aligned rows)
     const int tid = threadIdx.x;
-    const int ci = tid % CIN, cog = tid / CIN;        // lanes vary in ci -> conflict-free patch reads
+    const int ps = tid / NCOMP1, t1 = tid % NCOMP1;
+    const int ci = t1 % CIN, cog = t1 / CIN;          // lanes vary in ci -> conflict-free patch reads
     float acc[COB][9];
 #pragma unroll
     for (int i = 0; i < COB; ++i)
@@ -188,7 +191,7 @@ __global__ void __launch_bounds__(NTHR) conv3x3_wgrad_kernel(WgradArgs a) {
         if (tid < NCOMP) {
             for (int r = 0; r < TH; ++r) {
 #pragma unroll 4
-                for (int c = 0; c < TW; ++c) {
+                for (int c = ps; c < TW; c += PS) {
                     float d[COB];
                     const float* dp = Ds + (r * TW + c) * COUTP + cog * COB;
 #pragma unroll
@@ -203,12 +206,26 @@ __global__ void __launch_bounds__(NTHR) conv3x3_wgrad_kernel(WgradArgs a) {
             }
         }
     }
-    if (tid < NCOMP) {
-        float* out = a.partial + (size_t)blockIdx.x * COUT * CIN * 9;
+    float* out = a.partial + (size_t)blockIdx.x * COUT * CIN * 9;
+    if (PS == 1) {
+        if (tid < NCOMP) {
 #pragma unroll
-        for (int i = 0; i < COB; ++i)
+            for (int i = 0; i < COB; ++i)
 #pragma unroll
-            for (int tap = 0; tap < 9; ++tap) out[((cog * COB + i) * CIN + ci) * 9 + tap] = acc[i][tap];
+                for (int tap = 0; tap < 9; ++tap) out[((cog * COB + i) * CIN + ci) * 9 + tap] = acc[i][tap];
+        }
+    } else {
+        __syncthreads();
+        for (int i = tid; i < COUT * CIN * 9; i += NTHR) red[i] = 0.f;
+        __syncthreads();
+        if (tid < NCOMP) {
+#pragma unroll
+            for (int i = 0; i < COB; ++i)
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) atomicAdd(&red[((cog * COB + i) * CIN + ci) * 9 + tap], acc[i][tap]);
+        }
+        __syncthreads();
+        for (int i = tid; i < COUT * CIN * 9; i += NTHR) out[i] = red[i];
     }
 }
 
@@ -394,12 +411,12 @@ int launch_conv(cudaStream_t st, ConvArgs a) {
     return 0;
 }
 
-template <int CIN, int COUT, int COB, int NTHR>
+template <int CIN, int COUT, int COB, int NTHR, int PS = 1>
 int launch_wgrad(cudaStream_t st, WgradArgs a, int nctas) {
     constexpr int CINP = (CIN % 2 == 0) ? CIN + 1 : CIN;
     size_t smem = (size_t)(((PH * PW * CINP + 3) / 4) * 4 + TH * TW * (COUT + 4)) * sizeof(float);
-    PA2S_TRY(cudaFuncSetAttribute(conv3x3_wgrad_kernel<CIN, COUT, COB, NTHR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv3x3_wgrad_kernel<CIN, COUT, COB, NTHR><<<nctas, NTHR, smem, st>>>(a);
+    PA2S_TRY(cudaFuncSetAttribute(conv3x3_wgrad_kernel<CIN, COUT, COB, NTHR, PS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv3x3_wgrad_kernel<CIN, COUT, COB, NTHR, PS><<<nctas, NTHR, smem, st>>>(a);
     PA2S_CHECK_LAST();
     return 0;
 }
@@ -448,7 +465,7 @@ PA2S_API int pa2s_conv3x3_wgrad(void* stream, int B, int T, int F, int Cin, int 
     a.xf = XformFwd{in_scale, in_shift, in_relu};
     a.xb = XformBwd{Yraw, zs, zb, mean, invstd, k1, k2, k3};
     cudaStream_t st = (cudaStream_t)stream;
-    if (Cin == 1 && Cout == 20) return launch_wgrad<1, 20, 1, 128>(st, a, nctas);
+    if (Cin == 1 && Cout == 20) return launch_wgrad<1, 20, 1, 160, 8>(st, a, nctas);
     if (Cin == 20 && Cout == 20) return launch_wgrad<20, 20, 4, 128>(st, a, nctas);
     if (Cin == 20 && Cout == 40) return launch_wgrad<20, 40, 4, 224>(st, a, nctas);
     if (Cin == 40 && Cout == 40) return launch_wgrad<40, 40, 4, 416>(st, a, nctas);

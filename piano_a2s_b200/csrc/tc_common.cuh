@@ -85,6 +85,20 @@ __device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo
 }
 
 
+// One lane of a fully converged warp (the MMA-issuing warp runs its loops warp-uniformly so that descriptors live in
+// uniform registers; only the tcgen05.mma / tcgen05.commit themselves are predicated on the elected lane).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+// descriptor for (base + byte offset): the start-address field is the low 14 bits (16-byte units) and never carries out
+// of the field for shared-memory addresses, so advancing a descriptor is a plain 64-bit add.
+__device__ __forceinline__ uint64_t desc_advance(uint64_t d, uint32_t byte_off) { return d + (uint64_t)(byte_off >> 4); }
+
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot_in_smem, int ncols_pow2) {
     // one full warp; ncols must be a power of two >= 32
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_in_smem)), "r"(ncols_pow2));

@@ -143,10 +143,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(TcConvArgs a) {
             }
         }
     } else if (warp == N_EPI_WARPS) {
-        // ================================================================================= MMA issuer
-        if (lane == 0) {
+        // ================================================================================= MMA issuer (warp-uniform)
+        {
             const uint32_t idesc = make_idesc(BM, COUTP, 0, 0);
             const uint32_t w_base = smem_u32(wsm), win_base = smem_u32(win);
+            const uint64_t wdesc0 = make_desc(w_base, COUTP * 16, 128);
             uint32_t it = 0, wi = 0;
             for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
                 const int acc = it & 1;
@@ -157,27 +158,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(TcConvArgs a) {
                     const int slot = wi % NWIN;
                     mbar_wait(&full_bar[slot], (wi / NWIN) & 1);
                     tc_fence_after();
-                    const uint32_t hi_base = win_base + slot * SLOT_BYTES, lo_base = hi_base + NG * PLANE_BYTES;
+                    const uint64_t dah0 = make_desc(win_base + slot * SLOT_BYTES, PLANE_BYTES, 128);
+                    const uint64_t dal0 = desc_advance(dah0, NG * PLANE_BYTES);
+                    const uint64_t dbw = desc_advance(wdesc0, (uint32_t)(ky * 3 * KS * 2 * WBLK_BYTES));
+                    if (elect_one()) {
 #pragma unroll
-                    for (int kx = 0; kx < 3; ++kx) {
+                        for (int kx = 0; kx < 3; ++kx) {
 #pragma unroll
-                        for (int ks = 0; ks < KS; ++ks) {
-                            const uint32_t aoff = (uint32_t)(2 * ks * PLANE_BYTES + kx * 16);
-                            const uint64_t dah = make_desc(hi_base + aoff, PLANE_BYTES, 128);
-                            const uint64_t dal = make_desc(lo_base + aoff, PLANE_BYTES, 128);
-                            const uint32_t wb = w_base + (uint32_t)((((ky * 3 + kx) * KS + ks) * 2) * WBLK_BYTES);
-                            const uint64_t dbh = make_desc(wb, COUTP * 16, 128);
-                            const uint64_t dbl = make_desc(wb + WBLK_BYTES, COUTP * 16, 128);
-                            tc_mma(d_tmem, dah, dbh, idesc, (ky | kx | ks) != 0);
-                            if (a.nsplit > 1) {
-                                tc_mma(d_tmem, dah, dbl, idesc, 1);
-                                tc_mma(d_tmem, dal, dbh, idesc, 1);
+                            for (int ks = 0; ks < KS; ++ks) {
+                                const uint32_t aoff = (uint32_t)(2 * ks * PLANE_BYTES + kx * 16);
+                                const uint64_t dah = desc_advance(dah0, aoff), dal = desc_advance(dal0, aoff);
+                                const uint64_t dbh = desc_advance(dbw, (uint32_t)(((kx * KS + ks) * 2) * WBLK_BYTES));
+                                const uint64_t dbl = desc_advance(dbh, WBLK_BYTES);
+                                tc_mma(d_tmem, dah, dbh, idesc, (ky | kx | ks) != 0);
+                                if (a.nsplit > 1) {
+                                    tc_mma(d_tmem, dah, dbl, idesc, 1);
+                                    tc_mma(d_tmem, dal, dbh, idesc, 1);
+                                }
                             }
                         }
+                        tc_commit(&empty_bar[slot]);
+                        if (ky == 2) tc_commit(&tfull_bar[acc]);
                     }
-                    tc_commit(&empty_bar[slot]);
+                    __syncwarp();
                 }
-                tc_commit(&tfull_bar[acc]);
             }
         }
     } else {
@@ -365,8 +369,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_wgrad_kernel(TcWgradArgs 
         }
         tc_fence_before();
     } else if (warp == N_EPI_WARPS) {
-        // ================================================================================= MMA issuer
-        if (lane == 0) {
+        // ================================================================================= MMA issuer (warp-uniform)
+        {
             const uint32_t idesc = make_idesc(64, CINP, 1, 1);
             const uint32_t win_base = smem_u32(win), a_base0 = smem_u32(asm_);
             uint32_t it = 0, wi = 0;
@@ -374,33 +378,37 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_wgrad_kernel(TcWgradArgs 
                 const int aslot = it % NASLOT;
                 mbar_wait(&afull_bar[aslot], (it / NASLOT) & 1);
                 tc_fence_after();
-                const uint32_t ahi = a_base0 + aslot * ASLOT_BYTES, alo = ahi + NGA * APLANE_BYTES;
+                const uint64_t dah0 = make_desc(a_base0 + aslot * ASLOT_BYTES, 128, APLANE_BYTES);
+                const uint64_t dal0 = desc_advance(dah0, NGA * APLANE_BYTES);
                 for (int ky = 0; ky < 3; ++ky, ++wi) {
                     const int slot = wi % NWIN;
                     mbar_wait(&full_bar[slot], (wi / NWIN) & 1);
                     tc_fence_after();
-                    const uint32_t bhi = win_base + slot * SLOT_BYTES, blo = bhi + NGB * PLANE_BYTES;
+                    const uint64_t dbh0 = make_desc(win_base + slot * SLOT_BYTES, 128, PLANE_BYTES);
+                    const uint64_t dbl0 = desc_advance(dbh0, NGB * PLANE_BYTES);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int kx = 0; kx < 3; ++kx) {
-                        const uint32_t d_tmem = tmem_base + (uint32_t)((ky * 3 + kx) * CINP);
+                        for (int kx = 0; kx < 3; ++kx) {
+                            const uint32_t d_tmem = tmem_base + (uint32_t)((ky * 3 + kx) * CINP);
 #pragma unroll
-                        for (int ks = 0; ks < BM / 16; ++ks) {
-                            const uint64_t dah = make_desc(ahi + ks * 256, 128, APLANE_BYTES);
-                            const uint64_t dal = make_desc(alo + ks * 256, 128, APLANE_BYTES);
-                            const uint64_t dbh = make_desc(bhi + (kx + 16 * ks) * 16, 128, PLANE_BYTES);
-                            const uint64_t dbl = make_desc(blo + (kx + 16 * ks) * 16, 128, PLANE_BYTES);
-                            tc_mma(d_tmem, dah, dbh, idesc, (it | (uint32_t)ks) != 0);
-                            if (a.nsplit > 1) {
-                                tc_mma(d_tmem, dah, dbl, idesc, 1);
-                                tc_mma(d_tmem, dal, dbh, idesc, 1);
+                            for (int ks = 0; ks < BM / 16; ++ks) {
+                                const uint64_t dah = desc_advance(dah0, ks * 256), dal = desc_advance(dal0, ks * 256);
+                                const uint64_t dbh = desc_advance(dbh0, (kx + 16 * ks) * 16), dbl = desc_advance(dbl0, (kx + 16 * ks) * 16);
+                                tc_mma(d_tmem, dah, dbh, idesc, (it | (uint32_t)ks) != 0);
+                                if (a.nsplit > 1) {
+                                    tc_mma(d_tmem, dah, dbl, idesc, 1);
+                                    tc_mma(d_tmem, dal, dbh, idesc, 1);
+                                }
                             }
                         }
+                        tc_commit(&empty_bar[slot]);
+                        if (ky == 2) tc_commit(&aempty_bar[aslot]);
                     }
-                    tc_commit(&empty_bar[slot]);
+                    __syncwarp();
                 }
-                tc_commit(&aempty_bar[aslot]);
             }
-            tc_commit(&done_bar);
+            if (elect_one()) tc_commit(&done_bar);
+            __syncwarp();
         }
     } else {
         // ================================================================================= loaders (4 stages per tile)

@@ -27,6 +27,7 @@ constexpr int A_PLANE_BYTES = 4 * BM * 16;         // 8 KB  (one of hi / lo)
 constexpr int B_PLANE_BYTES = 4 * BNMAX * 16;      // 16 KB
 constexpr int STAGE_BYTES = 2 * A_PLANE_BYTES + 2 * B_PLANE_BYTES;   // 48 KB
 constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024;
+constexpr int TPMAX = 256;        // max period of the fused operand affine (kept in shared memory)
 
 struct TcArgs {
     const float* A; const float* B; float* C; const float* bias;
@@ -94,8 +95,8 @@ __device__ __forceinline__ void units_issue(Units<NIT>& u, const float* __restri
 }
 
 template <int NIT>
-__device__ __forceinline__ void units_store(const Units<NIT>& u, int limit, bool tf, const TcArgs& g, uint8_t* hi_plane, uint8_t* lo_plane,
-                                            bool want_lo) {
+__device__ __forceinline__ void units_store(const Units<NIT>& u, int limit, bool tf, const TcArgs& g, const float* s_scale,
+                                            const float* s_shift, uint8_t* hi_plane, uint8_t* lo_plane, bool want_lo) {
 #pragma unroll
     for (int it = 0; it < NIT; ++it) {
         if (u.off[it] < 0) continue;
@@ -105,7 +106,7 @@ __device__ __forceinline__ void units_store(const Units<NIT>& u, int limit, bool
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 if (u.c0[it] + i < limit) {
-                    float y = fmaf(x[i], __ldg(g.t_scale + c), __ldg(g.t_shift + c));
+                    float y = fmaf(x[i], s_scale[c], s_shift[c]);
                     x[i] = g.t_relu ? fmaxf(y, 0.f) : y;
                 }
                 c = (c + 1 == g.t_period) ? 0 : c + 1;
@@ -143,8 +144,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(TcArgs g) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t full_bar[NSTAGE], empty_bar[NSTAGE], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_s;
+    __shared__ float s_scale[TPMAX], s_shift[TPMAX];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int BN = g.BN;
+    if (g.t_scale != nullptr)
+        for (int i = tid; i < g.t_period; i += NTHREADS) { s_scale[i] = g.t_scale[i]; s_shift[i] = g.t_shift[i]; }
 
     if (warp == N_EPI_WARPS) {
         if (lane == 0) {
@@ -209,10 +213,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(TcArgs g) {
             mbar_arrive(&tempty_bar[acc]);
         }
     } else if (warp == N_EPI_WARPS) {
-        // ===================================================================== MMA issuer
-        if (lane == 0) {
+        // ===================================================================== MMA issuer (warp-uniform)
+        {
             const uint32_t idesc = make_idesc(BM, BN, A_KMAJ ? 0 : 1, B_KMAJ ? 0 : 1);
             const uint32_t smem_base = smem_u32(smem);
+            const uint32_t a_lbo = A_KMAJ ? BM * 16 : 128, a_sbo = A_KMAJ ? 128 : BK * 16;
+            const uint32_t b_lbo = B_KMAJ ? (uint32_t)BN * 16 : 128, b_sbo = B_KMAJ ? 128 : BK * 16;
+            const uint32_t a_step = A_KMAJ ? (uint32_t)(2 * BM * 16) : 256u;      // bytes per k-step of 16
+            const uint32_t b_step = B_KMAJ ? (uint32_t)(2 * BN * 16) : 256u;
             uint32_t it = 0, kit = 0;
             for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
                 const int z = (int)(tile / ((long long)g.tiles_n * g.tiles_m));
@@ -227,26 +235,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(TcArgs g) {
                     const int s = kit % NSTAGE;
                     mbar_wait(&full_bar[s], (kit / NSTAGE) & 1);
                     tc_fence_after();
-                    const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + A_PLANE_BYTES;
-                    const uint32_t b_hi = a_hi + 2 * A_PLANE_BYTES, b_lo = b_hi + B_PLANE_BYTES;
+                    const uint32_t st = smem_base + s * STAGE_BYTES;
+                    const uint64_t dah0 = make_desc(st, a_lbo, a_sbo), dal0 = desc_advance(dah0, A_PLANE_BYTES);
+                    const uint64_t dbh0 = make_desc(st + 2 * A_PLANE_BYTES, b_lbo, b_sbo), dbl0 = desc_advance(dbh0, B_PLANE_BYTES);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int ks = 0; ks < BK / 16; ++ks) {
-                        // K-major operand: two k-groups (planes) per MMA, plane pitch rows*16; MN-major: 16 k rows at 16 B
-                        const uint32_t a_off = A_KMAJ ? (uint32_t)(2 * ks * BM * 16) : (uint32_t)(ks * 256);
-                        const uint32_t b_off = B_KMAJ ? (uint32_t)(2 * ks * BN * 16) : (uint32_t)(ks * 256);
-                        const uint32_t a_lbo = A_KMAJ ? BM * 16 : 128, a_sbo = A_KMAJ ? 128 : BK * 16;
-                        const uint32_t b_lbo = B_KMAJ ? (uint32_t)BN * 16 : 128, b_sbo = B_KMAJ ? 128 : BK * 16;
-                        const uint64_t dah = make_desc(a_hi + a_off, a_lbo, a_sbo), dal = make_desc(a_lo + a_off, a_lbo, a_sbo);
-                        const uint64_t dbh = make_desc(b_hi + b_off, b_lbo, b_sbo), dbl = make_desc(b_lo + b_off, b_lbo, b_sbo);
-                        tc_mma(d_tmem, dah, dbh, idesc, (kb | ks) != 0);
-                        if (g.nsplit > 1) {
-                            tc_mma(d_tmem, dah, dbl, idesc, 1);
-                            tc_mma(d_tmem, dal, dbh, idesc, 1);
+                        for (int ks = 0; ks < BK / 16; ++ks) {
+                            const uint64_t dah = desc_advance(dah0, ks * a_step), dal = desc_advance(dal0, ks * a_step);
+                            const uint64_t dbh = desc_advance(dbh0, ks * b_step), dbl = desc_advance(dbl0, ks * b_step);
+                            tc_mma(d_tmem, dah, dbh, idesc, (kb | ks) != 0);
+                            if (g.nsplit > 1) {
+                                tc_mma(d_tmem, dah, dbl, idesc, 1);
+                                tc_mma(d_tmem, dal, dbh, idesc, 1);
+                            }
                         }
+                        tc_commit(&empty_bar[s]);
+                        if (kb == nkb - 1) tc_commit(&tfull_bar[acc]);
                     }
-                    tc_commit(&empty_bar[s]);
+                    __syncwarp();
                 }
-                tc_commit(&tfull_bar[acc]);
             }
         }
     } else {
@@ -275,8 +282,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(TcArgs g) {
             const int s = kit % NSTAGE;
             mbar_wait(&empty_bar[s], ((kit / NSTAGE) & 1) ^ 1);
             uint8_t* st = smem + (size_t)s * STAGE_BYTES;
-            units_store<NA>(ua, A_KMAJ ? cur.kend : g.M, tfA, g, st, st + A_PLANE_BYTES, want_lo);
-            units_store<NB>(ub, B_KMAJ ? cur.kend : g.N, tfB, g, st + 2 * A_PLANE_BYTES, st + 2 * A_PLANE_BYTES + B_PLANE_BYTES, want_lo);
+            units_store<NA>(ua, A_KMAJ ? cur.kend : g.M, tfA, g, s_scale, s_shift, st, st + A_PLANE_BYTES, want_lo);
+            units_store<NB>(ub, B_KMAJ ? cur.kend : g.N, tfB, g, s_scale, s_shift, st + 2 * A_PLANE_BYTES, st + 2 * A_PLANE_BYTES + B_PLANE_BYTES, want_lo);
             fence_proxy_async();            // generic-proxy smem writes -> visible to the tensor-core (async) proxy
             mbar_arrive(&full_bar[s]);
             ua = ua_n; ub = ub_n; cur = nxt; ++kit;
@@ -307,6 +314,7 @@ PA2S_API int pa2s_gemm_tc(void* stream, int transA, int transB, int M, int N, in
                           int splitk, int nsplit) {
     if (M <= 0 || N <= 0 || batch <= 0) return 0;
     if (K <= 0) return -1;
+    if (t_scale != nullptr && t_period > TPMAX) return -1;
     TcArgs g;
     g.A = A; g.B = B; g.C = C; g.bias = bias; g.M = M; g.N = N; g.K = K;
     int BN = N >= BNMAX ? BNMAX : ((N + 31) / 32) * 32;      // multiple of 32 keeps both loader flavours whole

@@ -17,6 +17,9 @@ import torch.nn.functional as F
 
 from . import ops, rng
 
+# the two staves run on two CUDA streams; their gradients meet in AccumulateGrad nodes of the default stream by design
+torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+
 # ---------------------------------------------------------------------------------------------------------------
 # Vocabulary (data_processing/humdrum.py:70-131 `LabelsMultiple(extended=True)`): 148 + 25 = 173 symbols.
 # ---------------------------------------------------------------------------------------------------------------

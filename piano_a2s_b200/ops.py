@@ -115,14 +115,18 @@ def module_precision(module):
 
 def gemm(A, B, C, M, N, K, *, transA=False, transB=False, lda=None, ldb=None, ldc=None, bias=None, accumulate=False,
          atomic=False, batch=1, strideA=0, strideB=0, strideC=0, t_scale=None, t_shift=None, t_period=1, t_relu=False,
-         t_on_b=False, splitk=1, a_off=0, b_off=0, c_off=0, precision=None):
-    """C = op(A) op(B); A/B/C are tensors used as raw storage (+ element offsets), see include/pa2s.h."""
+         t_on_b=False, splitk=1, a_off=0, b_off=0, c_off=0, precision=None, zeroed=False):
+    """C = op(A) op(B); A/B/C are tensors used as raw storage (+ element offsets), see include/pa2s.h.
+    `zeroed=True`: the caller guarantees C is zero-filled, so the wrapper may split K (atomic accumulation) to fill the GPU."""
     es = 4
     pa = ctypes.c_void_p(A.data_ptr() + a_off * es)
     pb = ctypes.c_void_p(B.data_ptr() + b_off * es)
     pc = ctypes.c_void_p(C.data_ptr() + c_off * es)
     prec = precision or current_precision()
-    if prec != "fp32" and K > 0 and 2.0 * M * N * K * batch >= TC_MIN_FLOP:
+    use_tc = prec != "fp32" and K > 0 and 2.0 * M * N * K * batch >= TC_MIN_FLOP
+    if zeroed and splitk == 1 and batch == 1:
+        splitk = _tc_splitk(M, N, K) if use_tc else _auto_splitk(M, N, K)
+    if use_tc:
         lib.pa2s_gemm_tc(stream(), int(transA), int(transB), M, N, K, pa, lda, pb, ldb, pc, ldc, ptr(bias), int(accumulate),
                          int(atomic), batch, strideA, strideB, strideC, ptr(t_scale), ptr(t_shift), t_period, int(t_relu),
                          int(t_on_b), splitk, 3 if prec == "bf16x3" else 1)
@@ -138,6 +142,20 @@ def _auto_splitk(M, N, K):
     if tiles >= N_SM or K < 2048:
         return 1
     return max(1, min(K // 512, (2 * N_SM) // tiles))
+
+
+def _tc_splitk(M, N, K):
+    """split-K factor for the persistent 128 x min(N,256) tensor-core tiles: minimise the makespan ceil(items/148)/split"""
+    bn = 256 if N >= 256 else (N + 31) // 32 * 32
+    tiles = ((M + 127) // 128) * ((N + bn - 1) // bn)
+    best, best_cost = 1, None
+    for sk in range(1, 9):
+        if sk > 1 and K // sk < 256:
+            break
+        cost = -(-tiles * sk // N_SM) / sk
+        if best_cost is None or cost < best_cost - 1e-9:
+            best, best_cost = sk, cost
+    return best
 
 
 def colsum(X2d: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate=False) -> torch.Tensor:
@@ -179,9 +197,8 @@ class LinearFn(torch.autograd.Function):
             gemm(dy2, W, dx, M, K, N, lda=N, ldb=W.stride(0), ldc=K)
             dx = dx.reshape(ctx.xshape)
         if ctx.needs_input_grad[1]:
-            sk = _auto_splitk(N, K, M)
-            dW = (torch.zeros if sk > 1 else torch.empty)(N, K, device=dy.device, dtype=F32)
-            gemm(dy2, x2, dW, N, K, M, transA=True, lda=N, ldb=K, ldc=K, splitk=sk)
+            dW = torch.zeros(N, K, device=dy.device, dtype=F32)
+            gemm(dy2, x2, dW, N, K, M, transA=True, lda=N, ldb=K, ldc=K, zeroed=True)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = colsum(dy2)
         return dx, dW, db
@@ -275,10 +292,10 @@ class ConvStackFn(torch.autograd.Function):
         # reference feature index is c*F+f (models.py:537); ours is f*C+c
         Wp_out = Wout.detach().view(O, C4, Fq).permute(0, 2, 1).reshape(O, Kf).contiguous()
         M = B * T
-        z = torch.empty(M, O, device=dev, dtype=F32)
+        z = torch.zeros(M, O, device=dev, dtype=F32)
         with ktime("out_linear_fwd"):
             gemm(ys[3], Wp_out, z, M, O, Kf, transB=True, lda=Kf, ldb=Kf, ldc=O,
-                 t_scale=affs[3][0], t_shift=affs[3][1], t_period=C4, t_relu=True)
+                 t_scale=affs[3][0], t_shift=affs[3][1], t_period=C4, t_relu=True, zeroed=True)
         aff5 = torch.empty(4, O, device=dev, dtype=F32)
         if training:
             nct = 4 * N_SM
@@ -346,13 +363,13 @@ class ConvStackFn(torch.autograd.Function):
         dWp = torch.zeros(O, Kf, device=dev, dtype=F32)
         with ktime("out_linear_wgrad"):
             gemm(dz, ys[3], dWp, O, Kf, M, transA=True, lda=O, ldb=Kf, ldc=Kf,
-                 t_scale=affs[3][0], t_shift=affs[3][1], t_period=C4, t_relu=True, t_on_b=True, splitk=_auto_splitk(O, Kf, M))
+                 t_scale=affs[3][0], t_shift=affs[3][1], t_period=C4, t_relu=True, t_on_b=True, zeroed=True)
         grads[12] = dWp.view(O, Fq, C4).permute(0, 2, 1).reshape(O, Kf).contiguous()
         # G4 = dL/d relu(bn4(y4))
         G = torch.empty(B, T, Fq, C4, device=dev, dtype=F32)
         with ktime("out_linear_dgrad"):
             gemm(dz, Wp_out, G, M, Kf, O, lda=O, ldb=Kf, ldc=Kf)
-        nw = 2 * N_SM
+        nw = 8 * N_SM
         for i in (3, 2, 1, 0):
             W = conv_w[i]
             Cout, Cin = W.shape[0], W.shape[1]
@@ -452,7 +469,7 @@ class BiGRULayerFn(torch.autograd.Function):
         dx = torch.empty(B, T, I, device=dev, dtype=F32)
         gemm(dgi, Wih, dx, M, I, 6 * H, lda=6 * H, ldb=I, ldc=I)
         dWih = torch.zeros(6 * H, I, device=dev, dtype=F32)
-        gemm(dgi, x, dWih, 6 * H, I, M, transA=True, lda=6 * H, ldb=I, ldc=I, splitk=_auto_splitk(6 * H, I, M))
+        gemm(dgi, x, dWih, 6 * H, I, M, transA=True, lda=6 * H, ldb=I, ldc=I, zeroed=True)
         dbih = colsum(dgi.view(M, 6 * H))
         dbhh = colsum(dgh.view(M, 6 * H))
         # dW_hh[dir] = sum_{b,t} dgh[b,t,dir]^T h_prev[b,t,dir];  h_prev = out at the previous step of that direction
@@ -684,19 +701,19 @@ class NoteDecoderFn(torch.autograd.Function):
             lib.pa2s_note_decoder_bwd(st, ctypes.byref(args))
         SB = S * B
         # deferred weight gradients: contractions over all (step, clip) rows
-        dW_out = e(V, 2 * D)
-        gemm(bw["dlogits_all"], hs, dW_out, V, D, SB, transA=True, lda=VP, ldb=D, ldc=2 * D, b_off=B * D)          # h' part
-        gemm(bw["dlogits_all"], ctxs, dW_out, V, D, SB, transA=True, lda=VP, ldb=D, ldc=2 * D, c_off=D)             # ctx part
+        dW_out = z(V, 2 * D)
+        gemm(bw["dlogits_all"], hs, dW_out, V, D, SB, transA=True, lda=VP, ldb=D, ldc=2 * D, b_off=B * D, zeroed=True)   # h' part
+        gemm(bw["dlogits_all"], ctxs, dW_out, V, D, SB, transA=True, lda=VP, ldb=D, ldc=2 * D, c_off=D, zeroed=True)      # ctx part
         db_out = colsum(bw["dlogits_all"].view(SB, VP))[:V].contiguous()
-        dW_ih = e(3 * D, X)
-        gemm(bw["dgi_all"], xtok, dW_ih, 3 * D, E, SB, transA=True, lda=3 * D, ldb=E, ldc=X)
-        gemm(bw["dgi_all"], ctxs, dW_ih, 3 * D, D, SB, transA=True, lda=3 * D, ldb=D, ldc=X, c_off=E)
+        dW_ih = z(3 * D, X)
+        gemm(bw["dgi_all"], xtok, dW_ih, 3 * D, E, SB, transA=True, lda=3 * D, ldb=E, ldc=X, zeroed=True)
+        gemm(bw["dgi_all"], ctxs, dW_ih, 3 * D, D, SB, transA=True, lda=3 * D, ldb=D, ldc=X, c_off=E, zeroed=True)
         db_ih = colsum(bw["dgi_all"].view(SB, 3 * D))
-        dW_hh = e(3 * D, D)
-        gemm(bw["dgh_all"], hs, dW_hh, 3 * D, D, SB, transA=True, lda=3 * D, ldb=D, ldc=D)
+        dW_hh = z(3 * D, D)
+        gemm(bw["dgh_all"], hs, dW_hh, 3 * D, D, SB, transA=True, lda=3 * D, ldb=D, ldc=D, zeroed=True)
         db_hh = colsum(bw["dgh_all"].view(SB, 3 * D))
         d_attn_w = z(A, 2 * D)
-        gemm(bw["dq_all"], hs, d_attn_w, A, D, SB, transA=True, lda=A, ldb=D, ldc=2 * D)                             # W_h half only
+        gemm(bw["dq_all"], hs, d_attn_w, A, D, SB, transA=True, lda=A, ldb=D, ldc=2 * D, zeroed=True)                    # W_h half only
         dv = colsum(bw["dv_part"]).reshape(vshape)
         # embedding: scatter-add of the (masked) token-input gradients
         dxt = bw["dxtok_all"]
