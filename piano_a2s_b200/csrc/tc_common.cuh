@@ -85,6 +85,22 @@ __device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo
 }
 
 
+// fp32 pair -> packed bf16x2 hi and lo (x = hi + lo up to 2^-17 relative): 2 packed converts, 2 bit ops, 2 subtracts.
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);              // low half = a, high half = b
+    const uint32_t hb = *reinterpret_cast<uint32_t*>(&h);
+    const float ha = __uint_as_float(hb << 16), hbf = __uint_as_float(hb & 0xffff0000u);
+    __nv_bfloat162 l = __floats2bfloat162_rn(a - ha, b - hbf);
+    hi = hb;
+    lo = *reinterpret_cast<uint32_t*>(&l);
+}
+__device__ __forceinline__ void split8_packed(const float (&x)[8], uint4& hi, uint4& lo) {
+    split2(x[0], x[1], hi.x, lo.x);
+    split2(x[2], x[3], hi.y, lo.y);
+    split2(x[4], x[5], hi.z, lo.z);
+    split2(x[6], x[7], hi.w, lo.w);
+}
+
 // One lane of a fully converged warp (the MMA-issuing warp runs its loops warp-uniformly so that descriptors live in
 // uniform registers; only the tcgen05.mma / tcgen05.commit themselves are predicated on the elected lane).
 __device__ __forceinline__ bool elect_one() {

@@ -73,10 +73,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(TcConvArgs a) {
     uint8_t* win = smem + ((W_BYTES + 127) / 128) * 128;              // NWIN * SLOT_BYTES
     __shared__ uint64_t full_bar[NWIN], empty_bar[NWIN], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(16) float cst[7][64];        // per-channel transform constants (mode 0: scale, shift; mode 1: zs,zb,mean,invstd,k1,k2,k3)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int T = a.T, F = a.F, PWD = F + 2;
+    const uint32_t pwd_magic = (uint32_t)((0x100000000ULL + (uint64_t)PWD - 1) / (uint64_t)PWD);   // w / PWD == umulhi(w, magic) for w < 2^32/PWD
     const int tiles_per_clip = (T * PWD + BM - 1) / BM;
     const long long ntiles = (long long)a.B * tiles_per_clip;
+    if (tid < 64) {
+        const bool in = tid < CIN;
+        if (MODE == 0) {
+            cst[0][tid] = (in && a.scale != nullptr) ? a.scale[tid] : 1.f;
+            cst[1][tid] = (in && a.scale != nullptr) ? a.shift[tid] : 0.f;
+        } else {
+            cst[0][tid] = in ? a.zs[tid] : 0.f; cst[1][tid] = in ? a.zb[tid] : 0.f; cst[2][tid] = in ? a.mean[tid] : 0.f;
+            cst[3][tid] = in ? a.invstd[tid] : 0.f; cst[4][tid] = in ? a.k1[tid] : 0.f; cst[5][tid] = in ? a.k2[tid] : 0.f;
+            cst[6][tid] = in ? a.k3[tid] : 0.f;
+        }
+    }
 
     // weights -> smem (already bf16, already in UMMA layout); zero the window ring once (pad planes / pad entries stay zero)
     for (int i = tid; i < W_BYTES / 16; i += NTHREADS) reinterpret_cast<uint4*>(wsm)[i] = __ldg(a.Wpack + i);
@@ -209,7 +222,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(TcConvArgs a) {
                 const int j = u / NGR, g = u - j * NGR;
                 const int w = w0 + j;
                 if (w < 0) continue;
-                const int t = w / PWD, fp = w - t * PWD;
+                const int t = (int)__umulhi((uint32_t)w, pwd_magic), fp = w - t * PWD;
                 if (t >= T || fp < 1 || fp > F) continue;
                 r.ok[i] = true;
                 const size_t base = (((size_t)b * T + t) * F + (fp - 1)) * CIN + 8 * g;
@@ -232,11 +245,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(TcConvArgs a) {
                 if (r.ok[i]) {
                     if (MODE == 0) {
                         if (a.scale != nullptr) {
+                            const float4 s0 = *reinterpret_cast<const float4*>(&cst[0][8 * g]), s1 = *reinterpret_cast<const float4*>(&cst[0][8 * g + 4]);
+                            const float4 h0 = *reinterpret_cast<const float4*>(&cst[1][8 * g]), h1 = *reinterpret_cast<const float4*>(&cst[1][8 * g + 4]);
+                            const float sc8[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                            const float sh8[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
 #pragma unroll
                             for (int e = 0; e < 8; ++e) {
-                                const int c = 8 * g + e;
-                                if (c < CIN) {
-                                    float y = fmaf(x[e], __ldg(a.scale + c), __ldg(a.shift + c));
+                                if (8 * g + e < CIN) {            // (pad channels keep their staged zeros)
+                                    float y = fmaf(x[e], sc8[e], sh8[e]);
                                     x[e] = a.relu ? fmaxf(y, 0.f) : y;
                                 }
                             }
@@ -248,10 +264,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(TcConvArgs a) {
                         for (int e = 0; e < 8; ++e) {
                             const int c = 8 * g + e;
                             if (c < CIN) {
-                                const float z = fmaf(yy[e], __ldg(a.zs + c), __ldg(a.zb + c));
+                                const float z = fmaf(yy[e], cst[0][c], cst[1][c]);
                                 const float gi = z > 0.f ? x[e] : 0.f;
-                                const float xh = (yy[e] - __ldg(a.mean + c)) * __ldg(a.invstd + c);
-                                x[e] = __ldg(a.k1 + c) * (gi - __ldg(a.k2 + c) - xh * __ldg(a.k3 + c));
+                                const float xh = (yy[e] - cst[2][c]) * cst[3][c];
+                                x[e] = cst[4][c] * (gi - cst[5][c] - xh * cst[6][c]);
                             } else {
                                 x[e] = 0.f;
                             }
@@ -259,7 +275,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(TcConvArgs a) {
                     }
                 }
                 uint4 hi, lo;
-                split8v(x, hi, lo);
+                split8_packed(x, hi, lo);
                 const int off = (g * WPIX + j) * 16;
                 *reinterpret_cast<uint4*>(hi_base + off) = hi;
                 if (want_lo) *reinterpret_cast<uint4*>(lo_base + off) = lo;
@@ -501,7 +517,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_wgrad_kernel(TcWgradArgs 
                     }
                 }
                 uint4 hi, lo;
-                split8v(x, hi, lo);
+                split8_packed(x, hi, lo);
                 *reinterpret_cast<uint4*>(hi_base + off) = hi;
                 if (want_lo) *reinterpret_cast<uint4*>(lo_base + off) = lo;
             }

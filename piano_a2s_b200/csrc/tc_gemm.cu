@@ -113,7 +113,7 @@ __device__ __forceinline__ void units_store(const Units<NIT>& u, int limit, bool
             }
         }
         uint4 hi, lo;
-        split8(x, hi, lo);
+        split8_packed(x, hi, lo);
         *reinterpret_cast<uint4*>(hi_plane + u.off[it]) = hi;
         if (want_lo) *reinterpret_cast<uint4*>(lo_plane + u.off[it]) = lo;
     }
