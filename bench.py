@@ -214,7 +214,12 @@ def run_b200(args):
         step_device()
     n0 = lib.pa2s_launch_count()
     ops.KernelTimers.reset(rank == 0)
+    prof = os.environ.get("PA2S_PROFILE_RANGE") == "1"      # ncu --profile-from-start off: capture the timed steps only
+    if prof:
+        torch.cuda.profiler.start()
     ms, w0, w1 = timed(step_device, args.steps)
+    if prof:
+        torch.cuda.profiler.stop()
     launches = lib.pa2s_launch_count() - n0
     ktimes = ops.KernelTimers.summary() if rank == 0 else {}
     ops.KernelTimers.reset(False)
