@@ -123,11 +123,21 @@ PA2S_API int pa2s_gru_gates_bwd(void* stream, int B, int H, const float* dh, con
                                 float* dgi, float* dgh, float* dhprev);
 
 /* ---- note-level attention decoder (models.py:366-420, 452-461) ------------------------------------------------
- * `args` points to a HOST struct DecArgs (layout in piano_a2s_b200/csrc/decoder.cu, mirrored by ctypes in
+ * `args` points to a HOST struct DecArgs (layout in piano_a2s_b200/csrc/dec_args.cuh, mirrored by ctypes in
  * piano_a2s_b200/_lib.py; pa2s_dec_args_size() lets the binding verify the layout). */
 PA2S_API int pa2s_dec_args_size(void);
 PA2S_API int pa2s_note_decoder_fwd(void* stream, const void* args, int sos_id, int eos_id);
 PA2S_API int pa2s_note_decoder_bwd(void* stream, const void* args);
+/* persistent variants: all steps of the call in ONE cooperative kernel of pa2s_dec_persist_grid() CTAs (weights and the
+ * recurrent state resident in shared memory, 3 grid barriers per step); args->sync = 2 zeroed uint32. */
+PA2S_API int pa2s_dec_persist_grid(void);
+PA2S_API int pa2s_note_decoder_fwd_persist(void* stream, const void* args, int sos_id, int eos_id);
+/* reverse pass: (1) pa2s_dec_dlogits fills args->dlogits_all (log-softmax backward of every step), (2) the caller forms
+ * args->dhc_all = dlogits_all @ W_out with pa2s_gemm_*, (3) pa2s_note_decoder_bwd_persist runs the sequential chain in one
+ * cooperative kernel and then the deferred dEp / dv accumulation (dv_part: B * pa2s_dec_deferred_blocks(T) rows). */
+PA2S_API int pa2s_dec_dlogits(void* stream, const void* args);
+PA2S_API int pa2s_dec_deferred_blocks(int T);
+PA2S_API int pa2s_note_decoder_bwd_persist(void* stream, const void* args);
 PA2S_API int pa2s_attn_step_fwd(void* stream, const void* args);
 PA2S_API int pa2s_attn_step_bwd(void* stream, const void* args);
 

@@ -56,7 +56,7 @@ class _Lib:
         fn = getattr(self.load(), name)
         if name in ("pa2s_launch_count", "pa2s_dec_args_size", "pa2s_gru_seq_max_bg", "pa2s_conv3x3_num_partials",
                     "pa2s_tc_conv_pack_bytes", "pa2s_tc_conv_num_partials", "pa2s_gemm_tc_supported",
-                    "pa2s_tc_conv_wgrad_num_partials"):
+                    "pa2s_tc_conv_wgrad_num_partials", "pa2s_dec_persist_grid", "pa2s_dec_deferred_blocks"):
             return fn
 
         def call(*args):
@@ -81,13 +81,13 @@ def ptr(t):
 
 
 class DecArgs(ctypes.Structure):
-    """Mirror of `struct DecArgs` in csrc/decoder.cu (field order and types must match exactly)."""
+    """Mirror of `struct DecArgs` in csrc/dec_args.cuh (field order and types must match exactly)."""
     _ints = ["B", "T", "V", "VP", "S", "max_steps", "NS", "tile", "inference", "save", "tile_pad", "reserved_"]
     _ptrs = ["enc", "Ep", "Wattn", "v", "emb", "W_ih", "W_hh", "b_ih", "b_hh", "W_out", "b_out",
              "W_outT", "W_hT", "W_ihT", "W_hhT", "gt", "use_gt", "mask", "logp", "lengths", "eos", "counters",
              "hs", "ctxs", "attn", "gates", "qs", "xtok", "toks", "xbuf", "hc", "logits", "pm", "pl", "pc", "tickets",
              "dlogp", "dlogits_all", "dgi_all", "dgh_all", "dq_all", "dctx_all", "dxtok_all", "dEp", "dv_part",
-             "d_hc", "dhq", "dx", "dq_part", "dh_carry", "dh_last"]
+             "d_hc", "dhq", "dx", "dq_part", "dh_carry", "dh_last", "sync", "dhc_all", "ds_all", "dv", "prof"]
     _fields_ = [(n, ctypes.c_int) for n in _ints] + [(n, ctypes.c_void_p) for n in _ptrs]
 
 

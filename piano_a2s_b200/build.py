@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpa2s.so")
-SOURCES = ["gemm.cu", "tc_gemm.cu", "tc_conv.cu", "conv.cu", "misc.cu", "gru.cu", "decoder.cu"]
+SOURCES = ["gemm.cu", "tc_gemm.cu", "tc_conv.cu", "conv.cu", "misc.cu", "gru.cu", "decoder.cu", "dec_persist.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-shared"]
 

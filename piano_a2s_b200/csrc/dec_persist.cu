@@ -1,0 +1,946 @@
+// Persistent note-level decoder (NoteDecoder.decode_notes, models.py:366-420): ALL steps of one (bar, staff) in ONE
+// cooperative kernel of 64 CTAs.  The GRU / output / query weights are sliced across the CTAs and stay in shared
+// memory for the whole sequence, the recurrent state of every clip stays in shared memory between the phases of a
+// step, and the CTAs meet at three grid barriers per step:
+//
+//   A(s)  attention over the encoder memory (clip x frame-range items, last-arriver combine)   [needs q_s]
+//         + D(s-1): log-softmax / argmax / teacher forcing / next-token embedding / EOS        [needs logits_{s-1}]
+//   B(s)  GRU cell 528 -> 512: each CTA owns 8 hidden units = 24 gate rows x 1040 weights      [needs ctx_s, tok_s]
+//   C(s)  logits_s = W_out [h'; ctx] + b and q_{s+1} = W_h h': 7 of the 429 rows per CTA       [needs h'_s]
+//
+// The reverse kernel has the same shape: P1 dhq = dq_{s+1} W_h | P2 GRU backward (W^T row-sliced) | P3 attention
+// backward.  Everything that does not sit on the sequential chain is hoisted out of the loop: the softmax/out-projection
+// gradient is one GEMM before it, dEp / dv (accumulations over steps) one kernel after it, weight gradients GEMMs.
+#include "dec_args.cuh"
+#include <cooperative_groups.h>
+
+namespace {
+
+constexpr int PG = 64;                 // CTAs of a persistent decoder grid (two staves run concurrently: 128 of 148 SMs)
+constexpr int NT = 256;                // threads per CTA
+constexpr int UPC = DD / PG;           // hidden units per CTA (8)
+constexpr int GR = 3 * UPC;            // gate rows per CTA (24): r[8], z[8], n[8]
+constexpr int CR = 7;                  // phase-C rows per CTA: PG*CR = 448 >= V + DA
+constexpr int XP = 2 * DD + DE;        // per-clip state row in shared memory: [h (512) | ctx (512) | tok (16)]
+constexpr int XP4 = XP / 4;
+constexpr int KM4 = 2 * DD / 4;        // float4 columns of the main part (256 = one per thread)
+static_assert(KM4 == NT, "one float4 column of [h|ctx] per thread");
+
+__device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+
+// Grid barrier for a co-resident grid: monotonically increasing arrival counter.  A watchdog turns a lost CTA into an
+// error flag instead of a hang.
+__device__ __forceinline__ void grid_sync(unsigned int* sync, unsigned int& target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += gridDim.x;
+        __threadfence();
+        atomicAdd(sync, 1u);
+        unsigned int spins = 0;
+        while (true) {
+            unsigned int v;
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(sync) : "memory");
+            if (v >= target) break;
+            if (++spins > (1u << 24)) { atomicExch(sync + 1, 1u); break; }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// optional phase timing (CTA 0, thread 0): prof[i] += ns since the previous mark
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define PROF_MARK(i)                                                                 \
+    do {                                                                             \
+        if (a.prof != nullptr && threadIdx.x == 0 && blockIdx.x == 0) {              \
+            const unsigned long long now_ = gtimer();                                \
+            a.prof[i] += now_ - prof_t;                                              \
+            prof_t = now_;                                                           \
+        }                                                                            \
+    } while (0)
+
+// Sum N values held by every lane across the warp so that each lane ends up with N/32 complete sums:
+// after the call v[i] (i < N/32) is the warp total of original element rs_base<N>(lane) + i.
+template <int N>
+__device__ __forceinline__ void reduce_scatter(float (&v)[N], int lane) {
+    static_assert(N % 32 == 0, "N must be a multiple of the warp size");
+#pragma unroll
+    for (int off = 16, n = N / 2; off >= 1; off >>= 1, n >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            const float send = up ? v[i] : v[i + n];
+            const float recv = __shfl_xor_sync(0xffffffffu, send, off);
+            v[i] = (up ? v[i + n] : v[i]) + recv;
+        }
+    }
+}
+template <int N>
+__device__ __forceinline__ int rs_base(int lane) {
+    int base = 0;
+#pragma unroll
+    for (int off = 16, n = N / 2; off >= 1; off >>= 1, n >>= 1) base += (lane & off) ? n : 0;
+    return base;
+}
+
+struct FwdSmem {
+    float* Wg;      // [GR][1024]   rows g*8+u: [W_hh row | W_ih row, context columns]
+    float* Wc;      // [CR][1024]   W_out rows / W_h rows (zero beyond 512) / zero rows
+    float* Wtok;    // [GR][16]     W_ih row, token columns
+    float* bias;    // [4][8]       b_r (ih+hh), b_z (ih+hh), b_in, b_hn
+    float* bc;      // [8]          b_out of the phase-C rows (0 for query rows)
+    float* xs;      // [BT][XP]
+    float* red;     // 4096 floats: cross-warp reduction scratch (B, C) | per-warp partial contexts (A)
+    float* qv;      // [DA]
+    float* vv;      // [DA]
+    float* sc;      // [tile_pad]
+};
+
+__device__ __forceinline__ FwdSmem carve(float* sm) {
+    FwdSmem s;
+    s.Wg = sm; sm += GR * 2 * DD;
+    s.Wc = sm; sm += CR * 2 * DD;
+    s.Wtok = sm; sm += GR * DE;
+    s.bias = sm; sm += 32;
+    s.bc = sm; sm += 8;
+    s.xs = sm; sm += BT * XP;
+    s.red = sm; sm += 8 * DD;
+    s.qv = sm; sm += DA;
+    s.vv = sm; sm += DA;
+    s.sc = sm;
+    return s;
+}
+constexpr int FWD_SMEM_FLOATS = GR * 2 * DD + CR * 2 * DD + GR * DE + 32 + 8 + BT * XP + 8 * DD + 2 * DA;
+
+// ------------------------------------------------------------------------------------------------ phase A
+// Attention for item (clip b, frame range js) of step s: scores, local softmax statistics, partial context; the last
+// CTA of a clip to arrive combines the partials (same algorithm as dec_attn_kernel in decoder.cu).
+__device__ void attn_item(const DecArgs& a, const FwdSmem& S, int s, int b, int js) {
+    __shared__ float red8[8];
+    __shared__ int is_last;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int T = a.T;
+    const int t0 = js * a.tile, t1 = min(T, t0 + a.tile);
+    const float* q = a.qs + ((size_t)hslot(a, s) * a.B + b) * DA;
+    __syncthreads();
+    S.qv[tid] = __ldcg(q + tid);
+    __syncthreads();
+    {
+        const float4 q0 = *reinterpret_cast<const float4*>(S.qv + lane * 4);
+        const float4 q1 = *reinterpret_cast<const float4*>(S.qv + 128 + lane * 4);
+        const float4 v0 = *reinterpret_cast<const float4*>(S.vv + lane * 4);
+        const float4 v1 = *reinterpret_cast<const float4*>(S.vv + 128 + lane * 4);
+        constexpr int FU = 4;
+        for (int tb = t0 + warp * FU; tb < t1; tb += 8 * FU) {
+            float4 e0[FU], e1[FU];
+#pragma unroll
+            for (int u = 0; u < FU; ++u) {
+                const int t = min(tb + u, t1 - 1);
+                const float4* ep = reinterpret_cast<const float4*>(a.Ep + ((size_t)b * T + t) * DA);
+                e0[u] = __ldg(ep + lane);
+                e1[u] = __ldg(ep + 32 + lane);
+            }
+#pragma unroll
+            for (int u = 0; u < FU; ++u) {
+                float e = v0.x * tanh_fast(q0.x + e0[u].x) + v0.y * tanh_fast(q0.y + e0[u].y) + v0.z * tanh_fast(q0.z + e0[u].z) +
+                          v0.w * tanh_fast(q0.w + e0[u].w) + v1.x * tanh_fast(q1.x + e1[u].x) + v1.y * tanh_fast(q1.y + e1[u].y) +
+                          v1.z * tanh_fast(q1.z + e1[u].z) + v1.w * tanh_fast(q1.w + e1[u].w);
+                e = warp_sum(e);
+                if (lane == 0 && tb + u < t1) S.sc[tb + u - t0] = e;
+            }
+        }
+    }
+    __syncthreads();
+    const int n = t1 - t0;
+    float m = -INFINITY;
+    for (int i = tid; i < n; i += NT) m = fmaxf(m, S.sc[i]);
+    m = warp_max(m);
+    if (lane == 0) red8[warp] = m;
+    __syncthreads();
+    m = red8[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, red8[i]);
+    __syncthreads();
+    float l = 0.f;
+    float* araw = a.attn + ((size_t)slot(a, s) * a.B + b) * T;
+    for (int i = tid; i < n; i += NT) {
+        const float e = S.sc[i];
+        araw[t0 + i] = e;                           // raw score; normalised by the combining CTA
+        const float p = expf(e - m);
+        S.sc[i] = p;
+        l += p;
+    }
+    l = warp_sum(l);
+    if (lane == 0) red8[warp] = l;
+    __syncthreads();
+    l = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) l += red8[i];
+    float c0 = 0.f, c1 = 0.f;
+    {
+        float4 cacc[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cacc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4* ebase = reinterpret_cast<const float4*>(a.enc + ((size_t)b * T + t0) * DD);
+        for (int i = warp; i < n; i += 16) {
+            const int i2 = i + 8;
+            const bool two = i2 < n;
+            float4 ea[4], eb[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ea[j] = __ldg(ebase + (size_t)i * (DD / 4) + j * 32 + lane);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) eb[j] = two ? __ldg(ebase + (size_t)i2 * (DD / 4) + j * 32 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float pa = S.sc[i], pb = two ? S.sc[i2] : 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                cacc[j].x = fmaf(pa, ea[j].x, fmaf(pb, eb[j].x, cacc[j].x));
+                cacc[j].y = fmaf(pa, ea[j].y, fmaf(pb, eb[j].y, cacc[j].y));
+                cacc[j].z = fmaf(pa, ea[j].z, fmaf(pb, eb[j].z, cacc[j].z));
+                cacc[j].w = fmaf(pa, ea[j].w, fmaf(pb, eb[j].w, cacc[j].w));
+            }
+        }
+        float* part = S.red;                         // 8 x DD per-warp partial rows
+#pragma unroll
+        for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(part + warp * DD + j * 128 + lane * 4) = cacc[j];
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { c0 += part[w * DD + 2 * tid]; c1 += part[w * DD + 2 * tid + 1]; }
+    }
+    if (n <= 0) { m = -INFINITY; l = 0.f; }
+    float* pc = a.pc + ((size_t)b * a.NS + js) * DD;
+    pc[2 * tid] = c0; pc[2 * tid + 1] = c1;
+    if (tid == 0) { a.pm[b * a.NS + js] = m; a.pl[b * a.NS + js] = l; }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const int tk = atomicAdd(a.tickets + b, 1);
+        is_last = (tk == a.NS - 1);
+        if (is_last) a.tickets[b] = 0;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    float M = -INFINITY;
+    for (int j = 0; j < a.NS; ++j) M = fmaxf(M, __ldcg(a.pm + b * a.NS + j));
+    float L = 0.f;
+    c0 = 0.f; c1 = 0.f;
+    for (int j = 0; j < a.NS; ++j) {
+        const float mj = __ldcg(a.pm + b * a.NS + j);
+        const float wgt = (mj == -INFINITY) ? 0.f : expf(mj - M);
+        L = fmaf(__ldcg(a.pl + b * a.NS + j), wgt, L);
+        const float2 pj = __ldcg(reinterpret_cast<const float2*>(a.pc + ((size_t)b * a.NS + j) * DD) + tid);
+        c0 = fmaf(pj.x, wgt, c0);
+        c1 = fmaf(pj.y, wgt, c1);
+    }
+    const float invL = 1.f / L;
+    c0 *= invL; c1 *= invL;
+    float* cs = a.ctxs + ((size_t)slot(a, s) * a.B + b) * DD;
+    reinterpret_cast<float2*>(cs)[tid] = make_float2(c0, c1);
+    for (int t = tid; t < T; t += NT) araw[t] = expf(__ldcg(araw + t) - M) * invL;
+}
+
+// ------------------------------------------------------------------------------------------------ phase D
+// Finalise step s for clip b: log-softmax row, greedy token, teacher forcing, EOS bookkeeping, next input embedding.
+__device__ void finalize_step(const DecArgs& a, int s, int b, int eos_id) {
+    __shared__ float redf[8];
+    __shared__ int redi[8];
+    __shared__ int s_tok;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int V = a.V;
+    __syncthreads();
+    const float x = tid < V ? __ldcg(a.logits + (size_t)b * a.VP + tid) : -INFINITY;
+    float m = x; int idx = tid < V ? tid : 0x7fffffff;          // first index of the maximum, like torch.argmax
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, m, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (om > m || (om == m && oi < idx)) { m = om; idx = oi; }
+    }
+    if (lane == 0) { redf[warp] = m; redi[warp] = idx; }
+    __syncthreads();
+    m = redf[0]; idx = redi[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i)
+        if (redf[i] > m || (redf[i] == m && redi[i] < idx)) { m = redf[i]; idx = redi[i]; }
+    __syncthreads();
+    float e = tid < V ? expf(x - m) : 0.f;
+    e = warp_sum(e);
+    if (lane == 0) redf[warp] = e;
+    __syncthreads();
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sum += redf[i];
+    const float lse = m + logf(sum);
+    if (tid < V) a.logp[((size_t)b * a.max_steps + s) * V + tid] = x - lse;
+    if (tid == 0) {
+        const long long g = a.gt != nullptr ? a.gt[(size_t)b * a.max_steps + s] : -1;
+        const bool tf = (!a.inference) && a.use_gt != nullptr && a.use_gt[s] != 0 && a.gt != nullptr;
+        const int tok = tf ? (int)g : idx;
+        s_tok = tok;
+        const bool hit = a.gt != nullptr ? (g == eos_id) : (idx == eos_id);
+        if (hit) {
+            a.lengths[b] = s + 1;
+            if (a.eos[b] == 0) { a.eos[b] = 1; atomicAdd(a.counters, 1); }
+        }
+        if (b == 0) atomicAdd(a.counters + 1, 1);
+        if (a.save && s + 1 <= a.S) a.toks[(size_t)(s + 1) * a.B + b] = tok;
+    }
+    __syncthreads();
+    if (tid < DE && s + 1 < a.S) {
+        const float mk = a.mask != nullptr ? a.mask[((size_t)(s + 1) * a.B + b) * DE + tid] : 1.f;
+        const float xv = a.emb[(size_t)s_tok * DE + tid] * mk;
+        a.xbuf[(size_t)b * DX + tid] = xv;
+        if (a.save) a.xtok[((size_t)(s + 1) * a.B + b) * DE + tid] = xv;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ phase B
+// GRU cell for the CTA's 8 hidden units and the clips [bb0, bb0+nb) staged in xs.
+__device__ void gru_phase(const DecArgs& a, const FwdSmem& S, int s, int bb0, int nb) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float4* xs4 = reinterpret_cast<const float4*>(S.xs);
+    const float4* wg4 = reinterpret_cast<const float4*>(S.Wg);
+    const int base = rs_base<GR * 4>(lane);
+#pragma unroll 1
+    for (int cg = 0; cg < BT / 4; ++cg) {
+        if (cg * 4 >= nb) break;
+        float acc[GR * 4];
+#pragma unroll
+        for (int i = 0; i < GR * 4; ++i) acc[i] = 0.f;
+        float4 xv[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) xv[c] = xs4[(cg * 4 + c) * XP4 + tid];
+#pragma unroll
+        for (int r = 0; r < GR; ++r) {
+            const float4 w = wg4[r * KM4 + tid];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[r * 4 + c] = dot4(w, xv[c]);
+        }
+        reduce_scatter<GR * 4>(acc, lane);
+        float* dst = S.red + (cg * 8 + warp) * (GR * 4) + base;
+#pragma unroll
+        for (int i = 0; i < GR * 4 / 32; ++i) dst[i] = acc[i];
+    }
+    __syncthreads();
+    if (tid < UPC * BT) {
+        const int b = tid >> 3, u = tid & 7;
+        if (b < nb) {
+            const int cg = b >> 2, c = b & 3;
+            float g3[3], nh = 0.f;
+#pragma unroll
+            for (int g = 0; g < 3; ++g) {
+                const int idx = (g * UPC + u) * 4 + c;
+                float lo = 0.f, hi = 0.f;
+#pragma unroll
+                for (int w = 0; w < 4; ++w) lo += S.red[(cg * 8 + w) * (GR * 4) + idx];       // hidden-state columns
+#pragma unroll
+                for (int w = 4; w < 8; ++w) hi += S.red[(cg * 8 + w) * (GR * 4) + idx];       // context columns
+                const float* wt = S.Wtok + (g * UPC + u) * DE;
+                const float* xt = S.xs + b * XP + 2 * DD;
+#pragma unroll
+                for (int k = 0; k < DE; ++k) hi = fmaf(wt[k], xt[k], hi);
+                if (g < 2) g3[g] = lo + hi;
+                else { g3[2] = hi; nh = lo; }
+            }
+            const int j = blockIdx.x * UPC + u, bg = bb0 + b;
+            const float r = sigmoidf_(g3[0] + S.bias[u]);
+            const float z = sigmoidf_(g3[1] + S.bias[8 + u]);
+            const float hnl = nh + S.bias[24 + u];
+            const float n = tanhf(g3[2] + S.bias[16 + u] + r * hnl);
+            const float hp = S.xs[b * XP + j];
+            const float hn = (1.f - z) * n + z * hp;
+            a.hs[((size_t)hslot(a, s + 1) * a.B + bg) * DD + j] = hn;
+            if (a.save) {
+                float* gs = a.gates + ((size_t)s * a.B + bg) * 4 * DD + j;
+                gs[0] = r; gs[DD] = z; gs[2 * DD] = n; gs[3 * DD] = hnl;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ phase C
+// logits and next query for the CTA's 7 rows and the clips staged in xs ([h' | ctx]).
+__device__ void out_phase(const DecArgs& a, const FwdSmem& S, int qslot, int bb0, int nb, bool only_q) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float4* xs4 = reinterpret_cast<const float4*>(S.xs);
+    const float4* wc4 = reinterpret_cast<const float4*>(S.Wc);
+    float4 wr[CR];
+#pragma unroll
+    for (int r = 0; r < CR; ++r) wr[r] = wc4[r * KM4 + tid];
+    const int base = rs_base<64>(lane);
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+        if (half * 8 >= nb) break;
+        float acc[64];
+#pragma unroll
+        for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float4 x = xs4[(half * 8 + c) * XP4 + tid];
+#pragma unroll
+            for (int r = 0; r < CR; ++r) acc[r * 8 + c] = dot4(wr[r], x);
+        }
+        reduce_scatter<64>(acc, lane);
+        float* dst = S.red + (half * 8 + warp) * 64 + base;
+        dst[0] = acc[0]; dst[1] = acc[1];
+    }
+    __syncthreads();
+    if (tid < CR * BT) {
+        const int rr = tid >> 4, b = tid & 15;
+        const int rg = blockIdx.x * CR + rr;
+        if (b < nb && rg < a.V + DA) {
+            const int half = b >> 3, c = b & 7;
+            float v = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) v += S.red[(half * 8 + w) * 64 + rr * 8 + c];
+            if (rg < a.V) {
+                if (!only_q) a.logits[(size_t)(bb0 + b) * a.VP + rg] = v + S.bc[rr];
+            } else {
+                a.qs[((size_t)qslot * a.B + bb0 + b) * DA + (rg - a.V)] = v;
+            }
+        }
+    }
+}
+
+// stage clip rows into xs: parts bit 0 = h (from hs[hs_slot]), bit 1 = ctx (from ctxs[ctx_slot]), bit 2 = token embedding
+__device__ void stage_xs(const DecArgs& a, const FwdSmem& S, int bb0, int nb, int parts, int hs_slot, int ctx_slot) {
+    float4* xs4 = reinterpret_cast<float4*>(S.xs);
+    const int tid = threadIdx.x;
+    if (parts & 1) {
+        const float* src = a.hs + ((size_t)hs_slot * a.B + bb0) * DD;
+        for (int i = tid; i < nb * (DD / 4); i += NT) xs4[(i >> 7) * XP4 + (i & 127)] = ldcg4(src + (size_t)i * 4);
+    }
+    if (parts & 2) {
+        const float* src = a.ctxs + ((size_t)ctx_slot * a.B + bb0) * DD;
+        for (int i = tid; i < nb * (DD / 4); i += NT) xs4[(i >> 7) * XP4 + 128 + (i & 127)] = ldcg4(src + (size_t)i * 4);
+    }
+    if (parts & 4) {
+        for (int i = tid; i < nb * (DE / 4); i += NT)
+            xs4[(i >> 2) * XP4 + 256 + (i & 3)] = ldcg4(a.xbuf + (size_t)(bb0 + (i >> 2)) * DX + (i & 3) * 4);
+    }
+}
+
+__global__ void __launch_bounds__(NT, 1) dec_persist_fwd_kernel(DecArgs a, int eos_id) {
+    extern __shared__ __align__(16) float smem_f[];
+    const FwdSmem S = carve(smem_f);
+    const int tid = threadIdx.x, cta = blockIdx.x;
+    unsigned int target = 0;
+
+    // ---- one-time: this CTA's weight slices -> shared memory
+    for (int i = tid; i < GR * KM4; i += NT) {
+        const int r = i / KM4, k4 = i % KM4;
+        const int row = (r / UPC) * DD + cta * UPC + (r % UPC);
+        const float4 w = k4 < 128 ? __ldg(reinterpret_cast<const float4*>(a.W_hh + (size_t)row * DD) + k4)
+                                  : __ldg(reinterpret_cast<const float4*>(a.W_ih + (size_t)row * DX + DE) + (k4 - 128));
+        reinterpret_cast<float4*>(S.Wg)[i] = w;
+    }
+    for (int i = tid; i < GR * DE; i += NT) {
+        const int r = i / DE, k = i % DE;
+        const int row = (r / UPC) * DD + cta * UPC + (r % UPC);
+        S.Wtok[i] = a.W_ih[(size_t)row * DX + k];
+    }
+    for (int i = tid; i < CR * KM4; i += NT) {
+        const int rr = i / KM4, k4 = i % KM4;
+        const int rg = cta * CR + rr;
+        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rg < a.V) w = __ldg(reinterpret_cast<const float4*>(a.W_out + (size_t)rg * 2 * DD) + k4);
+        else if (rg < a.V + DA && k4 < 128) w = __ldg(reinterpret_cast<const float4*>(a.Wattn + (size_t)(rg - a.V) * 2 * DD) + k4);
+        reinterpret_cast<float4*>(S.Wc)[i] = w;
+    }
+    if (tid < UPC) {
+        const int j = cta * UPC + tid;
+        S.bias[tid] = a.b_ih[j] + a.b_hh[j];
+        S.bias[8 + tid] = a.b_ih[DD + j] + a.b_hh[DD + j];
+        S.bias[16 + tid] = a.b_ih[2 * DD + j];
+        S.bias[24 + tid] = a.b_hh[2 * DD + j];
+        const int rg = cta * CR + tid;
+        S.bc[tid] = (tid < CR && rg < a.V) ? a.b_out[rg] : 0.f;
+    }
+    S.vv[tid] = a.v[tid];
+    for (int i = tid; i < BT * XP; i += NT) S.xs[i] = 0.f;
+    __syncthreads();
+
+    const int B = a.B;
+    const int nchunks = (B + BT - 1) / BT;
+    const bool resident = nchunks == 1;            // the recurrent state of all clips stays in shared memory across phases
+    const int nitems = B * a.NS;
+
+    unsigned long long prof_t = gtimer();
+    // ---- prologue: q_0 = W_h h_0
+    for (int ch = 0; ch < nchunks; ++ch) {
+        const int bb0 = ch * BT, nb = min(BT, B - bb0);
+        __syncthreads();
+        stage_xs(a, S, bb0, nb, 1, hslot(a, 0), 0);
+        __syncthreads();
+        out_phase(a, S, hslot(a, 0), bb0, nb, true);
+    }
+    grid_sync(a.sync, target);
+    PROF_MARK(6);
+
+    int s = 0;
+    for (; s < a.S; ++s) {
+        // ---- A(s) + D(s-1)
+        for (int item = cta; item < nitems; item += PG) {
+            const int b = item / a.NS, js = item - b * a.NS;
+            if (js == 0 && s > 0) finalize_step(a, s - 1, b, eos_id);
+            attn_item(a, S, s, b, js);
+        }
+        PROF_MARK(0);
+        grid_sync(a.sync, target);
+        PROF_MARK(1);
+        if (a.inference && __ldcg(a.counters) >= B) break;        // every clip has emitted <eos> (models.py:418-419)
+        // ---- B(s)
+        for (int ch = 0; ch < nchunks; ++ch) {
+            const int bb0 = ch * BT, nb = min(BT, B - bb0);
+            __syncthreads();
+            stage_xs(a, S, bb0, nb, resident ? 6 : 7, hslot(a, s), slot(a, s));
+            __syncthreads();
+            gru_phase(a, S, s, bb0, nb);
+        }
+        PROF_MARK(2);
+        grid_sync(a.sync, target);
+        PROF_MARK(3);
+        // ---- C(s)
+        for (int ch = 0; ch < nchunks; ++ch) {
+            const int bb0 = ch * BT, nb = min(BT, B - bb0);
+            __syncthreads();
+            stage_xs(a, S, bb0, nb, resident ? 1 : 3, hslot(a, s + 1), slot(a, s));
+            __syncthreads();
+            out_phase(a, S, hslot(a, s + 1), bb0, nb, false);
+        }
+        PROF_MARK(4);
+        grid_sync(a.sync, target);
+        PROF_MARK(5);
+    }
+    if (s == a.S)                                                  // loop ran to completion: finalise the last step
+        for (int b = cta; b < B; b += PG) finalize_step(a, a.S - 1, b, eos_id);
+}
+
+__global__ void dec_persist_init_kernel(DecArgs a, int sos) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < a.B * DE) {
+        const int b = i / DE, e = i % DE;
+        const float m = a.mask != nullptr ? a.mask[(size_t)b * DE + e] : 1.f;
+        const float x = a.emb[(size_t)sos * DE + e] * m;
+        a.xbuf[(size_t)b * DX + e] = x;
+        if (a.save) a.xtok[(size_t)b * DE + e] = x;
+    }
+    if (i < a.B && a.save) a.toks[i] = sos;
+}
+
+
+// ================================================================================================= backward
+constexpr int NTB = 384;               // threads of the reverse kernel: one float4 column of the 1536 gate gradients each
+constexpr int K3 = 3 * DD;             // GRU gate rows (reduction length of the transposed products)
+constexpr int RPB = 16;                // W^T rows per CTA (+1 token row on the first 16 CTAs)
+static_assert(K3 / 4 == NTB, "one float4 column of the gate gradients per thread");
+static_assert(PG == 64 && RPB * (PG / 2) == DD, "row slicing of the reverse kernel");
+
+struct BwdSmem {
+    float* WT;      // [RPB+1][K3]  rows of W_ih^T (context / token inputs) on CTAs < 32, of W_hh^T on CTAs >= 32
+    float* U;       // [BT][K3]     gate gradients of the staged clips (P2) | scratch of P1 and P3
+    float* red;     // [4][12][64] cross-warp reduction scratch + [12][BT] for the token row
+    float* Wq;      // [UPC][DA]    W_h^T rows of this CTA's hidden units
+};
+constexpr int BWD_RED_FLOATS = 4 * 12 * 64 + 12 * BT;
+constexpr int BWD_SMEM_FLOATS = (RPB + 1) * K3 + BT * K3 + BWD_RED_FLOATS + UPC * DA;
+
+// ---- P1: dh of this CTA's 8 hidden units (all clips), GRU gate gradients -> dgi_all / dgh_all / dh*z
+__device__ void bwd_gates_phase(const DecArgs& a, const BwdSmem& S, int s, int bb0, int nb) {
+    const int tid = threadIdx.x, cta = blockIdx.x;
+    float* dqs = S.U;                                 // [BT][DA]
+    const bool last_step = (s == a.S - 1);
+    __syncthreads();
+    if (!last_step)
+        for (int i = tid; i < nb * (DA / 4); i += NTB)
+            reinterpret_cast<float4*>(dqs)[i] = ldcg4(a.dq_all + ((size_t)(s + 1) * a.B + bb0) * DA + (size_t)i * 4);
+    __syncthreads();
+    if (tid < 2 * UPC * BT) {
+        const int b = tid >> 4, u = (tid >> 1) & 7, half = tid & 1;
+        float dhq = 0.f;
+        if (!last_step && b < nb) {
+            const float4* w4 = reinterpret_cast<const float4*>(S.Wq + u * DA + half * 128);
+            const float4* d4 = reinterpret_cast<const float4*>(dqs + b * DA + half * 128);
+#pragma unroll 8
+            for (int i = 0; i < 32; ++i) dhq += dot4(w4[i], d4[i]);
+        }
+        dhq += __shfl_xor_sync(0xffffffffu, dhq, 1);
+        if (half == 0 && b < nb) {
+            const int j = cta * UPC + u, bg = bb0 + b;
+            const size_t sb = (size_t)s * a.B + bg;
+            float dh = __ldg(a.dhc_all + sb * 2 * DD + j);
+            if (!last_step) dh += dhq + __ldcg(a.dh_carry + (size_t)bg * DD + j);
+            else if (a.dh_last != nullptr) dh += a.dh_last[(size_t)bg * DD + j];
+            const float* gs = a.gates + sb * 4 * DD + j;
+            const float rr = gs[0], z = gs[DD], n = gs[2 * DD], hnl = gs[3 * DD];
+            const float hp = a.hs[sb * DD + j];
+            const float dn_pre = dh * (1.f - z) * (1.f - n * n);
+            const float dr_pre = dn_pre * hnl * rr * (1.f - rr);
+            const float dz_pre = dh * (hp - n) * z * (1.f - z);
+            float* gi = a.dgi_all + sb * K3 + j;
+            float* gh = a.dgh_all + sb * K3 + j;
+            gi[0] = dr_pre; gi[DD] = dz_pre; gi[2 * DD] = dn_pre;
+            gh[0] = dr_pre; gh[DD] = dz_pre; gh[2 * DD] = dn_pre * rr;
+            a.d_hc[(size_t)bg * 2 * DD + j] = dh * z;                      // direct path of dh_prev
+        }
+    }
+}
+
+// ---- P2: dx = dgi W_ih (CTAs < 32; 16 context columns + 1 token column), dh_prev = dgh W_hh + dh*z (CTAs >= 32)
+__device__ void bwd_gemv_phase(const DecArgs& a, const BwdSmem& S, int s, int bb0, int nb) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, cta = blockIdx.x;
+    const bool is_dx = cta < PG / 2;
+    const bool has_tok = cta < DE;
+    const float* src = (is_dx ? a.dgi_all : a.dgh_all) + ((size_t)s * a.B + bb0) * K3;
+    __syncthreads();
+    for (int i = tid; i < nb * (K3 / 4); i += NTB) reinterpret_cast<float4*>(S.U)[i] = ldcg4(src + (size_t)i * 4);
+    __syncthreads();
+    const float4* x4 = reinterpret_cast<const float4*>(S.U);
+    const float4* w4 = reinterpret_cast<const float4*>(S.WT);
+    const int base = rs_base<RPB * 4>(lane);
+    float* tokred = S.red + 4 * 12 * 64;                // [12][BT]
+#pragma unroll 1
+    for (int cg = 0; cg < BT / 4; ++cg) {
+        if (cg * 4 >= nb) break;
+        float acc[RPB * 4];
+        float4 xv[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) xv[c] = x4[(cg * 4 + c) * (K3 / 4) + tid];
+#pragma unroll
+        for (int r = 0; r < RPB; ++r) {
+            const float4 w = w4[r * (K3 / 4) + tid];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[r * 4 + c] = dot4(w, xv[c]);
+        }
+        float tk[4] = {0.f, 0.f, 0.f, 0.f};
+        if (has_tok) {
+            const float4 w = w4[RPB * (K3 / 4) + tid];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) tk[c] = warp_sum(dot4(w, xv[c]));
+        }
+        reduce_scatter<RPB * 4>(acc, lane);
+        float* dst = S.red + (cg * 12 + warp) * 64 + base;
+        dst[0] = acc[0]; dst[1] = acc[1];
+        if (has_tok && lane < 4) tokred[warp * BT + cg * 4 + lane] = lane == 0 ? tk[0] : lane == 1 ? tk[1] : lane == 2 ? tk[2] : tk[3];
+    }
+    __syncthreads();
+    if (tid < RPB * BT) {
+        const int r = tid >> 4, b = tid & 15;
+        if (b < nb) {
+            const int cg = b >> 2, c = b & 3, bg = bb0 + b;
+            float v = 0.f;
+#pragma unroll
+            for (int w = 0; w < 12; ++w) v += S.red[(cg * 12 + w) * 64 + r * 4 + c];
+            if (is_dx) {
+                a.dx[(size_t)bg * DX + DE + cta * RPB + r] = v;
+            } else {
+                const int k = (cta - PG / 2) * RPB + r;
+                a.dh_carry[(size_t)bg * DD + k] = v + __ldcg(a.d_hc + (size_t)bg * 2 * DD + k);
+            }
+        }
+    } else if (has_tok && tid < RPB * BT + BT) {
+        const int b = tid - RPB * BT;
+        if (b < nb) {
+            float v = 0.f;
+#pragma unroll
+            for (int w = 0; w < 12; ++w) v += tokred[w * BT + b];
+            a.dxtok_all[((size_t)s * a.B + bb0 + b) * DE + cta] = v;
+        }
+    }
+}
+
+// ---- P3: attention backward for clip b, frames [t0,t1): d(score) -> ds_all, dq partials; last arriver sums dq -> dq_all[s]
+__device__ void bwd_attn_item(const DecArgs& a, const BwdSmem& S, int s, int b, int js) {
+    __shared__ float red12[12];
+    __shared__ int is_last;
+    float* dc = S.U;                 // [DD]
+    float* qv = S.U + DD;            // [DA]
+    float* vv = S.U + DD + DA;       // [DA]
+    float* accq = S.U + DD + 2 * DA; // [12][DA]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int T = a.T;
+    const int t0 = js * a.tile, t1 = min(T, t0 + a.tile);
+    const size_t sb = (size_t)s * a.B + b;
+    __syncthreads();
+    for (int d = tid; d < DD; d += NTB) {
+        const float v = __ldg(a.dhc_all + sb * 2 * DD + DD + d) + __ldcg(a.dx + (size_t)b * DX + DE + d);
+        dc[d] = v;
+        if (js == 0) a.dctx_all[sb * DD + d] = v;
+    }
+    if (tid < DA) { qv[tid] = a.qs[sb * DA + tid]; vv[tid] = a.v[tid]; }
+    __syncthreads();
+    const float* ctx = a.ctxs + sb * DD;
+    float c0 = 0.f;
+    for (int d = tid; d < DD; d += NTB) c0 += dc[d] * ctx[d];
+    c0 = warp_sum(c0);
+    if (lane == 0) red12[warp] = c0;
+    __syncthreads();
+    c0 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) c0 += red12[i];
+
+    float4 dcr[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dcr[i] = *reinterpret_cast<const float4*>(dc + i * 128 + lane * 4);
+    const float4 q0 = *reinterpret_cast<const float4*>(qv + lane * 4);
+    const float4 q1 = *reinterpret_cast<const float4*>(qv + 128 + lane * 4);
+    const float4 v0 = *reinterpret_cast<const float4*>(vv + lane * 4);
+    const float4 v1 = *reinterpret_cast<const float4*>(vv + 128 + lane * 4);
+    float dq[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const float* at = a.attn + sb * T;
+    float* dsrow = a.ds_all + sb * T;
+    const float vk[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    const float qk[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+    constexpr int FU = 2;
+    for (int tb = t0 + warp * FU; tb < t1; tb += 12 * FU) {
+        float4 en[FU][4], e0[FU], e1[FU];
+        float aw[FU];
+#pragma unroll
+        for (int u = 0; u < FU; ++u) {
+            const int t = min(tb + u, t1 - 1);
+            const float4* e4 = reinterpret_cast<const float4*>(a.enc + ((size_t)b * T + t) * DD);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) en[u][i] = __ldg(e4 + i * 32 + lane);
+            const float4* ep = reinterpret_cast<const float4*>(a.Ep + ((size_t)b * T + t) * DA);
+            e0[u] = __ldg(ep + lane); e1[u] = __ldg(ep + 32 + lane);
+            aw[u] = at[t];
+        }
+#pragma unroll
+        for (int u = 0; u < FU; ++u) {
+            const int t = tb + u;
+            float da = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) da += dot4(dcr[i], en[u][i]);
+            da = warp_sum(da);
+            if (t >= t1) continue;            // warp-uniform
+            const float ds = aw[u] * (da - c0);
+            if (lane == 0) dsrow[t] = ds;
+            const float ev[8] = {e0[u].x, e0[u].y, e0[u].z, e0[u].w, e1[u].x, e1[u].y, e1[u].z, e1[u].w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float uu = tanh_fast(qk[i] + ev[i]);
+                dq[i] = fmaf(ds * vk[i], 1.f - uu * uu, dq[i]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { accq[warp * DA + lane * 4 + i] = dq[i]; accq[warp * DA + 128 + lane * 4 + i] = dq[4 + i]; }
+    __syncthreads();
+    if (tid < DA) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 12; ++w) t += accq[w * DA + tid];
+        a.dq_part[((size_t)b * a.NS + js) * DA + tid] = t;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const int tk = atomicAdd(a.tickets + b, 1);
+        is_last = (tk == a.NS - 1);
+        if (is_last) a.tickets[b] = 0;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (tid < DA) {
+        float t = 0.f;
+        for (int j = 0; j < a.NS; ++j) t += __ldcg(a.dq_part + ((size_t)b * a.NS + j) * DA + tid);
+        a.dq_all[sb * DA + tid] = t;
+    }
+}
+
+__global__ void __launch_bounds__(NTB, 1) dec_persist_bwd_kernel(DecArgs a) {
+    extern __shared__ __align__(16) float smem_f[];
+    BwdSmem S;
+    S.WT = smem_f;
+    S.U = S.WT + (RPB + 1) * K3;
+    S.red = S.U + BT * K3;
+    S.Wq = S.red + BWD_RED_FLOATS;
+    const int tid = threadIdx.x, cta = blockIdx.x;
+    unsigned int target = 0;
+    // ---- one-time: W^T rows of this CTA (from the host-transposed copies) and its W_h^T rows
+    {
+        const bool is_dx = cta < PG / 2;
+        for (int i = tid; i < (RPB + 1) * (K3 / 4); i += NTB) {
+            const int r = i / (K3 / 4), k4 = i % (K3 / 4);
+            float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < RPB) {
+                const float* row = is_dx ? a.W_ihT + (size_t)(DE + cta * RPB + r) * K3 : a.W_hhT + (size_t)((cta - PG / 2) * RPB + r) * K3;
+                w = __ldg(reinterpret_cast<const float4*>(row) + k4);
+            } else if (cta < DE) {
+                w = __ldg(reinterpret_cast<const float4*>(a.W_ihT + (size_t)cta * K3) + k4);
+            }
+            reinterpret_cast<float4*>(S.WT)[i] = w;
+        }
+        for (int i = tid; i < UPC * DA; i += NTB) S.Wq[i] = a.W_hT[(size_t)(cta * UPC + i / DA) * DA + (i % DA)];
+    }
+    __syncthreads();
+    const int B = a.B;
+    const int nchunks = (B + BT - 1) / BT;
+    const int nitems = B * a.NS;
+    unsigned long long prof_t = gtimer();
+    for (int s = a.S - 1; s >= 0; --s) {
+        for (int ch = 0; ch < nchunks; ++ch) bwd_gates_phase(a, S, s, ch * BT, min(BT, B - ch * BT));
+        PROF_MARK(0);
+        grid_sync(a.sync, target);
+        PROF_MARK(1);
+        for (int ch = 0; ch < nchunks; ++ch) bwd_gemv_phase(a, S, s, ch * BT, min(BT, B - ch * BT));
+        PROF_MARK(2);
+        grid_sync(a.sync, target);
+        PROF_MARK(3);
+        for (int item = cta; item < nitems; item += PG) bwd_attn_item(a, S, s, item / a.NS, item % a.NS);
+        PROF_MARK(4);
+        grid_sync(a.sync, target);
+        PROF_MARK(5);
+    }
+    // ---- tail: dh_0 = dh_prev of step 0 + dq_0 W_h  -> a.dhq
+    for (int ch = 0; ch < nchunks; ++ch) {
+        const int bb0 = ch * BT, nb = min(BT, B - bb0);
+        float* dqs = S.U;
+        __syncthreads();
+        for (int i = tid; i < nb * (DA / 4); i += NTB) reinterpret_cast<float4*>(dqs)[i] = ldcg4(a.dq_all + (size_t)bb0 * DA + (size_t)i * 4);
+        __syncthreads();
+        if (tid < 2 * UPC * BT) {
+            const int b = tid >> 4, u = (tid >> 1) & 7, half = tid & 1;
+            float dhq = 0.f;
+            if (b < nb) {
+                const float4* w4 = reinterpret_cast<const float4*>(S.Wq + u * DA + half * 128);
+                const float4* d4 = reinterpret_cast<const float4*>(dqs + b * DA + half * 128);
+#pragma unroll 8
+                for (int i = 0; i < 32; ++i) dhq += dot4(w4[i], d4[i]);
+            }
+            dhq += __shfl_xor_sync(0xffffffffu, dhq, 1);
+            if (half == 0 && b < nb) {
+                const int j = cta * UPC + u;
+                a.dhq[(size_t)(bb0 + b) * DD + j] = dhq + __ldcg(a.dh_carry + (size_t)(bb0 + b) * DD + j);
+            }
+        }
+    }
+}
+
+// dlogits[s,b,:] = dlogp[b,s,:] - exp(logp[b,s,:]) * sum_v dlogp[b,s,v]   (log_softmax backward), zero padded to VP
+__global__ void dec_dlogits_kernel(DecArgs a) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= a.S * a.B) return;
+    const int s = row / a.B, b = row % a.B;
+    const size_t ro = ((size_t)b * a.max_steps + s) * a.V;
+    float sg = 0.f;
+    for (int vi = lane; vi < a.V; vi += 32) sg += __ldg(a.dlogp + ro + vi);
+    sg = warp_sum(sg);
+    for (int vi = lane; vi < a.VP; vi += 32) {
+        float d = 0.f;
+        if (vi < a.V) d = __ldg(a.dlogp + ro + vi) - expf(__ldg(a.logp + ro + vi)) * sg;
+        a.dlogits_all[(size_t)row * a.VP + vi] = d;
+    }
+}
+
+// Deferred accumulations over the steps (off the sequential chain):
+//   dEp[b,t,k] = sum_s ds[s,b,t] v_k (1 - u^2),  dv_k = sum_{s,b,t} ds[s,b,t] u,   u = tanh(q[s,b,k] + Ep[b,t,k])
+constexpr int DEF_FPW = 2, DEF_WARPS = 8, DEF_FPB = DEF_FPW * DEF_WARPS;
+__global__ void __launch_bounds__(DEF_WARPS * 32) dec_attn_deferred_kernel(DecArgs a) {
+    __shared__ float acc[DEF_WARPS][DA];
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int T = a.T;
+    const int tA = blockIdx.x * DEF_FPB + warp * DEF_FPW;
+    const float4 v0 = __ldg(reinterpret_cast<const float4*>(a.v) + lane), v1 = __ldg(reinterpret_cast<const float4*>(a.v) + 32 + lane);
+    const float vk[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    float ev[DEF_FPW][8], dE[DEF_FPW][8], dv[8];
+    bool ok[DEF_FPW];
+#pragma unroll
+    for (int f = 0; f < DEF_FPW; ++f) {
+        ok[f] = tA + f < T;
+        const float4* ep = reinterpret_cast<const float4*>(a.Ep + ((size_t)b * T + min(tA + f, T - 1)) * DA);
+        const float4 e0 = __ldg(ep + lane), e1 = __ldg(ep + 32 + lane);
+        ev[f][0] = e0.x; ev[f][1] = e0.y; ev[f][2] = e0.z; ev[f][3] = e0.w; ev[f][4] = e1.x; ev[f][5] = e1.y; ev[f][6] = e1.z; ev[f][7] = e1.w;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dE[f][i] = 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dv[i] = 0.f;
+    if (tA < T) {
+        for (int s = 0; s < a.S; ++s) {
+            const size_t sb = (size_t)s * a.B + b;
+            const float4 q0 = __ldg(reinterpret_cast<const float4*>(a.qs + sb * DA) + lane);
+            const float4 q1 = __ldg(reinterpret_cast<const float4*>(a.qs + sb * DA) + 32 + lane);
+            const float qk[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+            for (int f = 0; f < DEF_FPW; ++f) {
+                const float ds = ok[f] ? __ldg(a.ds_all + sb * T + tA + f) : 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float uu = tanh_fast(qk[i] + ev[f][i]);
+                    dE[f][i] = fmaf(ds * vk[i], 1.f - uu * uu, dE[f][i]);
+                    dv[i] = fmaf(ds, uu, dv[i]);
+                }
+            }
+        }
+#pragma unroll
+        for (int f = 0; f < DEF_FPW; ++f) {
+            if (!ok[f]) continue;
+            float4* dep = reinterpret_cast<float4*>(a.dEp + ((size_t)b * T + tA + f) * DA);
+            dep[lane] = make_float4(dE[f][0], dE[f][1], dE[f][2], dE[f][3]);
+            dep[32 + lane] = make_float4(dE[f][4], dE[f][5], dE[f][6], dE[f][7]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { acc[warp][lane * 4 + i] = dv[i]; acc[warp][128 + lane * 4 + i] = dv[4 + i]; }
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < DEF_WARPS; ++w) t += acc[w][tid];
+    a.dv_part[((size_t)b * gridDim.x + blockIdx.x) * DA + tid] = t;
+}
+
+}  // namespace
+
+PA2S_API int pa2s_dec_persist_grid(void) { return PG; }
+
+// All S steps of one (bar, staff) in one cooperative launch.  a.NS * a.tile must cover T with NS <= 16;
+// a.sync must point to >= 2 zeroed uint32.
+PA2S_API int pa2s_note_decoder_fwd_persist(void* stream, const void* args, int sos_id, int eos_id) {
+    DecArgs a = *reinterpret_cast<const DecArgs*>(args);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (a.B <= 0 || a.S <= 0) return 0;
+    if (a.V + DA > PG * CR || a.sync == nullptr) return -2;
+    a.tile_pad = (a.tile + 3) / 4 * 4;
+    const size_t smem = (size_t)(FWD_SMEM_FLOATS + a.tile_pad) * sizeof(float);
+    PA2S_TRY(cudaFuncSetAttribute(dec_persist_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dec_persist_init_kernel<<<ceil_div(a.B * DE, 128), 128, 0, st>>>(a, sos_id);
+    PA2S_CHECK_LAST();
+    void* kargs[] = {(void*)&a, (void*)&eos_id};
+    PA2S_TRY(cudaLaunchCooperativeKernel((const void*)dec_persist_fwd_kernel, dim3(PG), dim3(NT), kargs, smem, st));
+    PA2S_COUNT_LAUNCH();
+    return 0;
+}
+
+// rows per clip of the dv partials written by pa2s_note_decoder_bwd_persist (dv_part must hold B * this rows of DA floats)
+PA2S_API int pa2s_dec_deferred_blocks(int T) { return (T + DEF_FPB - 1) / DEF_FPB; }
+
+// Reverse pass over the S saved steps in one cooperative launch, bracketed by the two parallel kernels that carry the
+// work taken off the sequential chain.  Needs (besides the forward's saved state): dlogp, dlogits_all, dhc_all scratch is
+// formed by the CALLER between pa2s_dec_dlogits and this call (dhc_all = dlogits_all @ W_out); sync = 2 zeroed uint32.
+PA2S_API int pa2s_dec_dlogits(void* stream, const void* args) {
+    DecArgs a = *reinterpret_cast<const DecArgs*>(args);
+    if (a.B <= 0 || a.S <= 0) return 0;
+    dec_dlogits_kernel<<<ceil_div(a.S * a.B, 8), 256, 0, (cudaStream_t)stream>>>(a);
+    PA2S_CHECK_LAST();
+    return 0;
+}
+PA2S_API int pa2s_note_decoder_bwd_persist(void* stream, const void* args) {
+    DecArgs a = *reinterpret_cast<const DecArgs*>(args);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (a.B <= 0 || a.S <= 0) return 0;
+    if (a.sync == nullptr || a.dhc_all == nullptr || a.ds_all == nullptr) return -2;
+    const size_t smem = (size_t)BWD_SMEM_FLOATS * sizeof(float);
+    PA2S_TRY(cudaFuncSetAttribute(dec_persist_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    void* kargs[] = {(void*)&a};
+    PA2S_TRY(cudaLaunchCooperativeKernel((const void*)dec_persist_bwd_kernel, dim3(PG), dim3(NTB), kargs, smem, st));
+    PA2S_COUNT_LAUNCH();
+    dec_attn_deferred_kernel<<<dim3(ceil_div(a.T, DEF_FPB), a.B), DEF_WARPS * 32, 0, st>>>(a);
+    PA2S_CHECK_LAST();
+    return 0;
+}

@@ -5,7 +5,9 @@ raises if its inputs are not CUDA tensors -- there is no CPU path.
 """
 from __future__ import annotations
 
+import collections
 import ctypes
+import os
 from typing import Optional
 
 import torch
@@ -557,8 +559,9 @@ def gru_cell(x, h, w_ih, w_hh, b_ih, b_hh):
 # ----------------------------------------------------------------------------------------------------------------
 # Attention (models.py:440-461) -- one step, used by the bar-level decoder
 # ----------------------------------------------------------------------------------------------------------------
-def attn_split(B, T):
-    ns = max(1, min(16, N_SM // max(B, 1)))
+def attn_split(B, T, ctas=N_SM):
+    """frames of a clip are split over `ns` CTAs (ns * tile >= T) so that B * ns items fill `ctas` CTAs"""
+    ns = max(1, min(16, ctas // max(B, 1)))
     tile = (T + ns - 1) // ns
     ns = (T + tile - 1) // tile
     return ns, tile
@@ -624,6 +627,20 @@ def context_grad_enc(attn, dctx_all, B, T, D, S):
 # ----------------------------------------------------------------------------------------------------------------
 # Note decoder (models.py:366-420) -- all steps of one (bar, staff) in one call
 # ----------------------------------------------------------------------------------------------------------------
+# "persistent": one cooperative kernel per (bar, staff) call (dec_persist.cu); "steps": one launch per phase per step (decoder.cu)
+DECODER_IMPL = os.environ.get("PA2S_DECODER", "persistent")
+PROF = {}              # optional {"fwd": uint64[8] tensor, "bwd": ...}: per-phase ns of CTA 0 (tools/prof_decoder.py)
+SYNC_FLAGS = collections.deque(maxlen=256)        # [arrivals, watchdog flag] of recent persistent launches (tests / bench check flag == 0)
+
+
+def check_sync_flags():
+    """Raises if a grid-barrier watchdog fired in any persistent decoder launch since the last call (host sync)."""
+    flags = list(SYNC_FLAGS)
+    SYNC_FLAGS.clear()
+    if flags and int(torch.stack([f[1] for f in flags]).max().item()) != 0:
+        raise RuntimeError("persistent decoder: grid barrier watchdog fired (a CTA of the cooperative grid was lost)")
+
+
 class NoteDecoderFn(torch.autograd.Function):
     """Returns (logp (B,max_steps,V), lengths (B) int64 device, counters (2) int32 device = [eos_count, steps])."""
 
@@ -641,7 +658,8 @@ class NoteDecoderFn(torch.autograd.Function):
         gt, use_gt, mask = cfg.get("gt"), cfg.get("use_gt"), cfg.get("mask")
         save = any(ctx.needs_input_grad)
         VP = (V + 3) // 4 * 4
-        NS, tile = attn_split(B, T)
+        persist = DECODER_IMPL == "persistent"
+        NS, tile = attn_split(B, T, lib.pa2s_dec_persist_grid() if persist else N_SM)
         z = lambda *s, dt=F32: torch.zeros(*s, device=dev, dtype=dt)
         e = lambda *s, dt=F32: torch.empty(*s, device=dev, dtype=dt)
         SS = S if save else 1
@@ -654,7 +672,7 @@ class NoteDecoderFn(torch.autograd.Function):
         sv = dict(hs=hs, ctxs=e(SS, B, D), attn=e(SS, B, T), gates=e(SS, B, 4 * D) if save else None, qs=e(SS + 1, B, A),
                   xtok=e(SS + 1, B, E) if save else None, toks=e(SS + 1, B, dt=torch.int32) if save else None)
         scratch = dict(xbuf=e(B, E + D), hc=e(B, 2 * D), logits=z(B, VP), pm=e(B, NS), pl=e(B, NS), pc=e(B, NS, D),
-                       tickets=z(B, dt=torch.int32))
+                       tickets=z(B, dt=torch.int32), sync=z(2, dt=torch.int32))
         if gt is not None:
             gt = gt.contiguous()
             assert gt.shape == (B, max_steps) and gt.dtype == torch.int64
@@ -664,9 +682,13 @@ class NoteDecoderFn(torch.autograd.Function):
 
         args = make_dec_args(B=B, T=T, V=V, VP=VP, S=S, max_steps=max_steps, NS=NS, tile=tile, inference=int(inference), save=int(save),
                              enc=enc, Ep=Ep, gt=gt, use_gt=use_gt, mask=mask, logp=logp, lengths=lengths, eos=eos, counters=counters,
-                             **wts, **sv, **scratch)
+                             prof=PROF.get("fwd"), **wts, **sv, **scratch)
         with ktime("note_decoder_fwd"):
-            lib.pa2s_note_decoder_fwd(stream(), ctypes.byref(args), int(cfg["sos"]), int(cfg["eos"]))
+            if persist:
+                lib.pa2s_note_decoder_fwd_persist(stream(), ctypes.byref(args), int(cfg["sos"]), int(cfg["eos"]))
+            else:
+                lib.pa2s_note_decoder_fwd(stream(), ctypes.byref(args), int(cfg["sos"]), int(cfg["eos"]))
+        SYNC_FLAGS.append(scratch["sync"])
         ctx.mark_non_differentiable(lengths, counters)
         if save:
             ctx.save_for_backward(enc, Ep, attn_w, wts["v"], emb, W_ih, W_hh, W_out, logp, sv["hs"], sv["ctxs"], sv["attn"], sv["gates"],
@@ -685,20 +707,40 @@ class NoteDecoderFn(torch.autograd.Function):
         X = E + D
         z = lambda *s, dt=F32: torch.zeros(*s, device=dev, dtype=dt)
         e = lambda *s, dt=F32: torch.empty(*s, device=dev, dtype=dt)
-        W_outT = z(2 * D, VP)
-        W_outT[:, :V] = W_out.detach().t()
+        persist = DECODER_IMPL == "persistent"
         W_hT = attn_w.detach()[:, :D].t().contiguous()
         W_ihT = W_ih.detach().t().contiguous()
         W_hhT = W_hh.detach().t().contiguous()
-        bw = dict(dlogits_all=e(S, B, VP), dgi_all=e(S, B, 3 * D), dgh_all=e(S, B, 3 * D), dq_all=z(S + 1, B, A), dctx_all=e(S, B, D),
-                  dxtok_all=e(S, B, E), dEp=z(B, T, A), dv_part=z(B * NS, A), d_hc=z(B, 2 * D), dhq=z(B, D), dx=z(B, X),
-                  dq_part=z(B, NS, A), dh_carry=z(2, B, D))
-        args = make_dec_args(B=B, T=T, V=V, VP=VP, S=S, max_steps=max_steps, NS=NS, tile=tile, inference=0, save=1,
-                             enc=enc, Ep=Ep, Wattn=attn_w, v=v, emb=emb, W_ih=W_ih, W_hh=W_hh, W_out=W_out,
-                             W_outT=W_outT, W_hT=W_hT, W_ihT=W_ihT, W_hhT=W_hhT, logp=logp, hs=hs, ctxs=ctxs, attn=attn, gates=gates, qs=qs,
-                             dlogp=dlogp, **bw)
-        with ktime("note_decoder_bwd"):
-            lib.pa2s_note_decoder_bwd(st, ctypes.byref(args))
+        if persist:
+            # off-chain work first: log-softmax backward of every step and its out-projection gradient as one GEMM
+            nblk = lib.pa2s_dec_deferred_blocks(T)
+            bw = dict(dlogits_all=e(S, B, VP), dgi_all=e(S, B, 3 * D), dgh_all=e(S, B, 3 * D), dq_all=e(S + 1, B, A), dctx_all=e(S, B, D),
+                      dxtok_all=e(S, B, E), dEp=e(B, T, A), dv_part=e(B * nblk, A), d_hc=e(B, 2 * D), dhq=e(B, D), dx=e(B, X),
+                      dq_part=e(B, NS, A), dh_carry=e(2, B, D), dhc_all=e(S * B, 2 * D), ds_all=e(S, B, T),
+                      tickets=z(B, dt=torch.int32), sync=z(2, dt=torch.int32))
+            args = make_dec_args(B=B, T=T, V=V, VP=VP, S=S, max_steps=max_steps, NS=NS, tile=tile, inference=0, save=1,
+                                 enc=enc, Ep=Ep, Wattn=attn_w, v=v, emb=emb, W_ih=W_ih, W_hh=W_hh, W_out=W_out,
+                                 W_hT=W_hT, W_ihT=W_ihT, W_hhT=W_hhT, logp=logp, hs=hs, ctxs=ctxs, attn=attn, gates=gates, qs=qs,
+                                 dlogp=dlogp, prof=PROF.get("bwd"), **bw)
+            with ktime("note_decoder_bwd"):
+                lib.pa2s_dec_dlogits(st, ctypes.byref(args))
+                gemm(bw["dlogits_all"], W_out, bw["dhc_all"], S * B, 2 * D, V, lda=VP, ldb=2 * D, ldc=2 * D)
+                lib.pa2s_note_decoder_bwd_persist(st, ctypes.byref(args))
+            SYNC_FLAGS.append(bw["sync"])
+            dh0 = bw["dhq"]
+        else:
+            W_outT = z(2 * D, VP)
+            W_outT[:, :V] = W_out.detach().t()
+            bw = dict(dlogits_all=e(S, B, VP), dgi_all=e(S, B, 3 * D), dgh_all=e(S, B, 3 * D), dq_all=z(S + 1, B, A), dctx_all=e(S, B, D),
+                      dxtok_all=e(S, B, E), dEp=z(B, T, A), dv_part=z(B * NS, A), d_hc=z(B, 2 * D), dhq=z(B, D), dx=z(B, X),
+                      dq_part=z(B, NS, A), dh_carry=z(2, B, D))
+            args = make_dec_args(B=B, T=T, V=V, VP=VP, S=S, max_steps=max_steps, NS=NS, tile=tile, inference=0, save=1,
+                                 enc=enc, Ep=Ep, Wattn=attn_w, v=v, emb=emb, W_ih=W_ih, W_hh=W_hh, W_out=W_out,
+                                 W_outT=W_outT, W_hT=W_hT, W_ihT=W_ihT, W_hhT=W_hhT, logp=logp, hs=hs, ctxs=ctxs, attn=attn, gates=gates, qs=qs,
+                                 dlogp=dlogp, **bw)
+            with ktime("note_decoder_bwd"):
+                lib.pa2s_note_decoder_bwd(st, ctypes.byref(args))
+            dh0 = bw["dh_carry"][0] + bw["dhq"]
         SB = S * B
         # deferred weight gradients: contractions over all (step, clip) rows
         dW_out = z(V, 2 * D)
@@ -722,7 +764,6 @@ class NoteDecoderFn(torch.autograd.Function):
         d_emb = z(V, E)
         d_emb.index_add_(0, toks[:S].reshape(-1).long(), dxt.reshape(SB, E))
         denc = context_grad_enc(attn, bw["dctx_all"], B, T, D, S)
-        dh0 = bw["dh_carry"][0] + bw["dhq"]
         return (denc, bw["dEp"], dh0, d_attn_w, dv, d_emb, dW_ih, dW_hh, db_ih, db_hh, dW_out, db_out, None)
 
 
