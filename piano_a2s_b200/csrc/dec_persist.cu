@@ -17,14 +17,18 @@
 namespace {
 
 constexpr int PG = 64;                 // CTAs of a persistent decoder grid (two staves run concurrently: 128 of 148 SMs)
-constexpr int NT = 256;                // threads per CTA
+#ifndef PA2S_DEC_NT
+#define PA2S_DEC_NT 384
+#endif
+constexpr int NT = PA2S_DEC_NT;        // threads per CTA: 12 warps stream the attention memory, the first 8 own the GEMV columns
+constexpr int NW = NT / 32;
 constexpr int UPC = DD / PG;           // hidden units per CTA (8)
 constexpr int GR = 3 * UPC;            // gate rows per CTA (24): r[8], z[8], n[8]
 constexpr int CR = 7;                  // phase-C rows per CTA: PG*CR = 448 >= V + DA
 constexpr int XP = 2 * DD + DE;        // per-clip state row in shared memory: [h (512) | ctx (512) | tok (16)]
 constexpr int XP4 = XP / 4;
 constexpr int KM4 = 2 * DD / 4;        // float4 columns of the main part (256 = one per thread)
-static_assert(KM4 == NT, "one float4 column of [h|ctx] per thread");
+static_assert(KM4 <= NT, "one float4 column of [h|ctx] per thread of the first 8 warps");
 
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 
@@ -94,10 +98,9 @@ struct FwdSmem {
     float* bias;    // [4][8]       b_r (ih+hh), b_z (ih+hh), b_in, b_hn
     float* bc;      // [8]          b_out of the phase-C rows (0 for query rows)
     float* xs;      // [BT][XP]
-    float* red;     // 4096 floats: cross-warp reduction scratch (B, C) | per-warp partial contexts (A)
+    float* red;     // NW*512 floats: cross-warp reduction scratch (B, C) | per-warp partial contexts (A)
     float* qv;      // [DA]
     float* vv;      // [DA]
-    float* sc;      // [tile_pad]
 };
 
 __device__ __forceinline__ FwdSmem carve(float* sm) {
@@ -108,112 +111,106 @@ __device__ __forceinline__ FwdSmem carve(float* sm) {
     s.bias = sm; sm += 32;
     s.bc = sm; sm += 8;
     s.xs = sm; sm += BT * XP;
-    s.red = sm; sm += 8 * DD;
+    s.red = sm; sm += NW * DD;
     s.qv = sm; sm += DA;
     s.vv = sm; sm += DA;
-    s.sc = sm;
     return s;
 }
-constexpr int FWD_SMEM_FLOATS = GR * 2 * DD + CR * 2 * DD + GR * DE + 32 + 8 + BT * XP + 8 * DD + 2 * DA;
+constexpr int FWD_SMEM_FLOATS = GR * 2 * DD + CR * 2 * DD + GR * DE + 32 + 8 + BT * XP + NW * DD + 2 * DA;
 
 // ------------------------------------------------------------------------------------------------ phase A
-// Attention for item (clip b, frame range js) of step s: scores, local softmax statistics, partial context; the last
-// CTA of a clip to arrive combines the partials (same algorithm as dec_attn_kernel in decoder.cu).
+// Attention for item (clip b, frame range js) of step s in ONE pass over the frames: every warp keeps an online-softmax
+// partial (running max, sum, 512-wide context) while the Ep / enc rows of its next two frames are already in flight;
+// warps are combined in shared memory, CTAs of a clip by the last one to arrive.
+struct AttnRows { float4 e0[1], e1[1], en[1][4]; };
+
 __device__ void attn_item(const DecArgs& a, const FwdSmem& S, int s, int b, int js) {
-    __shared__ float red8[8];
+    __shared__ float wm[NW], wl[NW];
     __shared__ int is_last;
+    constexpr int FU = 1;                                       // frames per warp iteration (one more is in flight)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int T = a.T;
     const int t0 = js * a.tile, t1 = min(T, t0 + a.tile);
     const float* q = a.qs + ((size_t)hslot(a, s) * a.B + b) * DA;
     __syncthreads();
-    S.qv[tid] = __ldcg(q + tid);
+    if (tid < DA) S.qv[tid] = __ldcg(q + tid);
     __syncthreads();
+    float* araw = a.attn + ((size_t)slot(a, s) * a.B + b) * T;
+    float m = -INFINITY, l = 0.f;
+    float4 cacc[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) cacc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     {
         const float4 q0 = *reinterpret_cast<const float4*>(S.qv + lane * 4);
         const float4 q1 = *reinterpret_cast<const float4*>(S.qv + 128 + lane * 4);
         const float4 v0 = *reinterpret_cast<const float4*>(S.vv + lane * 4);
         const float4 v1 = *reinterpret_cast<const float4*>(S.vv + 128 + lane * 4);
-        constexpr int FU = 4;
-        for (int tb = t0 + warp * FU; tb < t1; tb += 8 * FU) {
-            float4 e0[FU], e1[FU];
+        auto load = [&](AttnRows& r, int tb) {
 #pragma unroll
             for (int u = 0; u < FU; ++u) {
                 const int t = min(tb + u, t1 - 1);
                 const float4* ep = reinterpret_cast<const float4*>(a.Ep + ((size_t)b * T + t) * DA);
-                e0[u] = __ldg(ep + lane);
-                e1[u] = __ldg(ep + 32 + lane);
+                r.e0[u] = __ldg(ep + lane);
+                r.e1[u] = __ldg(ep + 32 + lane);
+                const float4* en = reinterpret_cast<const float4*>(a.enc + ((size_t)b * T + t) * DD);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) r.en[u][j] = __ldg(en + j * 32 + lane);
             }
+        };
+        AttnRows cur, nxt;
+        int tb = t0 + warp * FU;
+        if (tb < t1) load(cur, tb);
+        for (; tb < t1; tb += NW * FU) {
+            if (tb + NW * FU < t1) load(nxt, tb + NW * FU);
 #pragma unroll
             for (int u = 0; u < FU; ++u) {
-                float e = v0.x * tanh_fast(q0.x + e0[u].x) + v0.y * tanh_fast(q0.y + e0[u].y) + v0.z * tanh_fast(q0.z + e0[u].z) +
-                          v0.w * tanh_fast(q0.w + e0[u].w) + v1.x * tanh_fast(q1.x + e1[u].x) + v1.y * tanh_fast(q1.y + e1[u].y) +
-                          v1.z * tanh_fast(q1.z + e1[u].z) + v1.w * tanh_fast(q1.w + e1[u].w);
+                float e = v0.x * tanh_fast(q0.x + cur.e0[u].x) + v0.y * tanh_fast(q0.y + cur.e0[u].y) + v0.z * tanh_fast(q0.z + cur.e0[u].z) +
+                          v0.w * tanh_fast(q0.w + cur.e0[u].w) + v1.x * tanh_fast(q1.x + cur.e1[u].x) + v1.y * tanh_fast(q1.y + cur.e1[u].y) +
+                          v1.z * tanh_fast(q1.z + cur.e1[u].z) + v1.w * tanh_fast(q1.w + cur.e1[u].w);
                 e = warp_sum(e);
-                if (lane == 0 && tb + u < t1) S.sc[tb + u - t0] = e;
+                if (tb + u < t1) {                              // warp-uniform
+                    if (lane == 0) araw[tb + u] = e;            // raw score; normalised by the combining CTA
+                    if (e > m) {
+                        const float sc = expf(m - e);           // 0 on the first frame (m = -inf)
+                        l *= sc;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) { cacc[j].x *= sc; cacc[j].y *= sc; cacc[j].z *= sc; cacc[j].w *= sc; }
+                        m = e;
+                    }
+                    const float p = expf(e - m);
+                    l += p;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        cacc[j].x = fmaf(p, cur.en[u][j].x, cacc[j].x);
+                        cacc[j].y = fmaf(p, cur.en[u][j].y, cacc[j].y);
+                        cacc[j].z = fmaf(p, cur.en[u][j].z, cacc[j].z);
+                        cacc[j].w = fmaf(p, cur.en[u][j].w, cacc[j].w);
+                    }
+                }
             }
+            cur = nxt;
         }
     }
+    float* part = S.red;                                        // NW x DD per-warp partial contexts
+#pragma unroll
+    for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(part + warp * DD + j * 128 + lane * 4) = cacc[j];
+    if (lane == 0) { wm[warp] = m; wl[warp] = l; }
     __syncthreads();
-    const int n = t1 - t0;
-    float m = -INFINITY;
-    for (int i = tid; i < n; i += NT) m = fmaxf(m, S.sc[i]);
-    m = warp_max(m);
-    if (lane == 0) red8[warp] = m;
-    __syncthreads();
-    m = red8[0];
+    float M = -INFINITY, L = 0.f, c0 = 0.f, c1 = 0.f;
 #pragma unroll
-    for (int i = 1; i < 8; ++i) m = fmaxf(m, red8[i]);
-    __syncthreads();
-    float l = 0.f;
-    float* araw = a.attn + ((size_t)slot(a, s) * a.B + b) * T;
-    for (int i = tid; i < n; i += NT) {
-        const float e = S.sc[i];
-        araw[t0 + i] = e;                           // raw score; normalised by the combining CTA
-        const float p = expf(e - m);
-        S.sc[i] = p;
-        l += p;
-    }
-    l = warp_sum(l);
-    if (lane == 0) red8[warp] = l;
-    __syncthreads();
-    l = 0.f;
+    for (int w = 0; w < NW; ++w) M = fmaxf(M, wm[w]);
+    if (tid < DD / 2) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) l += red8[i];
-    float c0 = 0.f, c1 = 0.f;
-    {
-        float4 cacc[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) cacc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4* ebase = reinterpret_cast<const float4*>(a.enc + ((size_t)b * T + t0) * DD);
-        for (int i = warp; i < n; i += 16) {
-            const int i2 = i + 8;
-            const bool two = i2 < n;
-            float4 ea[4], eb[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) ea[j] = __ldg(ebase + (size_t)i * (DD / 4) + j * 32 + lane);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) eb[j] = two ? __ldg(ebase + (size_t)i2 * (DD / 4) + j * 32 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
-            const float pa = S.sc[i], pb = two ? S.sc[i2] : 0.f;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                cacc[j].x = fmaf(pa, ea[j].x, fmaf(pb, eb[j].x, cacc[j].x));
-                cacc[j].y = fmaf(pa, ea[j].y, fmaf(pb, eb[j].y, cacc[j].y));
-                cacc[j].z = fmaf(pa, ea[j].z, fmaf(pb, eb[j].z, cacc[j].z));
-                cacc[j].w = fmaf(pa, ea[j].w, fmaf(pb, eb[j].w, cacc[j].w));
-            }
+        for (int w = 0; w < NW; ++w) {
+            const float wgt = (wm[w] == -INFINITY) ? 0.f : expf(wm[w] - M);
+            L = fmaf(wl[w], wgt, L);
+            const float2 pw = *reinterpret_cast<const float2*>(part + w * DD + 2 * tid);
+            c0 = fmaf(pw.x, wgt, c0);
+            c1 = fmaf(pw.y, wgt, c1);
         }
-        float* part = S.red;                         // 8 x DD per-warp partial rows
-#pragma unroll
-        for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(part + warp * DD + j * 128 + lane * 4) = cacc[j];
-        __syncthreads();
-#pragma unroll
-        for (int w = 0; w < 8; ++w) { c0 += part[w * DD + 2 * tid]; c1 += part[w * DD + 2 * tid + 1]; }
+        reinterpret_cast<float2*>(a.pc + ((size_t)b * a.NS + js) * DD)[tid] = make_float2(c0, c1);
+        if (tid == 0) { a.pm[b * a.NS + js] = M; a.pl[b * a.NS + js] = L; }
     }
-    if (n <= 0) { m = -INFINITY; l = 0.f; }
-    float* pc = a.pc + ((size_t)b * a.NS + js) * DD;
-    pc[2 * tid] = c0; pc[2 * tid + 1] = c1;
-    if (tid == 0) { a.pm[b * a.NS + js] = m; a.pl[b * a.NS + js] = l; }
     __threadfence();
     __syncthreads();
     if (tid == 0) {
@@ -224,30 +221,34 @@ __device__ void attn_item(const DecArgs& a, const FwdSmem& S, int s, int b, int 
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    float M = -INFINITY;
+    M = -INFINITY;
     for (int j = 0; j < a.NS; ++j) M = fmaxf(M, __ldcg(a.pm + b * a.NS + j));
-    float L = 0.f;
-    c0 = 0.f; c1 = 0.f;
+    L = 0.f;
     for (int j = 0; j < a.NS; ++j) {
         const float mj = __ldcg(a.pm + b * a.NS + j);
-        const float wgt = (mj == -INFINITY) ? 0.f : expf(mj - M);
-        L = fmaf(__ldcg(a.pl + b * a.NS + j), wgt, L);
-        const float2 pj = __ldcg(reinterpret_cast<const float2*>(a.pc + ((size_t)b * a.NS + j) * DD) + tid);
-        c0 = fmaf(pj.x, wgt, c0);
-        c1 = fmaf(pj.y, wgt, c1);
+        L = fmaf(__ldcg(a.pl + b * a.NS + j), (mj == -INFINITY) ? 0.f : expf(mj - M), L);
     }
     const float invL = 1.f / L;
-    c0 *= invL; c1 *= invL;
-    float* cs = a.ctxs + ((size_t)slot(a, s) * a.B + b) * DD;
-    reinterpret_cast<float2*>(cs)[tid] = make_float2(c0, c1);
+    if (tid < DD / 2) {
+        c0 = 0.f; c1 = 0.f;
+        for (int j = 0; j < a.NS; ++j) {
+            const float mj = __ldcg(a.pm + b * a.NS + j);
+            const float wgt = (mj == -INFINITY) ? 0.f : expf(mj - M);
+            const float2 pj = __ldcg(reinterpret_cast<const float2*>(a.pc + ((size_t)b * a.NS + j) * DD) + tid);
+            c0 = fmaf(pj.x, wgt, c0);
+            c1 = fmaf(pj.y, wgt, c1);
+        }
+        float* cs = a.ctxs + ((size_t)slot(a, s) * a.B + b) * DD;
+        reinterpret_cast<float2*>(cs)[tid] = make_float2(c0 * invL, c1 * invL);
+    }
     for (int t = tid; t < T; t += NT) araw[t] = expf(__ldcg(araw + t) - M) * invL;
 }
 
 // ------------------------------------------------------------------------------------------------ phase D
 // Finalise step s for clip b: log-softmax row, greedy token, teacher forcing, EOS bookkeeping, next input embedding.
 __device__ void finalize_step(const DecArgs& a, int s, int b, int eos_id) {
-    __shared__ float redf[8];
-    __shared__ int redi[8];
+    __shared__ float redf[NW];
+    __shared__ int redi[NW];
     __shared__ int s_tok;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int V = a.V;
@@ -264,7 +265,7 @@ __device__ void finalize_step(const DecArgs& a, int s, int b, int eos_id) {
     __syncthreads();
     m = redf[0]; idx = redi[0];
 #pragma unroll
-    for (int i = 1; i < 8; ++i)
+    for (int i = 1; i < NW; ++i)
         if (redf[i] > m || (redf[i] == m && redi[i] < idx)) { m = redf[i]; idx = redi[i]; }
     __syncthreads();
     float e = tid < V ? expf(x - m) : 0.f;
@@ -273,7 +274,7 @@ __device__ void finalize_step(const DecArgs& a, int s, int b, int eos_id) {
     __syncthreads();
     float sum = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) sum += redf[i];
+    for (int i = 0; i < NW; ++i) sum += redf[i];
     const float lse = m + logf(sum);
     if (tid < V) a.logp[((size_t)b * a.max_steps + s) * V + tid] = x - lse;
     if (tid == 0) {
@@ -304,26 +305,26 @@ __device__ void gru_phase(const DecArgs& a, const FwdSmem& S, int s, int bb0, in
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float4* xs4 = reinterpret_cast<const float4*>(S.xs);
     const float4* wg4 = reinterpret_cast<const float4*>(S.Wg);
-    const int base = rs_base<GR * 4>(lane);
+    const int base = rs_base<UPC * 4>(lane);
 #pragma unroll 1
     for (int cg = 0; cg < BT / 4; ++cg) {
-        if (cg * 4 >= nb) break;
-        float acc[GR * 4];
-#pragma unroll
-        for (int i = 0; i < GR * 4; ++i) acc[i] = 0.f;
+        if (cg * 4 >= nb || tid >= KM4) break;
         float4 xv[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) xv[c] = xs4[(cg * 4 + c) * XP4 + tid];
-#pragma unroll
-        for (int r = 0; r < GR; ++r) {
-            const float4 w = wg4[r * KM4 + tid];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) acc[r * 4 + c] = dot4(w, xv[c]);
-        }
-        reduce_scatter<GR * 4>(acc, lane);
         float* dst = S.red + (cg * 8 + warp) * (GR * 4) + base;
 #pragma unroll
-        for (int i = 0; i < GR * 4 / 32; ++i) dst[i] = acc[i];
+        for (int g = 0; g < 3; ++g) {                  // one gate (8 rows x 4 clips) at a time keeps the register tile small
+            float acc[UPC * 4];
+#pragma unroll
+            for (int u = 0; u < UPC; ++u) {
+                const float4 w = wg4[(g * UPC + u) * KM4 + tid];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[u * 4 + c] = dot4(w, xv[c]);
+            }
+            reduce_scatter<UPC * 4>(acc, lane);
+            dst[g * UPC * 4] = acc[0];
+        }
     }
     __syncthreads();
     if (tid < UPC * BT) {
@@ -370,33 +371,32 @@ __device__ void out_phase(const DecArgs& a, const FwdSmem& S, int qslot, int bb0
     const float4* wc4 = reinterpret_cast<const float4*>(S.Wc);
     float4 wr[CR];
 #pragma unroll
-    for (int r = 0; r < CR; ++r) wr[r] = wc4[r * KM4 + tid];
-    const int base = rs_base<64>(lane);
+    for (int r = 0; r < CR; ++r) wr[r] = wc4[r * KM4 + (tid & (KM4 - 1))];
+    const int base = rs_base<32>(lane);
 #pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
-        if (half * 8 >= nb) break;
-        float acc[64];
+    for (int cg = 0; cg < BT / 4; ++cg) {
+        if (cg * 4 >= nb || tid >= KM4) break;
+        float acc[32];                                 // 8 rows (7 real) x 4 clips
 #pragma unroll
-        for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+        for (int i = 0; i < 32; ++i) acc[i] = 0.f;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const float4 x = xs4[(half * 8 + c) * XP4 + tid];
+        for (int c = 0; c < 4; ++c) {
+            const float4 x = xs4[(cg * 4 + c) * XP4 + tid];
 #pragma unroll
-            for (int r = 0; r < CR; ++r) acc[r * 8 + c] = dot4(wr[r], x);
+            for (int r = 0; r < CR; ++r) acc[r * 4 + c] = dot4(wr[r], x);
         }
-        reduce_scatter<64>(acc, lane);
-        float* dst = S.red + (half * 8 + warp) * 64 + base;
-        dst[0] = acc[0]; dst[1] = acc[1];
+        reduce_scatter<32>(acc, lane);
+        S.red[(cg * 8 + warp) * 32 + base] = acc[0];
     }
     __syncthreads();
     if (tid < CR * BT) {
         const int rr = tid >> 4, b = tid & 15;
         const int rg = blockIdx.x * CR + rr;
         if (b < nb && rg < a.V + DA) {
-            const int half = b >> 3, c = b & 7;
+            const int cg = b >> 2, c = b & 3;
             float v = 0.f;
 #pragma unroll
-            for (int w = 0; w < 8; ++w) v += S.red[(half * 8 + w) * 64 + rr * 8 + c];
+            for (int w = 0; w < 8; ++w) v += S.red[(cg * 8 + w) * 32 + rr * 4 + c];
             if (rg < a.V) {
                 if (!only_q) a.logits[(size_t)(bb0 + b) * a.VP + rg] = v + S.bc[rr];
             } else {
@@ -410,18 +410,29 @@ __device__ void out_phase(const DecArgs& a, const FwdSmem& S, int qslot, int bb0
 __device__ void stage_xs(const DecArgs& a, const FwdSmem& S, int bb0, int nb, int parts, int hs_slot, int ctx_slot) {
     float4* xs4 = reinterpret_cast<float4*>(S.xs);
     const int tid = threadIdx.x;
-    if (parts & 1) {
-        const float* src = a.hs + ((size_t)hs_slot * a.B + bb0) * DD;
-        for (int i = tid; i < nb * (DD / 4); i += NT) xs4[(i >> 7) * XP4 + (i & 127)] = ldcg4(src + (size_t)i * 4);
+    constexpr int NLD = (BT * (DD / 4) + NT - 1) / NT;          // float4 loads per thread and part
+    const int n4 = nb * (DD / 4);
+    // all global loads of the call are issued before the first shared-memory store: one L2 round trip per part
+    float4 tk = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool has_tk = (parts & 4) && tid < nb * (DE / 4);
+    if (has_tk) tk = ldcg4(a.xbuf + (size_t)(bb0 + (tid >> 2)) * DX + (tid & 3) * 4);
+#pragma unroll
+    for (int part = 0; part < 2; ++part) {
+        if (!(parts & (1 << part))) continue;
+        const float* src = part == 0 ? a.hs + ((size_t)hs_slot * a.B + bb0) * DD : a.ctxs + ((size_t)ctx_slot * a.B + bb0) * DD;
+        float4 v[NLD];
+#pragma unroll
+        for (int j = 0; j < NLD; ++j) {
+            const int i = tid + j * NT;
+            if (i < n4) v[j] = ldcg4(src + (size_t)i * 4);
+        }
+#pragma unroll
+        for (int j = 0; j < NLD; ++j) {
+            const int i = tid + j * NT;
+            if (i < n4) xs4[(i >> 7) * XP4 + part * 128 + (i & 127)] = v[j];
+        }
     }
-    if (parts & 2) {
-        const float* src = a.ctxs + ((size_t)ctx_slot * a.B + bb0) * DD;
-        for (int i = tid; i < nb * (DD / 4); i += NT) xs4[(i >> 7) * XP4 + 128 + (i & 127)] = ldcg4(src + (size_t)i * 4);
-    }
-    if (parts & 4) {
-        for (int i = tid; i < nb * (DE / 4); i += NT)
-            xs4[(i >> 2) * XP4 + 256 + (i & 3)] = ldcg4(a.xbuf + (size_t)(bb0 + (i >> 2)) * DX + (i & 3) * 4);
-    }
+    if (has_tk) xs4[(tid >> 2) * XP4 + 256 + (tid & 3)] = tk;
 }
 
 __global__ void __launch_bounds__(NT, 1) dec_persist_fwd_kernel(DecArgs a, int eos_id) {
@@ -460,7 +471,7 @@ __global__ void __launch_bounds__(NT, 1) dec_persist_fwd_kernel(DecArgs a, int e
         const int rg = cta * CR + tid;
         S.bc[tid] = (tid < CR && rg < a.V) ? a.b_out[rg] : 0.f;
     }
-    S.vv[tid] = a.v[tid];
+    if (tid < DA) S.vv[tid] = a.v[tid];
     for (int i = tid; i < BT * XP; i += NT) S.xs[i] = 0.f;
     __syncthreads();
 
@@ -544,10 +555,11 @@ struct BwdSmem {
     float* WT;      // [RPB+1][K3]  rows of W_ih^T (context / token inputs) on CTAs < 32, of W_hh^T on CTAs >= 32
     float* U;       // [BT][K3]     gate gradients of the staged clips (P2) | scratch of P1 and P3
     float* red;     // [4][12][64] cross-warp reduction scratch + [12][BT] for the token row
-    float* Wq;      // [UPC][DA]    W_h^T rows of this CTA's hidden units
+    float* Wq;      // [UPC*2][QP]  W_h^T rows of this CTA's hidden units, split in two 128-column halves (padded pitch)
 };
+constexpr int QP = 132;                // pitch of the half-rows: 16 half-rows hit 8 distinct 16-byte bank groups
 constexpr int BWD_RED_FLOATS = 4 * 12 * 64 + 12 * BT;
-constexpr int BWD_SMEM_FLOATS = (RPB + 1) * K3 + BT * K3 + BWD_RED_FLOATS + UPC * DA;
+constexpr int BWD_SMEM_FLOATS = (RPB + 1) * K3 + BT * K3 + BWD_RED_FLOATS + UPC * 2 * 132;
 
 // ---- P1: dh of this CTA's 8 hidden units (all clips), GRU gate gradients -> dgi_all / dgh_all / dh*z
 __device__ void bwd_gates_phase(const DecArgs& a, const BwdSmem& S, int s, int bb0, int nb) {
@@ -557,14 +569,14 @@ __device__ void bwd_gates_phase(const DecArgs& a, const BwdSmem& S, int s, int b
     __syncthreads();
     if (!last_step)
         for (int i = tid; i < nb * (DA / 4); i += NTB)
-            reinterpret_cast<float4*>(dqs)[i] = ldcg4(a.dq_all + ((size_t)(s + 1) * a.B + bb0) * DA + (size_t)i * 4);
+            *reinterpret_cast<float4*>(dqs + (i >> 5) * QP + (i & 31) * 4) = ldcg4(a.dq_all + ((size_t)(s + 1) * a.B + bb0) * DA + (size_t)i * 4);
     __syncthreads();
     if (tid < 2 * UPC * BT) {
         const int b = tid >> 4, u = (tid >> 1) & 7, half = tid & 1;
         float dhq = 0.f;
         if (!last_step && b < nb) {
-            const float4* w4 = reinterpret_cast<const float4*>(S.Wq + u * DA + half * 128);
-            const float4* d4 = reinterpret_cast<const float4*>(dqs + b * DA + half * 128);
+            const float4* w4 = reinterpret_cast<const float4*>(S.Wq + (u * 2 + half) * QP);
+            const float4* d4 = reinterpret_cast<const float4*>(dqs + (b * 2 + half) * QP);
 #pragma unroll 8
             for (int i = 0; i < 32; ++i) dhq += dot4(w4[i], d4[i]);
         }
@@ -597,24 +609,43 @@ __device__ void bwd_gemv_phase(const DecArgs& a, const BwdSmem& S, int s, int bb
     const bool has_tok = cta < DE;
     const float* src = (is_dx ? a.dgi_all : a.dgh_all) + ((size_t)s * a.B + bb0) * K3;
     __syncthreads();
-    for (int i = tid; i < nb * (K3 / 4); i += NTB) reinterpret_cast<float4*>(S.U)[i] = ldcg4(src + (size_t)i * 4);
+    {
+        // NTB == K3/4: thread tid moves float4 column tid of every staged clip; 8 loads in flight per thread
+        float4* u4 = reinterpret_cast<float4*>(S.U);
+#pragma unroll
+        for (int b0 = 0; b0 < BT; b0 += 8) {
+            float4 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (b0 + j < nb) v[j] = ldcg4(src + ((size_t)(b0 + j) * (K3 / 4) + tid) * 4);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (b0 + j < nb) u4[(b0 + j) * (K3 / 4) + tid] = v[j];
+        }
+    }
     __syncthreads();
     const float4* x4 = reinterpret_cast<const float4*>(S.U);
     const float4* w4 = reinterpret_cast<const float4*>(S.WT);
-    const int base = rs_base<RPB * 4>(lane);
+    const int base = rs_base<32>(lane);
     float* tokred = S.red + 4 * 12 * 64;                // [12][BT]
 #pragma unroll 1
     for (int cg = 0; cg < BT / 4; ++cg) {
         if (cg * 4 >= nb) break;
-        float acc[RPB * 4];
         float4 xv[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) xv[c] = x4[(cg * 4 + c) * (K3 / 4) + tid];
+        float* dst = S.red + (cg * 12 + warp) * 64 + base;
 #pragma unroll
-        for (int r = 0; r < RPB; ++r) {
-            const float4 w = w4[r * (K3 / 4) + tid];
+        for (int h = 0; h < 2; ++h) {                  // 8 rows x 4 clips at a time keeps the register tile small
+            float acc[32];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) acc[r * 4 + c] = dot4(w, xv[c]);
+            for (int r = 0; r < 8; ++r) {
+                const float4 w = w4[(h * 8 + r) * (K3 / 4) + tid];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[r * 4 + c] = dot4(w, xv[c]);
+            }
+            reduce_scatter<32>(acc, lane);
+            dst[h * 32] = acc[0];
         }
         float tk[4] = {0.f, 0.f, 0.f, 0.f};
         if (has_tok) {
@@ -622,9 +653,6 @@ __device__ void bwd_gemv_phase(const DecArgs& a, const BwdSmem& S, int s, int bb
 #pragma unroll
             for (int c = 0; c < 4; ++c) tk[c] = warp_sum(dot4(w, xv[c]));
         }
-        reduce_scatter<RPB * 4>(acc, lane);
-        float* dst = S.red + (cg * 12 + warp) * 64 + base;
-        dst[0] = acc[0]; dst[1] = acc[1];
         if (has_tok && lane < 4) tokred[warp * BT + cg * 4 + lane] = lane == 0 ? tk[0] : lane == 1 ? tk[1] : lane == 2 ? tk[2] : tk[3];
     }
     __syncthreads();
@@ -695,37 +723,33 @@ __device__ void bwd_attn_item(const DecArgs& a, const BwdSmem& S, int s, int b, 
     float* dsrow = a.ds_all + sb * T;
     const float vk[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
     const float qk[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-    constexpr int FU = 2;
-    for (int tb = t0 + warp * FU; tb < t1; tb += 12 * FU) {
-        float4 en[FU][4], e0[FU], e1[FU];
-        float aw[FU];
+    struct Rows { float4 en[4], e0, e1; float aw; };
+    auto load = [&](Rows& r, int t) {
+        const float4* e4 = reinterpret_cast<const float4*>(a.enc + ((size_t)b * T + t) * DD);
 #pragma unroll
-        for (int u = 0; u < FU; ++u) {
-            const int t = min(tb + u, t1 - 1);
-            const float4* e4 = reinterpret_cast<const float4*>(a.enc + ((size_t)b * T + t) * DD);
+        for (int i = 0; i < 4; ++i) r.en[i] = __ldg(e4 + i * 32 + lane);
+        const float4* ep = reinterpret_cast<const float4*>(a.Ep + ((size_t)b * T + t) * DA);
+        r.e0 = __ldg(ep + lane); r.e1 = __ldg(ep + 32 + lane);
+        r.aw = at[t];
+    };
+    Rows cur, nxt;
+    int t = t0 + warp;
+    if (t < t1) load(cur, t);
+    for (; t < t1; t += NTB / 32) {                   // one frame per warp iteration, the next one already in flight
+        if (t + NTB / 32 < t1) load(nxt, t + NTB / 32);
+        float da = 0.f;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) en[u][i] = __ldg(e4 + i * 32 + lane);
-            const float4* ep = reinterpret_cast<const float4*>(a.Ep + ((size_t)b * T + t) * DA);
-            e0[u] = __ldg(ep + lane); e1[u] = __ldg(ep + 32 + lane);
-            aw[u] = at[t];
+        for (int i = 0; i < 4; ++i) da += dot4(dcr[i], cur.en[i]);
+        da = warp_sum(da);
+        const float ds = cur.aw * (da - c0);
+        if (lane == 0) dsrow[t] = ds;
+        const float ev[8] = {cur.e0.x, cur.e0.y, cur.e0.z, cur.e0.w, cur.e1.x, cur.e1.y, cur.e1.z, cur.e1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float uu = tanh_fast(qk[i] + ev[i]);
+            dq[i] = fmaf(ds * vk[i], 1.f - uu * uu, dq[i]);
         }
-#pragma unroll
-        for (int u = 0; u < FU; ++u) {
-            const int t = tb + u;
-            float da = 0.f;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) da += dot4(dcr[i], en[u][i]);
-            da = warp_sum(da);
-            if (t >= t1) continue;            // warp-uniform
-            const float ds = aw[u] * (da - c0);
-            if (lane == 0) dsrow[t] = ds;
-            const float ev[8] = {e0[u].x, e0[u].y, e0[u].z, e0[u].w, e1[u].x, e1[u].y, e1[u].z, e1[u].w};
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float uu = tanh_fast(qk[i] + ev[i]);
-                dq[i] = fmaf(ds * vk[i], 1.f - uu * uu, dq[i]);
-            }
-        }
+        cur = nxt;
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) { accq[warp * DA + lane * 4 + i] = dq[i]; accq[warp * DA + 128 + lane * 4 + i] = dq[4 + i]; }
@@ -776,7 +800,8 @@ __global__ void __launch_bounds__(NTB, 1) dec_persist_bwd_kernel(DecArgs a) {
             }
             reinterpret_cast<float4*>(S.WT)[i] = w;
         }
-        for (int i = tid; i < UPC * DA; i += NTB) S.Wq[i] = a.W_hT[(size_t)(cta * UPC + i / DA) * DA + (i % DA)];
+        for (int i = tid; i < UPC * DA; i += NTB)
+            S.Wq[(i >> 7) * QP + (i & 127)] = a.W_hT[(size_t)cta * UPC * DA + i];      // half-row (u*2+half) = i / 128
     }
     __syncthreads();
     const int B = a.B;
@@ -802,14 +827,15 @@ __global__ void __launch_bounds__(NTB, 1) dec_persist_bwd_kernel(DecArgs a) {
         const int bb0 = ch * BT, nb = min(BT, B - bb0);
         float* dqs = S.U;
         __syncthreads();
-        for (int i = tid; i < nb * (DA / 4); i += NTB) reinterpret_cast<float4*>(dqs)[i] = ldcg4(a.dq_all + (size_t)bb0 * DA + (size_t)i * 4);
+        for (int i = tid; i < nb * (DA / 4); i += NTB)
+            *reinterpret_cast<float4*>(dqs + (i >> 5) * QP + (i & 31) * 4) = ldcg4(a.dq_all + (size_t)bb0 * DA + (size_t)i * 4);
         __syncthreads();
         if (tid < 2 * UPC * BT) {
             const int b = tid >> 4, u = (tid >> 1) & 7, half = tid & 1;
             float dhq = 0.f;
             if (b < nb) {
-                const float4* w4 = reinterpret_cast<const float4*>(S.Wq + u * DA + half * 128);
-                const float4* d4 = reinterpret_cast<const float4*>(dqs + b * DA + half * 128);
+                const float4* w4 = reinterpret_cast<const float4*>(S.Wq + (u * 2 + half) * QP);
+                const float4* d4 = reinterpret_cast<const float4*>(dqs + (b * 2 + half) * QP);
 #pragma unroll 8
                 for (int i = 0; i < 32; ++i) dhq += dot4(w4[i], d4[i]);
             }
@@ -906,8 +932,7 @@ PA2S_API int pa2s_note_decoder_fwd_persist(void* stream, const void* args, int s
     cudaStream_t st = (cudaStream_t)stream;
     if (a.B <= 0 || a.S <= 0) return 0;
     if (a.V + DA > PG * CR || a.sync == nullptr) return -2;
-    a.tile_pad = (a.tile + 3) / 4 * 4;
-    const size_t smem = (size_t)(FWD_SMEM_FLOATS + a.tile_pad) * sizeof(float);
+    const size_t smem = (size_t)FWD_SMEM_FLOATS * sizeof(float);
     PA2S_TRY(cudaFuncSetAttribute(dec_persist_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dec_persist_init_kernel<<<ceil_div(a.B * DE, 128), 128, 0, st>>>(a, sos_id);
     PA2S_CHECK_LAST();

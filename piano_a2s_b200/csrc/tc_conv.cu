@@ -1,15 +1,16 @@
 // 3x3 convolution (ConvStack conv2..conv4, models.py:481-498, :526-534) as an implicit GEMM on the tcgen05 tensor cores,
 // forward and data-gradient, with the neighbouring BatchNorm/ReLU work fused into the operand load / epilogue.
 //
-// Formulation.  Activations are (B,T,F,C) fp32, channels innermost.  Per clip the output positions are linearised over a
-// width-padded grid q = t*(F+2) + (f+1); one tile = 128 consecutive q = the 128 rows (TMEM lanes) of a UMMA accumulator.
-// For tap (ky,kx) the A operand row i is the input pixel at q + (ky-1)*(F+2) + (kx-1): a constant shift of the row index.
-// The loader warps therefore stage, per tile, three "windows" (one per ky) of 130 consecutive positions as
-// bf16 planes [8-channel group][position][8 ch] at a 16-byte pitch.  In that no-swizzle K-major UMMA layout the row index
-// advances by exactly 16 bytes, so the three kx taps of a window are the SAME shared-memory bytes addressed with a
-// descriptor start address shifted by kx*16 bytes: 9 taps are fed from 3 staged windows, no im2col copy.
-// Halo positions (f = -1, F and t = -1, T) are staged as zeros and their output rows are simply not stored
-// (2 of every F+2 rows are wasted).
+// Formulation.  Activations are (B,T,F,C) fp32, channels innermost.  A frame row is padded to fp = f+1 in [0, F+2) and cut
+// into blocks of 128 padded positions; one tile = (clip b, row t, block fb) = the 128 rows (TMEM lanes) of a UMMA
+// accumulator.  For tap (ky,kx) the A operand row i is the input pixel (t+ky-1, fp+kx-1).  The loader warps stage
+// "windows": 130 consecutive padded positions (fb*128-1 ...) of ONE input row as bf16 planes
+// [8-channel group][position][8 ch] at a 16-byte pitch.  In that no-swizzle K-major UMMA layout the row index advances
+// by exactly 16 bytes, so the three kx taps of a window are the SAME shared-memory bytes addressed with a descriptor
+// start address shifted by kx*16 bytes.  A CTA walks DOWN a strip (b, fb): tile t uses the windows of rows t-1, t, t+1,
+// so consecutive tiles share two of their three windows and every input pixel is loaded, transformed and split ONCE
+// per strip: 9 taps are fed from one new window per tile, no im2col copy.
+// Halo positions (fp = 0, F+1 and t = -1, T) are staged as zeros and their output rows are simply not stored.
 //
 // Precision: fp32 activations/weights are split into bf16 hi + lo and accumulated in TMEM (fp32) as
 // hi*hi + hi*lo + lo*hi (nsplit = 3), or hi*hi only (nsplit = 1).
@@ -25,10 +26,38 @@ using namespace tc;
 constexpr int BM = 128;
 constexpr int WENT = 130;          // window entries used (128 rows + kx in {0,1,2})
 constexpr int WPIX = 137;          // plane pitch in 16-byte units (odd mod 8: conflict-free plane-strided stores)
-constexpr int NWIN = 4;            // window ring slots
+constexpr int NWIN = 5;            // window ring slots: three rows in use by the MMAs + two being filled
 constexpr int N_EPI_WARPS = 4, N_LOAD_WARPS = 8;
 constexpr int NTHREADS = (N_EPI_WARPS + 1 + N_LOAD_WARPS) * 32;
 constexpr int N_LOAD_THREADS = N_LOAD_WARPS * 32;
+
+// A CTA owns the contiguous range [begin, end) of the linearised (strip, row) space, strip = b * nfb + fb; it is
+// walked as chunks of consecutive rows of one strip.
+struct Chunk { int b, fb, t0, n; };            // rows [t0, t0+n) of strip (b, fb)
+struct Walk {
+    long long pos, end; int T, nfb;
+    __device__ __forceinline__ void init(int B, int T_, int F) {
+        T = T_; nfb = (F + 2 + BM - 1) / BM;
+        const long long total = (long long)B * nfb * T;
+        const long long per = (total + gridDim.x - 1) / gridDim.x;
+        pos = (long long)blockIdx.x * per;
+        end = pos + per < total ? pos + per : total;
+    }
+    __device__ __forceinline__ bool next(Chunk& c) {
+        if (pos >= end) return false;
+        const int strip = (int)(pos / T);
+        c.t0 = (int)(pos - (long long)strip * T);
+        c.b = strip / nfb; c.fb = strip - c.b * nfb;
+        const long long left = end - pos;
+        c.n = (int)(left < (long long)(T - c.t0) ? left : (long long)(T - c.t0));
+        pos += c.n;
+        return true;
+    }
+};
+static int conv_grid(int B, int T, int F) {
+    const long long total = (long long)B * ((F + 2 + BM - 1) / BM) * T;
+    return (int)(total < 148 ? total : 148);
+}
 
 struct TcConvArgs {
     const float* X;        // mode 0: raw input (B,T,F,CIN);  mode 1: G = dL/d(relu out) of this layer (B,T,F,CIN=channels of dy)
@@ -75,10 +104,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(TcConvArgs a) {
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(16) float cst[7][64];        // per-channel transform constants (mode 0: scale, shift; mode 1: zs,zb,mean,invstd,k1,k2,k3)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int T = a.T, F = a.F, PWD = F + 2;
-    const uint32_t pwd_magic = (uint32_t)((0x100000000ULL + (uint64_t)PWD - 1) / (uint64_t)PWD);   // w / PWD == umulhi(w, magic) for w < 2^32/PWD
-    const int tiles_per_clip = (T * PWD + BM - 1) / BM;
-    const long long ntiles = (long long)a.B * tiles_per_clip;
+    const int T = a.T, F = a.F;
     if (tid < 64) {
         const bool in = tid < CIN;
         if (MODE == 0) {
@@ -108,44 +134,47 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(TcConvArgs a) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
+    Walk walk;
+    walk.init(a.B, T, F);
+    Chunk ch;
 
     if (warp < N_EPI_WARPS) {
         // ================================================================================= epilogue
         float ssum[2] = {0.f, 0.f}, ssq[2] = {0.f, 0.f};              // lane c keeps channels c and c+32
         uint32_t it = 0;
-        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-            const int b = (int)(tile / tiles_per_clip);
-            const int q = (int)(tile % tiles_per_clip) * BM + warp * 32 + lane;
-            const int t = q / PWD, fp = q - t * PWD;
-            const bool valid = (t < T) && (fp >= 1) && (fp <= F);
-            const int acc = it & 1;
-            mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
-            tc_fence_after();
-            float* yrow = a.Y + (((size_t)b * T + t) * F + (fp - 1)) * COUT;
+        while (walk.next(ch)) {
+            const int fp = ch.fb * BM + warp * 32 + lane;
+            const bool valid = (fp >= 1) && (fp <= F);
+            for (int k = 0; k < ch.n; ++k, ++it) {
+                const int acc = it & 1;
+                mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
+                tc_fence_after();
+                float* yrow = a.Y + (((size_t)ch.b * T + ch.t0 + k) * F + (fp - 1)) * COUT;
 #pragma unroll
-            for (int c0 = 0; c0 < COUTP; c0 += 16) {
-                float v[16];
-                tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * TM_COLS + c0), v);
-                if (valid) {
+                for (int c0 = 0; c0 < COUTP; c0 += 16) {
+                    float v[16];
+                    tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * TM_COLS + c0), v);
+                    if (valid) {
 #pragma unroll
-                    for (int qd = 0; qd < 4; ++qd)
-                        if (c0 + 4 * qd < COUT)
-                            reinterpret_cast<float4*>(yrow + c0)[qd] = make_float4(v[4 * qd], v[4 * qd + 1], v[4 * qd + 2], v[4 * qd + 3]);
-                }
-                if (a.partial != nullptr) {
+                        for (int qd = 0; qd < 4; ++qd)
+                            if (c0 + 4 * qd < COUT)
+                                reinterpret_cast<float4*>(yrow + c0)[qd] = make_float4(v[4 * qd], v[4 * qd + 1], v[4 * qd + 2], v[4 * qd + 3]);
+                    }
+                    if (a.partial != nullptr) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int c = c0 + i;
-                        if (c < COUT) {
-                            const float x = valid ? v[i] : 0.f;
-                            const float s1 = warp_sum(x), s2 = warp_sum(x * x);
-                            if (lane == (c & 31)) { ssum[c >> 5] += s1; ssq[c >> 5] += s2; }
+                        for (int i = 0; i < 16; ++i) {
+                            const int c = c0 + i;
+                            if (c < COUT) {
+                                const float x = valid ? v[i] : 0.f;
+                                const float s1 = warp_sum(x), s2 = warp_sum(x * x);
+                                if (lane == (c & 31)) { ssum[c >> 5] += s1; ssq[c >> 5] += s2; }
+                            }
                         }
                     }
                 }
+                tc_fence_before();
+                mbar_arrive(&tempty_bar[acc]);
             }
-            tc_fence_before();
-            mbar_arrive(&tempty_bar[acc]);
         }
         if (a.partial != nullptr) {
             float* pr = a.partial + ((size_t)blockIdx.x * N_EPI_WARPS + warp) * 2 * COUT;
@@ -157,20 +186,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(TcConvArgs a) {
         }
     } else if (warp == N_EPI_WARPS) {
         // ================================================================================= MMA issuer (warp-uniform)
-        {
-            const uint32_t idesc = make_idesc(BM, COUTP, 0, 0);
-            const uint32_t w_base = smem_u32(wsm), win_base = smem_u32(win);
-            const uint64_t wdesc0 = make_desc(w_base, COUTP * 16, 128);
-            uint32_t it = 0, wi = 0;
-            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const uint32_t idesc = make_idesc(BM, COUTP, 0, 0);
+        const uint32_t w_base = smem_u32(wsm), win_base = smem_u32(win);
+        const uint64_t wdesc0 = make_desc(w_base, COUTP * 16, 128);
+        uint32_t it = 0, wbase = 0;                                   // wbase = ring index of the chunk's first window (row t0-1)
+        while (walk.next(ch)) {
+            for (int k = 0; k < ch.n; ++k, ++it) {
                 const int acc = it & 1;
                 mbar_wait(&tempty_bar[acc], ((it >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TM_COLS);
-                for (int ky = 0; ky < 3; ++ky, ++wi) {
+                const bool last = (k == ch.n - 1);
+                for (int ky = 0; ky < 3; ++ky) {
+                    const uint32_t wi = wbase + k + ky;               // window of input row t0 + k + ky - 1
                     const int slot = wi % NWIN;
-                    mbar_wait(&full_bar[slot], (wi / NWIN) & 1);
-                    tc_fence_after();
+                    if (k == 0 || ky == 2) {                          // the two older windows were awaited by the previous tile
+                        mbar_wait(&full_bar[slot], (wi / NWIN) & 1);
+                        tc_fence_after();
+                    }
                     const uint64_t dah0 = make_desc(win_base + slot * SLOT_BYTES, PLANE_BYTES, 128);
                     const uint64_t dal0 = desc_advance(dah0, NG * PLANE_BYTES);
                     const uint64_t dbw = desc_advance(wdesc0, (uint32_t)(ky * 3 * KS * 2 * WBLK_BYTES));
@@ -190,12 +223,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(TcConvArgs a) {
                                 }
                             }
                         }
-                        tc_commit(&empty_bar[slot]);
+                        // a window is free once the last tile that reads it has been issued: row t0+k-1 after tile k,
+                        // all three after the chunk's last tile
+                        if (ky == 0 || last) tc_commit(&empty_bar[slot]);
                         if (ky == 2) tc_commit(&tfull_bar[acc]);
                     }
                     __syncwarp();
                 }
             }
+            wbase += ch.n + 2;
         }
     } else {
         // ================================================================================= window loaders
@@ -208,10 +244,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(TcConvArgs a) {
         constexpr bool HALF_LAST = (CIN % 8) != 0;      // CIN = 20: the last real plane holds 4 channels only
         struct Raw { float4 v[NU][NV]; bool ok[NU]; };
         Raw cur, nxt;
-        auto issue = [&](Raw& r, long long tile, int ky) {
-            const int b = (int)(tile / tiles_per_clip);
-            const int q0 = (int)(tile % tiles_per_clip) * BM;
-            const int w0 = q0 + (ky - 1) * PWD - 1;                     // padded-linear position of window entry 0
+        // window = the 130 padded positions fb*128-1 .. fb*128+128 of input row trow of clip b
+        auto issue = [&](Raw& r, int b, int fb, int trow) {
+            const bool row_ok = trow >= 0 && trow < T;
+            const size_t rowbase = ((size_t)b * T + (row_ok ? trow : 0)) * F;
 #pragma unroll
             for (int i = 0; i < NU; ++i) {
                 const int u = ltid + i * N_LOAD_THREADS;
@@ -220,12 +256,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(TcConvArgs a) {
                 for (int k = 0; k < NV; ++k) r.v[i][k] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (u >= WENT * NGR) continue;
                 const int j = u / NGR, g = u - j * NGR;
-                const int w = w0 + j;
-                if (w < 0) continue;
-                const int t = (int)__umulhi((uint32_t)w, pwd_magic), fp = w - t * PWD;
-                if (t >= T || fp < 1 || fp > F) continue;
+                const int fp = fb * BM - 1 + j;
+                if (!row_ok || fp < 1 || fp > F) continue;
                 r.ok[i] = true;
-                const size_t base = (((size_t)b * T + t) * F + (fp - 1)) * CIN + 8 * g;
+                const size_t base = (rowbase + (fp - 1)) * CIN + 8 * g;
                 const bool half = HALF_LAST && (g == NGR - 1);
                 r.v[i][0] = __ldg(reinterpret_cast<const float4*>(a.X + base));
                 if (!half) r.v[i][1] = __ldg(reinterpret_cast<const float4*>(a.X + base) + 1);
@@ -281,21 +315,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(TcConvArgs a) {
                 if (want_lo) *reinterpret_cast<uint4*>(lo_base + off) = lo;
             }
         };
-        long long tile = blockIdx.x;
-        int ky = 0;
+        // flattened window sequence of this CTA: for every chunk the rows t0-1 .. t0+n
+        Chunk nch;
+        bool have = walk.next(ch);
+        int j = 0;                                                    // window j of chunk ch = input row t0 - 1 + j
         uint32_t wi = 0;
-        if (tile < ntiles) issue(cur, tile, 0);
-        while (tile < ntiles) {
-            long long ntile = tile; int nky = ky + 1;
-            if (nky == 3) { nky = 0; ntile += gridDim.x; }
-            if (ntile < ntiles) issue(nxt, ntile, nky);
+        if (have) issue(cur, ch.b, ch.fb, ch.t0 - 1);
+        while (have) {
+            // successor window
+            bool nhave = true; int nj = j + 1; nch = ch;
+            if (nj == ch.n + 2) { nj = 0; nhave = walk.next(nch); }
+            if (nhave) issue(nxt, nch.b, nch.fb, nch.t0 - 1 + nj);
             const int slot = wi % NWIN;
             mbar_wait(&empty_bar[slot], ((wi / NWIN) & 1) ^ 1);
             uint8_t* hi_base = win + (size_t)slot * SLOT_BYTES;
             convert_store(cur, hi_base, hi_base + NG * PLANE_BYTES);
             fence_proxy_async();
             mbar_arrive(&full_bar[slot]);
-            cur = nxt; tile = ntile; ky = nky; ++wi;
+            cur = nxt; ch = nch; j = nj; have = nhave; ++wi;
         }
     }
 
