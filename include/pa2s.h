@@ -47,6 +47,21 @@ PA2S_API int pa2s_gemm_tc(void* stream, int transA, int transB, int M, int N, in
                           const float* t_scale, const float* t_shift, int t_period, int t_relu, int t_on_b,
                           int splitk, int nsplit);
 
+/* TMA-fed tcgen05 GEMM on pre-split bf16 operands (tc_gemm_tma.cu).  pa2s_split_bf16 writes an fp32 matrix (optionally through
+ * relu?(x*t_scale[c%t_period]+t_shift[c%t_period]), c = column) as 1..3 bf16 pieces x ~ p0+p1(+p2): piece p, batch b, row r at
+ * dst + p*piece_stride + b*batch_stride_dst + r*ld_dst (elements; all multiples of 8).  pa2s_gemm_bf16_tma contracts
+ * C[b] (+)= sum_{i+j<=max(nA,nB)-1} A_i[b] B_j[b]^T with fp32 TMEM accumulation; an operand is stored [mn][k] (x_mn = 0) or
+ * [k][mn] (x_mn = 1) with row pitch x_ld, which may be smaller than the row length (overlapping frames: the VQT filterbank
+ * contraction, utilities.py:246).  x_batch_stride = 0 shares the operand between batches.  Replaces the same reference
+ * lines as pa2s_gemm_f32. */
+PA2S_API int pa2s_split_bf16(void* stream, const float* src, long long rows, long long cols, long long ld_src, long long batch_stride_src,
+                             void* dst, long long ld_dst, long long piece_stride, long long batch_stride_dst, int npieces, int batch,
+                             const float* t_scale, const float* t_shift, int t_period, int t_relu);
+PA2S_API int pa2s_gemm_bf16_tma(void* stream, int M, int N, int K,
+                                const void* A, long long a_ld, long long a_piece_stride, long long a_batch_stride, int a_pieces, int a_mn,
+                                const void* B, long long b_ld, long long b_piece_stride, long long b_batch_stride, int b_pieces, int b_mn,
+                                float* C, long long ldc, long long strideC, const float* bias, int atomic, int batch, int splitk);
+
 /* ---- VQT front end (utilities.py:246-253) -------------------------------------------------------------------
  * C: (nclips*rows_per_clip, 2*nb) filterbank responses (re,im interleaved).  Writes
  * out = amplitude_to_db(|V|, ref=max over the clip, amin=1e-5, top_db=80)/80 + 1 as (nclips, rows_per_clip, nb). */

@@ -1,14 +1,21 @@
-"""Builds libpa2s.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+"""Builds libpa2s.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).  Sources are compiled to objects in
+parallel (only the stale ones) and linked into one shared library."""
 import os
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libpa2s.so")
-SOURCES = ["gemm.cu", "tc_gemm.cu", "tc_conv.cu", "conv.cu", "misc.cu", "gru.cu", "decoder.cu", "dec_persist.cu"]
+SOURCES = ["gemm.cu", "tc_gemm.cu", "tc_gemm_tma.cu", "tc_conv.cu", "conv.cu", "misc.cu", "gru.cu", "decoder.cu", "dec_persist.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-shared"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
+
+
+def _headers_mtime():
+    return max(os.path.getmtime(os.path.join(CSRC, f)) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
 
 
 def _stale():
@@ -23,7 +30,23 @@ def build(force=False, verbose=False):
     if not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + os.environ.get("PA2S_NVCC_DEFS", "").split() + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    defs = os.environ.get("PA2S_NVCC_DEFS", "").split()
+    os.makedirs(OBJ, exist_ok=True)
+    hdr_t = max(_headers_mtime(), os.path.getmtime(os.path.abspath(__file__)))
+    srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+
+    def compile_one(s):
+        src, obj = os.path.join(CSRC, s), os.path.join(OBJ, s[:-3] + ".o")
+        if not force and not defs and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_t):
+            return obj
+        cmd = [nvcc] + NVCC_FLAGS + defs + ["-c", src, "-o", obj]
+        if verbose:
+            print(" ".join(cmd), file=sys.stderr)
+        subprocess.run(cmd, check=True, cwd=CSRC)
+        return obj
+    with ThreadPoolExecutor(max_workers=min(len(srcs), os.cpu_count() or 4)) as ex:
+        objs = list(ex.map(compile_one, srcs))
+    cmd = [nvcc, "-shared", "-Xcompiler", "-fPIC", "-o", LIB] + objs
     if verbose:
         print(" ".join(cmd), file=sys.stderr)
     subprocess.run(cmd, check=True, cwd=CSRC)

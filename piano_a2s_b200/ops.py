@@ -79,7 +79,7 @@ def set_precision(train=None, eval=None):
     """Contraction precision used by modules in train() / eval() mode."""
     for k, v in (("train", train), ("eval", eval)):
         if v is not None:
-            assert v in ("fp32", "bf16x3", "bf16")
+            assert v in ("fp32", "bf16x3", "bf16", "bf16x6")
             PRECISION[k] = v
 
 
@@ -92,7 +92,7 @@ class use_precision:
     forward and remember it for their backward."""
 
     def __init__(self, prec):
-        assert prec in ("fp32", "bf16x3", "bf16")
+        assert prec in ("fp32", "bf16x3", "bf16", "bf16x6")
         self.prec = prec
 
     def __enter__(self):
@@ -115,24 +115,80 @@ def module_precision(module):
     return use_precision(PRECISION["train" if module.training else "eval"])
 
 
+class Bf16Operand:
+    """An fp32 matrix [rows][cols] (x batch) held as 1..3 bf16 pieces for the TMA-fed tensor-core GEMM (tc_gemm_tma.cu)."""
+    __slots__ = ("buf", "rows", "cols", "ld", "npieces", "batch", "piece_stride", "batch_stride")
+
+    def __init__(self, buf, rows, cols, ld, npieces, batch, piece_stride, batch_stride):
+        self.buf, self.rows, self.cols, self.ld, self.npieces, self.batch = buf, rows, cols, ld, npieces, batch
+        self.piece_stride, self.batch_stride = piece_stride, batch_stride
+
+
+def npieces_for(prec):
+    return {"bf16": 1, "bf16x3": 2, "bf16x6": 3}[prec]
+
+
+def split_operand(src, rows, cols, ld_src, *, off=0, batch=1, batch_stride=0, npieces=2, t_scale=None, t_shift=None, t_period=1,
+                  t_relu=False):
+    """fp32 storage `src` (+ element offset) viewed as `batch` matrices [rows][cols] of row pitch ld_src -> Bf16Operand."""
+    ld = (cols + 7) // 8 * 8
+    shared = batch > 1 and batch_stride == 0
+    nb = 1 if shared else batch
+    buf = torch.empty(nb, npieces, rows, ld, device=src.device, dtype=torch.bfloat16)
+    lib.pa2s_split_bf16(stream(), ctypes.c_void_p(src.data_ptr() + off * 4), rows, cols, ld_src, batch_stride, ptr(buf), ld, rows * ld,
+                        npieces * rows * ld, npieces, nb, ptr(t_scale), ptr(t_shift), t_period, int(t_relu))
+    return Bf16Operand(buf, rows, cols, ld, npieces, batch, rows * ld, 0 if (shared or batch == 1) else npieces * rows * ld)
+
+
+def gemm_bf16(Aop, a_mn, Bop, b_mn, C, M, N, K, *, ldc, bias=None, atomic=False, batch=1, strideC=0, splitk=1, c_off=0,
+              a_ld=None, b_ld=None):
+    """C (+)= sum of piece products of two Bf16Operands (see include/pa2s.h: pa2s_gemm_bf16_tma)."""
+    lib.pa2s_gemm_bf16_tma(stream(), M, N, K,
+                           ptr(Aop.buf), a_ld or Aop.ld, Aop.piece_stride, Aop.batch_stride, Aop.npieces, int(a_mn),
+                           ptr(Bop.buf), b_ld or Bop.ld, Bop.piece_stride, Bop.batch_stride, Bop.npieces, int(b_mn),
+                           ctypes.c_void_p(C.data_ptr() + c_off * 4), ldc, strideC, ptr(bias), int(atomic), batch, splitk)
+    return C
+
+
+def _operand(X, trans, mn, k, ld, off, batch, stride, npieces, tf):
+    """Storage X described BLAS-style -> (Bf16Operand, mn_major, row pitch override).  Non-transposed A / transposed B are stored
+    [mn][k] (K-major); the other two [k][mn].  ld < row length (overlapping rows, the VQT framing) splits the underlying
+    1-D signal once and lets the tensor map stride over it."""
+    if isinstance(X, Bf16Operand):
+        return X, trans, None
+    rows, cols = (k, mn) if trans else (mn, k)
+    if ld < cols:
+        span = (rows - 1) * ld + cols
+        op = split_operand(X, 1, span, span, off=off, batch=batch, batch_stride=stride, npieces=npieces, **tf)
+        assert ld % 8 == 0
+        op.rows, op.cols = rows, cols
+        return op, trans, ld
+    return split_operand(X, rows, cols, ld, off=off, batch=batch, batch_stride=stride, npieces=npieces, **tf), trans, None
+
+
 def gemm(A, B, C, M, N, K, *, transA=False, transB=False, lda=None, ldb=None, ldc=None, bias=None, accumulate=False,
          atomic=False, batch=1, strideA=0, strideB=0, strideC=0, t_scale=None, t_shift=None, t_period=1, t_relu=False,
          t_on_b=False, splitk=1, a_off=0, b_off=0, c_off=0, precision=None, zeroed=False):
-    """C = op(A) op(B); A/B/C are tensors used as raw storage (+ element offsets), see include/pa2s.h.
+    """C = op(A) op(B); A/B/C are tensors used as raw storage (+ element offsets), see include/pa2s.h.  A / B may also be
+    pre-split Bf16Operands (tensor-core precisions only).
     `zeroed=True`: the caller guarantees C is zero-filled, so the wrapper may split K (atomic accumulation) to fill the GPU."""
     es = 4
-    pa = ctypes.c_void_p(A.data_ptr() + a_off * es)
-    pb = ctypes.c_void_p(B.data_ptr() + b_off * es)
-    pc = ctypes.c_void_p(C.data_ptr() + c_off * es)
     prec = precision or current_precision()
     use_tc = prec != "fp32" and K > 0 and 2.0 * M * N * K * batch >= TC_MIN_FLOP
     if zeroed and splitk == 1 and batch == 1:
         splitk = _tc_splitk(M, N, K) if use_tc else _auto_splitk(M, N, K)
     if use_tc:
-        lib.pa2s_gemm_tc(stream(), int(transA), int(transB), M, N, K, pa, lda, pb, ldb, pc, ldc, ptr(bias), int(accumulate),
-                         int(atomic), batch, strideA, strideB, strideC, ptr(t_scale), ptr(t_shift), t_period, int(t_relu),
-                         int(t_on_b), splitk, 3 if prec == "bf16x3" else 1)
-        return C
+        tf = dict(t_scale=t_scale, t_shift=t_shift, t_period=t_period, t_relu=t_relu)
+        none = dict(t_scale=None, t_shift=None, t_period=1, t_relu=False)
+        npc = npieces_for(prec)
+        Aop, a_mn, a_ld = _operand(A, transA, M, K, lda, a_off, batch, strideA, npc, none if (t_on_b or t_scale is None) else tf)
+        Bop, b_mn, b_ld = _operand(B, not transB, N, K, ldb, b_off, batch, strideB, npc, tf if (t_on_b and t_scale is not None) else none)
+        return gemm_bf16(Aop, a_mn, Bop, b_mn, C, M, N, K, ldc=ldc, bias=bias, atomic=atomic or accumulate, batch=batch,
+                         strideC=strideC, splitk=splitk, c_off=c_off, a_ld=a_ld, b_ld=b_ld)
+    assert not isinstance(A, Bf16Operand) and not isinstance(B, Bf16Operand)
+    pa = ctypes.c_void_p(A.data_ptr() + a_off * es)
+    pb = ctypes.c_void_p(B.data_ptr() + b_off * es)
+    pc = ctypes.c_void_p(C.data_ptr() + c_off * es)
     lib.pa2s_gemm_f32(stream(), int(transA), int(transB), M, N, K, pa, lda, pb, ldb, pc, ldc, ptr(bias), int(accumulate),
                       int(atomic), batch, strideA, strideB, strideC, ptr(t_scale), ptr(t_shift), t_period, int(t_relu),
                       int(t_on_b), splitk)

@@ -8,6 +8,8 @@ epilogue.  Filter design (host, float64, once): librosa's wavelet definition -- 
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -40,7 +42,7 @@ def design_filters(sample_rate=16000, bins_per_octave=60, n_octaves=8, gamma=20,
             raise ValueError("filter longer than the analysis window")
         G[k, j] = sig * np.sqrt(lengths[k])
     nz = np.nonzero(np.abs(G).sum(0))[0]
-    j0 = (nz.min() // 4) * 4                               # keep 16-byte alignment of the frame rows
+    j0 = (nz.min() // 8) * 8                               # keep 16-byte alignment of the (fp32 and bf16) frame rows
     j1 = ((nz.max() + 1 + 15) // 16) * 16
     j1 = min(max(j1, j0 + 16), window)
     W = np.empty((2 * n_bins, j1 - j0), dtype=np.float32)
@@ -60,8 +62,10 @@ class VQT(torch.nn.Module):
         self.j0 = j0
         self.register_buffer("filters", torch.from_numpy(W), persistent=False)
         # bins 80 dB below the clip maximum must keep ~1e-3 relative accuracy through the dB epilogue, which a bf16x3
-        # product (error ~5e-6 of the *dominant* terms) cannot give: the fp32 configuration contracts on the FFMA pipe.
-        self.precision = "fp32"
+        # product (error ~5e-6 of the *dominant* terms) cannot give: audio and filters are split into THREE bf16 pieces
+        # and the six leading piece products are accumulated in TMEM ("bf16x6", ~2^-24: fp32-level accuracy on tcgen05).
+        self.precision = os.environ.get("PA2S_VQT_PRECISION", "bf16x6")
+        self._fop = None
 
     @torch.no_grad()
     def forward(self, audio):
@@ -77,7 +81,12 @@ class VQT(torch.nn.Module):
         ypad[:, half:half + n] = audio
         C = torch.empty(B, T, 2 * self.n_bins, device=audio.device, dtype=torch.float32)
         # frames[t, j] = ypad[t*hop + j0 + j]: overlapping rows, lda = hop
-        ops.gemm(ypad, self.filters, C, T, 2 * self.n_bins, K, transB=True, lda=self.hop, ldb=K, ldc=2 * self.n_bins,
+        filt = self.filters
+        if self.precision != "fp32":                 # the filter bank is constant: split it into bf16 pieces once
+            if self._fop is None or self._fop[0] != (self.precision, filt.device):
+                self._fop = ((self.precision, filt.device), ops.split_operand(filt, 2 * self.n_bins, K, K, npieces=ops.npieces_for(self.precision)))
+            filt = self._fop[1]
+        ops.gemm(ypad, filt, C, T, 2 * self.n_bins, K, transB=True, lda=self.hop, ldb=K, ldc=2 * self.n_bins,
                  batch=B, strideA=plen, strideB=0, strideC=T * 2 * self.n_bins, a_off=self.j0, precision=self.precision)
         out = torch.empty(B, T, self.n_bins, device=audio.device, dtype=torch.float32)
         cmax = torch.empty(B, device=audio.device, dtype=torch.int32)
