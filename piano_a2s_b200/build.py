@@ -46,7 +46,7 @@ def build(force=False, verbose=False):
         return obj
     with ThreadPoolExecutor(max_workers=min(len(srcs), os.cpu_count() or 4)) as ex:
         objs = list(ex.map(compile_one, srcs))
-    cmd = [nvcc, "-shared", "-Xcompiler", "-fPIC", "-o", LIB] + objs
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-o", LIB] + objs
     if verbose:
         print(" ".join(cmd), file=sys.stderr)
     subprocess.run(cmd, check=True, cwd=CSRC)

@@ -176,6 +176,162 @@ __global__ void __launch_bounds__(NT) gemm_f32_kernel(GemmArgs g) {
     }
 }
 
+
+// ---- skinny contractions (the bar-level decoder: batch-of-clips x weight matrix) ----------------------------------------------
+// The bar GRU cell, the attention query and the time-signature / key heads (models.py:117-132, 242-286) contract a (B x K)
+// activation block, B <= 32 clips, with a weight matrix: a 128 x 128 tile would be 90 % padding and leave 140 SMs idle.
+constexpr int SK_MAX = 32;      // max rows of the skinny operand
+
+__device__ __forceinline__ void skinny_store(float* c, float v, int atomic, int accumulate) {
+    if (atomic) atomicAdd(c, v);
+    else if (accumulate) *c += v;
+    else *c = v;
+}
+
+// C[m][n] = sum_k A[m][k] * B[n][k] (+bias[n]);  M <= 32.  One warp per pair of output columns: lanes stride over k with
+// 128-bit loads of the two weight rows (read once overall), the M activation rows come from L1, butterfly reduction at the end.
+template <int MR>
+__global__ void __launch_bounds__(256) gemm_skinny_nt_kernel(GemmArgs g) {
+    const int warp = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int n0 = warp * 2;
+    if (n0 >= g.N) return;
+    const bool two = n0 + 1 < g.N;
+    const float* b0 = g.B + (long long)n0 * g.ldb;
+    const float* b1 = g.B + (long long)(two ? n0 + 1 : n0) * g.ldb;
+    float acc0[MR], acc1[MR];
+#pragma unroll
+    for (int m = 0; m < MR; ++m) { acc0[m] = 0.f; acc1[m] = 0.f; }
+    const bool vec = g.vecA && g.vecB;
+    const int K4 = vec ? (g.K & ~3) : 0;
+    for (int k = lane * 4; k < K4; k += 128) {
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(b0 + k)), w1 = __ldg(reinterpret_cast<const float4*>(b1 + k));
+#pragma unroll
+        for (int m = 0; m < MR; ++m) {
+            if (m < g.M) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(g.A + (long long)m * g.lda + k));
+                acc0[m] = fmaf(a.x, w0.x, fmaf(a.y, w0.y, fmaf(a.z, w0.z, fmaf(a.w, w0.w, acc0[m]))));
+                acc1[m] = fmaf(a.x, w1.x, fmaf(a.y, w1.y, fmaf(a.z, w1.z, fmaf(a.w, w1.w, acc1[m]))));
+            }
+        }
+    }
+    for (int k = K4 + lane; k < g.K; k += 32) {
+        const float w0 = __ldg(b0 + k), w1 = __ldg(b1 + k);
+#pragma unroll
+        for (int m = 0; m < MR; ++m) {
+            if (m < g.M) {
+                const float a = __ldg(g.A + (long long)m * g.lda + k);
+                acc0[m] = fmaf(a, w0, acc0[m]);
+                acc1[m] = fmaf(a, w1, acc1[m]);
+            }
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < MR; ++m) {
+        const float s0 = warp_sum(acc0[m]), s1 = warp_sum(acc1[m]);
+        if (lane == (m & 31) && m < g.M) {
+            skinny_store(g.C + (long long)m * g.ldc + n0, s0 + (g.bias ? __ldg(g.bias + n0) : 0.f), g.atomic, g.accumulate);
+            if (two) skinny_store(g.C + (long long)m * g.ldc + n0 + 1, s1 + (g.bias ? __ldg(g.bias + n0 + 1) : 0.f), g.atomic, g.accumulate);
+        }
+    }
+}
+
+// C[m][n] = sum_k A[m][k] * B[k][n] (+bias[n]);  M <= 32.  CTA = 32 output columns x 8 k-slices; a warp reads 128-byte rows of
+// B, the A values are warp-uniform; the 8 slices are summed through shared memory.
+template <int MR>
+__global__ void __launch_bounds__(256) gemm_skinny_nn_kernel(GemmArgs g) {
+    __shared__ float red[8][MR][33];
+    const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    const int n = blockIdx.x * 32 + lane;
+    const int kper = (g.K + 7) / 8;
+    const int kb = slice * kper, ke = min(g.K, kb + kper);
+    float acc[MR];
+#pragma unroll
+    for (int m = 0; m < MR; ++m) acc[m] = 0.f;
+    if (n < g.N) {
+        for (int k = kb; k < ke; ++k) {
+            const float b = __ldg(g.B + (long long)k * g.ldb + n);
+#pragma unroll
+            for (int m = 0; m < MR; ++m)
+                if (m < g.M) acc[m] = fmaf(__ldg(g.A + (long long)m * g.lda + k), b, acc[m]);
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < MR; ++m) red[slice][m][lane] = acc[m];
+    __syncthreads();
+    for (int m = slice; m < g.M; m += 8) {
+        float v = 0.f;
+#pragma unroll
+        for (int s = 0; s < 8; ++s) v += red[s][m][lane];
+        if (n < g.N) skinny_store(g.C + (long long)m * g.ldc + n, v + (g.bias ? __ldg(g.bias + n) : 0.f), g.atomic, g.accumulate);
+    }
+}
+
+// C[i][j] = sum_{m < K} A[m][i] * B[m][j];  K <= 32 (weight gradient of a skinny Linear: dW = dy^T x).  CTA tile 32 x 128,
+// both operand slabs staged in shared memory, 16 outputs per thread, coalesced 128-bit stores.
+__global__ void __launch_bounds__(256) gemm_skinny_tn_kernel(GemmArgs g) {
+    __shared__ __align__(16) float As[SK_MAX][32], Bs[SK_MAX][128];
+    const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 128;
+    for (int e = threadIdx.x; e < g.K * 32; e += 256) {
+        const int m = e >> 5, i = e & 31;
+        As[m][i] = (i0 + i < g.M) ? __ldg(g.A + (long long)m * g.lda + i0 + i) : 0.f;
+    }
+    for (int e = threadIdx.x; e < g.K * 128; e += 256) {
+        const int m = e >> 7, j = e & 127;
+        Bs[m][j] = (j0 + j < g.N) ? __ldg(g.B + (long long)m * g.ldb + j0 + j) : 0.f;
+    }
+    __syncthreads();
+    const int ty = threadIdx.x >> 5, tx = threadIdx.x & 31;
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+    for (int m = 0; m < g.K; ++m) {
+        const float4 av = *reinterpret_cast<const float4*>(&As[m][ty * 4]);
+        const float4 bv = *reinterpret_cast<const float4*>(&Bs[m][tx * 4]);
+        const float a[4] = {av.x, av.y, av.z, av.w}, b[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(a[x], b[y], acc[x][y]);
+    }
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+        const int i = i0 + ty * 4 + x;
+        if (i >= g.M) continue;
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+            const int j = j0 + tx * 4 + y;
+            if (j < g.N) skinny_store(g.C + (long long)i * g.ldc + j, acc[x][y], g.atomic, g.accumulate);
+        }
+    }
+}
+
+// Returns true if the contraction was handled by a skinny kernel.
+bool launch_skinny(const GemmArgs& g0, int transA, int transB, cudaStream_t st) {
+    if (g0.batch != 1 || g0.t_scale != nullptr || g0.K <= 0) return false;
+    GemmArgs g = g0;
+    if (g.splitk > 1) g.atomic = 1;
+    g.splitk = 1;
+    if (!transA && g.M <= SK_MAX && g.N >= 64) {
+        if (transB) {
+            const int warps = (g.N + 1) / 2, grid = ceil_div(warps, 8);
+            if (g.M <= 16) gemm_skinny_nt_kernel<16><<<grid, 256, 0, st>>>(g);
+            else gemm_skinny_nt_kernel<32><<<grid, 256, 0, st>>>(g);
+        } else {
+            const int grid = ceil_div(g.N, 32);
+            if (g.M <= 16) gemm_skinny_nn_kernel<16><<<grid, 256, 0, st>>>(g);
+            else gemm_skinny_nn_kernel<32><<<grid, 256, 0, st>>>(g);
+        }
+        return true;
+    }
+    if (transA && !transB && g.K <= SK_MAX && g.bias == nullptr && (long long)g.M * g.N >= 4096) {
+        gemm_skinny_tn_kernel<<<dim3(ceil_div(g.N, 128), ceil_div(g.M, 32)), 256, 0, st>>>(g);
+        return true;
+    }
+    return false;
+}
+
 }  // namespace
 
 unsigned long long g_pa2s_launches = 0;
@@ -207,6 +363,10 @@ PA2S_API int pa2s_gemm_f32(void* stream, int transA, int transB, int M, int N, i
     g.vecB = (ldb % 4 == 0) && (strideB % 4 == 0) && ((uintptr_t)B % 16 == 0);
     dim3 grid(ceil_div(N, BN), ceil_div(M, BM), batch * splitk);
     cudaStream_t st = (cudaStream_t)stream;
+    if (launch_skinny(g, transA, transB, st)) {
+        PA2S_CHECK_LAST();
+        return 0;
+    }
     if (!transA && !transB) gemm_f32_kernel<false, false><<<grid, NT, 0, st>>>(g);
     else if (!transA && transB) gemm_f32_kernel<false, true><<<grid, NT, 0, st>>>(g);
     else if (transA && !transB) gemm_f32_kernel<true, false><<<grid, NT, 0, st>>>(g);

@@ -174,7 +174,8 @@ def gemm(A, B, C, M, N, K, *, transA=False, transB=False, lda=None, ldb=None, ld
     `zeroed=True`: the caller guarantees C is zero-filled, so the wrapper may split K (atomic accumulation) to fill the GPU."""
     es = 4
     prec = precision or current_precision()
-    use_tc = prec != "fp32" and K > 0 and 2.0 * M * N * K * batch >= TC_MIN_FLOP
+    presplit = isinstance(A, Bf16Operand) or isinstance(B, Bf16Operand)
+    use_tc = prec != "fp32" and K > 0 and (presplit or 2.0 * M * N * K * batch >= TC_MIN_FLOP)
     if zeroed and splitk == 1 and batch == 1:
         splitk = _tc_splitk(M, N, K) if use_tc else _auto_splitk(M, N, K)
     if use_tc:
@@ -351,9 +352,22 @@ class ConvStackFn(torch.autograd.Function):
         Wp_out = Wout.detach().view(O, C4, Fq).permute(0, 2, 1).reshape(O, Kf).contiguous()
         M = B * T
         z = torch.zeros(M, O, device=dev, dtype=F32)
-        with ktime("out_linear_fwd"):
-            gemm(ys[3], Wp_out, z, M, O, Kf, transB=True, lda=Kf, ldb=Kf, ldc=O,
-                 t_scale=affs[3][0], t_shift=affs[3][1], t_period=C4, t_relu=True, zeroed=True)
+        ctx.lin_ops = None
+        if ctx.prec == "fp32":
+            with ktime("out_linear_fwd"):
+                gemm(ys[3], Wp_out, z, M, O, Kf, transB=True, lda=Kf, ldb=Kf, ldc=O,
+                     t_scale=affs[3][0], t_shift=affs[3][1], t_period=C4, t_relu=True, zeroed=True)
+        else:
+            # a4 = relu(bn4(y4)) and the permuted weight are split into bf16 pieces ONCE; the forward contraction, the weight
+            # gradient (a4 as MN-major operand) and the data gradient (W as MN-major operand) all read these pieces through TMA
+            npc = npieces_for(ctx.prec)
+            with ktime("out_linear_split"):
+                a4op = split_operand(ys[3], M, Kf, Kf, npieces=npc, t_scale=affs[3][0], t_shift=affs[3][1], t_period=C4, t_relu=True)
+                Wop = split_operand(Wp_out, O, Kf, Kf, npieces=npc)
+            with ktime("out_linear_fwd"):
+                gemm(a4op, Wop, z, M, O, Kf, transB=True, ldc=O, zeroed=True)
+            if training:
+                ctx.lin_ops = (a4op, Wop)
         aff5 = torch.empty(4, O, device=dev, dtype=F32)
         if training:
             nct = 4 * N_SM
@@ -419,14 +433,23 @@ class ConvStackFn(torch.autograd.Function):
         Kf = Fq * C4
         # dW_out[n,k] = sum_m dz[m,n] * relu(bn4(y4))[m,k]
         dWp = torch.zeros(O, Kf, device=dev, dtype=F32)
-        with ktime("out_linear_wgrad"):
-            gemm(dz, ys[3], dWp, O, Kf, M, transA=True, lda=O, ldb=Kf, ldc=Kf,
-                 t_scale=affs[3][0], t_shift=affs[3][1], t_period=C4, t_relu=True, t_on_b=True, zeroed=True)
+        G = torch.empty(B, T, Fq, C4, device=dev, dtype=F32)           # G4 = dL/d relu(bn4(y4))
+        if ctx.lin_ops is None:
+            with ktime("out_linear_wgrad"):
+                gemm(dz, ys[3], dWp, O, Kf, M, transA=True, lda=O, ldb=Kf, ldc=Kf,
+                     t_scale=affs[3][0], t_shift=affs[3][1], t_period=C4, t_relu=True, t_on_b=True, zeroed=True)
+            with ktime("out_linear_dgrad"):
+                gemm(dz, Wp_out, G, M, Kf, O, lda=O, ldb=Kf, ldc=Kf)
+        else:
+            a4op, Wop = ctx.lin_ops
+            ctx.lin_ops = None
+            dzop = split_operand(dz, M, O, O, npieces=a4op.npieces)
+            with ktime("out_linear_wgrad"):
+                gemm(dzop, a4op, dWp, O, Kf, M, transA=True, ldc=Kf, zeroed=True)
+            del a4op
+            with ktime("out_linear_dgrad"):
+                gemm(dzop, Wop, G, M, Kf, O, ldc=Kf)
         grads[12] = dWp.view(O, Fq, C4).permute(0, 2, 1).reshape(O, Kf).contiguous()
-        # G4 = dL/d relu(bn4(y4))
-        G = torch.empty(B, T, Fq, C4, device=dev, dtype=F32)
-        with ktime("out_linear_dgrad"):
-            gemm(dz, Wp_out, G, M, Kf, O, lda=O, ldb=Kf, ldc=Kf)
         nw = 8 * N_SM
         for i in (3, 2, 1, 0):
             W = conv_w[i]

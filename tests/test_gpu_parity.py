@@ -50,6 +50,28 @@ def test_gemm_shapes(cuda, ta, tb, M, N, K):
     assert rel_err(C2, ref + 1) < 1e-5
 
 
+@pytest.mark.parametrize("M,N,K", [(16, 1024, 1024), (2, 1536, 653), (16, 256, 512), (32, 173, 1027), (5, 64, 33)])
+def test_gemm_skinny_forms(cuda, M, N, K):
+    """The bar-level decoder's batch-of-clips x weight contractions (forward, data gradient, weight gradient) take the skinny
+    fp32 kernels of gemm.cu."""
+    from piano_a2s_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    x = torch.randn(M, K, generator=g); W = torch.randn(N, K, generator=g); bias = torch.randn(N, generator=g)
+    dy = torch.randn(M, N, generator=g)
+    xd, Wd, dyd = x.to(cuda), W.to(cuda), dy.to(cuda)
+    y = torch.empty(M, N, device=cuda)
+    ops.gemm(xd, Wd, y, M, N, K, transB=True, lda=K, ldb=K, ldc=N, bias=bias.to(cuda), precision="fp32")
+    assert rel_err(y, x.double() @ W.double().t() + bias.double()) < 1e-5
+    dx = torch.empty(M, K, device=cuda)
+    ops.gemm(dyd, Wd, dx, M, K, N, lda=N, ldb=K, ldc=K, precision="fp32")
+    assert rel_err(dx, dy.double() @ W.double()) < 1e-5
+    dW = torch.zeros(N, K, device=cuda)
+    ops.gemm(dyd, xd, dW, N, K, M, transA=True, lda=N, ldb=K, ldc=K, zeroed=True, precision="fp32")
+    assert rel_err(dW, dy.double().t() @ x.double()) < 1e-5
+    ops.gemm(dyd, xd, dW, N, K, M, transA=True, lda=N, ldb=K, ldc=K, atomic=True, precision="fp32")
+    assert rel_err(dW, 2 * (dy.double().t() @ x.double())) < 1e-5
+
+
 def test_gemm_batched_transform_overlap(cuda):
     from piano_a2s_b200 import ops
     g = torch.Generator().manual_seed(3)
