@@ -94,6 +94,24 @@ PA2S_API int pa2s_tc_conv3x3_wgrad(void* stream, int B, int T, int F, int Cin, i
                                    float* partial, int nsplit, const float* in_scale, const float* in_shift, int in_relu,
                                    const float* Yraw, const float* zs, const float* zb, const float* mean, const float* invstd,
                                    const float* k1, const float* k2, const float* k3);
+/* The same three convolutions fed by bulk async copies only (tc_conv_tma.cu).  Activation operands are bf16 "plane" tensors
+ * P[b][t+1][piece][8-channel group][f+2][8] with zero halos (pa2s_planes_bytes bytes), written once per tensor by
+ * pa2s_planes_fwd (BatchNorm-apply + ReLU + hi/lo split; replaces bn_i + relu of models.py:525-534 on the operand side) or
+ * pa2s_planes_bwd (BatchNorm/ReLU backward + split) and read by two kernels each.  pa2s_conv_tma is the forward convolution
+ * (Wpack from pa2s_tc_conv_pack with dgrad = 0) or the data gradient (planes = dy, dgrad = 1); pa2s_conv_tma_wgrad the weight
+ * gradient (partial: pa2s_conv_tma_wgrad_num_partials rows of Cout*Cin*9, torch order). */
+PA2S_API long long pa2s_planes_bytes(int B, int T, int F, int C, int npieces);
+PA2S_API int pa2s_planes_fwd(void* stream, int B, int T, int F, int C, const float* X, const float* scale, const float* shift, int relu,
+                             void* planes, int npieces);
+PA2S_API int pa2s_planes_bwd(void* stream, int B, int T, int F, int C, const float* G, const float* Yraw, const float* zs, const float* zb,
+                             const float* mean, const float* invstd, const float* k1, const float* k2, const float* k3,
+                             void* planes, int npieces);
+PA2S_API int pa2s_conv_tma_num_partials(int B, int T, int F);
+PA2S_API int pa2s_conv_tma_wgrad_num_partials(int B, int T, int F);
+PA2S_API int pa2s_conv_tma(void* stream, int B, int T, int F, int Cin, int Cout, const void* planes, int npieces, const void* Wpack,
+                           float* Y, float* partial);
+PA2S_API int pa2s_conv_tma_wgrad(void* stream, int B, int T, int F, int Cin, int Cout, const void* planes_in, const void* planes_dy,
+                                 int npieces, float* partial);
 /* conv2d backward wrt weight; partial is [nctas][Cout*Cin*9] in torch (Cout,Cin,3,3) order. */
 PA2S_API int pa2s_conv3x3_wgrad(void* stream, int B, int T, int F, int Cin, int Cout, const float* Xin, const float* G,
                                 float* partial, int nctas, const float* in_scale, const float* in_shift, int in_relu,

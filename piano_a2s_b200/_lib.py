@@ -56,7 +56,8 @@ class _Lib:
         fn = getattr(self.load(), name)
         if name in ("pa2s_launch_count", "pa2s_dec_args_size", "pa2s_gru_seq_max_bg", "pa2s_conv3x3_num_partials",
                     "pa2s_tc_conv_pack_bytes", "pa2s_tc_conv_num_partials", "pa2s_gemm_tc_supported",
-                    "pa2s_tc_conv_wgrad_num_partials", "pa2s_dec_persist_grid", "pa2s_dec_deferred_blocks"):
+                    "pa2s_tc_conv_wgrad_num_partials", "pa2s_dec_persist_grid", "pa2s_dec_deferred_blocks", "pa2s_planes_bytes",
+                    "pa2s_conv_tma_num_partials", "pa2s_conv_tma_wgrad_num_partials"):
             return fn
 
         def call(*args):

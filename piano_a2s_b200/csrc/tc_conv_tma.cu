@@ -1,0 +1,567 @@
+// 3x3 convolution of ConvStack (conv2..conv4, models.py:481-498, :526-534) as implicit GEMMs on the tcgen05 tensor cores,
+// forward, data gradient and weight gradient, fed ONLY by bulk async copies (TMA engine, cp.async.bulk) -- no thread touches
+// operand data.
+//
+// Activation operands live in global memory as bf16 "planes", produced once per tensor by pa2s_planes_fwd / pa2s_planes_bwd
+// (BatchNorm-apply + ReLU, resp. the BatchNorm/ReLU backward transform, fused with the fp32 -> bf16 hi/lo split) and consumed
+// by two kernels each (forward conv + next layer's weight gradient; data gradient + weight gradient):
+//
+//     P[b][t' = t+1 in 0..T+1][piece (hi, lo)][g = 8-channel group][q = f+2 in 0..FP-1][8 channels]      (16-byte units)
+//
+// Rows t' = 0, T+1 and columns q < 2, q >= F+2 are zero (written by the producers), so the 3x3 halo needs no predication.
+// A "window" = the 130 positions q0 .. q0+129, q0 = fb*128, of one row of one channel group: ONE contiguous 2080-byte chunk,
+// and in shared memory exactly the UMMA no-swizzle canonical layout (K-major for the convolution: row = position at a 16-byte
+// pitch; MN-major for the weight gradient: K = position).  The three kx taps of a window are the same bytes addressed with the
+// descriptor start shifted by kx*16 B; a CTA walks DOWN a strip (b, fb) so consecutive tiles share two of their three windows:
+// every activation byte is copied into shared memory once per strip.
+//
+// Warp roles (192 threads, one persistent CTA per SM): warps 0-3 epilogue (TMEM -> registers -> global, BatchNorm batch
+// statistics of the produced tensor), warp 4 TMEM allocation + single-lane tcgen05.mma issue, warp 5 single-lane copy producer.
+#include "tc_common.cuh"
+
+namespace {
+using namespace tc;
+
+constexpr int BM = 128;
+constexpr int WENT = 130;                    // window entries: 128 output positions + 2 halo
+constexpr int PLANE_BYTES = WENT * 16;       // 2080
+constexpr int NWIN = 5;                      // window ring: three rows in use by the MMAs + two in flight
+constexpr int NTHREADS = 192;
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+struct Geom {
+    int B, T, F, nfb, FP, NP;                // FP = plane row pitch in positions, NP = pieces (1 or 2)
+};
+__host__ __device__ inline int geom_nfb(int F) { return (F + 2 + BM - 1) / BM; }
+__host__ __device__ inline int geom_fp(int F) { return geom_nfb(F) * BM + 8; }
+// 16-byte unit index of (b, t', piece, g, q) in a plane tensor with NGR stored channel groups
+__device__ __forceinline__ size_t plane_unit(const Geom& g, int NGR, int b, int tp, int piece, int grp, int q) {
+    return ((((size_t)b * (g.T + 2) + tp) * g.NP + piece) * NGR + grp) * g.FP + q;
+}
+
+// A CTA owns the contiguous range [begin, end) of the linearised (strip, row) space, strip = b * nfb + fb, walked as chunks
+// of consecutive rows of one strip.
+struct Chunk { int b, fb, t0, n; };
+struct Walk {
+    long long pos, end; int T, nfb;
+    __device__ __forceinline__ void init(const Geom& g) {
+        T = g.T; nfb = g.nfb;
+        const long long total = (long long)g.B * nfb * T;
+        const long long per = (total + gridDim.x - 1) / gridDim.x;
+        pos = (long long)blockIdx.x * per;
+        end = pos + per < total ? pos + per : total;
+    }
+    __device__ __forceinline__ bool next(Chunk& c) {
+        if (pos >= end) return false;
+        const int strip = (int)(pos / T);
+        c.t0 = (int)(pos - (long long)strip * T);
+        c.b = strip / nfb; c.fb = strip - c.b * nfb;
+        const long long left = end - pos;
+        c.n = (int)(left < (long long)(T - c.t0) ? left : (long long)(T - c.t0));
+        pos += c.n;
+        return true;
+    }
+};
+// number of CTAs such that every CTA owns at least one tile under Walk's ceil-division
+static int conv_grid(int B, int T, int F) {
+    const long long total = (long long)B * geom_nfb(F) * T;
+    const long long g0 = total < 148 ? total : 148;
+    const long long per = (total + g0 - 1) / g0;
+    return (int)((total + per - 1) / per);
+}
+
+// ====================================================================================================================
+// plane producers
+// ====================================================================================================================
+struct PlaneArgs {
+    const float* X;            // fwd: raw conv output y (B,T,F,C);  bwd: G = dL/d relu(bn(y))
+    const float* Yraw;         // bwd only
+    uint4* P;
+    Geom g;
+    const float* c0; const float* c1; const float* c2; const float* c3; const float* c4; const float* c5; const float* c6;
+    int relu;
+};
+// MODE 0: a = relu?(x*c0[c] + c1[c])  (c0 null: identity)
+// MODE 1: dy = c4*(gm - c5 - xhat*c6), gm = G*(y*c0+c1 > 0), xhat = (y-c2)*c3      (BatchNorm + ReLU backward, see conv.cu)
+template <int C, int MODE>
+__global__ void __launch_bounds__(128 * ((C + 7) / 8)) planes_kernel(PlaneArgs a) {
+    constexpr int NGR = (C + 7) / 8;
+    constexpr bool HALF = (C % 8) != 0;
+    const int q = blockIdx.x * 128 + threadIdx.x, grp = threadIdx.y;
+    const int tp = blockIdx.y, b = blockIdx.z;
+    if (q >= a.g.FP) return;
+    const int f = q - 2, t = tp - 1;
+    float x[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x[e] = 0.f;
+    if (t >= 0 && t < a.g.T && f >= 0 && f < a.g.F) {
+        const size_t base = (((size_t)b * a.g.T + t) * a.g.F + f) * C + 8 * grp;
+        const bool half = HALF && grp == NGR - 1;
+        const float4 v0 = __ldg(reinterpret_cast<const float4*>(a.X + base));
+        float4 v1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!half) v1 = __ldg(reinterpret_cast<const float4*>(a.X + base) + 1);
+        x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w; x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
+        if (MODE == 0) {
+            if (a.c0 != nullptr) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int c = 8 * grp + e;
+                    if (c < C) {
+                        const float y = fmaf(x[e], __ldg(a.c0 + c), __ldg(a.c1 + c));
+                        x[e] = a.relu ? fmaxf(y, 0.f) : y;
+                    }
+                }
+            }
+        } else {
+            const float4 y0 = __ldg(reinterpret_cast<const float4*>(a.Yraw + base));
+            float4 y1 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!half) y1 = __ldg(reinterpret_cast<const float4*>(a.Yraw + base) + 1);
+            const float yy[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int c = 8 * grp + e;
+                if (c < C) {
+                    const float z = fmaf(yy[e], __ldg(a.c0 + c), __ldg(a.c1 + c));
+                    const float gm = z > 0.f ? x[e] : 0.f;
+                    const float xh = (yy[e] - __ldg(a.c2 + c)) * __ldg(a.c3 + c);
+                    x[e] = __ldg(a.c4 + c) * (gm - __ldg(a.c5 + c) - xh * __ldg(a.c6 + c));
+                } else {
+                    x[e] = 0.f;
+                }
+            }
+        }
+    }
+    uint4 hi, lo;
+    split8_packed(x, hi, lo);
+    a.P[plane_unit(a.g, NGR, b, tp, 0, grp, q)] = hi;
+    if (a.g.NP > 1) a.P[plane_unit(a.g, NGR, b, tp, 1, grp, q)] = lo;
+}
+
+// ====================================================================================================================
+// forward / data-gradient convolution
+// ====================================================================================================================
+struct ConvArgs2 {
+    const uint4* P;        // input planes (CIN channels)
+    const uint4* Wpack;    // packed bf16 weights (pa2s_tc_conv_pack)
+    float* Y;              // (B,T,F,COUT) fp32
+    float* partial;        // [gridDim.x*4][2*COUT] per-warp [sum y, sum y^2] or null
+    Geom g;
+};
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(ConvArgs2 a) {
+    constexpr int CINP = (CIN + 15) / 16 * 16, COUTP = (COUT + 15) / 16 * 16;
+    constexpr int NG = CINP / 8, NGR = (CIN + 7) / 8, KS = CINP / 16;
+    constexpr int SLOT_BYTES = 2 * NG * PLANE_BYTES;                 // hi planes then lo planes
+    constexpr int WBLK_BYTES = 2 * COUTP * 16;                        // one (tap, ks, split) weight block: 2 k-groups x COUTP rows
+    constexpr int W_BYTES = 9 * KS * 2 * WBLK_BYTES;
+    constexpr int TM_COLS = 64;
+    static_assert(COUTP <= TM_COLS, "accumulator width");
+
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* wsm = smem;
+    uint8_t* win = smem + ((W_BYTES + 127) / 128) * 128;
+    __shared__ uint64_t full_bar[NWIN], empty_bar[NWIN], tfull_bar[2], tempty_bar[2];
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int T = a.g.T, F = a.g.F;
+    const int NP = a.g.NP;
+
+    for (int i = tid; i < W_BYTES / 16; i += NTHREADS) reinterpret_cast<uint4*>(wsm)[i] = __ldg(a.Wpack + i);
+    for (int i = tid; i < NWIN * SLOT_BYTES / 16; i += NTHREADS) reinterpret_cast<uint4*>(win)[i] = make_uint4(0, 0, 0, 0);
+    if (warp == 4) {
+        if (lane == 0) {
+            for (int s = 0; s < NWIN; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+            for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 128); }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        tmem_alloc(&tmem_base_s, 2 * TM_COLS);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    Walk walk;
+    walk.init(a.g);
+    Chunk ch;
+
+    if (warp < 4) {
+        // ================================================================================= epilogue
+        float ssum[2] = {0.f, 0.f}, ssq[2] = {0.f, 0.f};              // lane c keeps channels c and c+32
+        uint32_t it = 0;
+        while (walk.next(ch)) {
+            const int fp = ch.fb * BM + warp * 32 + lane;
+            const bool valid = (fp >= 1) && (fp <= F);
+            for (int k = 0; k < ch.n; ++k, ++it) {
+                const int acc = it & 1;
+                mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
+                tc_fence_after();
+                float* yrow = a.Y + (((size_t)ch.b * T + ch.t0 + k) * F + (fp - 1)) * COUT;
+#pragma unroll
+                for (int c0 = 0; c0 < COUTP; c0 += 16) {
+                    float v[16];
+                    tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * TM_COLS + c0), v);
+                    if (valid) {
+#pragma unroll
+                        for (int qd = 0; qd < 4; ++qd)
+                            if (c0 + 4 * qd < COUT)
+                                reinterpret_cast<float4*>(yrow + c0)[qd] = make_float4(v[4 * qd], v[4 * qd + 1], v[4 * qd + 2], v[4 * qd + 3]);
+                    }
+                    if (a.partial != nullptr) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const int c = c0 + i;
+                            if (c < COUT) {
+                                const float x = valid ? v[i] : 0.f;
+                                const float s1 = warp_sum(x), s2 = warp_sum(x * x);
+                                if (lane == (c & 31)) { ssum[c >> 5] += s1; ssq[c >> 5] += s2; }
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&tempty_bar[acc]);
+            }
+        }
+        if (a.partial != nullptr) {
+            float* pr = a.partial + ((size_t)blockIdx.x * 4 + warp) * 2 * COUT;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int c = lane + 32 * h;
+                if (c < COUT) { pr[c] = ssum[h]; pr[COUT + c] = ssq[h]; }
+            }
+        }
+    } else if (warp == 4) {
+        // ================================================================================= MMA issuer (warp-uniform)
+        const uint32_t idesc = make_idesc(BM, COUTP, 0, 0);
+        const uint32_t w_base = smem_u32(wsm), win_base = smem_u32(win);
+        const uint64_t wdesc0 = make_desc(w_base, COUTP * 16, 128);
+        uint32_t it = 0, wbase = 0;                                   // wbase = ring index of the chunk's first window (row t0-1)
+        while (walk.next(ch)) {
+            for (int k = 0; k < ch.n; ++k, ++it) {
+                const int acc = it & 1;
+                mbar_wait(&tempty_bar[acc], ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TM_COLS);
+                const bool last = (k == ch.n - 1);
+                for (int ky = 0; ky < 3; ++ky) {
+                    const uint32_t wi = wbase + k + ky;               // window of input row t0 + k + ky - 1
+                    const int slot = wi % NWIN;
+                    if (k == 0 || ky == 2) {                          // the two older windows were awaited by the previous tile
+                        mbar_wait(&full_bar[slot], (wi / NWIN) & 1);
+                        tc_fence_after();
+                    }
+                    const uint64_t dah0 = make_desc(win_base + slot * SLOT_BYTES, PLANE_BYTES, 128);
+                    const uint64_t dal0 = desc_advance(dah0, NG * PLANE_BYTES);
+                    const uint64_t dbw = desc_advance(wdesc0, (uint32_t)(ky * 3 * KS * 2 * WBLK_BYTES));
+                    if (elect_one()) {
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll
+                            for (int ks = 0; ks < KS; ++ks) {
+                                const uint32_t aoff = (uint32_t)(2 * ks * PLANE_BYTES + kx * 16);
+                                const uint64_t dah = desc_advance(dah0, aoff), dal = desc_advance(dal0, aoff);
+                                const uint64_t dbh = desc_advance(dbw, (uint32_t)(((kx * KS + ks) * 2) * WBLK_BYTES));
+                                const uint64_t dbl = desc_advance(dbh, WBLK_BYTES);
+                                tc_mma(d_tmem, dah, dbh, idesc, (ky | kx | ks) != 0);
+                                if (NP > 1) {
+                                    tc_mma(d_tmem, dah, dbl, idesc, 1);
+                                    tc_mma(d_tmem, dal, dbh, idesc, 1);
+                                }
+                            }
+                        }
+                        // a window is free once the last tile that reads it has been issued
+                        if (ky == 0 || last) tc_commit(&empty_bar[slot]);
+                        if (ky == 2) tc_commit(&tfull_bar[acc]);
+                    }
+                    __syncwarp();
+                }
+            }
+            wbase += ch.n + 2;
+        }
+    } else if (lane == 0) {
+        // ================================================================================= copy producer (one thread)
+        const uint32_t win_base = smem_u32(win);
+        uint32_t wi = 0;
+        while (walk.next(ch)) {
+            for (int j = 0; j < ch.n + 2; ++j, ++wi) {                // input rows t0-1 .. t0+n  ->  t' = t0 + j
+                const int slot = wi % NWIN;
+                mbar_wait(&empty_bar[slot], ((wi / NWIN) & 1) ^ 1);
+                mbar_expect_tx(&full_bar[slot], (uint32_t)(NP * NGR * PLANE_BYTES));
+                for (int p = 0; p < NP; ++p)
+                    for (int grp = 0; grp < NGR; ++grp)
+                        bulk_g2s(win_base + slot * SLOT_BYTES + (p * NG + grp) * PLANE_BYTES,
+                                 a.P + plane_unit(a.g, NGR, ch.b, ch.t0 + j, p, grp, ch.fb * BM), PLANE_BYTES, &full_bar[slot]);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 2 * TM_COLS);
+    }
+}
+
+// ====================================================================================================================
+// weight gradient:  dW[co][ci][ky][kx] = sum_pixels dy[pixel][co] * a_in[pixel + (ky-1, kx-1)][ci]
+// The reduction runs over pixels, so BOTH operands are MN-major UMMA operands (K = position at a 16-byte pitch):
+//   A = dy   (M = 64 >= COUT)  window of row t,  entries 1..128
+//   B = a_in (N = CINP)        windows of rows t-1, t, t+1 (shared between consecutive tiles); tap kx = start + kx*16 bytes
+// Nine accumulators (one per tap, CINP columns, 64 lanes) stay in TMEM for ALL tiles of the persistent CTA and are read out
+// once at the end into a per-CTA partial (summed by pa2s_reduce_rows).
+// ====================================================================================================================
+constexpr int NASLOT = 3;
+struct WgradArgs2 {
+    const uint4* Pin;      // a_in planes (CIN channels)
+    const uint4* Pdy;      // dy planes (COUT channels)
+    float* partial;        // [gridDim.x][COUT*CIN*9]
+    Geom g;
+};
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(NTHREADS, 1) conv_wgrad_tma_kernel(WgradArgs2 a) {
+    constexpr int CINP = (CIN + 15) / 16 * 16;
+    constexpr int NGB = CINP / 8, NGRB = (CIN + 7) / 8;
+    constexpr int NGA = 8, NGRA = (COUT + 7) / 8;                 // dy planes: M = 64
+    constexpr int SLOT_BYTES = 2 * NGB * PLANE_BYTES, ASLOT_BYTES = 2 * NGA * PLANE_BYTES;
+    constexpr int TM_COLS = 512;
+    static_assert(9 * CINP <= TM_COLS && COUT <= 64, "accumulators must fit TMEM");
+
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* win = smem;
+    uint8_t* asm_ = smem + NWIN * SLOT_BYTES;
+    __shared__ uint64_t full_bar[NWIN], empty_bar[NWIN], afull_bar[NASLOT], aempty_bar[NASLOT], done_bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int NP = a.g.NP;
+
+    for (int i = tid; i < (NWIN * SLOT_BYTES + NASLOT * ASLOT_BYTES) / 16; i += NTHREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    if (warp == 4) {
+        if (lane == 0) {
+            for (int s = 0; s < NWIN; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+            for (int s = 0; s < NASLOT; ++s) { mbar_init(&afull_bar[s], 1); mbar_init(&aempty_bar[s], 1); }
+            mbar_init(&done_bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        tmem_alloc(&tmem_base_s, TM_COLS);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    Walk walk;
+    walk.init(a.g);
+    Chunk ch;
+
+    if (warp < 4) {
+        // ================================================================================= final read-out
+        mbar_wait(&done_bar, 0);
+        tc_fence_after();
+        const bool has_tiles = walk.pos < walk.end;                // a CTA without tiles never initialised its accumulators
+        const int co = 16 * warp + lane;                           // M = 64: row r lives in lane (r%16) + 32*(r/16)
+        float* out = a.partial + (size_t)blockIdx.x * COUT * CIN * 9;
+#pragma unroll 1
+        for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+            for (int c0 = 0; c0 < CINP; c0 += 16) {
+                float v[16];
+                tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(tap * CINP + c0), v);
+                if (lane < 16 && co < COUT) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (c0 + i < CIN) out[((size_t)co * CIN + c0 + i) * 9 + tap] = has_tiles ? v[i] : 0.f;
+                }
+            }
+        }
+        tc_fence_before();
+    } else if (warp == 4) {
+        // ================================================================================= MMA issuer (warp-uniform)
+        const uint32_t idesc = make_idesc(64, CINP, 1, 1);
+        const uint32_t win_base = smem_u32(win), a_base0 = smem_u32(asm_);
+        uint32_t it = 0, wbase = 0;
+        bool any = false;
+        while (walk.next(ch)) {
+            any = true;
+            for (int k = 0; k < ch.n; ++k, ++it) {
+                const int aslot = it % NASLOT;
+                mbar_wait(&afull_bar[aslot], (it / NASLOT) & 1);
+                tc_fence_after();
+                const uint64_t dah0 = make_desc(a_base0 + aslot * ASLOT_BYTES + 16, 128, PLANE_BYTES);     // entries 1..128
+                const uint64_t dal0 = desc_advance(dah0, NGA * PLANE_BYTES);
+                const bool last = (k == ch.n - 1);
+                for (int ky = 0; ky < 3; ++ky) {
+                    const uint32_t wi = wbase + k + ky;
+                    const int slot = wi % NWIN;
+                    if (k == 0 || ky == 2) {
+                        mbar_wait(&full_bar[slot], (wi / NWIN) & 1);
+                        tc_fence_after();
+                    }
+                    const uint64_t dbh0 = make_desc(win_base + slot * SLOT_BYTES, 128, PLANE_BYTES);
+                    const uint64_t dbl0 = desc_advance(dbh0, NGB * PLANE_BYTES);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) {
+                            const uint32_t d_tmem = tmem_base + (uint32_t)((ky * 3 + kx) * CINP);
+#pragma unroll
+                            for (int ks = 0; ks < BM / 16; ++ks) {
+                                const uint64_t dah = desc_advance(dah0, ks * 256), dal = desc_advance(dal0, ks * 256);
+                                const uint64_t dbh = desc_advance(dbh0, (kx + 16 * ks) * 16), dbl = desc_advance(dbl0, (kx + 16 * ks) * 16);
+                                tc_mma(d_tmem, dah, dbh, idesc, (it | (uint32_t)ks) != 0);
+                                if (NP > 1) {
+                                    tc_mma(d_tmem, dah, dbl, idesc, 1);
+                                    tc_mma(d_tmem, dal, dbh, idesc, 1);
+                                }
+                            }
+                        }
+                        if (ky == 0 || last) tc_commit(&empty_bar[slot]);
+                        if (ky == 2) tc_commit(&aempty_bar[aslot]);
+                    }
+                    __syncwarp();
+                }
+            }
+            wbase += ch.n + 2;
+        }
+        (void)any;
+        if (elect_one()) tc_commit(&done_bar);
+        __syncwarp();
+    } else if (lane == 0) {
+        // ================================================================================= copy producer
+        // order per chunk: [dy(0), in(-1), in(0), in(1)], [dy(1), in(2)], [dy(2), in(3)], ... = the MMA warp's wait order
+        const uint32_t win_base = smem_u32(win), a_base0 = smem_u32(asm_);
+        uint32_t wi = 0, it = 0;
+        auto put_in = [&](int tp) {
+            const int slot = wi % NWIN;
+            mbar_wait(&empty_bar[slot], ((wi / NWIN) & 1) ^ 1);
+            mbar_expect_tx(&full_bar[slot], (uint32_t)(NP * NGRB * PLANE_BYTES));
+            for (int p = 0; p < NP; ++p)
+                for (int grp = 0; grp < NGRB; ++grp)
+                    bulk_g2s(win_base + slot * SLOT_BYTES + (p * NGB + grp) * PLANE_BYTES,
+                             a.Pin + plane_unit(a.g, NGRB, ch.b, tp, p, grp, ch.fb * BM), PLANE_BYTES, &full_bar[slot]);
+            ++wi;
+        };
+        while (walk.next(ch)) {
+            for (int k = 0; k < ch.n; ++k, ++it) {
+                const int aslot = it % NASLOT;
+                mbar_wait(&aempty_bar[aslot], ((it / NASLOT) & 1) ^ 1);
+                mbar_expect_tx(&afull_bar[aslot], (uint32_t)(NP * NGRA * PLANE_BYTES));
+                for (int p = 0; p < NP; ++p)
+                    for (int grp = 0; grp < NGRA; ++grp)
+                        bulk_g2s(a_base0 + aslot * ASLOT_BYTES + (p * NGA + grp) * PLANE_BYTES,
+                                 a.Pdy + plane_unit(a.g, NGRA, ch.b, ch.t0 + k + 1, p, grp, ch.fb * BM), PLANE_BYTES, &afull_bar[aslot]);
+                if (k == 0) { put_in(ch.t0); put_in(ch.t0 + 1); }      // t' of input rows t0-1, t0
+                put_in(ch.t0 + k + 2);                                  // t' of input row t0+k+1
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TM_COLS);
+    }
+}
+
+template <int C, int MODE>
+int launch_planes(cudaStream_t st, const PlaneArgs& a) {
+    constexpr int NGR = (C + 7) / 8;
+    dim3 grid((a.g.FP + 127) / 128, a.g.T + 2, a.g.B), block(128, NGR);
+    planes_kernel<C, MODE><<<grid, block, 0, st>>>(a);
+    PA2S_CHECK_LAST();
+    return 0;
+}
+template <int CIN, int COUT>
+int launch_conv(cudaStream_t st, const ConvArgs2& a) {
+    constexpr int CINP = (CIN + 15) / 16 * 16, COUTP = (COUT + 15) / 16 * 16;
+    constexpr int NG = CINP / 8, KS = CINP / 16;
+    constexpr int W_BYTES = 9 * KS * 2 * (2 * COUTP * 16);
+    constexpr int SMEM = ((W_BYTES + 127) / 128) * 128 + NWIN * (2 * NG * PLANE_BYTES) + 1024;
+    static_assert(SMEM <= 227 * 1024, "shared memory");
+    PA2S_TRY(cudaFuncSetAttribute(conv_tma_kernel<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    conv_tma_kernel<CIN, COUT><<<conv_grid(a.g.B, a.g.T, a.g.F), NTHREADS, SMEM, st>>>(a);
+    PA2S_CHECK_LAST();
+    return 0;
+}
+template <int CIN, int COUT>
+int launch_wgrad(cudaStream_t st, const WgradArgs2& a) {
+    constexpr int CINP = (CIN + 15) / 16 * 16;
+    constexpr int SMEM = NWIN * (2 * (CINP / 8) * PLANE_BYTES) + NASLOT * (2 * 8 * PLANE_BYTES) + 1024;
+    static_assert(SMEM <= 227 * 1024, "shared memory");
+    PA2S_TRY(cudaFuncSetAttribute(conv_wgrad_tma_kernel<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    conv_wgrad_tma_kernel<CIN, COUT><<<conv_grid(a.g.B, a.g.T, a.g.F), NTHREADS, SMEM, st>>>(a);
+    PA2S_CHECK_LAST();
+    return 0;
+}
+Geom make_geom(int B, int T, int F, int npieces) {
+    Geom g;
+    g.B = B; g.T = T; g.F = F; g.nfb = geom_nfb(F); g.FP = geom_fp(F); g.NP = npieces >= 2 ? 2 : 1;
+    return g;
+}
+
+}  // namespace
+
+// bytes of the plane tensor of a (B,T,F,C) activation with `npieces` (1 or 2) bf16 pieces
+PA2S_API long long pa2s_planes_bytes(int B, int T, int F, int C, int npieces) {
+    return (long long)B * (T + 2) * (npieces >= 2 ? 2 : 1) * ((C + 7) / 8) * geom_fp(F) * 16;
+}
+// planes of relu?(X*scale + shift) (scale NULL: identity): the BatchNorm-apply + ReLU between two convolutions (models.py:525-534)
+PA2S_API int pa2s_planes_fwd(void* stream, int B, int T, int F, int C, const float* X, const float* scale, const float* shift, int relu,
+                             void* planes, int npieces) {
+    PlaneArgs a;
+    a.X = X; a.Yraw = nullptr; a.P = (uint4*)planes; a.g = make_geom(B, T, F, npieces);
+    a.c0 = scale; a.c1 = shift; a.c2 = a.c3 = a.c4 = a.c5 = a.c6 = nullptr; a.relu = relu;
+    if (C == 20) return launch_planes<20, 0>((cudaStream_t)stream, a);
+    if (C == 40) return launch_planes<40, 0>((cudaStream_t)stream, a);
+    return -1;
+}
+// planes of dy = k1*(G*(Yraw*zs+zb > 0) - k2 - (Yraw-mean)*invstd*k3): BatchNorm + ReLU backward (autograd of models.py:525-534)
+PA2S_API int pa2s_planes_bwd(void* stream, int B, int T, int F, int C, const float* G, const float* Yraw, const float* zs, const float* zb,
+                             const float* mean, const float* invstd, const float* k1, const float* k2, const float* k3,
+                             void* planes, int npieces) {
+    PlaneArgs a;
+    a.X = G; a.Yraw = Yraw; a.P = (uint4*)planes; a.g = make_geom(B, T, F, npieces);
+    a.c0 = zs; a.c1 = zb; a.c2 = mean; a.c3 = invstd; a.c4 = k1; a.c5 = k2; a.c6 = k3; a.relu = 1;
+    if (C == 20) return launch_planes<20, 1>((cudaStream_t)stream, a);
+    if (C == 40) return launch_planes<40, 1>((cudaStream_t)stream, a);
+    return -1;
+}
+PA2S_API int pa2s_conv_tma_num_partials(int B, int T, int F) { return conv_grid(B, T, F) * 4; }
+PA2S_API int pa2s_conv_tma_wgrad_num_partials(int B, int T, int F) { return conv_grid(B, T, F); }
+// Y (B,T,F,Cout) = conv3x3 of the planes tensor (Cin channels) with Wpack (pa2s_tc_conv_pack: dgrad = 0 the forward filter,
+// dgrad = 1 the flipped / transposed filter, which makes this the data gradient: planes = dy, Cin = channels of dy).
+// partial (or NULL): pa2s_conv_tma_num_partials rows of [sum y, sum y^2].
+PA2S_API int pa2s_conv_tma(void* stream, int B, int T, int F, int Cin, int Cout, const void* planes, int npieces, const void* Wpack,
+                           float* Y, float* partial) {
+    ConvArgs2 a;
+    a.P = (const uint4*)planes; a.Wpack = (const uint4*)Wpack; a.Y = Y; a.partial = partial; a.g = make_geom(B, T, F, npieces);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (Cin == 20 && Cout == 20) return launch_conv<20, 20>(st, a);
+    if (Cin == 20 && Cout == 40) return launch_conv<20, 40>(st, a);
+    if (Cin == 40 && Cout == 40) return launch_conv<40, 40>(st, a);
+    if (Cin == 40 && Cout == 20) return launch_conv<40, 20>(st, a);
+    return -1;
+}
+// partial: pa2s_conv_tma_wgrad_num_partials rows of Cout*Cin*9 in torch (Cout,Cin,3,3) order.
+PA2S_API int pa2s_conv_tma_wgrad(void* stream, int B, int T, int F, int Cin, int Cout, const void* planes_in, const void* planes_dy,
+                                 int npieces, float* partial) {
+    WgradArgs2 a;
+    a.Pin = (const uint4*)planes_in; a.Pdy = (const uint4*)planes_dy; a.partial = partial; a.g = make_geom(B, T, F, npieces);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (Cin == 20 && Cout == 20) return launch_wgrad<20, 20>(st, a);
+    if (Cin == 20 && Cout == 40) return launch_wgrad<20, 40>(st, a);
+    if (Cin == 40 && Cout == 40) return launch_wgrad<40, 40>(st, a);
+    return -1;
+}

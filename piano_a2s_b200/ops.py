@@ -310,7 +310,7 @@ class ConvStackFn(torch.autograd.Function):
         O = Wout.shape[0]
         world = dist.get_world_size() if (sync and _dist_on()) else 1
         ntile = 4
-        ys, affs = [], []
+        ys, affs, planes = [], [], [None]
         xin, in_scale, in_shift = spec, None, None           # (B,1,T,F) == (B,T,F,1) channels-last
         for i in range(4):
             W = conv_w[i]
@@ -318,12 +318,17 @@ class ConvStackFn(torch.autograd.Function):
             y = torch.empty(B, T, Fq, Cout, device=dev, dtype=F32)
             use_tc = ctx.prec != "fp32" and Cin >= 16
             if use_tc:
+                # a_{i-1} = relu(bn(y_{i-1})) as bf16 planes: written once, read by this convolution and by its weight gradient
+                npc = min(npieces_for(ctx.prec), 2)
+                Pin = torch.empty(lib.pa2s_planes_bytes(B, T, Fq, Cin, npc), device=dev, dtype=torch.uint8)
+                with ktime(f"conv{i + 1}_planes"):
+                    lib.pa2s_planes_fwd(st, B, T, Fq, Cin, ptr(xin), ptr(in_scale), ptr(in_shift), 1, ptr(Pin), npc)
+                planes.append(Pin)
                 Wpk = _tc_pack(W, Cout, Cin, 0)
-                nparts = lib.pa2s_tc_conv_num_partials(B, T, Fq)
+                nparts = lib.pa2s_conv_tma_num_partials(B, T, Fq)
                 partial = torch.empty(nparts, 2 * Cout, device=dev, dtype=F32) if training else None
                 with ktime(f"conv{i + 1}_fwd"):
-                    lib.pa2s_tc_conv3x3(st, 0, B, T, Fq, Cin, Cout, ptr(xin), ptr(Wpk), ptr(y), ptr(partial), _nsplit(ctx.prec),
-                                        ptr(in_scale), ptr(in_shift), 1, None, None, None, None, None, None, None, None)
+                    lib.pa2s_conv_tma(st, B, T, Fq, Cin, Cout, ptr(Pin), npc, ptr(Wpk), ptr(y), ptr(partial))
             else:
                 Wp = W.detach().permute(2, 3, 1, 0).contiguous()
                 nparts = lib.pa2s_conv3x3_num_partials(B, T, Fq, ntile)
@@ -368,6 +373,7 @@ class ConvStackFn(torch.autograd.Function):
                 gemm(a4op, Wop, z, M, O, Kf, transB=True, ldc=O, zeroed=True)
             if training:
                 ctx.lin_ops = (a4op, Wop)
+        ctx.planes = planes if training else None
         aff5 = torch.empty(4, O, device=dev, dtype=F32)
         if training:
             nct = 4 * N_SM
@@ -463,12 +469,19 @@ class ConvStackFn(torch.autograd.Function):
             xin = ys[i - 1] if i > 0 else spec
             isc = affs[i - 1][0] if i > 0 else None
             ish = affs[i - 1][1] if i > 0 else None
-            if ctx.prec != "fp32" and Cin >= 16:
-                nwp = lib.pa2s_tc_conv_wgrad_num_partials(B, T, Fq)
+            tc = ctx.prec != "fp32" and Cin >= 16
+            if tc:
+                # dy_i = BatchNorm/ReLU backward of (G_i, y_i) as bf16 planes: read by the weight gradient and the data gradient
+                npc = min(npieces_for(ctx.prec), 2)
+                Pdy = torch.empty(lib.pa2s_planes_bytes(B, T, Fq, Cout, npc), device=dev, dtype=torch.uint8)
+                with ktime(f"conv{i + 1}_dy_planes"):
+                    lib.pa2s_planes_bwd(st, B, T, Fq, Cout, ptr(G), ptr(y), ptr(aff[0]), ptr(aff[1]), ptr(aff[2]), ptr(aff[3]),
+                                        ptr(k[0]), ptr(k[1]), ptr(k[2]), ptr(Pdy), npc)
+                nwp = lib.pa2s_conv_tma_wgrad_num_partials(B, T, Fq)
                 partial = torch.empty(nwp, Cout * Cin * 9, device=dev, dtype=F32)
                 with ktime(f"conv{i + 1}_wgrad"):
-                    lib.pa2s_tc_conv3x3_wgrad(st, B, T, Fq, Cin, Cout, ptr(xin), ptr(G), ptr(partial), _nsplit(ctx.prec), ptr(isc), ptr(ish), 1,
-                                              ptr(y), ptr(aff[0]), ptr(aff[1]), ptr(aff[2]), ptr(aff[3]), ptr(k[0]), ptr(k[1]), ptr(k[2]))
+                    lib.pa2s_conv_tma_wgrad(st, B, T, Fq, Cin, Cout, ptr(ctx.planes[i]), ptr(Pdy), npc, ptr(partial))
+                ctx.planes[i] = None
             else:
                 nwp = nw
                 partial = torch.empty(nw, Cout * Cin * 9, device=dev, dtype=F32)
@@ -480,11 +493,11 @@ class ConvStackFn(torch.autograd.Function):
             grads[3 * i] = dW
             if i > 0:
                 Gp = torch.empty(B, T, Fq, Cin, device=dev, dtype=F32)
-                if ctx.prec != "fp32":
+                if tc:
                     W2 = _tc_pack(W, Cout, Cin, 1)
                     with ktime(f"conv{i + 1}_dgrad"):
-                        lib.pa2s_tc_conv3x3(st, 1, B, T, Fq, Cout, Cin, ptr(G), ptr(W2), ptr(Gp), None, _nsplit(ctx.prec), None, None, 1,
-                                            ptr(y), ptr(aff[0]), ptr(aff[1]), ptr(aff[2]), ptr(aff[3]), ptr(k[0]), ptr(k[1]), ptr(k[2]))
+                        lib.pa2s_conv_tma(st, B, T, Fq, Cout, Cin, ptr(Pdy), npc, ptr(W2), ptr(Gp), None)
+                    del Pdy
                 else:
                     W2 = W.detach().flip(2, 3).permute(2, 3, 0, 1).contiguous()        # [tap][co][ci]
                     with ktime(f"conv{i + 1}_dgrad"):

@@ -135,3 +135,61 @@ def test_tc_conv_forward_and_dgrad_match_torch(cuda, Cin, Cout, B, T, Fq):
     e = rel_err(dW, ref_dw)
     print(f"tc conv wgrad: rel err {e:.2e}")
     assert e < 2e-5
+
+
+@pytest.mark.parametrize("Cin,Cout", [(20, 20), (20, 40), (40, 40)])
+@pytest.mark.parametrize("B,T,Fq,npieces", [(2, 9, 30, 2), (1, 70, 481, 2), (3, 5, 130, 1)])
+def test_conv_tma_planes_forward_dgrad_wgrad_match_torch(cuda, Cin, Cout, B, T, Fq, npieces):
+    """tc_conv_tma.cu: plane producers (BatchNorm-apply+ReLU / BatchNorm-ReLU backward, fused with the bf16 split) feeding the
+    bulk-copy-fed tcgen05 convolution (forward with batch-statistics epilogue, data gradient, weight gradient) vs float64 torch."""
+    from piano_a2s_b200 import ops
+    from piano_a2s_b200._lib import lib, ptr, stream
+    tol = 2e-5 if npieces == 2 else 2e-2
+    g = torch.Generator().manual_seed(Cin * 100 + Cout + T)
+    xraw = torch.randn(B, T, Fq, Cin, generator=g)
+    sc = torch.rand(Cin, generator=g) + 0.5
+    sh = torch.randn(Cin, generator=g) * 0.3
+    W = torch.randn(Cout, Cin, 3, 3, generator=g) * (1.0 / (3 * Cin ** 0.5))
+    a_in = F.relu(xraw.double() * sc.double() + sh.double())
+    ref = F.conv2d(a_in.permute(0, 3, 1, 2), W.double(), None, 1, 1).permute(0, 2, 3, 1)
+    xd, scd, shd, Wd = xraw.to(cuda), sc.to(cuda), sh.to(cuda), W.to(cuda)
+    Pin = torch.empty(lib.pa2s_planes_bytes(B, T, Fq, Cin, npieces), device=cuda, dtype=torch.uint8)
+    Pin.fill_(0x7f)                                     # the producer must write every halo byte itself
+    lib.pa2s_planes_fwd(stream(), B, T, Fq, Cin, ptr(xd), ptr(scd), ptr(shd), 1, ptr(Pin), npieces)
+    Wpk = ops._tc_pack(Wd, Cout, Cin, 0)
+    y = torch.empty(B, T, Fq, Cout, device=cuda)
+    partial = torch.zeros(lib.pa2s_conv_tma_num_partials(B, T, Fq), 2 * Cout, device=cuda)
+    lib.pa2s_conv_tma(stream(), B, T, Fq, Cin, Cout, ptr(Pin), npieces, ptr(Wpk), ptr(y), ptr(partial))
+    e = rel_err(y, ref)
+    print(f"conv_tma fwd {Cin}->{Cout} B{B} T{T} F{Fq} pieces {npieces}: rel err {e:.2e}")
+    assert e < tol
+    sums = partial.double().sum(0).cpu()
+    assert rel_err(sums[Cout:], (y.double().cpu() ** 2).sum((0, 1, 2))) < 1e-4
+    assert (sums[:Cout] - y.double().cpu().sum((0, 1, 2))).abs().max() < 1e-3 * (y.double().cpu().abs().sum((0, 1, 2)).max())
+    # backward: dy = BN/ReLU backward transform of (G, yraw)
+    yraw = ref.float()
+    G = torch.randn(B, T, Fq, Cout, generator=g)
+    zs = torch.rand(Cout, generator=g) + 0.5; zb = torch.randn(Cout, generator=g) * 0.2
+    mean = torch.randn(Cout, generator=g) * 0.1; invstd = torch.rand(Cout, generator=g) + 0.5
+    k1 = torch.rand(Cout, generator=g) + 0.5; k2 = torch.randn(Cout, generator=g) * 0.1; k3 = torch.randn(Cout, generator=g) * 0.1
+    z = yraw.double() * zs.double() + zb.double()
+    gg = torch.where(z > 0, G.double(), torch.zeros_like(z))
+    dy = k1.double() * (gg - k2.double() - (yraw.double() - mean.double()) * invstd.double() * k3.double())
+    cs = [t.to(cuda) for t in (yraw, zs, zb, mean, invstd, k1, k2, k3)]
+    Pdy = torch.empty(lib.pa2s_planes_bytes(B, T, Fq, Cout, npieces), device=cuda, dtype=torch.uint8)
+    Pdy.fill_(0x7f)
+    lib.pa2s_planes_bwd(stream(), B, T, Fq, Cout, ptr(G.to(cuda)), *[ptr(t) for t in cs], ptr(Pdy), npieces)
+    ref_dx = F.conv_transpose2d(dy.permute(0, 3, 1, 2), W.double(), None, 1, 1).permute(0, 2, 3, 1)
+    W2 = ops._tc_pack(Wd, Cout, Cin, 1)
+    dx = torch.empty(B, T, Fq, Cin, device=cuda)
+    lib.pa2s_conv_tma(stream(), B, T, Fq, Cout, Cin, ptr(Pdy), npieces, ptr(W2), ptr(dx), None)
+    e = rel_err(dx, ref_dx)
+    print(f"conv_tma dgrad: rel err {e:.2e}")
+    assert e < tol
+    ref_dw = torch.nn.grad.conv2d_weight(a_in.permute(0, 3, 1, 2), W.shape, dy.permute(0, 3, 1, 2), 1, 1)
+    part = torch.zeros(lib.pa2s_conv_tma_wgrad_num_partials(B, T, Fq), Cout * Cin * 9, device=cuda)
+    lib.pa2s_conv_tma_wgrad(stream(), B, T, Fq, Cin, Cout, ptr(Pin), ptr(Pdy), npieces, ptr(part))
+    dW = part.double().sum(0).view(Cout, Cin, 3, 3)
+    e = rel_err(dW, ref_dw)
+    print(f"conv_tma wgrad: rel err {e:.2e}")
+    assert e < tol
