@@ -238,7 +238,12 @@ def run_b200(args):
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        roof = roofline(ktimes, B, peaks)
+        traffic = {}
+        try:        # per-launch dram__bytes_read+write from the committed `ncu --set full` capture (profiles/), keyed by timer name
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        except Exception:
+            pass
+        roof, roof_all = roofline(ktimes, B, peaks, S, traffic)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cstep, threads = cpu_step_factory(args.cpu_clips)
@@ -258,25 +263,80 @@ def run_b200(args):
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(w0, w2),
-            "roofline": roof, "cpu_baseline": cpu}), flush=True)
+            "roofline": roof, "roofline_all": [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items()} for r in roof_all],
+            "cpu_baseline": cpu}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def roofline(ktimes, B, peaks):
-    """Dominant kernel of the step = the 40->40 3x3 convolution forward (conv4): algorithmic FLOPs per launch
-    2*T*F*9*Cin*Cout*B (16.603 GFLOP/clip) over its mean CUDA-event duration, against the measured dense
-    bf16 tensor peak (the contraction belongs on tcgen05; this round it still runs exact-fp32 FFMA)."""
-    name = "conv4_fwd"
-    if name not in ktimes:
-        return None
-    n, ms = ktimes[name]
-    flops = 2.0 * 1201 * 480 * 9 * 40 * 40 * B
-    achieved = flops / (ms * 1e-3) / 1e12
-    peak = peaks.get("bf16_tflops_sustained") or 1400.0
-    src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks.get("bf16_tflops_sustained") else "fallback 1.4 PFLOP/s sustained"
-    return {"kernel": "conv3x3_kernel<40,40,0> (conv4 forward)", "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-            "frac": achieved / peak, "traffic": None, "launches_timed": n, "ms_per_launch": ms, "peak_source": src}
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}     # B200_PROFILING.md fallback
+
+
+def algorithmic_work(B, S_total, n_dec_calls):
+    """{timer name: (kernel, FLOP per launch, compulsory HBM bytes per launch)} at T=1201, F=480 -- SURVEY 8(d)'s per-clip
+    figures x the B clips one launch processes.  Activations count as 4 B/element (fp32, or the two
+    bf16 pieces the bf16x3 contractions read); FLOPs are the single-precision-equivalent 2*MAC count, NOT x3 for the split."""
+    T, F = 1201, 480
+    px = float(T * F * B)
+    ch = [1, 20, 20, 40, 40]
+    w = {}
+    w["conv1_fwd"] = ("conv3x3_kernel<1,20> fp32 FFMA (conv1+stats)", 2 * 9 * 1 * 20 * px, px * 4 * (1 + 20))
+    w["conv1_wgrad"] = ("conv3x3_wgrad_kernel<1,20> fp32 FFMA", 2 * 9 * 1 * 20 * px, px * 4 * (1 + 20 + 20))
+    for i in (2, 3, 4):
+        ci, co = ch[i - 1], ch[i]
+        fl = 2.0 * 9 * ci * co * px
+        w[f"conv{i}_planes"] = (f"planes_kernel<{ci}> relu(bn(y)) -> bf16 hi/lo planes", 2 * ci * px, px * ci * (4 + 4))
+        w[f"conv{i}_fwd"] = (f"conv_tma_kernel<{ci},{co}> tcgen05 implicit GEMM fwd (+BN sums)", fl, px * 4 * (ci + co))
+        w[f"conv{i}_dy_planes"] = (f"planes_bwd_kernel<{co}> BN/ReLU backward -> bf16 planes", 8 * co * px, px * co * (4 + 4 + 4))
+        w[f"conv{i}_wgrad"] = (f"conv_wgrad_tma_kernel<{ci},{co}> tcgen05 weight gradient", fl, px * 4 * (ci + co))
+        w[f"conv{i}_dgrad"] = (f"conv_tma_kernel<{co},{ci}> tcgen05 data gradient", fl, px * 4 * (ci + co))
+    M, K, N = float(B * T), 19200.0, 256.0
+    lin = 2 * M * K * N
+    w["out_linear_split"] = ("split_bf16_kernel (a4 = relu(bn4(y4)) -> 3 bf16 pieces, W -> 3 pieces)", 2 * M * K, (M * K + N * K) * (4 + 6))
+    w["out_linear_fwd"] = ("tc_gemm_tma_kernel out Linear fwd", lin, (M * K + N * K) * 6 + M * N * 4)
+    w["out_linear_wgrad"] = ("tc_gemm_tma_kernel out Linear weight gradient", lin, (M * K + M * N) * 6 + N * K * 4)
+    w["out_linear_dgrad"] = ("tc_gemm_tma_kernel out Linear data gradient", lin, (M * N + N * K) * 6 + M * K * 4)
+    # encoder BiGRU recurrence, one launch = one layer, both directions: 2 dirs x T steps x B x 2*768*256 FLOP; reads gi, writes out (+gates)
+    w["encoder_gru_fwd"] = ("gru_seq_fwd_kernel (cluster-of-8 persistent BiGRU layer)", 2 * T * B * 2.0 * 768 * 256, B * T * 2 * (768 + 256 + 1024) * 4.0)
+    w["encoder_gru_bwd"] = ("gru_seq_bwd_kernel", 2 * 2 * T * B * 2.0 * 768 * 256, B * T * 2 * (768 + 256 + 1024 + 768) * 4.0)
+    # note decoder: per executed step and clip 6.27 MFLOP and 3.69 MB streamed (enc 2.46 MB + Ep 1.23 MB; L2-resident at B=16)
+    steps = S_total / max(n_dec_calls, 1)
+    w["note_decoder_fwd"] = ("dec_persist_fwd_kernel (all steps of one (bar, staff), cooperative)", 6.27e6 * B * steps, 3.69e6 * B * steps)
+    w["note_decoder_bwd"] = ("dec_persist_bwd_kernel (+dlogits, out-projection GEMM, deferred dEp/dv)", 2 * 6.27e6 * B * steps, 3.69e6 * B * steps)
+    return w
+
+
+def roofline(ktimes, B, peaks, S_total, traffic=None):
+    """One entry per timed kernel group; the headline `roofline` object is the group with the largest share of the step.
+    achieved = algorithmic FLOPs (or bytes) per launch / mean CUDA-event duration of the launch (events recorded on the
+    launching stream inside the timed region); the bound reported is the roof that binds for the algorithmic numbers."""
+    measured = bool(peaks.get("hbm_gbs"))
+    pk = peaks if measured else FALLBACK_PEAKS
+    hbm = float(pk.get("hbm_gbs") or FALLBACK_PEAKS["hbm_gbs"])
+    tf = float(pk.get("bf16_tflops_sustained") or pk.get("bf16_tflops") or FALLBACK_PEAKS["bf16_tflops_sustained"])
+    src = "MEASURED_PEAKS.json (hbm_gbs, bf16_tflops_sustained)" if measured else "fallback of B200_PROFILING.md (6.65 TB/s, 1.4 PFLOP/s sustained)"
+    n_dec = ktimes.get("note_decoder_fwd", (10, 0))[0] // max(ktimes.get("conv1_fwd", (1, 0))[0], 1)
+    work = algorithmic_work(B, S_total, n_dec)
+    rows = []
+    for name, (n, ms) in ktimes.items():
+        if name not in work or ms <= 0:
+            continue
+        kern, fl, by = work[name]
+        t_tensor, t_hbm = fl / (tf * 1e12), by / (hbm * 1e9)
+        bound = "tensor" if t_tensor > t_hbm else "hbm"
+        if bound == "tensor":
+            ach, peak, unit = fl / (ms * 1e-3) / 1e12, tf, "TFLOP/s"
+        else:
+            ach, peak, unit = by / (ms * 1e-3) / 1e9, hbm, "GB/s"
+        rows.append({"timer": name, "kernel": kern, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+                     "traffic": (traffic or {}).get(name), "launches_timed": n, "ms_per_launch": ms, "ms_total": n * ms,
+                     "tflops_algorithmic": fl / (ms * 1e-3) / 1e12, "gbs_algorithmic": by / (ms * 1e-3) / 1e9})
+    if not rows:
+        return None, []
+    rows.sort(key=lambda r: -r["ms_total"])
+    top = dict(rows[0])
+    top["peak_source"] = src
+    return top, rows
 
 
 if __name__ == "__main__":

@@ -3,8 +3,11 @@ pretrain.py:56-129; finetune.py:55-127) without speechbrain: 4 NLL losses, backw
 averaging, gradient clipping and the Adadelta update (pretrain.yaml:44-47), all on libpa2s kernels.
 
 Data parallelism: one process per GPU, batch-sharded; BatchNorm statistics are reduced across
-ranks inside ConvStackFn (SyncBatchNorm semantics) and parameter gradients are averaged with ONE NCCL all-reduce over
-a flat fp32 gradient buffer (16.36 M elements = 65.4 MB).
+ranks inside ConvStackFn (SyncBatchNorm semantics) and parameter gradients are averaged by NCCL all-reduces over
+contiguous buckets of a flat fp32 gradient buffer (16.36 M elements = 65.4 MB).  A bucket is reduced as soon as
+autograd has accumulated its last gradient (post-accumulate hooks), on NCCL's own stream, so the decoder and
+encoder buckets travel over NVLink while the ConvStack backward is still running (what torch DDP does for the
+reference under speechbrain).
 """
 from __future__ import annotations
 
@@ -29,7 +32,7 @@ class FlatAdadelta:
     """All parameters (and their .grad) re-pointed into two flat fp32 buffers; clip_grad_norm_(max_grad_norm) +
     torch.optim.Adadelta(lr, rho, eps) semantics in two kernels (sum of squares, fused update)."""
 
-    def __init__(self, model, lr=1.0, rho=0.95, eps=1e-8, max_grad_norm=5.0):
+    def __init__(self, model, lr=1.0, rho=0.95, eps=1e-8, max_grad_norm=5.0, bucket_bytes=24 << 20, overlap=True):
         self.params = [p for p in model.parameters() if p.requires_grad]
         # every parameter starts on a 256-byte boundary: the kernels read weight rows with 128-bit loads
         al = lambda k: (k + 63) // 64 * 64
@@ -42,22 +45,77 @@ class FlatAdadelta:
         self.sumsq = torch.zeros(1, device=dev, dtype=torch.float64)
         self.norm = torch.zeros(1, device=dev, dtype=torch.float32)
         off = 0
+        self.offsets = []
         for p in self.params:
             k = p.numel()
             self.flat[off:off + k].copy_(p.data.reshape(-1))
             p.data = self.flat[off:off + k].view_as(p.data)
             p.grad = self.grad[off:off + k].view_as(p.data)
+            self.offsets.append(off)
             off += al(k)
         self.n = n
         self.lr, self.rho, self.eps, self.max_grad_norm = lr, rho, eps, max_grad_norm
+        # gradient buckets: contiguous parameter ranges of <= bucket_bytes, formed from the LAST parameter backwards because
+        # backward produces gradients in roughly reverse registration order (decoder, encoder, ConvStack)
+        self.buckets = []            # [lo, hi) element ranges of the flat buffer
+        hi, members = n, []
+        for i in range(len(self.params) - 1, -1, -1):
+            members.append(i)
+            if (hi - self.offsets[i]) * 4 >= bucket_bytes or i == 0:
+                self.buckets.append((self.offsets[i], hi, members))
+                hi, members = self.offsets[i], []
+        self.bucket_of = [0] * len(self.params)
+        for b, (_, _, idx) in enumerate(self.buckets):
+            for i in idx:
+                self.bucket_of[i] = b
+        self._pending = [len(idx) for _, _, idx in self.buckets]
+        self._works = [None] * len(self.buckets)
+        self.overlap = overlap
+        self.launched_early = 0      # buckets whose all-reduce started from a hook (i.e. before backward returned)
+        if overlap:
+            for i, p in enumerate(self.params):
+                p.register_post_accumulate_grad_hook(self._make_hook(i))
+
+    @staticmethod
+    def _world():
+        return dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+
+    def _reduce_bucket(self, b):
+        lo, hi, _ = self.buckets[b]
+        view = self.grad[lo:hi]
+        if dist.get_backend() == "nccl":
+            self._works[b] = (dist.all_reduce(view, op=dist.ReduceOp.AVG, async_op=True), None)
+        else:
+            self._works[b] = (dist.all_reduce(view, async_op=True), view)
+
+    def _make_hook(self, i):
+        def hook(_p):
+            if self._world() == 1:
+                return
+            b = self.bucket_of[i]
+            self._pending[b] -= 1
+            if self._pending[b] == 0 and self._works[b] is None:
+                self._reduce_bucket(b)
+                self.launched_early += 1
+        return hook
 
     def zero_grad(self):
         self.grad.zero_()
 
     def allreduce_mean(self):
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.grad)
-            self.grad.div_(dist.get_world_size())
+        """Completes the gradient mean over ranks: buckets not yet started by a hook (parameters without a gradient this
+        step, or overlap=False) are reduced now, then the compute stream waits for every bucket."""
+        world = self._world()
+        if world > 1:
+            for b in range(len(self.buckets)):
+                if self._works[b] is None:
+                    self._reduce_bucket(b)
+            for b, (work, view) in enumerate(self._works):
+                work.wait()
+                if view is not None:
+                    view.div_(world)
+        self._pending = [len(idx) for _, _, idx in self.buckets]
+        self._works = [None] * len(self.buckets)
 
     def step(self):
         st = stream()

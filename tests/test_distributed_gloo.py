@@ -30,6 +30,27 @@ def _worker(rank, world, port, q):
             p.grad.fill_(float(rank + 1) * (i + 1))
         opt.allreduce_mean()
         ok = all(torch.allclose(p.grad, torch.full_like(p.grad, 1.5 * (i + 1))) for i, p in enumerate(lin.parameters()))
+        # overlapped path: buckets are reduced from post-accumulate hooks during backward; result = mean of the per-rank gradients
+        torch.manual_seed(0)
+        net = torch.nn.Sequential(torch.nn.Linear(7, 173), torch.nn.Tanh(), torch.nn.Linear(173, 3))
+        opt2 = FlatAdadelta(net, bucket_bytes=1024)
+        assert len(opt2.buckets) >= 2 and sorted(i for b in opt2.buckets for i in b[2]) == list(range(4))
+        assert all(b[0] < b[1] for b in opt2.buckets) and opt2.buckets[0][1] == opt2.n and opt2.buckets[-1][0] == 0
+        xs_all = [torch.randn(5, 7, generator=torch.Generator().manual_seed(100 + r)) for r in range(world)]
+        expect = []
+        for r in range(world):
+            ref = torch.nn.Sequential(torch.nn.Linear(7, 173), torch.nn.Tanh(), torch.nn.Linear(173, 3))
+            ref.load_state_dict({k: v.clone() for k, v in net.state_dict().items()})
+            ref(xs_all[r]).square().sum().backward()
+            expect.append([q_.grad.clone() for q_ in ref.parameters()])
+        for _ in range(2):                      # twice: the bucket bookkeeping must reset between steps
+            opt2.zero_grad()
+            opt2.launched_early = 0
+            net(xs_all[rank]).square().sum().backward()
+            ok = ok and opt2.launched_early == len(opt2.buckets)
+            opt2.allreduce_mean()
+            for i, q_ in enumerate(net.parameters()):
+                ok = ok and torch.allclose(q_.grad, sum(e[i] for e in expect) / world, rtol=1e-5, atol=1e-6)
         # SyncBatchNorm statistics: global mean/var from all-reduced fp64 (sum, sumsq) equals the statistics of the union
         x = torch.randn(5 + rank, 4, dtype=torch.float64)
         sums = torch.cat([x.sum(0), (x * x).sum(0), torch.tensor([float(x.shape[0])], dtype=torch.float64)])
