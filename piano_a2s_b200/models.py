@@ -140,7 +140,7 @@ class HierarchicalDecoder(nn.Module):
                                      nn.Linear(hidden_size * 2, num_keys))
         self.consume_python_rng = True      # keep the reference's python-`random` consumption count in inference too
         self.parallel_staves = True
-        self._side_stream = None
+        self._side_streams = None
         self.init_weight()
 
     def init_weight(self):
@@ -205,7 +205,7 @@ class HierarchicalDecoder(nn.Module):
 
         token = self.get_SOS_token(B)[0].squeeze(1)                      # (B, 4*staff+ts+key)
         h = hidden[0]
-        ts_outs, key_outs, up_outs, lo_outs, counters = [], [], [], [], []
+        ts_outs, key_outs, up_outs, lo_outs, counters, pending = [], [], [], [], [], []
         for bar in range(self.max_bars):
             if training:
                 token = token * src.dropout_mask((B, 1, token.shape[-1]), 0.1, dev, "bar_token").view(B, -1)
@@ -214,26 +214,36 @@ class HierarchicalDecoder(nn.Module):
             g = self.gru
             h = ops.gru_cell(torch.cat([token, context], dim=1), h, g.weight_ih_l0, g.weight_hh_l0, g.bias_ih_l0, g.bias_hh_l0)
             bar_summary = h
-            # the two staves only depend on bar_summary (models.py:261-275): decode them concurrently on two streams
+            # The two staves only depend on bar_summary (models.py:261-275), and the bar-level chain itself only depends on
+            # their OUTPUT when the next bar token is built from predictions (models.py:289-311).  So the note decoders run on
+            # two side streams, alternating so that the long (upper) and short (lower) staves balance, while the bar chain
+            # (heads, staff summaries, next bar's attention + GRU) runs ahead on the current stream; it waits for the decoders
+            # only when it has to read their predictions.
             res = []
             main = torch.cuda.current_stream() if enc.is_cuda else None
+            use_streams = self.parallel_staves and main is not None
+            if use_streams and self._side_streams is None:
+                self._side_streams = (torch.cuda.Stream(), torch.cuda.Stream())
+            ready = main.record_event() if use_streams else None
+            done = []
             for si, (dec, Ep) in enumerate(((self.upper_decoder, Ep_up), (self.lower_decoder, Ep_lo))):
                 gt_staff = (upper_gt, lower_gt)[si][:, bar, :] if have_gt else None
                 tf_in = teacher_forcing_ratio if have_gt else 0.
-                if si == 1 and self.parallel_staves and main is not None:
-                    if self._side_stream is None:
-                        self._side_stream = torch.cuda.Stream()
-                    side = self._side_stream
-                    side.wait_stream(main)
+                if use_streams:
+                    side = self._side_streams[(bar + si) % 2]
+                    side.wait_event(ready)
+                    for t_ in (enc, Ep, bar_summary) + ((gt_staff,) if gt_staff is not None else ()):
+                        t_.record_stream(side)
                     with torch.cuda.stream(side):
                         out = dec._decode(enc, Ep, bar_summary, inference, gt_staff, tf_in, steps[si][bar], src)
-                    main.wait_stream(side)
+                    done.append(side.record_event())
                     for t_ in out:
                         t_.record_stream(main)
                     res.append(out)
                 else:
                     res.append(dec._decode(enc, Ep, bar_summary, inference, gt_staff, tf_in, steps[si][bar], src))
             (up_p, up_len, up_cnt), (lo_p, lo_len, lo_cnt) = res
+            pending += done
             counters += [up_cnt, lo_cnt]
             up_outs.append(up_p)
             lo_outs.append(lo_p)
@@ -243,17 +253,24 @@ class HierarchicalDecoder(nn.Module):
             ts_outs.append(ts_lp)
             key_outs.append(key_lp)
             teacher_force = src.coin() < teacher_forcing_ratio
+            if bar == self.max_bars - 1:
+                break                                                    # the token built after the last bar is never used
             if teacher_force and not inference and have_gt:
                 us = self._staff_summary(upper_gt[:, bar, :], upper_len_gt[:, bar])
                 ls = self._staff_summary(lower_gt[:, bar, :], lower_len_gt[:, bar])
                 tst = self.time_sig_emb(time_sig_gt[:, bar])
                 kyt = self.key_emb(key_gt[:, bar])
             else:
+                for ev in pending:                                       # predictions of this bar feed the next bar token
+                    main.wait_event(ev)
+                pending = []
                 us = self._staff_summary(torch.argmax(up_p, dim=-1), up_len)
                 ls = self._staff_summary(torch.argmax(lo_p, dim=-1), lo_len)
                 tst = self.time_sig_emb(torch.argmax(ts_lp, dim=-1))
                 kyt = self.key_emb(torch.argmax(key_lp, dim=-1))
             token = torch.cat([us, ls, tst, kyt], dim=-1)
+        for ev in pending:
+            main.wait_event(ev)
         if not have_gt and self.consume_python_rng:
             # the reference draws one coin per executed note step (models.py:404); only the count matters here
             src.coins(int(torch.stack(counters)[:, 1].sum().item()))
