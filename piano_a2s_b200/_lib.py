@@ -8,7 +8,7 @@ import re
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpa2s.so")
+LIB_PATH = os.environ.get("PA2S_LIB") or os.path.join(HERE, "libpa2s.so")      # PA2S_LIB: an alternative build (kernel experiments)
 HEADER = os.path.join(os.path.dirname(HERE), "include", "pa2s.h")
 
 _SCALARS = {"int": ctypes.c_int, "long long": ctypes.c_longlong, "float": ctypes.c_float, "double": ctypes.c_double,

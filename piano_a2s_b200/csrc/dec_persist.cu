@@ -20,6 +20,10 @@ constexpr int PG = 64;                 // CTAs of a persistent decoder grid (two
 #ifndef PA2S_DEC_NT
 #define PA2S_DEC_NT 384
 #endif
+#ifndef PA2S_DEC_PD
+#define PA2S_DEC_PD 2
+#endif
+constexpr int PD = PA2S_DEC_PD;        // frames per warp in flight in the attention phases (register ring depth)
 constexpr int NT = PA2S_DEC_NT;        // threads per CTA: 12 warps stream the attention memory, the first 8 own the GEMV columns
 constexpr int NW = NT / 32;
 constexpr int UPC = DD / PG;           // hidden units per CTA (8)
@@ -31,6 +35,26 @@ constexpr int KM4 = 2 * DD / 4;        // float4 columns of the main part (256 =
 static_assert(KM4 <= NT, "one float4 column of [h|ctx] per thread of the first 8 warps");
 
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+
+// streaming 16-byte load of the encoder memory (read once per step by exactly one warp)
+#ifndef PA2S_DEC_LD
+#define PA2S_DEC_LD 0
+#endif
+__device__ __forceinline__ float4 lds4(const float4* p) {
+#if PA2S_DEC_LD == 0
+    return __ldg(p);
+#else
+    float4 v;
+#if PA2S_DEC_LD == 1
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+#elif PA2S_DEC_LD == 2
+    asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+#else
+    asm volatile("ld.global.nc.L1::evict_first.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+#endif
+    return v;
+#endif
+}
 
 // Grid barrier for a co-resident grid: monotonically increasing arrival counter.  A watchdog turns a lost CTA into an
 // error flag instead of a hang.
@@ -64,6 +88,17 @@ __device__ __forceinline__ unsigned long long gtimer() {
             const unsigned long long now_ = gtimer();                                \
             a.prof[i] += now_ - prof_t;                                              \
             prof_t = now_;                                                           \
+        }                                                                            \
+    } while (0)
+
+// sub-phase timing inside a device function (CTA 0, thread 0): prof[i] += ns since sub_t0, without moving the phase clock
+#define SUB_BEGIN() unsigned long long sub_t = (a.prof != nullptr && threadIdx.x == 0 && blockIdx.x == 0) ? gtimer() : 0ull
+#define SUB_MARK(i)                                                                  \
+    do {                                                                             \
+        if (a.prof != nullptr && threadIdx.x == 0 && blockIdx.x == 0) {              \
+            const unsigned long long now_ = gtimer();                                \
+            a.prof[i] += now_ - sub_t;                                               \
+            sub_t = now_;                                                            \
         }                                                                            \
     } while (0)
 
@@ -132,9 +167,11 @@ __device__ void attn_item(const DecArgs& a, const FwdSmem& S, int s, int b, int 
     const int T = a.T;
     const int t0 = js * a.tile, t1 = min(T, t0 + a.tile);
     const float* q = a.qs + ((size_t)hslot(a, s) * a.B + b) * DA;
+    SUB_BEGIN();
     __syncthreads();
     if (tid < DA) S.qv[tid] = __ldcg(q + tid);
     __syncthreads();
+    SUB_MARK(8);
     float* araw = a.attn + ((size_t)slot(a, s) * a.B + b) * T;
     float m = -INFINITY, l = 0.f;
     float4 cacc[4];
@@ -150,47 +187,56 @@ __device__ void attn_item(const DecArgs& a, const FwdSmem& S, int s, int b, int 
             for (int u = 0; u < FU; ++u) {
                 const int t = min(tb + u, t1 - 1);
                 const float4* ep = reinterpret_cast<const float4*>(a.Ep + ((size_t)b * T + t) * DA);
-                r.e0[u] = __ldg(ep + lane);
-                r.e1[u] = __ldg(ep + 32 + lane);
+                r.e0[u] = lds4(ep + lane);
+                r.e1[u] = lds4(ep + 32 + lane);
                 const float4* en = reinterpret_cast<const float4*>(a.enc + ((size_t)b * T + t) * DD);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) r.en[u][j] = __ldg(en + j * 32 + lane);
+                for (int j = 0; j < 4; ++j) r.en[u][j] = lds4(en + j * 32 + lane);
             }
         };
-        AttnRows cur, nxt;
-        int tb = t0 + warp * FU;
-        if (tb < t1) load(cur, tb);
-        for (; tb < t1; tb += NW * FU) {
-            if (tb + NW * FU < t1) load(nxt, tb + NW * FU);
+        // PD frames per warp in flight: slot i of the register ring is refilled as soon as its frame has been consumed
+        AttnRows ring[PD];
+        const int tb0 = t0 + warp * FU;
 #pragma unroll
-            for (int u = 0; u < FU; ++u) {
-                float e = v0.x * tanh_fast(q0.x + cur.e0[u].x) + v0.y * tanh_fast(q0.y + cur.e0[u].y) + v0.z * tanh_fast(q0.z + cur.e0[u].z) +
-                          v0.w * tanh_fast(q0.w + cur.e0[u].w) + v1.x * tanh_fast(q1.x + cur.e1[u].x) + v1.y * tanh_fast(q1.y + cur.e1[u].y) +
-                          v1.z * tanh_fast(q1.z + cur.e1[u].z) + v1.w * tanh_fast(q1.w + cur.e1[u].w);
-                e = warp_sum(e);
-                if (tb + u < t1) {                              // warp-uniform
-                    if (lane == 0) araw[tb + u] = e;            // raw score; normalised by the combining CTA
-                    if (e > m) {
-                        const float sc = expf(m - e);           // 0 on the first frame (m = -inf)
-                        l *= sc;
+        for (int i = 0; i < PD; ++i)
+            if (tb0 + i * NW * FU < t1) load(ring[i], tb0 + i * NW * FU);
+        for (int tb = tb0; tb < t1; tb += PD * NW * FU) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) { cacc[j].x *= sc; cacc[j].y *= sc; cacc[j].z *= sc; cacc[j].w *= sc; }
-                        m = e;
-                    }
-                    const float p = expf(e - m);
-                    l += p;
+            for (int i = 0; i < PD; ++i) {
+                const int tc = tb + i * NW * FU;
+                if (tc >= t1) break;                            // warp-uniform
+                const AttnRows cur = ring[i];
+                if (tc + PD * NW * FU < t1) load(ring[i], tc + PD * NW * FU);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        cacc[j].x = fmaf(p, cur.en[u][j].x, cacc[j].x);
-                        cacc[j].y = fmaf(p, cur.en[u][j].y, cacc[j].y);
-                        cacc[j].z = fmaf(p, cur.en[u][j].z, cacc[j].z);
-                        cacc[j].w = fmaf(p, cur.en[u][j].w, cacc[j].w);
+                for (int u = 0; u < FU; ++u) {
+                    float e = v0.x * tanh_fast(q0.x + cur.e0[u].x) + v0.y * tanh_fast(q0.y + cur.e0[u].y) + v0.z * tanh_fast(q0.z + cur.e0[u].z) +
+                              v0.w * tanh_fast(q0.w + cur.e0[u].w) + v1.x * tanh_fast(q1.x + cur.e1[u].x) + v1.y * tanh_fast(q1.y + cur.e1[u].y) +
+                              v1.z * tanh_fast(q1.z + cur.e1[u].z) + v1.w * tanh_fast(q1.w + cur.e1[u].w);
+                    e = warp_sum(e);
+                    if (tc + u < t1) {                          // warp-uniform
+                        if (lane == 0) araw[tc + u] = e;        // raw score; normalised by the combining CTA
+                        if (e > m) {
+                            const float sc = expf(m - e);       // 0 on the first frame (m = -inf)
+                            l *= sc;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) { cacc[j].x *= sc; cacc[j].y *= sc; cacc[j].z *= sc; cacc[j].w *= sc; }
+                            m = e;
+                        }
+                        const float p = expf(e - m);
+                        l += p;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            cacc[j].x = fmaf(p, cur.en[u][j].x, cacc[j].x);
+                            cacc[j].y = fmaf(p, cur.en[u][j].y, cacc[j].y);
+                            cacc[j].z = fmaf(p, cur.en[u][j].z, cacc[j].z);
+                            cacc[j].w = fmaf(p, cur.en[u][j].w, cacc[j].w);
+                        }
                     }
                 }
             }
-            cur = nxt;
         }
     }
+    SUB_MARK(9);
     float* part = S.red;                                        // NW x DD per-warp partial contexts
 #pragma unroll
     for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(part + warp * DD + j * 128 + lane * 4) = cacc[j];
@@ -219,6 +265,7 @@ __device__ void attn_item(const DecArgs& a, const FwdSmem& S, int s, int b, int 
         if (is_last) a.tickets[b] = 0;
     }
     __syncthreads();
+    SUB_MARK(10);
     if (!is_last) return;
     __threadfence();
     M = -INFINITY;
@@ -242,6 +289,7 @@ __device__ void attn_item(const DecArgs& a, const FwdSmem& S, int s, int b, int 
         reinterpret_cast<float2*>(cs)[tid] = make_float2(c0 * invL, c1 * invL);
     }
     for (int t = tid; t < T; t += NT) araw[t] = expf(__ldcg(araw + t) - M) * invL;
+    SUB_MARK(11);
 }
 
 // ------------------------------------------------------------------------------------------------ phase D
@@ -693,6 +741,7 @@ __device__ void bwd_attn_item(const DecArgs& a, const BwdSmem& S, int s, int b, 
     const int T = a.T;
     const int t0 = js * a.tile, t1 = min(T, t0 + a.tile);
     const size_t sb = (size_t)s * a.B + b;
+    SUB_BEGIN();
     __syncthreads();
     for (int d = tid; d < DD; d += NTB) {
         const float v = __ldg(a.dhc_all + sb * 2 * DD + DD + d) + __ldcg(a.dx + (size_t)b * DX + DE + d);
@@ -719,6 +768,7 @@ __device__ void bwd_attn_item(const DecArgs& a, const BwdSmem& S, int s, int b, 
     const float4 v0 = *reinterpret_cast<const float4*>(vv + lane * 4);
     const float4 v1 = *reinterpret_cast<const float4*>(vv + 128 + lane * 4);
     float dq[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    SUB_MARK(8);
     const float* at = a.attn + sb * T;
     float* dsrow = a.ds_all + sb * T;
     const float vk[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
@@ -727,30 +777,38 @@ __device__ void bwd_attn_item(const DecArgs& a, const BwdSmem& S, int s, int b, 
     auto load = [&](Rows& r, int t) {
         const float4* e4 = reinterpret_cast<const float4*>(a.enc + ((size_t)b * T + t) * DD);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) r.en[i] = __ldg(e4 + i * 32 + lane);
+        for (int i = 0; i < 4; ++i) r.en[i] = lds4(e4 + i * 32 + lane);
         const float4* ep = reinterpret_cast<const float4*>(a.Ep + ((size_t)b * T + t) * DA);
-        r.e0 = __ldg(ep + lane); r.e1 = __ldg(ep + 32 + lane);
+        r.e0 = lds4(ep + lane); r.e1 = lds4(ep + 32 + lane);
         r.aw = at[t];
     };
-    Rows cur, nxt;
-    int t = t0 + warp;
-    if (t < t1) load(cur, t);
-    for (; t < t1; t += NTB / 32) {                   // one frame per warp iteration, the next one already in flight
-        if (t + NTB / 32 < t1) load(nxt, t + NTB / 32);
-        float da = 0.f;
+    Rows ring[PD];                                    // PD frames per warp in flight (register ring)
+    constexpr int NWB = NTB / 32;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) da += dot4(dcr[i], cur.en[i]);
-        da = warp_sum(da);
-        const float ds = cur.aw * (da - c0);
-        if (lane == 0) dsrow[t] = ds;
-        const float ev[8] = {cur.e0.x, cur.e0.y, cur.e0.z, cur.e0.w, cur.e1.x, cur.e1.y, cur.e1.z, cur.e1.w};
+    for (int i = 0; i < PD; ++i)
+        if (t0 + warp + i * NWB < t1) load(ring[i], t0 + warp + i * NWB);
+    for (int tb = t0 + warp; tb < t1; tb += PD * NWB) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float uu = tanh_fast(qk[i] + ev[i]);
-            dq[i] = fmaf(ds * vk[i], 1.f - uu * uu, dq[i]);
+        for (int i = 0; i < PD; ++i) {
+            const int t = tb + i * NWB;
+            if (t >= t1) break;                       // warp-uniform
+            const Rows cur = ring[i];
+            if (t + PD * NWB < t1) load(ring[i], t + PD * NWB);
+            float da = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) da += dot4(dcr[k], cur.en[k]);
+            da = warp_sum(da);
+            const float ds = cur.aw * (da - c0);
+            if (lane == 0) dsrow[t] = ds;
+            const float ev[8] = {cur.e0.x, cur.e0.y, cur.e0.z, cur.e0.w, cur.e1.x, cur.e1.y, cur.e1.z, cur.e1.w};
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float uu = tanh_fast(qk[k] + ev[k]);
+                dq[k] = fmaf(ds * vk[k], 1.f - uu * uu, dq[k]);
+            }
         }
-        cur = nxt;
     }
+    SUB_MARK(9);
 #pragma unroll
     for (int i = 0; i < 4; ++i) { accq[warp * DA + lane * 4 + i] = dq[i]; accq[warp * DA + 128 + lane * 4 + i] = dq[4 + i]; }
     __syncthreads();
@@ -768,6 +826,7 @@ __device__ void bwd_attn_item(const DecArgs& a, const BwdSmem& S, int s, int b, 
         if (is_last) a.tickets[b] = 0;
     }
     __syncthreads();
+    SUB_MARK(10);
     if (!is_last) return;
     __threadfence();
     if (tid < DA) {

@@ -203,6 +203,14 @@ class HierarchicalDecoder(nn.Module):
             return ops.linear(enc2, att.attn.weight[:, D:], att.attn.bias).view(B, T, -1)
         Ep_bar, Ep_up, Ep_lo = ep(self.attn), ep(self.upper_decoder.attn), ep(self.lower_decoder.attn)
 
+        # weight gradients of the two note decoders: one set of contractions per backward pass over all bars (ops.DecoderWeightSinkFn)
+        sunk = [None, None]
+        if torch.is_grad_enabled() and enc.is_cuda:
+            for si, dec in enumerate((self.upper_decoder, self.lower_decoder)):
+                if all(w.requires_grad for w in dec._weights()):
+                    sink = ops.DecoderGradSink()
+                    sunk[si] = (sink, ops.DecoderWeightSinkFn.apply(sink, *dec._weights()))
+
         token = self.get_SOS_token(B)[0].squeeze(1)                      # (B, 4*staff+ts+key)
         h = hidden[0]
         ts_outs, key_outs, up_outs, lo_outs, counters, pending = [], [], [], [], [], []
@@ -235,13 +243,13 @@ class HierarchicalDecoder(nn.Module):
                     for t_ in (enc, Ep, bar_summary) + ((gt_staff,) if gt_staff is not None else ()):
                         t_.record_stream(side)
                     with torch.cuda.stream(side):
-                        out = dec._decode(enc, Ep, bar_summary, inference, gt_staff, tf_in, steps[si][bar], src)
+                        out = dec._decode(enc, Ep, bar_summary, inference, gt_staff, tf_in, steps[si][bar], src, sunk[si])
                     done.append(side.record_event())
                     for t_ in out:
                         t_.record_stream(main)
                     res.append(out)
                 else:
-                    res.append(dec._decode(enc, Ep, bar_summary, inference, gt_staff, tf_in, steps[si][bar], src))
+                    res.append(dec._decode(enc, Ep, bar_summary, inference, gt_staff, tf_in, steps[si][bar], src, sunk[si]))
             (up_p, up_len, up_cnt), (lo_p, lo_len, lo_cnt) = res
             pending += done
             counters += [up_cnt, lo_cnt]
@@ -303,8 +311,14 @@ class NoteDecoder(nn.Module):
         init_gru(self.gru)
         init_layer(self.out)
 
-    def _decode(self, enc, Ep, h0, inference, gt, tf_ratio, S, src):
-        """All steps of one (bar, staff).  Coins/masks are pre-drawn in the reference's order (models.py:391,404)."""
+    def _weights(self):
+        g = self.gru
+        return (self.attn.attn.weight, self.attn.v.weight, self.embedding.weight, g.weight_ih_l0, g.weight_hh_l0, g.bias_ih_l0,
+                g.bias_hh_l0, self.out.weight, self.out.bias)
+
+    def _decode(self, enc, Ep, h0, inference, gt, tf_ratio, S, src, sunk=None):
+        """All steps of one (bar, staff).  Coins/masks are pre-drawn in the reference's order (models.py:391,404).
+        `sunk` = (DecoderGradSink, weight aliases from DecoderWeightSinkFn) when the caller defers the weight gradients."""
         B = enc.shape[0]
         dev = enc.device
         training = self.training
@@ -318,9 +332,10 @@ class NoteDecoder(nn.Module):
             mask = src.dropout_mask((S, B, self.note_emb_size), 0.1, dev, "note_steps").contiguous()
         cfg = dict(S=S, max_steps=self.max_steps, inference=inference or not have_gt, gt=gt.contiguous() if have_gt else None,
                    use_gt=use_gt, mask=mask, sos=SOS, eos=EOS)
-        g = self.gru
-        return ops.NoteDecoderFn.apply(enc, Ep, h0, self.attn.attn.weight, self.attn.v.weight, self.embedding.weight,
-                                       g.weight_ih_l0, g.weight_hh_l0, g.bias_ih_l0, g.bias_hh_l0, self.out.weight, self.out.bias, cfg)
+        wts = self._weights()
+        if sunk is not None:
+            cfg["sink"], wts = sunk
+        return ops.NoteDecoderFn.apply(enc, Ep, h0, *wts, cfg)
 
     def decode_notes(self, encoder_outputs, hidden, inference=True, ground_truth=None, teacher_forcing_ratio=0):
         if inference:

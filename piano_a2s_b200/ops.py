@@ -786,6 +786,7 @@ class NoteDecoderFn(torch.autograd.Function):
             ctx.save_for_backward(enc, Ep, attn_w, wts["v"], emb, W_ih, W_hh, W_out, logp, sv["hs"], sv["ctxs"], sv["attn"], sv["gates"],
                                   sv["qs"], sv["xtok"], sv["toks"], mask if mask is not None else torch.empty(0, device=dev))
             ctx.meta = (B, T, D, A, V, E, VP, S, max_steps, NS, tile, mask is not None, attn_v.shape)
+            ctx.sink = cfg.get("sink")
         return logp, lengths, counters
 
     @staticmethod
@@ -833,30 +834,102 @@ class NoteDecoderFn(torch.autograd.Function):
             with ktime("note_decoder_bwd"):
                 lib.pa2s_note_decoder_bwd(st, ctypes.byref(args))
             dh0 = bw["dh_carry"][0] + bw["dhq"]
-        SB = S * B
-        # deferred weight gradients: contractions over all (step, clip) rows
-        dW_out = z(V, 2 * D)
-        gemm(bw["dlogits_all"], hs, dW_out, V, D, SB, transA=True, lda=VP, ldb=D, ldc=2 * D, b_off=B * D, zeroed=True)   # h' part
-        gemm(bw["dlogits_all"], ctxs, dW_out, V, D, SB, transA=True, lda=VP, ldb=D, ldc=2 * D, c_off=D, zeroed=True)      # ctx part
-        db_out = colsum(bw["dlogits_all"].view(SB, VP))[:V].contiguous()
-        dW_ih = z(3 * D, X)
-        gemm(bw["dgi_all"], xtok, dW_ih, 3 * D, E, SB, transA=True, lda=3 * D, ldb=E, ldc=X, zeroed=True)
-        gemm(bw["dgi_all"], ctxs, dW_ih, 3 * D, D, SB, transA=True, lda=3 * D, ldb=D, ldc=X, c_off=E, zeroed=True)
-        db_ih = colsum(bw["dgi_all"].view(SB, 3 * D))
-        dW_hh = z(3 * D, D)
-        gemm(bw["dgh_all"], hs, dW_hh, 3 * D, D, SB, transA=True, lda=3 * D, ldb=D, ldc=D, zeroed=True)
-        db_hh = colsum(bw["dgh_all"].view(SB, 3 * D))
-        d_attn_w = z(A, 2 * D)
-        gemm(bw["dq_all"], hs, d_attn_w, A, D, SB, transA=True, lda=A, ldb=D, ldc=2 * D, zeroed=True)                    # W_h half only
-        dv = colsum(bw["dv_part"]).reshape(vshape)
-        # embedding: scatter-add of the (masked) token-input gradients
         dxt = bw["dxtok_all"]
         if has_mask:
             dxt = dxt * mask[:S]
-        d_emb = z(V, E)
-        d_emb.index_add_(0, toks[:S].reshape(-1).long(), dxt.reshape(SB, E))
+        rec = dict(S=S, B=B, dlogits=bw["dlogits_all"], hs=hs, ctxs=ctxs, dgi=bw["dgi_all"], dgh=bw["dgh_all"], dq=bw["dq_all"],
+                   xtok=xtok, dv_part=bw["dv_part"], dxt=dxt, toks=toks)
+        dims = (D, A, V, E, VP, vshape)
+        sink = ctx.sink
+        if sink is not None:
+            # weight gradients of this module are formed once per backward pass, over the rows of ALL its calls (one per bar)
+            rec["event"] = torch.cuda.current_stream().record_event()
+            rec["stream"] = torch.cuda.current_stream()
+            sink.records.append(rec)
+            sink.dims = dims
+            wg = (None,) * 9
+        else:
+            wg = decoder_weight_grads([rec], dims)
         denc = context_grad_enc(attn, bw["dctx_all"], B, T, D, S)
-        return (denc, bw["dEp"], dh0, d_attn_w, dv, d_emb, dW_ih, dW_hh, db_ih, db_hh, dW_out, db_out, None)
+        return (denc, bw["dEp"], dh0) + tuple(wg) + (None,)
+
+
+def decoder_weight_grads(recs, dims):
+    """Deferred weight gradients of a NoteDecoder: contractions over the (step, clip) rows saved by one or several calls.
+    -> (d_attn_w, dv, d_emb, dW_ih, dW_hh, db_ih, db_hh, dW_out, db_out), the parameter order of NoteDecoderFn."""
+    D, A, V, E, VP, vshape = dims
+    X = E + D
+    dev = recs[0]["hs"].device
+    z = lambda *s_: torch.zeros(*s_, device=dev, dtype=F32)
+
+    def rows(key, lo=0):
+        parts = [r[key][lo:lo + r["S"]].reshape(r["S"] * r["B"], -1) for r in recs]
+        return parts[0] if len(parts) == 1 else torch.cat(parts)
+    SB = sum(r["S"] * r["B"] for r in recs)
+    dlogits, dgi, dgh, dq = rows("dlogits"), rows("dgi"), rows("dgh"), rows("dq")
+    h_prev, h_new, ctxs, xtok = rows("hs"), rows("hs", 1), rows("ctxs"), rows("xtok")
+    dW_out = z(V, 2 * D)
+    gemm(dlogits, h_new, dW_out, V, D, SB, transA=True, lda=VP, ldb=D, ldc=2 * D, zeroed=True)                # h' part
+    gemm(dlogits, ctxs, dW_out, V, D, SB, transA=True, lda=VP, ldb=D, ldc=2 * D, c_off=D, zeroed=True)        # ctx part
+    db_out = colsum(dlogits)[:V].contiguous()
+    dW_ih = z(3 * D, X)
+    gemm(dgi, xtok, dW_ih, 3 * D, E, SB, transA=True, lda=3 * D, ldb=E, ldc=X, zeroed=True)
+    gemm(dgi, ctxs, dW_ih, 3 * D, D, SB, transA=True, lda=3 * D, ldb=D, ldc=X, c_off=E, zeroed=True)
+    db_ih = colsum(dgi)
+    dW_hh = z(3 * D, D)
+    gemm(dgh, h_prev, dW_hh, 3 * D, D, SB, transA=True, lda=3 * D, ldb=D, ldc=D, zeroed=True)
+    db_hh = colsum(dgh)
+    d_attn_w = z(A, 2 * D)
+    gemm(dq, h_prev, d_attn_w, A, D, SB, transA=True, lda=A, ldb=D, ldc=2 * D, zeroed=True)                  # W_h half only
+    dvp = [r["dv_part"] for r in recs]
+    dv = colsum(dvp[0] if len(dvp) == 1 else torch.cat(dvp)).reshape(vshape)
+    # embedding: scatter-add of the (masked) token-input gradients
+    d_emb = z(V, E)
+    toks = torch.cat([r["toks"][:r["S"]].reshape(-1) for r in recs]).long()
+    d_emb.index_add_(0, toks, rows("dxt"))
+    return d_attn_w, dv, d_emb, dW_ih, dW_hh, db_ih, db_hh, dW_out, db_out
+
+
+class DecoderGradSink:
+    """Per NoteDecoder module and forward pass: the step buffers its calls (one per bar) leave behind in backward."""
+    def __init__(self):
+        self.records, self.dims = [], None
+
+
+class DecoderWeightSinkFn(torch.autograd.Function):
+    """Identity on the nine NoteDecoder weights.  Every NoteDecoderFn call that uses the returned aliases hands its weight
+    gradients here as saved rows instead of computing them: autograd runs this node after the last of those calls, and the
+    gradients are then ONE set of contractions over all bars (K = sum of S*B) on the stream the forward ran on.  Besides the
+    5x fewer small GEMMs this keeps parameter-gradient accumulation off the two decoder streams, where autograd's
+    AccumulateGrad (pinned to the stream of a parameter's first use) serialised the two staves of every other bar."""
+
+    @staticmethod
+    def forward(ctx, sink, *weights):
+        ctx.prec = current_precision()
+        ctx.sink = sink
+        ctx.set_materialize_grads(False)
+        return tuple(w.view_as(w) for w in weights)
+
+    @staticmethod
+    @_bwd_precision
+    def backward(ctx, *grads):
+        sink = ctx.sink
+        recs, sink.records = sink.records, []
+        out = [None] * 9
+        if recs:
+            cur = torch.cuda.current_stream()
+            for r in recs:
+                if r["stream"] != cur:
+                    cur.wait_event(r["event"])
+                    for v in r.values():
+                        if torch.is_tensor(v):
+                            v.record_stream(cur)
+            out = list(decoder_weight_grads(recs, sink.dims))
+        for i, g in enumerate(grads):            # uses of the aliases outside NoteDecoderFn (none on the hot path)
+            if g is not None:
+                out[i] = g if out[i] is None else out[i] + g
+        return (None,) + tuple(out)
+
 
 
 # ----------------------------------------------------------------------------------------------------------------

@@ -34,8 +34,8 @@ def run():
 for _ in range(2):
     run()
 torch.cuda.synchronize()
-ops.PROF["fwd"] = torch.zeros(8, dtype=torch.int64, device=dev)
-ops.PROF["bwd"] = torch.zeros(8, dtype=torch.int64, device=dev)
+ops.PROF["fwd"] = torch.zeros(16, dtype=torch.int64, device=dev)
+ops.PROF["bwd"] = torch.zeros(16, dtype=torch.int64, device=dev)
 ops.KernelTimers.reset(True)
 run()
 torch.cuda.synchronize()
@@ -44,6 +44,8 @@ kt = ops.KernelTimers.summary()
 for k, names in (("fwd", ["A attention(+D)", "barrier", "B gru", "barrier", "C logits+q", "barrier", "prologue"]),
                  ("bwd", ["P1 gates", "barrier", "P2 gemv", "barrier", "P3 attention", "barrier"])):
     v = ops.PROF[k].cpu().tolist()
-    print(f"{k}: B={B} S={S} total {sum(v) / 1e3:.1f} us  ({sum(v) / 1e3 / S:.2f} us/step)   call {kt.get('note_decoder_' + k, (0, 0))[1]:.3f} ms")
+    print(f"{k}: B={B} S={S} total {sum(v[:7]) / 1e3:.1f} us  ({sum(v[:7]) / 1e3 / S:.2f} us/step)   call {kt.get('note_decoder_' + k, (0, 0))[1]:.3f} ms")
     for n, x in zip(names, v):
         print(f"    {n:18s} {x / 1e3 / S:8.2f} us/step")
+    for n, x in zip(["attn: stage q/dc", "attn: frame loop", "attn: combine+ticket", "attn: last-arriver"], v[8:12]):
+        print(f"      {n:22s} {x / 1e3 / S:8.2f} us/step")

@@ -41,6 +41,20 @@ def main():
         step()
         torch.cuda.synchronize()
     evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+    if os.environ.get("PA2S_TIMELINE"):
+        # coarse timeline: per stream (device_index of a CUDA event = stream id in kineto), kernels >= 100 us, and per-stream busy time
+        import re
+        tl = sorted(((e.time_range.start, e.time_range.end, getattr(e, "device_resource_id", -1), e.name) for e in evs), key=lambda x: x[0])
+        t00 = tl[0][0]
+        busy = collections.defaultdict(float)
+        for s_, e_, st, n in tl:
+            busy[st] += e_ - s_
+        print("per-stream kernel time (ms):", {k: round(v * 1e-3, 2) for k, v in busy.items()})
+        for s_, e_, st, n in tl:
+            lo, hi = [float(x) for x in os.environ.get("PA2S_TIMELINE_WINDOW", "0,0").split(",")]
+            if e_ - s_ >= 100 or lo <= 1e-3 * (s_ - t00) <= hi:
+                short = re.sub(r"\(anonymous namespace\)::|void ", "", n)[:60]
+                print(f"  t={1e-3 * (s_ - t00):8.3f}  dur={1e-3 * (e_ - s_):7.3f}  stream={st}  {short}")
     ks = sorted(((e.time_range.start, e.time_range.end, e.name) for e in evs), key=lambda x: x[0])
     t0, t1 = ks[0][0], max(k[1] for k in ks)
     # union of busy intervals
