@@ -292,10 +292,11 @@ def algorithmic_work(B, S_total, n_dec_calls):
         w[f"conv{i}_dgrad"] = (f"conv_tma_kernel<{co},{ci}> tcgen05 data gradient", fl, px * 4 * (ci + co))
     M, K, N = float(B * T), 19200.0, 256.0
     lin = 2 * M * K * N
-    w["out_linear_split"] = ("split_bf16_kernel (a4 = relu(bn4(y4)) -> 3 bf16 pieces, W -> 3 pieces)", 2 * M * K, (M * K + N * K) * (4 + 6))
-    w["out_linear_fwd"] = ("tc_gemm_tma_kernel out Linear fwd", lin, (M * K + N * K) * 6 + M * N * 4)
-    w["out_linear_wgrad"] = ("tc_gemm_tma_kernel out Linear weight gradient", lin, (M * K + M * N) * 6 + N * K * 4)
-    w["out_linear_dgrad"] = ("tc_gemm_tma_kernel out Linear data gradient", lin, (M * N + N * K) * 6 + M * K * 4)
+    # bf16x3 holds an fp32 operand as TWO bf16 pieces (hi, lo): 4 B/element read by the GEMM, 4 B read + 4 B written by the split
+    w["out_linear_split"] = ("split_bf16_kernel (a4 = relu(bn4(y4)) -> bf16 hi/lo, W -> hi/lo)", 2 * M * K, (M * K + N * K) * (4 + 4))
+    w["out_linear_fwd"] = ("tc_gemm_tma_kernel out Linear fwd", lin, (M * K + N * K) * 4 + M * N * 4)
+    w["out_linear_wgrad"] = ("tc_gemm_tma_kernel out Linear weight gradient", lin, (M * K + M * N) * 4 + N * K * 4)
+    w["out_linear_dgrad"] = ("tc_gemm_tma_kernel out Linear data gradient", lin, (M * N + N * K) * 4 + M * K * 4)
     # encoder BiGRU recurrence, one launch = one layer, both directions: 2 dirs x T steps x B x 2*768*256 FLOP; reads gi, writes out (+gates)
     w["encoder_gru_fwd"] = ("gru_seq_fwd_kernel (cluster-of-8 persistent BiGRU layer)", 2 * T * B * 2.0 * 768 * 256, B * T * 2 * (768 + 256 + 1024) * 4.0)
     w["encoder_gru_bwd"] = ("gru_seq_bwd_kernel", 2 * 2 * T * B * 2.0 * 768 * 256, B * T * 2 * (768 + 256 + 1024 + 768) * 4.0)

@@ -119,6 +119,10 @@ PA2S_API int pa2s_conv3x3_wgrad(void* stream, int B, int T, int F, int Cin, int 
                                 const float* k1, const float* k2, const float* k3);
 /* out[n] (=|+=) sum_r partial[r][n], accumulated in fp64. */
 PA2S_API int pa2s_reduce_rows(void* stream, const float* partial, int R, int N, double* out64, float* out32, int accumulate);
+/* Same sum for a TALL matrix (bias gradients: R = B*T rows), two deterministic stages over `nchunks` row chunks;
+ * scratch holds nchunks*N doubles.  Replaces the bias-gradient reductions autograd derives for nn.GRU / nn.Linear
+ * (models.py:63-67,444). */
+PA2S_API int pa2s_colsum(void* stream, const float* X, int R, int N, double* scratch, int nchunks, float* out32, int accumulate);
 /* per-channel sums over (npix, C): mode 0 [sum x, sum x^2]; mode 1 [sum g, sum g*xhat] (BatchNorm backward). */
 PA2S_API int pa2s_colstats(void* stream, int mode, const float* X, const float* G, const float* mask, long long npix, int C,
                            const float* zs, const float* zb, const float* mean, const float* invstd, float* partial, int nctas);
@@ -181,4 +185,9 @@ PA2S_API int pa2s_nll_bwd(void* stream, float* grad, const long long* tgt, long 
 PA2S_API int pa2s_sumsq(void* stream, const float* g, long long n, double* out, int zero_first);
 PA2S_API int pa2s_adadelta(void* stream, float* p, const float* g, float* sq, float* acc, long long n, const double* sumsq,
                            float max_norm, float lr, float rho, float eps, float* norm_out);
+/* ---- token post-processing -----------------------------------------------------------------------
+ * tokens[seq][r] = argmax_v logp[seq][r][v] (lowest index on ties, like torch.argmax) and lengths[seq] = index of the first
+ * <eos> token (L if none): `pred = outs.argmax(-1)` + `unpad` of pretrain.py:97-117,245-249 / finetune.py:86-108 for all
+ * (clip, bar) sequences of one staff in one launch.  tokens is int64 (nseq, L), lengths int32 (nseq). */
+PA2S_API int pa2s_greedy_tokens(void* stream, const float* logp, long long nseq, int L, int V, int eos, long long* tokens, int* lengths);
 #endif

@@ -232,7 +232,8 @@ __global__ void __launch_bounds__(NTHR) conv3x3_wgrad_kernel(WgradArgs a) {
 // ---------------------------------------------------------------------------------------------------------
 // Reductions over rows of partials
 // ---------------------------------------------------------------------------------------------------------
-__global__ void reduce_rows_kernel(const float* __restrict__ partial, int R, int N, double* __restrict__ out64,
+template <typename TIN>
+__global__ void reduce_rows_kernel(const TIN* __restrict__ partial, int R, int N, double* __restrict__ out64,
                                    float* __restrict__ out32, int accumulate) {
     // one CTA per column block of 32; 8 row-lanes x 32 columns, double accumulation
     __shared__ double s[8][33];
@@ -248,6 +249,36 @@ __global__ void reduce_rows_kernel(const float* __restrict__ partial, int R, int
         for (int i = 0; i < 8; ++i) t += s[i][threadIdx.x & 31];
         if (out64 != nullptr) out64[col] = accumulate ? out64[col] + t : t;
         if (out32 != nullptr) out32[col] = accumulate ? out32[col] + (float)t : (float)t;
+    }
+}
+
+// Column sums of a TALL (R, N) matrix, stage 1: CTA (x, y) sums rows [y*rpc, (y+1)*rpc) of columns [32x, 32x+32) in double
+// (8 row-lanes, 4 rows in flight per lane) and writes partial[y][col]; stage 2 is reduce_rows_kernel<double> over the chunks.
+// Deterministic (no atomics): bias gradients of the GRU / attention projections sum 19 216 rows (models.py:63-67,444).
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ X, int R, int N, int rpc,
+                                                             double* __restrict__ partial) {
+    __shared__ double s[8][33];
+    const int lane = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int col = blockIdx.x * 32 + lane;
+    const int r0 = blockIdx.y * rpc, r1 = min(R, r0 + rpc);
+    double acc = 0.0;
+    if (col < N) {
+        const float* p = X + col;
+        int r = r0 + rl;
+        for (; r + 24 < r1; r += 32) {
+            const float a0 = __ldg(p + (size_t)r * N), a1 = __ldg(p + (size_t)(r + 8) * N);
+            const float a2 = __ldg(p + (size_t)(r + 16) * N), a3 = __ldg(p + (size_t)(r + 24) * N);
+            acc += ((double)a0 + (double)a1) + ((double)a2 + (double)a3);
+        }
+        for (; r < r1; r += 8) acc += (double)__ldg(p + (size_t)r * N);
+    }
+    s[rl][lane] = acc;
+    __syncthreads();
+    if (rl == 0 && col < N) {
+        double t = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += s[i][lane];
+        partial[(size_t)blockIdx.y * N + col] = t;
     }
 }
 
@@ -473,7 +504,19 @@ PA2S_API int pa2s_conv3x3_wgrad(void* stream, int B, int T, int F, int Cin, int 
 }
 
 PA2S_API int pa2s_reduce_rows(void* stream, const float* partial, int R, int N, double* out64, float* out32, int accumulate) {
-    reduce_rows_kernel<<<ceil_div(N, 32), 256, 0, (cudaStream_t)stream>>>(partial, R, N, out64, out32, accumulate);
+    reduce_rows_kernel<float><<<ceil_div(N, 32), 256, 0, (cudaStream_t)stream>>>(partial, R, N, out64, out32, accumulate);
+    PA2S_CHECK_LAST();
+    return 0;
+}
+
+PA2S_API int pa2s_colsum(void* stream, const float* X, int R, int N, double* scratch, int nchunks, float* out32, int accumulate) {
+    if (R <= 0 || N <= 0 || nchunks <= 0) return -1;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int rpc = ceil_div(R, nchunks);
+    nchunks = ceil_div(R, rpc);
+    colsum_partial_kernel<<<dim3(ceil_div(N, 32), nchunks), 256, 0, st>>>(X, R, N, rpc, scratch);
+    PA2S_CHECK_LAST();
+    reduce_rows_kernel<double><<<ceil_div(N, 32), 256, 0, st>>>(scratch, nchunks, N, nullptr, out32, accumulate);
     PA2S_CHECK_LAST();
     return 0;
 }

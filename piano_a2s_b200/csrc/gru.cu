@@ -33,6 +33,16 @@ struct GruSeqArgs {
     int B, T, ND, G;
 };
 
+// 16-byte asynchronous global -> shared copy (LDGSTS).  Unlike a register load, it is not waited for by the release
+// fence of the per-step cluster barrier, so a stage issued several steps ahead stays in flight across barriers.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+constexpr int EPF = 4;           // stages of per-step operands in flight (encoder recurrences)
+
 template <int BG>
 __device__ __forceinline__ float pick(const float (&v)[BG], int s) {
     float r = v[0];
@@ -73,13 +83,27 @@ __global__ void __launch_bounds__(ENT, 1) gru_seq_fwd_kernel(GruSeqArgs a) {
     const int b = b0 + s;
     const bool gate_thread = (s < BG) && (b < a.B);
     int p = 0;
+    // Input pre-activations (gi: a 118 MB stream) are staged EPF-1 steps ahead with asynchronous copies, so their DRAM latency
+    // never sits on the sequential chain: threads 0..BG*3*8-1 each move 16 bytes of the [sample][gate][32 units] slice per step.
+    __shared__ __align__(16) float gis[EPF][BG][3][EU];
+    auto issue = [&](int step_) {
+        if (step_ < T && tid < BG * 3 * 8) {
+            const int seg = tid >> 3, q = tid & 7, bb = seg / 3, g = seg % 3;
+            if (b0 + bb < a.B) {
+                const int t_ = dir == 0 ? step_ : T - 1 - step_;
+                cp_async16(&gis[step_ % EPF][bb][g][q * 4],
+                           a.gi + ((size_t)(b0 + bb) * T + t_) * ND * 3 * H + dir * 3 * H + g * H + rank * EU + q * 4);
+            }
+        }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int i = 0; i < EPF - 1; ++i) issue(i);
+    cp_async_wait<EPF - 2>();
+    __syncthreads();
     for (int step = 0; step < T; ++step) {
         const int t = dir == 0 ? step : T - 1 - step;
-        float gir = 0.f, giz = 0.f, gin = 0.f;
-        if (gate_thread) {
-            const float* gp = a.gi + ((size_t)b * T + t) * ND * 3 * H + dir * 3 * H + j;
-            gir = __ldg(gp); giz = __ldg(gp + H); gin = __ldg(gp + 2 * H);
-        }
+        issue(step + EPF - 1);
         float acc[3][BG];
 #pragma unroll
         for (int g = 0; g < 3; ++g)
@@ -110,6 +134,7 @@ __global__ void __launch_bounds__(ENT, 1) gru_seq_fwd_kernel(GruSeqArgs a) {
                 acc[g][bb] = v;
             }
         if (gate_thread) {
+            const float gir = gis[step % EPF][s][0][u], giz = gis[step % EPF][s][1][u], gin = gis[step % EPF][s][2][u];
             float ghr = pick<BG>(acc[0], s) + bhr, ghz = pick<BG>(acc[1], s) + bhz, ghn = pick<BG>(acc[2], s) + bhn;
             float r = sigmoidf_(gir + ghr), z = sigmoidf_(giz + ghz);
             float n = tanhf(gin + r * ghn);
@@ -125,6 +150,7 @@ __global__ void __launch_bounds__(ENT, 1) gru_seq_fwd_kernel(GruSeqArgs a) {
 #pragma unroll
             for (int c = 0; c < ECL; ++c) remote[c][off] = hn;
         }
+        cp_async_wait<EPF - 2>();          // the stage of step+1 has landed (made visible CTA-wide by the barrier below)
         cluster.sync();
         p ^= 1;
     }
@@ -162,19 +188,39 @@ __global__ void __launch_bounds__(ENT, 1) gru_seq_bwd_kernel(GruSeqArgs a) {
     cluster.sync();
 
     int p = 0;
+    // Saved gates (157 MB per layer), previous state and upstream gradient of each step are staged EPF-1 steps ahead with
+    // asynchronous copies: [r, z, n, hn_lin, h_prev, dOut][sample][32 units], 16 bytes per thread of the first BG*6*8.
+    __shared__ __align__(16) float stg[EPF][6][BG][EU];
+    auto issue = [&](int step_) {          // step_ counts DOWN from T-1; slot = step_ % EPF
+        if (step_ >= 0 && tid < BG * 6 * 8) {
+            const int seg = tid >> 3, q = tid & 7, bb = seg / 6, c = seg % 6;
+            if (b0 + bb < a.B) {
+                const int t_ = dir == 0 ? step_ : T - 1 - step_;
+                const size_t bt_ = (size_t)(b0 + bb) * T + t_;
+                float* dst = &stg[step_ % EPF][c][bb][q * 4];
+                const int col = rank * EU + q * 4;
+                if (c < 4) cp_async16(dst, a.gates + (bt_ * ND + dir) * 4 * H + c * H + col);
+                else if (c == 5) cp_async16(dst, a.dOut + bt_ * ND * H + dir * H + col);
+                else if (step_ > 0) cp_async16(dst, a.out + ((size_t)(b0 + bb) * T + (dir == 0 ? t_ - 1 : t_ + 1)) * ND * H + dir * H + col);
+                else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int i = 0; i < EPF - 1; ++i) issue(T - 1 - i);
+    cp_async_wait<EPF - 2>();
+    __syncthreads();
     for (int step = T - 1; step >= 0; --step) {
         const int t = dir == 0 ? step : T - 1 - step;
         float dh_direct = 0.f;
+        issue(step - (EPF - 1));
         if (gate_thread) {
             const size_t bt = (size_t)b * T + t;
-            const float* gs = a.gates + (bt * ND + dir) * 4 * H + j;
-            float r = gs[0], z = gs[H], n = gs[2 * H], hnl = gs[3 * H];
-            float hp = 0.f;
-            if (step > 0) {
-                const int tp = dir == 0 ? t - 1 : t + 1;
-                hp = a.out[((size_t)b * T + tp) * ND * H + dir * H + j];
-            }
-            float dh = a.dOut[bt * ND * H + dir * H + j] + dhc;
+            const int sl = step % EPF;
+            const float r = stg[sl][0][s][u], z = stg[sl][1][s][u], n = stg[sl][2][s][u], hnl = stg[sl][3][s][u];
+            const float hp = stg[sl][4][s][u], dout_t = stg[sl][5][s][u];
+            float dh = dout_t + dhc;
             float dn = dh * (1.f - z), dzv = dh * (hp - n);
             float dn_pre = dn * (1.f - n * n);
             float dr_pre = dn_pre * hnl * r * (1.f - r);
@@ -191,6 +237,7 @@ __global__ void __launch_bounds__(ENT, 1) gru_seq_bwd_kernel(GruSeqArgs a) {
                 remote[c][off] = dr_pre; remote[c][off + H] = dz_pre; remote[c][off + 2 * H] = dhn_lin;
             }
         }
+        cp_async_wait<EPF - 2>();          // the stage of step-1 has landed; the barrier below makes it visible CTA-wide
         cluster.sync();
         float acc[BG];
 #pragma unroll
@@ -416,6 +463,7 @@ PA2S_API int pa2s_gru_seq_max_bg(void) { return 4; }
 PA2S_API int pa2s_gru_seq_fwd(void* stream, int B, int T, int ND, int H, int bg, const float* gi, const float* Whh, const float* bhh,
                               float* out, float* gates, float* hN) {
     if (H != EH) return -1;
+    if (((uintptr_t)gi & 15) != 0) return -1;          // staged with 16-byte asynchronous copies
     GruSeqArgs a = {};
     a.gi = gi; a.Whh = Whh; a.bhh = bhh; a.out = out; a.gates = gates; a.hN = hN; a.B = B; a.T = T; a.ND = ND;
     a.G = ceil_div(B, bg);
@@ -430,6 +478,7 @@ PA2S_API int pa2s_gru_seq_fwd(void* stream, int B, int T, int ND, int H, int bg,
 PA2S_API int pa2s_gru_seq_bwd(void* stream, int B, int T, int ND, int H, int bg, const float* Whh, const float* out, const float* gates,
                               const float* dOut, const float* dhN, float* dgi, float* dgh) {
     if (H != EH) return -1;
+    if ((((uintptr_t)out | (uintptr_t)gates | (uintptr_t)dOut) & 15) != 0) return -1;          // staged with 16-byte asynchronous copies
     GruSeqArgs a = {};
     a.Whh = Whh; a.out = const_cast<float*>(out); a.gates = const_cast<float*>(gates); a.dOut = dOut; a.dhN = dhN; a.dgi = dgi; a.dgh = dgh;
     a.B = B; a.T = T; a.ND = ND;

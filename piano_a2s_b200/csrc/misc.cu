@@ -101,6 +101,49 @@ __global__ void adadelta_kernel(float* __restrict__ p, const float* __restrict__
     }
 }
 
+
+// argmax over the vocabulary + cut at the first <eos> (pretrain.py:97-117 `pred = outs.argmax(-1)` and `unpad`,
+// pretrain.py:245-249): one CTA per sequence (clip, bar), one warp per row; ties resolve to the LOWEST index like
+// torch.argmax; NaN rows resolve to the first NaN (torch treats NaN as the maximum).
+__global__ void greedy_tokens_kernel(const float* __restrict__ logp, int L, int V, int eos, long long* __restrict__ tokens,
+                                     int* __restrict__ lengths) {
+    const long long seq = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __shared__ int first_eos;
+    if (threadIdx.x == 0) first_eos = L;
+    __syncthreads();
+    for (int r = warp; r < L; r += nw) {
+        const float* row = logp + (seq * L + r) * V;
+        float best = -INFINITY;
+        int bi = V;
+        bool bnan = false;
+        for (int c = lane; c < V; c += 32) {
+            const float x = __ldg(row + c);
+            const bool xn = x != x;
+            if (bnan) continue;
+            if (xn || x > best || bi == V) { best = x; bi = c; bnan = xn; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            const bool on = ob != ob;
+            bool take;
+            if (oi == V) take = false;
+            else if (bi == V) take = true;
+            else if (bnan || on) take = on && (!bnan || oi < bi);
+            else take = ob > best || (ob == best && oi < bi);
+            if (take) { best = ob; bi = oi; bnan = on; }
+        }
+        if (lane == 0) {
+            tokens[seq * L + r] = bi;
+            if (bi == eos) atomicMin(&first_eos, r);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) lengths[seq] = first_eos;
+}
+
 }  // namespace
 
 PA2S_API int pa2s_vqt_post(void* stream, const float* C, float* out, unsigned int* clip_max, int nclips, int rows_per_clip, int nb) {
@@ -145,6 +188,13 @@ PA2S_API int pa2s_sumsq(void* stream, const float* g, long long n, double* out, 
 PA2S_API int pa2s_adadelta(void* stream, float* p, const float* g, float* sq, float* acc, long long n, const double* sumsq,
                            float max_norm, float lr, float rho, float eps, float* norm_out) {
     adadelta_kernel<<<592, 256, 0, (cudaStream_t)stream>>>(p, g, sq, acc, n, sumsq, max_norm, lr, rho, eps, norm_out);
+    PA2S_CHECK_LAST();
+    return 0;
+}
+
+PA2S_API int pa2s_greedy_tokens(void* stream, const float* logp, long long nseq, int L, int V, int eos, long long* tokens, int* lengths) {
+    if (nseq <= 0 || L <= 0 || V <= 0) return nseq == 0 ? 0 : -1;
+    greedy_tokens_kernel<<<(unsigned)nseq, 256, 0, (cudaStream_t)stream>>>(logp, L, V, eos, tokens, lengths);
     PA2S_CHECK_LAST();
     return 0;
 }

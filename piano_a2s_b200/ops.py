@@ -222,7 +222,13 @@ def colsum(X2d: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate=Fal
     R, N = X2d.shape
     if out is None:
         out = torch.empty(N, device=X2d.device, dtype=F32)
-    lib.pa2s_reduce_rows(stream(), ptr(X2d), R, N, None, ptr(out), int(accumulate))
+    if R >= 512:
+        # tall: spread the rows over ~2 CTAs per SM (two deterministic stages) instead of ceil(N/32) CTAs walking all rows
+        nchunks = max(1, min((R + 63) // 64, (2 * N_SM) // ((N + 31) // 32)))
+        scratch = torch.empty(nchunks, N, device=X2d.device, dtype=torch.float64)
+        lib.pa2s_colsum(stream(), ptr(X2d), R, N, ptr(scratch), nchunks, ptr(out), int(accumulate))
+    else:
+        lib.pa2s_reduce_rows(stream(), ptr(X2d), R, N, None, ptr(out), int(accumulate))
     return out
 
 

@@ -172,7 +172,7 @@ def test_convstack_eval_train_backward(cuda, B, T, Fq):
 
 
 # ------------------------------------------------------------------------------------------------ Encoder
-@pytest.mark.parametrize("B,T", [(1, 9), (3, 17), (5, 6)])
+@pytest.mark.parametrize("B,T", [(1, 9), (3, 17), (5, 6), (2, 1), (4, 3), (9, 40)])
 def test_encoder_forward_backward(cuda, B, T):
     import models
     torch.manual_seed(0)
