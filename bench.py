@@ -192,6 +192,8 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_ms = []
+
     def timed(fn, k):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -200,6 +202,7 @@ def run_b200(args):
         for _ in range(k):
             fn()
         e1.record()
+        host_ms.append((time.time() - w0) * 1e3 / k)        # host time to ENQUEUE one step (launch-bound if ~= the device time)
         barrier()
         w1 = time.time()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
@@ -261,6 +264,7 @@ def run_b200(args):
                        "parallelism": f"dp{world}", "l2": "working set >> 126 MB L2 (4.4 GB of conv activations per step), no flush needed",
                        "kernel_ms": {k: round(v[1], 4) for k, v in sorted(ktimes.items())}},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+            "host_enqueue_ms_per_step": round(host_ms[0], 3),
             "gpu_launches": int(launches),
             "clocks": sampler.summary(w0, w2),
             "roofline": roof, "roofline_all": [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items()} for r in roof_all],

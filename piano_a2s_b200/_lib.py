@@ -70,8 +70,17 @@ class _Lib:
 lib = _Lib()
 
 
+_DEVICE_INDEX = None
+
+
 def stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """Raw handle of torch's CURRENT stream on this process's device (one process per GPU).  Goes through the C binding
+    directly: torch.cuda.current_stream() costs ~5 us of Python per call, which at ~1500 kernel launches per training step
+    was 8 ms of host time per step."""
+    global _DEVICE_INDEX
+    if _DEVICE_INDEX is None:
+        _DEVICE_INDEX = torch.cuda.current_device()
+    return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(_DEVICE_INDEX))
 
 
 def ptr(t):

@@ -43,14 +43,37 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 constexpr int EPF = 4;           // stages of per-step operands in flight (encoder recurrences)
 
-template <int BG>
-__device__ __forceinline__ float pick(const float (&v)[BG], int s) {
+constexpr int CPT = 4;           // hidden units per warp (8 warps x 4 = the CTA's 32 units); a warp's 32 lanes are 32 k-slices
+
+// Sum NV (power of two <= 32) per-lane values across the warp: lane L returns the warp total of value index L >> (5 - log2 NV).
+// Halving exchange (NV/2 + NV/4 + ... + 1 shuffles) followed by a plain butterfly over the remaining lane bits.
+template <int NV>
+__device__ __forceinline__ float reduce_scatter_nv(float (&v)[NV], int lane) {
+    static_assert(NV == 1 || NV == 2 || NV == 4 || NV == 8 || NV == 16 || NV == 32, "NV must be a power of two <= 32");
+    int off = 16;
+#pragma unroll
+    for (int n = NV / 2; n >= 1; n >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            const float send = up ? v[i] : v[i + n];
+            const float recv = __shfl_xor_sync(0xffffffffu, send, off);
+            v[i] = (up ? v[i + n] : v[i]) + recv;
+        }
+        off >>= 1;
+    }
     float r = v[0];
 #pragma unroll
-    for (int i = 1; i < BG; ++i) r = (s == i) ? v[i] : r;
+    for (int o = 16; o >= 1; o >>= 1)
+        if (o <= off) r += __shfl_xor_sync(0xffffffffu, r, o);
     return r;
 }
+template <int NV> struct LaneShift { static constexpr int value = NV == 16 ? 1 : (NV == 8 ? 2 : (NV == 4 ? 3 : (NV == 2 ? 4 : 5))); };
 
+// Thread layout of both recurrence kernels: warp w owns units 4w..4w+3 of the CTA's 32, lane l the k-slice {(q*32+l)*4..+3}.
+// Each shared-memory read of the state vector is then a conflict-free 512-byte row shared by 12 (fwd) / 4 (bwd) weight rows,
+// instead of the same 128 bytes re-read by every quarter warp.  After the reduce-scatter the total for (unit c, sample bb)
+// sits in lanes (c*BG+bb) << SH, which do the gate math for that (unit, sample).
 template <int BG>
 __global__ void __launch_bounds__(ENT, 1) gru_seq_fwd_kernel(GruSeqArgs a) {
     cg::cluster_group cluster = cg::this_cluster();
@@ -58,8 +81,8 @@ __global__ void __launch_bounds__(ENT, 1) gru_seq_fwd_kernel(GruSeqArgs a) {
     const int cid = blockIdx.x / ECL;
     const int dir = cid / a.G, grp = cid % a.G;
     const int b0 = grp * BG;
-    const int tid = threadIdx.x, u = tid >> 3, s = tid & 7;
-    const int j = rank * EU + u;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NV = CPT * BG, SH = LaneShift<NV>::value;
     const int H = EH, T = a.T, ND = a.ND;
 
     __shared__ __align__(16) float hbuf[2][BG][EH];
@@ -67,21 +90,25 @@ __global__ void __launch_bounds__(ENT, 1) gru_seq_fwd_kernel(GruSeqArgs a) {
 #pragma unroll
     for (int c = 0; c < ECL; ++c) remote[c] = cluster.map_shared_rank(&hbuf[0][0][0], c);
 
-    // W_hh slice in registers: rows (g*H + j), columns (kk*8+s)*4 + i
-    float w[3][32];
+    // W_hh slice in registers: rows g*H + (rank*32 + warp*4 + c), columns (q*32 + lane)*4 + i
+    float w[3][CPT][8];
 #pragma unroll
     for (int g = 0; g < 3; ++g)
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-            float4 v = __ldg(reinterpret_cast<const float4*>(a.Whh + ((size_t)dir * 3 * H + g * H + j) * H + (kk * 8 + s) * 4));
-            w[g][kk * 4 + 0] = v.x; w[g][kk * 4 + 1] = v.y; w[g][kk * 4 + 2] = v.z; w[g][kk * 4 + 3] = v.w;
-        }
+        for (int c = 0; c < CPT; ++c)
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(
+                    a.Whh + ((size_t)dir * 3 * H + g * H + rank * EU + warp * CPT + c) * H + (q * 32 + lane) * 4));
+                w[g][c][q * 4 + 0] = v.x; w[g][c][q * 4 + 1] = v.y; w[g][c][q * 4 + 2] = v.z; w[g][c][q * 4 + 3] = v.w;
+            }
+    const int idx = lane >> SH, gb = idx % BG;
+    const int u = warp * CPT + idx / BG, j = rank * EU + u, b = b0 + gb;
+    const bool gate_thread = ((lane & ((1 << SH) - 1)) == 0) && (b < a.B);
     const float bhr = a.bhh[dir * 3 * H + j], bhz = a.bhh[dir * 3 * H + H + j], bhn = a.bhh[dir * 3 * H + 2 * H + j];
     for (int i = tid; i < 2 * BG * EH; i += ENT) (&hbuf[0][0][0])[i] = 0.f;
     cluster.sync();
 
-    const int b = b0 + s;
-    const bool gate_thread = (s < BG) && (b < a.B);
     int p = 0;
     // Input pre-activations (gi: a 118 MB stream) are staged EPF-1 steps ahead with asynchronous copies, so their DRAM latency
     // never sits on the sequential chain: threads 0..BG*3*8-1 each move 16 bytes of the [sample][gate][32 units] slice per step.
@@ -104,54 +131,58 @@ __global__ void __launch_bounds__(ENT, 1) gru_seq_fwd_kernel(GruSeqArgs a) {
     for (int step = 0; step < T; ++step) {
         const int t = dir == 0 ? step : T - 1 - step;
         issue(step + EPF - 1);
-        float acc[3][BG];
+        float acc[3][NV];
 #pragma unroll
         for (int g = 0; g < 3; ++g)
 #pragma unroll
-            for (int bb = 0; bb < BG; ++bb) acc[g][bb] = 0.f;
+            for (int i = 0; i < NV; ++i) acc[g][i] = 0.f;
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
+        for (int q = 0; q < 2; ++q) {
 #pragma unroll
             for (int bb = 0; bb < BG; ++bb) {
-                float4 hv = *reinterpret_cast<const float4*>(&hbuf[p][bb][(kk * 8 + s) * 4]);
+                const float4 hv = *reinterpret_cast<const float4*>(&hbuf[p][bb][(q * 32 + lane) * 4]);
 #pragma unroll
-                for (int g = 0; g < 3; ++g) {
-                    acc[g][bb] = fmaf(w[g][kk * 4 + 0], hv.x, acc[g][bb]);
-                    acc[g][bb] = fmaf(w[g][kk * 4 + 1], hv.y, acc[g][bb]);
-                    acc[g][bb] = fmaf(w[g][kk * 4 + 2], hv.z, acc[g][bb]);
-                    acc[g][bb] = fmaf(w[g][kk * 4 + 3], hv.w, acc[g][bb]);
-                }
+                for (int g = 0; g < 3; ++g)
+#pragma unroll
+                    for (int c = 0; c < CPT; ++c) {
+                        float v = acc[g][c * BG + bb];
+                        v = fmaf(w[g][c][q * 4 + 0], hv.x, v);
+                        v = fmaf(w[g][c][q * 4 + 1], hv.y, v);
+                        v = fmaf(w[g][c][q * 4 + 2], hv.z, v);
+                        v = fmaf(w[g][c][q * 4 + 3], hv.w, v);
+                        acc[g][c * BG + bb] = v;
+                    }
             }
         }
-#pragma unroll
-        for (int g = 0; g < 3; ++g)
-#pragma unroll
-            for (int bb = 0; bb < BG; ++bb) {
-                float v = acc[g][bb];
-                v += __shfl_xor_sync(0xffffffffu, v, 1);
-                v += __shfl_xor_sync(0xffffffffu, v, 2);
-                v += __shfl_xor_sync(0xffffffffu, v, 4);
-                acc[g][bb] = v;
-            }
+        const float sr = reduce_scatter_nv<NV>(acc[0], lane);
+        const float sz = reduce_scatter_nv<NV>(acc[1], lane);
+        const float sn = reduce_scatter_nv<NV>(acc[2], lane);
+        float hn = 0.f, sv_r = 0.f, sv_z = 0.f, sv_n = 0.f, sv_hn = 0.f;
         if (gate_thread) {
-            const float gir = gis[step % EPF][s][0][u], giz = gis[step % EPF][s][1][u], gin = gis[step % EPF][s][2][u];
-            float ghr = pick<BG>(acc[0], s) + bhr, ghz = pick<BG>(acc[1], s) + bhz, ghn = pick<BG>(acc[2], s) + bhn;
+            const float gir = gis[step % EPF][gb][0][u], giz = gis[step % EPF][gb][1][u], gin = gis[step % EPF][gb][2][u];
+            float ghr = sr + bhr, ghz = sz + bhz, ghn = sn + bhn;
             float r = sigmoidf_(gir + ghr), z = sigmoidf_(giz + ghz);
             float n = tanhf(gin + r * ghn);
-            float hp = hbuf[p][s][j];
-            float hn = (1.f - z) * n + z * hp;
+            float hp = hbuf[p][gb][j];
+            hn = (1.f - z) * n + z * hp;
+            const int off = ((p ^ 1) * BG + gb) * EH + j;
+#pragma unroll
+            for (int c = 0; c < ECL; ++c) remote[c][off] = hn;
+            sv_r = r; sv_z = z; sv_n = n; sv_hn = ghn;
+        }
+        // split barrier: the new state is on its way to the 8 CTAs; the global stores of this step (off the sequential chain)
+        // are issued while the arrivals propagate
+        cluster.barrier_arrive();
+        if (gate_thread) {
             a.out[((size_t)b * T + t) * ND * H + dir * H + j] = hn;
             if (a.gates != nullptr) {
                 float* gs = a.gates + (((size_t)b * T + t) * ND + dir) * 4 * H + j;
-                gs[0] = r; gs[H] = z; gs[2 * H] = n; gs[3 * H] = ghn;
+                gs[0] = sv_r; gs[H] = sv_z; gs[2 * H] = sv_n; gs[3 * H] = sv_hn;
             }
             if (step == T - 1) a.hN[((size_t)dir * a.B + b) * H + j] = hn;
-            const int off = ((p ^ 1) * BG + s) * EH + j;
-#pragma unroll
-            for (int c = 0; c < ECL; ++c) remote[c][off] = hn;
         }
-        cp_async_wait<EPF - 2>();          // the stage of step+1 has landed (made visible CTA-wide by the barrier below)
-        cluster.sync();
+        cp_async_wait<EPF - 2>();          // the stage of step+1 has landed (made visible CTA-wide by the barrier)
+        cluster.barrier_wait();
         p ^= 1;
     }
 }
@@ -163,8 +194,8 @@ __global__ void __launch_bounds__(ENT, 1) gru_seq_bwd_kernel(GruSeqArgs a) {
     const int cid = blockIdx.x / ECL;
     const int dir = cid / a.G, grp = cid % a.G;
     const int b0 = grp * BG;
-    const int tid = threadIdx.x, u = tid >> 3, s = tid & 7;
-    const int j = rank * EU + u;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NV = CPT * BG, SH = LaneShift<NV>::value;
     const int H = EH, T = a.T, ND = a.ND;
 
     __shared__ __align__(16) float dbuf[2][BG][3 * EH];
@@ -172,16 +203,19 @@ __global__ void __launch_bounds__(ENT, 1) gru_seq_bwd_kernel(GruSeqArgs a) {
 #pragma unroll
     for (int c = 0; c < ECL; ++c) remote[c] = cluster.map_shared_rank(&dbuf[0][0][0], c);
 
-    // W_hh^T slice in registers: column j, rows (kk*8+s)*4 + i  (kk < 24)
-    float w[96];
+    // W_hh^T slice in registers: columns rank*32 + warp*4 + c, rows (q*32 + lane)*4 + i  (q < 6)
+    float w[CPT][24];
 #pragma unroll
-    for (int kk = 0; kk < 24; ++kk)
+    for (int c = 0; c < CPT; ++c)
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-            w[kk * 4 + i] = __ldg(a.Whh + ((size_t)dir * 3 * H + (kk * 8 + s) * 4 + i) * H + j);
+        for (int q = 0; q < 6; ++q)
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                w[c][q * 4 + i] = __ldg(a.Whh + ((size_t)dir * 3 * H + (q * 32 + lane) * 4 + i) * H + rank * EU + warp * CPT + c);
 
-    const int b = b0 + s;
-    const bool gate_thread = (s < BG) && (b < a.B);
+    const int idx = lane >> SH, gb = idx % BG;
+    const int u = warp * CPT + idx / BG, j = rank * EU + u, b = b0 + gb;
+    const bool gate_thread = ((lane & ((1 << SH) - 1)) == 0) && (b < a.B);
     float dhc = 0.f;
     if (gate_thread && a.dhN != nullptr) dhc = a.dhN[((size_t)dir * a.B + b) * H + j];
     for (int i = tid; i < 2 * BG * 3 * EH; i += ENT) (&dbuf[0][0][0])[i] = 0.f;
@@ -213,13 +247,12 @@ __global__ void __launch_bounds__(ENT, 1) gru_seq_bwd_kernel(GruSeqArgs a) {
     __syncthreads();
     for (int step = T - 1; step >= 0; --step) {
         const int t = dir == 0 ? step : T - 1 - step;
-        float dh_direct = 0.f;
+        float dh_direct = 0.f, g_r = 0.f, g_z = 0.f, g_n = 0.f, g_hn = 0.f;
         issue(step - (EPF - 1));
         if (gate_thread) {
-            const size_t bt = (size_t)b * T + t;
             const int sl = step % EPF;
-            const float r = stg[sl][0][s][u], z = stg[sl][1][s][u], n = stg[sl][2][s][u], hnl = stg[sl][3][s][u];
-            const float hp = stg[sl][4][s][u], dout_t = stg[sl][5][s][u];
+            const float r = stg[sl][0][gb][u], z = stg[sl][1][gb][u], n = stg[sl][2][gb][u], hnl = stg[sl][3][gb][u];
+            const float hp = stg[sl][4][gb][u], dout_t = stg[sl][5][gb][u];
             float dh = dout_t + dhc;
             float dn = dh * (1.f - z), dzv = dh * (hp - n);
             float dn_pre = dn * (1.f - n * n);
@@ -227,41 +260,44 @@ __global__ void __launch_bounds__(ENT, 1) gru_seq_bwd_kernel(GruSeqArgs a) {
             float dhn_lin = dn_pre * r;
             float dz_pre = dzv * z * (1.f - z);
             dh_direct = dh * z;
-            float* gi = a.dgi + bt * ND * 3 * H + dir * 3 * H + j;
-            gi[0] = dr_pre; gi[H] = dz_pre; gi[2 * H] = dn_pre;
-            float* gh = a.dgh + bt * ND * 3 * H + dir * 3 * H + j;
-            gh[0] = dr_pre; gh[H] = dz_pre; gh[2 * H] = dhn_lin;
-            const int off = (p * BG + s) * 3 * EH + j;
+            const int off = (p * BG + gb) * 3 * EH + j;
 #pragma unroll
             for (int c = 0; c < ECL; ++c) {
                 remote[c][off] = dr_pre; remote[c][off + H] = dz_pre; remote[c][off + 2 * H] = dhn_lin;
             }
+            g_r = dr_pre; g_z = dz_pre; g_n = dn_pre; g_hn = dhn_lin;
         }
-        cp_async_wait<EPF - 2>();          // the stage of step-1 has landed; the barrier below makes it visible CTA-wide
-        cluster.sync();
-        float acc[BG];
+        cluster.barrier_arrive();          // split barrier: the global stores below overlap the arrival latency
+        if (gate_thread) {
+            const size_t bt = (size_t)b * T + t;
+            float* gi = a.dgi + bt * ND * 3 * H + dir * 3 * H + j;
+            gi[0] = g_r; gi[H] = g_z; gi[2 * H] = g_n;
+            float* gh = a.dgh + bt * ND * 3 * H + dir * 3 * H + j;
+            gh[0] = g_r; gh[H] = g_z; gh[2 * H] = g_hn;
+        }
+        cp_async_wait<EPF - 2>();          // the stage of step-1 has landed; the barrier makes it visible CTA-wide
+        cluster.barrier_wait();
+        float acc[NV];
 #pragma unroll
-        for (int bb = 0; bb < BG; ++bb) acc[bb] = 0.f;
+        for (int i = 0; i < NV; ++i) acc[i] = 0.f;
 #pragma unroll
-        for (int kk = 0; kk < 24; ++kk) {
+        for (int q = 0; q < 6; ++q) {
 #pragma unroll
             for (int bb = 0; bb < BG; ++bb) {
-                float4 dv = *reinterpret_cast<const float4*>(&dbuf[p][bb][(kk * 8 + s) * 4]);
-                acc[bb] = fmaf(w[kk * 4 + 0], dv.x, acc[bb]);
-                acc[bb] = fmaf(w[kk * 4 + 1], dv.y, acc[bb]);
-                acc[bb] = fmaf(w[kk * 4 + 2], dv.z, acc[bb]);
-                acc[bb] = fmaf(w[kk * 4 + 3], dv.w, acc[bb]);
+                const float4 dv = *reinterpret_cast<const float4*>(&dbuf[p][bb][(q * 32 + lane) * 4]);
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) {
+                    float v = acc[c * BG + bb];
+                    v = fmaf(w[c][q * 4 + 0], dv.x, v);
+                    v = fmaf(w[c][q * 4 + 1], dv.y, v);
+                    v = fmaf(w[c][q * 4 + 2], dv.z, v);
+                    v = fmaf(w[c][q * 4 + 3], dv.w, v);
+                    acc[c * BG + bb] = v;
+                }
             }
         }
-#pragma unroll
-        for (int bb = 0; bb < BG; ++bb) {
-            float v = acc[bb];
-            v += __shfl_xor_sync(0xffffffffu, v, 1);
-            v += __shfl_xor_sync(0xffffffffu, v, 2);
-            v += __shfl_xor_sync(0xffffffffu, v, 4);
-            acc[bb] = v;
-        }
-        if (gate_thread) dhc = dh_direct + pick<BG>(acc, s);
+        const float tot = reduce_scatter_nv<NV>(acc, lane);
+        if (gate_thread) dhc = dh_direct + tot;
         p ^= 1;
     }
 }

@@ -75,6 +75,10 @@ class ScoreTranscription(nn.Module):
                 device=torch.device("cuda" if torch.cuda.is_available() else "cpu")):
         self.device = device
         with ops.module_precision(self):
+            if ground_truth is not None and not inference:
+                # executed decoder steps per (staff, bar) are a function of the targets alone: fetch them on a side stream now,
+                # so that the one host read the decoder needs does not wait for the ConvStack / encoder kernels queued below
+                self.decoder.prefetch_steps(ground_truth)
             conv_outputs = self.convstack(spectrogram)                   # (B, T, conv_feature_size)
             encoder_outputs, hidden = self.encoder(conv_outputs)         # (B, T, 2H), (1, B, 2H)
             return self.decoder(encoder_outputs, hidden, inference, ground_truth, teacher_forcing_ratio, device)
@@ -141,6 +145,9 @@ class HierarchicalDecoder(nn.Module):
         self.consume_python_rng = True      # keep the reference's python-`random` consumption count in inference too
         self.parallel_staves = True
         self._side_streams = None
+        self._aux_stream = None
+        self._steps_host = None
+        self._steps_pending = None
         self.init_weight()
 
     def init_weight(self):
@@ -176,6 +183,29 @@ class HierarchicalDecoder(nn.Module):
         first = torch.where(is_eos.any(-1), is_eos.int().argmax(-1), torch.full_like(gt_staff[..., 0], L - 1))
         return first.max(0).values + 1
 
+    def prefetch_steps(self, ground_truth):
+        """Starts the device->host read of `_steps_from_gt` for both staves on an auxiliary stream (which only waits for the work
+        queued so far, i.e. the arrival of the targets).  decode_bars() picks the result up; without a prefetch it computes the
+        same numbers with a blocking read."""
+        upper_gt, lower_gt = ground_truth[2], ground_truth[4]
+        self._steps_pending = None
+        if not upper_gt.is_cuda:
+            return
+        main = torch.cuda.current_stream()
+        if self._aux_stream is None:
+            self._aux_stream = torch.cuda.Stream()
+        side = self._aux_stream
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            st = torch.stack([self._steps_from_gt(upper_gt), self._steps_from_gt(lower_gt)])
+            if self._steps_host is None or self._steps_host.shape != st.shape:
+                self._steps_host = torch.empty(st.shape, dtype=st.dtype, pin_memory=True)
+            self._steps_host.copy_(st, non_blocking=True)
+            ev = side.record_event()
+        upper_gt.record_stream(side)
+        lower_gt.record_stream(side)
+        self._steps_pending = (ev, upper_gt, lower_gt)
+
     def _heads(self, seq, x):
         x = F.relu(ops.linear(x, seq[0].weight, seq[0].bias))
         x = F.relu(ops.linear(x, seq[2].weight, seq[2].bias))
@@ -193,7 +223,12 @@ class HierarchicalDecoder(nn.Module):
         have_gt = ground_truth is not None
         if have_gt:
             time_sig_gt, key_gt, upper_gt, upper_len_gt, lower_gt, lower_len_gt = ground_truth
-            steps = torch.stack([self._steps_from_gt(upper_gt), self._steps_from_gt(lower_gt)]).cpu().tolist()   # one sync
+            pend, self._steps_pending = self._steps_pending, None
+            if pend is not None and pend[1] is upper_gt and pend[2] is lower_gt:
+                pend[0].synchronize()                                    # waits for the tiny side-stream read only
+                steps = self._steps_host.tolist()
+            else:
+                steps = torch.stack([self._steps_from_gt(upper_gt), self._steps_from_gt(lower_gt)]).cpu().tolist()   # one sync
         else:
             steps = [[self.max_length[0]] * self.max_bars, [self.max_length[1]] * self.max_bars]
 
