@@ -19,6 +19,10 @@
 // statistics of the produced tensor), warp 4 TMEM allocation + single-lane tcgen05.mma issue, warp 5 single-lane copy producer.
 #include "tc_common.cuh"
 
+#ifndef PA2S_CONV_NCAT
+#define PA2S_CONV_NCAT 1          // 1: hi/lo weight blocks concatenated along N (2 MMAs per tap and k-step), 0: 3 MMAs of N = COUTP
+#endif
+
 namespace {
 using namespace tc;
 
@@ -162,8 +166,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(ConvArgs2 a) {
     constexpr int SLOT_BYTES = 2 * NG * PLANE_BYTES;                 // hi planes then lo planes
     constexpr int WBLK_BYTES = 2 * COUTP * 16;                        // one (tap, ks, split) weight block: 2 k-groups x COUTP rows
     constexpr int W_BYTES = 9 * KS * 2 * WBLK_BYTES;
-    constexpr int TM_COLS = 64;
-    static_assert(COUTP <= TM_COLS, "accumulator width");
+    // bf16x3 (NP = 2): the hi and lo weight blocks sit side by side along N, so ONE MMA of N = 2*COUTP forms A_hi*W_hi (columns
+    // [0,COUTP)) and A_hi*W_lo (columns [COUTP,2*COUTP)) from a single read of the A window; A_lo*W_hi follows with N = COUTP.
+    // These small-N MMAs are bound by the shared-memory read of A (4 KB per MMA), so 2 reads per (tap, k-step) instead of 3.
+    constexpr bool NCAT = PA2S_CONV_NCAT != 0;
+    constexpr int TM_COLS = 2 * COUTP <= 64 ? 64 : 128;
+    static_assert(2 * COUTP <= TM_COLS, "accumulator width");
 
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* wsm = smem;
@@ -174,7 +182,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(ConvArgs2 a) {
     const int T = a.g.T, F = a.g.F;
     const int NP = a.g.NP;
 
-    for (int i = tid; i < W_BYTES / 16; i += NTHREADS) reinterpret_cast<uint4*>(wsm)[i] = __ldg(a.Wpack + i);
+    // pa2s_tc_conv_pack order is [tap][ks][split][kgroup][n]; staged as [tap][ks][kgroup][split][n] (16-byte units) so that
+    // rows n = 0..2*COUTP-1 of a k-group are [W_hi | W_lo]
+    for (int i = tid; i < W_BYTES / 16; i += NTHREADS) {
+        const int n = i % COUTP, r = i / COUTP, kg = r & 1, split = (r >> 1) & 1, blk = r >> 2;
+        reinterpret_cast<uint4*>(wsm)[((blk * 2 + kg) * 2 + split) * COUTP + n] = __ldg(a.Wpack + i);
+    }
     for (int i = tid; i < NWIN * SLOT_BYTES / 16; i += NTHREADS) reinterpret_cast<uint4*>(win)[i] = make_uint4(0, 0, 0, 0);
     if (warp == 4) {
         if (lane == 0) {
@@ -196,7 +209,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(ConvArgs2 a) {
 
     if (warp < 4) {
         // ================================================================================= epilogue
-        float ssum[2] = {0.f, 0.f}, ssq[2] = {0.f, 0.f};              // lane c keeps channels c and c+32
+        // BatchNorm batch statistics: every thread (= one output pixel column of the tile) keeps its own running sum y, sum y^2
+        // per channel over all its tiles (~500 pixels per thread at B=16); the 32 rows of a warp are combined ONCE after the
+        // walk.  (Reducing per tile cost 10 shuffles per channel per tile and made the epilogue the slowest stage.)
+        float ps[COUT], pq[COUT];
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) { ps[c] = 0.f; pq[c] = 0.f; }
         uint32_t it = 0;
         while (walk.next(ch)) {
             const int fp = ch.fb * BM + warp * 32 + lane;
@@ -210,21 +228,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(ConvArgs2 a) {
                 for (int c0 = 0; c0 < COUTP; c0 += 16) {
                     float v[16];
                     tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * TM_COLS + c0), v);
+                    if (NCAT && NP > 1) {                             // + A_hi * W_lo
+                        float v2[16];
+                        tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * TM_COLS + COUTP + c0), v2);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] += v2[i];
+                    }
                     if (valid) {
 #pragma unroll
                         for (int qd = 0; qd < 4; ++qd)
                             if (c0 + 4 * qd < COUT)
                                 reinterpret_cast<float4*>(yrow + c0)[qd] = make_float4(v[4 * qd], v[4 * qd + 1], v[4 * qd + 2], v[4 * qd + 3]);
                     }
-                    if (a.partial != nullptr) {
+                    if (a.partial != nullptr && valid) {
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
                             const int c = c0 + i;
-                            if (c < COUT) {
-                                const float x = valid ? v[i] : 0.f;
-                                const float s1 = warp_sum(x), s2 = warp_sum(x * x);
-                                if (lane == (c & 31)) { ssum[c >> 5] += s1; ssq[c >> 5] += s2; }
-                            }
+                            if (c < COUT) { ps[c] += v[i]; pq[c] = fmaf(v[i], v[i], pq[c]); }
                         }
                     }
                 }
@@ -235,16 +255,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(ConvArgs2 a) {
         if (a.partial != nullptr) {
             float* pr = a.partial + ((size_t)blockIdx.x * 4 + warp) * 2 * COUT;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int c = lane + 32 * h;
-                if (c < COUT) { pr[c] = ssum[h]; pr[COUT + c] = ssq[h]; }
+            for (int c = 0; c < COUT; ++c) {
+                const float s1 = warp_sum(ps[c]), s2 = warp_sum(pq[c]);
+                if (lane == 0) { pr[c] = s1; pr[COUT + c] = s2; }
             }
         }
     } else if (warp == 4) {
         // ================================================================================= MMA issuer (warp-uniform)
-        const uint32_t idesc = make_idesc(BM, COUTP, 0, 0);
+        const uint32_t idesc = make_idesc(BM, COUTP, 0, 0), idesc2 = make_idesc(BM, 2 * COUTP, 0, 0);
         const uint32_t w_base = smem_u32(wsm), win_base = smem_u32(win);
-        const uint64_t wdesc0 = make_desc(w_base, COUTP * 16, 128);
+        const uint64_t wdesc0 = make_desc(w_base, 2 * COUTP * 16, 128);      // k-group pitch: hi rows + lo rows
         uint32_t it = 0, wbase = 0;                                   // wbase = ring index of the chunk's first window (row t0-1)
         while (walk.next(ch)) {
             for (int k = 0; k < ch.n; ++k, ++it) {
@@ -271,11 +291,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(ConvArgs2 a) {
                                 const uint32_t aoff = (uint32_t)(2 * ks * PLANE_BYTES + kx * 16);
                                 const uint64_t dah = desc_advance(dah0, aoff), dal = desc_advance(dal0, aoff);
                                 const uint64_t dbh = desc_advance(dbw, (uint32_t)(((kx * KS + ks) * 2) * WBLK_BYTES));
-                                const uint64_t dbl = desc_advance(dbh, WBLK_BYTES);
-                                tc_mma(d_tmem, dah, dbh, idesc, (ky | kx | ks) != 0);
-                                if (NP > 1) {
-                                    tc_mma(d_tmem, dah, dbl, idesc, 1);
+                                if (NCAT && NP > 1) {
+                                    tc_mma(d_tmem, dah, dbh, idesc2, (ky | kx | ks) != 0);     // A_hi * [W_hi | W_lo]
+                                    tc_mma(d_tmem, dal, dbh, idesc, 1);                        // A_lo * W_hi
+                                } else if (NP > 1) {                                           // three N = COUTP products
+                                    tc_mma(d_tmem, dah, dbh, idesc, (ky | kx | ks) != 0);
+                                    tc_mma(d_tmem, dah, desc_advance(dbh, COUTP * 16), idesc, 1);
                                     tc_mma(d_tmem, dal, dbh, idesc, 1);
+                                } else {
+                                    tc_mma(d_tmem, dah, dbh, idesc, (ky | kx | ks) != 0);
                                 }
                             }
                         }

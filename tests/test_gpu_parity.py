@@ -128,8 +128,19 @@ def test_vqt_matches_direct_form_oracle(cuda):
 
 
 # ------------------------------------------------------------------------------------------------ ConvStack
+# ReLU follows every BatchNorm, and among the 1e4..1e5 pre-activations of these inputs the smallest |z| is ~1e-5 (checked on the
+# oracle): the exact-fp32 kernels (error ~1e-7) never flip such a pixel, the split-operand tensor-core path (error ~1e-5 of the
+# output scale) can, and ONE flipped pixel of 1 280 moves a convolution weight gradient by ~1e-3 of its largest entry.  So the
+# fp32 mode is held to GRAD_TOL, and bf16x3 to 1e-2 (a handful of borderline pixels), with the activations at ACT_TOL for both.
+@pytest.mark.parametrize("prec", ["fp32", "bf16x3"])
 @pytest.mark.parametrize("B,T,Fq", [(2, 20, 32), (3, 21, 37)])
-def test_convstack_eval_train_backward(cuda, B, T, Fq):
+def test_convstack_eval_train_backward(cuda, B, T, Fq, prec):
+    from piano_a2s_b200 import ops
+    with ops.use_precision(prec):
+        _convstack_eval_train_backward(cuda, B, T, Fq, GRAD_TOL if prec == "fp32" else 1e-2)
+
+
+def _convstack_eval_train_backward(cuda, B, T, Fq, grad_tol):
     import models
     torch.manual_seed(0)
     cs = models.ConvStack(1, Fq, 256)
@@ -165,7 +176,7 @@ def test_convstack_eval_train_backward(cuda, B, T, Fq):
     for k, p in cs.named_parameters():
         ge = rel_err(p.grad, sdg["convstack." + k].grad)
         print("  grad", k, ge)
-        assert ge < GRAD_TOL, k
+        assert ge < grad_tol, k
     for k, v in ns.items():
         got = cs.state_dict()[k[len("convstack."):]]
         assert rel_err(got.float(), v.float()) < 1e-5, k
