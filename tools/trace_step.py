@@ -50,9 +50,9 @@ def main():
         for s_, e_, st, n in tl:
             busy[st] += e_ - s_
         print("per-stream kernel time (ms):", {k: round(v * 1e-3, 2) for k, v in busy.items()})
+        wins = [[float(x) for x in w.split(",")] for w in os.environ.get("PA2S_TIMELINE_WINDOW", "0,0").split(";")]
         for s_, e_, st, n in tl:
-            lo, hi = [float(x) for x in os.environ.get("PA2S_TIMELINE_WINDOW", "0,0").split(",")]
-            if e_ - s_ >= 100 or lo <= 1e-3 * (s_ - t00) <= hi:
+            if e_ - s_ >= 100 or any(lo <= 1e-3 * (s_ - t00) <= hi for lo, hi in wins):
                 short = re.sub(r"\(anonymous namespace\)::|void ", "", n)[:60]
                 print(f"  t={1e-3 * (s_ - t00):8.3f}  dur={1e-3 * (e_ - s_):7.3f}  stream={st}  {short}")
     ks = sorted(((e.time_range.start, e.time_range.end, e.name) for e in evs), key=lambda x: x[0])
