@@ -165,6 +165,7 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
     torch.manual_seed(1234)
@@ -216,7 +217,7 @@ def run_b200(args):
         sampler.start()
     for _ in range(max(args.warmup, 3)):
         step_device()
-    # the step enqueues ~4 000 launches from Python; a generation-2 garbage collection over torch's heap inside the timed region
+    # the step enqueues ~1 500 launches from Python; a generation-2 garbage collection over torch's heap inside the timed region
     # stalls the launch thread for tens of ms (seen as 64 vs 76 ms/step between otherwise identical runs): collect now and move
     # the survivors out of the collector's reach, as a training loop would after its first iterations
     gc.collect()
