@@ -117,6 +117,14 @@ PA2S_API int pa2s_conv3x3_wgrad(void* stream, int B, int T, int F, int Cin, int 
                                 float* partial, int nctas, const float* in_scale, const float* in_shift, int in_relu,
                                 const float* Yraw, const float* zs, const float* zb, const float* mean, const float* invstd,
                                 const float* k1, const float* k2, const float* k3);
+/* conv1 (models.py:526: Conv2d(1, 20, 3x3, padding 1, bias=False) on the spectrogram) as a coalesced fp32 stream: X (B,T,F),
+ * W (20,1,3,3) in torch layout, Y (B,T,F,20); partial (or NULL) = nctas rows of [sum y (20), sum y^2 (20)] for the BatchNorm
+ * batch statistics.  pa2s_conv1_wgrad: conv1.weight gradient for dy = k1*(G*(Yraw*zs+zb > 0) - k2 - (Yraw-mean)*invstd*k3)
+ * (BatchNorm + ReLU backward formed on the fly); partial = nctas rows of 180 (torch order), summed by pa2s_reduce_rows. */
+PA2S_API int pa2s_conv1_fwd(void* stream, int B, int T, int F, const float* X, const float* W, float* Y, float* partial, int nctas);
+PA2S_API int pa2s_conv1_wgrad(void* stream, int B, int T, int F, const float* X, const float* G, const float* Yraw, const float* zs,
+                              const float* zb, const float* mean, const float* invstd, const float* k1, const float* k2, const float* k3,
+                              float* partial, int nctas);
 /* out[n] (=|+=) sum_r partial[r][n], accumulated in fp64. */
 PA2S_API int pa2s_reduce_rows(void* stream, const float* partial, int R, int N, double* out64, float* out32, int accumulate);
 /* Same sum for a TALL matrix (bias gradients: R = B*T rows), two deterministic stages over `nchunks` row chunks;

@@ -335,6 +335,12 @@ class ConvStackFn(torch.autograd.Function):
                 partial = torch.empty(nparts, 2 * Cout, device=dev, dtype=F32) if training else None
                 with ktime(f"conv{i + 1}_fwd"):
                     lib.pa2s_conv_tma(st, B, T, Fq, Cin, Cout, ptr(Pin), npc, ptr(Wpk), ptr(y), ptr(partial))
+            elif Cin == 1 and Cout == 20:
+                # conv1: one input channel, nothing to contract on the tensor cores -- a coalesced fp32 stream (conv1.cu), every mode
+                nparts = 2 * N_SM
+                partial = torch.empty(nparts, 2 * Cout, device=dev, dtype=F32) if training else None
+                with ktime(f"conv{i + 1}_fwd"):
+                    lib.pa2s_conv1_fwd(st, B, T, Fq, ptr(xin), ptr(W.detach().contiguous()), ptr(y), ptr(partial), nparts)
             else:
                 Wp = W.detach().permute(2, 3, 1, 0).contiguous()
                 nparts = lib.pa2s_conv3x3_num_partials(B, T, Fq, ntile)
@@ -488,6 +494,12 @@ class ConvStackFn(torch.autograd.Function):
                 with ktime(f"conv{i + 1}_wgrad"):
                     lib.pa2s_conv_tma_wgrad(st, B, T, Fq, Cin, Cout, ptr(ctx.planes[i]), ptr(Pdy), npc, ptr(partial))
                 ctx.planes[i] = None
+            elif Cin == 1 and Cout == 20:
+                nwp = 2 * N_SM
+                partial = torch.empty(nwp, Cout * Cin * 9, device=dev, dtype=F32)
+                with ktime(f"conv{i + 1}_wgrad"):
+                    lib.pa2s_conv1_wgrad(st, B, T, Fq, ptr(xin), ptr(G), ptr(y), ptr(aff[0]), ptr(aff[1]), ptr(aff[2]), ptr(aff[3]),
+                                         ptr(k[0]), ptr(k[1]), ptr(k[2]), ptr(partial), nwp)
             else:
                 nwp = nw
                 partial = torch.empty(nw, Cout * Cin * 9, device=dev, dtype=F32)
