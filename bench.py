@@ -194,19 +194,26 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    host_ms = []
+    host_ms, per_step = [], []
 
     def timed(fn, k):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         w0 = time.time()
         e0.record()
+        marks, hmarks = [e0], [w0]
         for _ in range(k):
             fn()
-        e1.record()
+            marks.append(torch.cuda.Event(enable_timing=True))
+            marks[-1].record()
+            hmarks.append(time.time())
+        e1 = marks[-1]
         host_ms.append((time.time() - w0) * 1e3 / k)        # host time to ENQUEUE one step (launch-bound if ~= the device time)
         barrier()
         w1 = time.time()
+        # per-step device time (between the step-end events) and host enqueue time: shows whether a slow run is uniformly slow or has outliers
+        per_step.append({"device_ms": [round(marks[i].elapsed_time(marks[i + 1]), 2) for i in range(k)],
+                         "host_ms": [round(1e3 * (hmarks[i + 1] - hmarks[i]), 2) for i in range(k)]})
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -215,13 +222,14 @@ def run_b200(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(args.warmup, 3) - 1):
         step_device()
     # the step enqueues ~1 500 launches from Python; a generation-2 garbage collection over torch's heap inside the timed region
     # stalls the launch thread for tens of ms (seen as 64 vs 76 ms/step between otherwise identical runs): collect now and move
     # the survivors out of the collector's reach, as a training loop would after its first iterations
     gc.collect()
     gc.freeze()
+    step_device()                                # last warm-up step, after the collection (the first step after it is the slow one)
     n0 = lib.pa2s_launch_count()
     ops.KernelTimers.reset(rank == 0)
     prof = os.environ.get("PA2S_PROFILE_RANGE") == "1"      # ncu --profile-from-start off: capture the timed steps only
@@ -271,7 +279,7 @@ def run_b200(args):
                        "parallelism": f"dp{world}", "l2": "working set >> 126 MB L2 (4.4 GB of conv activations per step), no flush needed",
                        "kernel_ms": {k: round(v[1], 4) for k, v in sorted(ktimes.items())}},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
-            "host_enqueue_ms_per_step": round(host_ms[0], 3),
+            "host_enqueue_ms_per_step": round(host_ms[0], 3), "per_step": {"device_resident": per_step[0], "e2e": per_step[-1]},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(w0, w2),
             "roofline": roof, "roofline_all": [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items()} for r in roof_all],
