@@ -36,10 +36,15 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=16, help="clips per GPU per step")
+    ap.add_argument("--workload", default="train", choices=["train", "infer"],
+                    help="train = BASELINE configs[1] (the headline metric); infer = configs[4], batched greedy decode (evaluate path)")
+    ap.add_argument("--batch", type=int, default=None, help="clips per GPU per step (default 16 for train, 32 for infer)")
     ap.add_argument("--cpu-clips", type=int, default=1, help="clips per step of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.batch is None:
+        a.batch = 16 if a.workload == "train" else 32
+    return a
 
 
 def workload_name(batch):
@@ -177,7 +182,7 @@ def run_b200(args):
     gt_h = [t.pin_memory() for t in make_ground_truth(B, 5, 398, 189, seed=1234 + rank)]
     S = executed_steps(gt_h)
     audio_d = audio_h.to(dev)
-    gt_d = [t.to(dev) for t in gt_h]
+    gt_d = train.targets_to_device(gt_h, dev)
 
     def step_device():
         spec = vqt(audio_d).unsqueeze(1)
@@ -185,7 +190,7 @@ def run_b200(args):
 
     def step_e2e():
         a = audio_h.to(dev, non_blocking=True)
-        g = [t.to(dev, non_blocking=True) for t in gt_h]
+        g = train.targets_to_device(gt_h, dev)
         spec = vqt(a).unsqueeze(1)
         return train.fit_batch(model, opt, spec, g, TF_RATIO).item()          # D2H read of the step's loss
 
@@ -288,6 +293,108 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------- B200 arm, greedy decode
+def run_b200_infer(args):
+    """BASELINE configs[4]: batched greedy hierarchical decode (pretrain.py:302-306 evaluate path) of synthetic 12-s clips,
+    model.eval() => exact-fp32 kernels, 32 clips per GPU per step (8 steps = 256 clips), audio -> VQT -> ConvStack -> encoder ->
+    5 bars x (398 + 189) note steps (a random-init model never emits <eos>) -> argmax/unpad token lists on the host."""
+    import torch
+    import torch.distributed as dist
+    import models
+    from piano_a2s_b200 import kern, ops
+    from piano_a2s_b200.synthetic import make_audio
+    from piano_a2s_b200.vqt import VQT
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:                                        # replicas only: the group exists for the barrier and the max over ranks
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    torch.manual_seed(1234)
+    model = models.ScoreTranscription(**CFG).to(dev).eval()
+    model.decoder.consume_python_rng = False             # the per-step coin count of models.py:404 is irrelevant without teacher forcing
+    vqt = VQT().to(dev)
+    audio_h = make_audio(B, N_SAMPLES, seed=1234 + rank).pin_memory()
+    audio_d = audio_h.to(dev)
+    d2h = [0]
+
+    def step_device():
+        with torch.no_grad():
+            return model(vqt(audio_d).unsqueeze(1), device=dev)
+
+    def step_e2e():
+        with torch.no_grad():
+            outs = model(vqt(audio_h.to(dev, non_blocking=True)).unsqueeze(1), device=dev)
+            toks = kern.greedy_tokens(outs)              # argmax + first-<eos> on the device, token lists on the host
+        d2h[0] = B * 5 * (8 * sum(CFG["max_length"]) + 2 * 4 + 2 * 8)      # int64 tokens + int32 lengths per staff, int64 key / time signature
+        return toks
+
+    def timed(fn, k):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.time()
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), w0, time.time()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    from piano_a2s_b200._lib import lib
+    n0 = lib.pa2s_launch_count()
+    ops.KernelTimers.reset(rank == 0)
+    ms, w0, _ = timed(step_device, args.steps)
+    launches = lib.pa2s_launch_count() - n0
+    ktimes = ops.KernelTimers.summary() if rank == 0 else {}
+    ops.KernelTimers.reset(False)
+    step_e2e()
+    ms_e2e, _, w2 = timed(step_e2e, args.steps)
+    if rank == 0:
+        sampler.stop()
+        ops.check_sync_flags()
+        clips = B * world * args.steps
+        S = 5 * (CFG["max_length"][0] + CFG["max_length"][1])
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        roof, roof_all = roofline({k: v for k, v in ktimes.items() if k.startswith("note_decoder")}, B, peaks, S, n_dec=10)
+        print(json.dumps({
+            "metric": "clips_per_sec_greedy_decode", "value": clips / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"pretrain.yaml model, batched greedy hierarchical decode of synthetic 12-s clips, {B} clips/GPU per step "
+                                   f"({B * world * args.steps} clips), eval mode, exact-fp32 kernels, audio -> VQT -> tokens",
+                       "global_batch": B * world, "decoder_steps_per_forward": S, "parallelism": f"replicas{world}",
+                       "l2": "inputs larger than L2 (5.9 GB of conv activations per step)",
+                       "kernel_ms": {k: round(v[1], 4) for k, v in sorted(ktimes.items())}},
+            "e2e": {"value": clips / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": audio_h.numel() * 4, "d2h_bytes_per_step": d2h[0],
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "clocks": sampler.summary(w0, w2),
+            "roofline": roof, "roofline_all": [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items()} for r in roof_all],
+            "cpu_baseline": None}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}     # B200_PROFILING.md fallback
 
 
@@ -326,7 +433,7 @@ def algorithmic_work(B, S_total, n_dec_calls):
     return w
 
 
-def roofline(ktimes, B, peaks, S_total, traffic=None):
+def roofline(ktimes, B, peaks, S_total, traffic=None, n_dec=None):
     """One entry per timed kernel group; the headline `roofline` object is the group with the largest share of the step.
     achieved = algorithmic FLOPs (or bytes) per launch / mean CUDA-event duration of the launch (events recorded on the
     launching stream inside the timed region); the bound reported is the roof that binds for the algorithmic numbers."""
@@ -335,7 +442,8 @@ def roofline(ktimes, B, peaks, S_total, traffic=None):
     hbm = float(pk.get("hbm_gbs") or FALLBACK_PEAKS["hbm_gbs"])
     tf = float(pk.get("bf16_tflops_sustained") or pk.get("bf16_tflops") or FALLBACK_PEAKS["bf16_tflops_sustained"])
     src = "MEASURED_PEAKS.json (hbm_gbs, bf16_tflops_sustained)" if measured else "fallback of B200_PROFILING.md (6.65 TB/s, 1.4 PFLOP/s sustained)"
-    n_dec = ktimes.get("note_decoder_fwd", (10, 0))[0] // max(ktimes.get("conv1_fwd", (1, 0))[0], 1)
+    if n_dec is None:
+        n_dec = ktimes.get("note_decoder_fwd", (10, 0))[0] // max(ktimes.get("conv1_fwd", (1, 0))[0], 1)
     work = algorithmic_work(B, S_total, n_dec)
     rows = []
     for name, (n, ms) in ktimes.items():
@@ -363,5 +471,7 @@ if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.workload == "infer":
+        run_b200_infer(a)
     else:
         run_b200(a)

@@ -79,6 +79,8 @@ class ScoreTranscription(nn.Module):
                 # executed decoder steps per (staff, bar) are a function of the targets alone: fetch them on a side stream now,
                 # so that the one host read the decoder needs does not wait for the ConvStack / encoder kernels queued below
                 self.decoder.prefetch_steps(ground_truth)
+            if torch.is_grad_enabled() and spectrogram.is_cuda:
+                self.decoder._presunk = self.decoder.weight_sinks()
             conv_outputs = self.convstack(spectrogram)                   # (B, T, conv_feature_size)
             encoder_outputs, hidden = self.encoder(conv_outputs)         # (B, T, 2H), (1, B, 2H)
             return self.decoder(encoder_outputs, hidden, inference, ground_truth, teacher_forcing_ratio, device)
@@ -146,6 +148,7 @@ class HierarchicalDecoder(nn.Module):
         self.parallel_staves = True
         self._side_streams = None
         self._aux_stream = None
+        self._presunk = None
         self._steps_host = None
         self._steps_pending = None
         self.init_weight()
@@ -189,7 +192,7 @@ class HierarchicalDecoder(nn.Module):
         same numbers with a blocking read."""
         upper_gt, lower_gt = ground_truth[2], ground_truth[4]
         self._steps_pending = None
-        if not upper_gt.is_cuda:
+        if not upper_gt.is_cuda or (hasattr(upper_gt, "_pa2s_steps") and hasattr(lower_gt, "_pa2s_steps")):
             return
         main = torch.cuda.current_stream()
         if self._aux_stream is None:
@@ -205,6 +208,19 @@ class HierarchicalDecoder(nn.Module):
         upper_gt.record_stream(side)
         lower_gt.record_stream(side)
         self._steps_pending = (ev, upper_gt, lower_gt)
+
+    def weight_sinks(self):
+        """[(DecoderGradSink, weight aliases) or None] for the upper / lower note decoder (ops.DecoderWeightSinkFn).  Autograd runs
+        nodes in reverse creation order: ScoreTranscription.forward creates the sinks BEFORE the ConvStack, so their node -- which
+        only hands over gradients that were formed on a side stream long before -- is the last of a backward pass instead
+        of sitting between the decoder and the encoder on the main stream."""
+        sunk = [None, None]
+        if torch.is_grad_enabled():
+            for si, dec in enumerate((self.upper_decoder, self.lower_decoder)):
+                if all(w.requires_grad for w in dec._weights()):
+                    sink = ops.DecoderGradSink()
+                    sunk[si] = (sink, ops.DecoderWeightSinkFn.apply(sink, *dec._weights()))
+        return sunk
 
     def _heads(self, seq, x):
         x = F.relu(ops.linear(x, seq[0].weight, seq[0].bias))
@@ -224,7 +240,10 @@ class HierarchicalDecoder(nn.Module):
         if have_gt:
             time_sig_gt, key_gt, upper_gt, upper_len_gt, lower_gt, lower_len_gt = ground_truth
             pend, self._steps_pending = self._steps_pending, None
-            if pend is not None and pend[1] is upper_gt and pend[2] is lower_gt:
+            hint = (getattr(upper_gt, "_pa2s_steps", None), getattr(lower_gt, "_pa2s_steps", None))
+            if hint[0] is not None and hint[1] is not None:
+                steps = [list(hint[0]), list(hint[1])]                   # counted on the host by the loader (train.targets_to_device)
+            elif pend is not None and pend[1] is upper_gt and pend[2] is lower_gt:
                 pend[0].synchronize()                                    # waits for the tiny side-stream read only
                 steps = self._steps_host.tolist()
             else:
@@ -239,12 +258,16 @@ class HierarchicalDecoder(nn.Module):
         Ep_bar, Ep_up, Ep_lo = ep(self.attn), ep(self.upper_decoder.attn), ep(self.lower_decoder.attn)
 
         # weight gradients of the two note decoders: one set of contractions per backward pass over all bars (ops.DecoderWeightSinkFn)
-        sunk = [None, None]
-        if torch.is_grad_enabled() and enc.is_cuda:
-            for si, dec in enumerate((self.upper_decoder, self.lower_decoder)):
-                if all(w.requires_grad for w in dec._weights()):
-                    sink = ops.DecoderGradSink()
-                    sunk[si] = (sink, ops.DecoderWeightSinkFn.apply(sink, *dec._weights()))
+        sunk, self._presunk = self._presunk, None
+        if sunk is None:
+            sunk = self.weight_sinks() if enc.is_cuda else [None, None]
+
+        # ... and their data gradients: every (bar, staff) backward is enqueued as soon as the loss gradient exists (ops.StackLogpFn)
+        early = ops.DecoderEarlyBackward() if (torch.is_grad_enabled() and enc.is_cuda and self.parallel_staves) else None
+        if early is not None:
+            if self._side_streams is None:
+                self._side_streams = (torch.cuda.Stream(), torch.cuda.Stream())
+            early.sinks = [(sk[0], self._side_streams[si]) for si, sk in enumerate(sunk) if sk is not None]
 
         token = self.get_SOS_token(B)[0].squeeze(1)                      # (B, 4*staff+ts+key)
         h = hidden[0]
@@ -277,8 +300,8 @@ class HierarchicalDecoder(nn.Module):
                     side.wait_event(ready)
                     for t_ in (enc, Ep, bar_summary) + ((gt_staff,) if gt_staff is not None else ()):
                         t_.record_stream(side)
-                    with torch.cuda.stream(side):
-                        out = dec._decode(enc, Ep, bar_summary, inference, gt_staff, tf_in, steps[si][bar], src, sunk[si])
+                    out = dec._decode(enc, Ep, bar_summary, inference, gt_staff, tf_in, steps[si][bar], src, sunk[si],
+                                      side=side, early=(early, (si, bar)) if early is not None else None)
                     done.append(side.record_event())
                     for t_ in out:
                         t_.record_stream(main)
@@ -318,7 +341,11 @@ class HierarchicalDecoder(nn.Module):
             # the reference draws one coin per executed note step (models.py:404); only the count matters here
             src.coins(int(torch.stack(counters)[:, 1].sum().item()))
         self.last_step_counters = counters
-        return (torch.stack(ts_outs, 1), torch.stack(key_outs, 1), torch.stack(up_outs, 1), torch.stack(lo_outs, 1))
+        if early is not None:
+            up_all, lo_all = ops.StackLogpFn.apply(early, len(up_outs), *up_outs, *lo_outs)
+        else:
+            up_all, lo_all = torch.stack(up_outs, 1), torch.stack(lo_outs, 1)
+        return (torch.stack(ts_outs, 1), torch.stack(key_outs, 1), up_all, lo_all)
 
     def forward(self, encoder_outputs, hidden, inference=True, ground_truth=None, teacher_forcing_ratio=0,
                 device=torch.device("cuda" if torch.cuda.is_available() else "cpu")):
@@ -351,22 +378,26 @@ class NoteDecoder(nn.Module):
         return (self.attn.attn.weight, self.attn.v.weight, self.embedding.weight, g.weight_ih_l0, g.weight_hh_l0, g.bias_ih_l0,
                 g.bias_hh_l0, self.out.weight, self.out.bias)
 
-    def _decode(self, enc, Ep, h0, inference, gt, tf_ratio, S, src, sunk=None):
+    def _decode(self, enc, Ep, h0, inference, gt, tf_ratio, S, src, sunk=None, side=None, early=None):
         """All steps of one (bar, staff).  Coins/masks are pre-drawn in the reference's order (models.py:391,404).
-        `sunk` = (DecoderGradSink, weight aliases from DecoderWeightSinkFn) when the caller defers the weight gradients."""
+        `sunk` = (DecoderGradSink, weight aliases from DecoderWeightSinkFn) when the caller defers the weight gradients;
+        `side` = the CUDA stream the call is enqueued on (the caller orders it against the current stream with events);
+        `early` = (ops.DecoderEarlyBackward, key) when the caller launches the backward of all its calls at once."""
         B = enc.shape[0]
         dev = enc.device
         training = self.training
         have_gt = gt is not None
         use_gt = mask = None
-        if have_gt:
-            coins = src.coins(S)
-            if not inference:
-                use_gt = torch.tensor([1 if c < tf_ratio else 0 for c in coins], dtype=torch.int32).to(dev, non_blocking=True)
-        if training:
-            mask = src.dropout_mask((S, B, self.note_emb_size), 0.1, dev, "note_steps").contiguous()
-        cfg = dict(S=S, max_steps=self.max_steps, inference=inference or not have_gt, gt=gt.contiguous() if have_gt else None,
-                   use_gt=use_gt, mask=mask, sos=SOS, eos=EOS)
+        with ops._on_stream(side):
+            if have_gt:
+                coins = src.coins(S)
+                if not inference:
+                    use_gt = torch.tensor([1 if c < tf_ratio else 0 for c in coins], dtype=torch.int32).to(dev, non_blocking=True)
+                gt = gt.contiguous()
+            if training:
+                mask = src.dropout_mask((S, B, self.note_emb_size), 0.1, dev, "note_steps").contiguous()
+        cfg = dict(S=S, max_steps=self.max_steps, inference=inference or not have_gt, gt=gt if have_gt else None,
+                   use_gt=use_gt, mask=mask, sos=SOS, eos=EOS, stream=side, early=early)
         wts = self._weights()
         if sunk is not None:
             cfg["sink"], wts = sunk

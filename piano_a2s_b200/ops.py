@@ -6,6 +6,7 @@ raises if its inputs are not CUDA tensors -- there is no CPU path.
 from __future__ import annotations
 
 import collections
+import contextlib
 import ctypes
 import os
 from typing import Optional
@@ -57,6 +58,10 @@ class ktime:
             b = torch.cuda.Event(enable_timing=True)
             b.record()
             KernelTimers.events.setdefault(self.name, []).append((self.a, b))
+
+
+def _on_stream(s):
+    return torch.cuda.stream(s) if s is not None else contextlib.nullcontext()
 
 
 def _dist_on() -> bool:
@@ -756,6 +761,15 @@ class NoteDecoderFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, enc, Ep, h0, attn_w, attn_v, emb, W_ih, W_hh, b_ih, b_hh, W_out, b_out, cfg):
+        # cfg["stream"]: the call is ENQUEUED on that side stream (which the caller has made wait for the inputs) while
+        # autograd sees a node of the current stream; the caller waits for the side stream before it reads the outputs.
+        side = cfg.get("stream")
+        ctx.side, ctx.pre = side, None
+        with _on_stream(side):
+            return NoteDecoderFn._forward(ctx, enc, Ep, h0, attn_w, attn_v, emb, W_ih, W_hh, b_ih, b_hh, W_out, b_out, cfg)
+
+    @staticmethod
+    def _forward(ctx, enc, Ep, h0, attn_w, attn_v, emb, W_ih, W_hh, b_ih, b_hh, W_out, b_out, cfg):
         ctx.prec = current_precision()
         enc, Ep, h0 = _f(enc), _f(Ep), _f(h0)
         B, T, D = enc.shape
@@ -805,11 +819,42 @@ class NoteDecoderFn(torch.autograd.Function):
                                   sv["qs"], sv["xtok"], sv["toks"], mask if mask is not None else torch.empty(0, device=dev))
             ctx.meta = (B, T, D, A, V, E, VP, S, max_steps, NS, tile, mask is not None, attn_v.shape)
             ctx.sink = cfg.get("sink")
+            early = cfg.get("early")
+            if early is not None:
+                early[0].calls[early[1]] = ctx
         return logp, lengths, counters
 
     @staticmethod
-    @_bwd_precision
     def backward(ctx, dlogp, _dl, _dc):
+        pre, ctx.pre = ctx.pre, None
+        if pre is None:
+            pre = NoteDecoderFn.launch_backward(ctx, dlogp)
+        grads, done = pre
+        if done is not None:
+            torch.cuda.current_stream().wait_event(done)
+        return grads
+
+    @staticmethod
+    def launch_backward(ctx, dlogp):
+        """Enqueues the whole backward of this call on the stream its forward ran on -> (input gradients, completion event or
+        None).  Called by backward(), or ahead of it by StackLogpFn.backward as soon as the loss gradient exists."""
+        side = ctx.side
+        with use_precision(ctx.prec):
+            if side is None:
+                return NoteDecoderFn._backward(ctx, dlogp), None
+            cur = torch.cuda.current_stream()
+            side.wait_event(cur.record_event())
+            dlogp.record_stream(side)
+            with torch.cuda.stream(side):
+                grads = NoteDecoderFn._backward(ctx, dlogp)
+                done = side.record_event()
+            for g in grads:
+                if torch.is_tensor(g):
+                    g.record_stream(cur)
+            return grads, done
+
+    @staticmethod
+    def _backward(ctx, dlogp):
         (enc, Ep, attn_w, v, emb, W_ih, W_hh, W_out, logp, hs, ctxs, attn, gates, qs, xtok, toks, mask) = ctx.saved_tensors
         B, T, D, A, V, E, VP, S, max_steps, NS, tile, has_mask, vshape = ctx.meta
         dev = enc.device
@@ -909,9 +954,30 @@ def decoder_weight_grads(recs, dims):
 
 
 class DecoderGradSink:
-    """Per NoteDecoder module and forward pass: the step buffers its calls (one per bar) leave behind in backward."""
+    """Per NoteDecoder module and forward pass: the step buffers its calls (one per bar) leave behind in backward, and --
+    when StackLogpFn has already enqueued the contractions over them on a side stream -- their result `pre`."""
     def __init__(self):
-        self.records, self.dims = [], None
+        self.records, self.dims, self.pre = [], None, None
+
+    def take(self, cur):
+        """Weight gradients over all records, enqueued on stream `cur` (which is made to wait for the records' streams)."""
+        recs, self.records = self.records, []
+        if not recs:
+            return None
+        for r in recs:
+            if r["stream"] != cur:
+                cur.wait_event(r["event"])
+                for v in r.values():
+                    if torch.is_tensor(v):
+                        v.record_stream(cur)
+        return list(decoder_weight_grads(recs, self.dims))
+
+    def launch(self, side):
+        """take() on `side`, ahead of the sink node -> self.pre = (gradients, completion event)."""
+        with torch.cuda.stream(side):
+            grads = self.take(side)
+            if grads is not None:
+                self.pre = (grads, side.record_event())
 
 
 class DecoderWeightSinkFn(torch.autograd.Function):
@@ -932,22 +998,59 @@ class DecoderWeightSinkFn(torch.autograd.Function):
     @_bwd_precision
     def backward(ctx, *grads):
         sink = ctx.sink
-        recs, sink.records = sink.records, []
-        out = [None] * 9
-        if recs:
-            cur = torch.cuda.current_stream()
-            for r in recs:
-                if r["stream"] != cur:
-                    cur.wait_event(r["event"])
-                    for v in r.values():
-                        if torch.is_tensor(v):
-                            v.record_stream(cur)
-            out = list(decoder_weight_grads(recs, sink.dims))
+        cur = torch.cuda.current_stream()
+        pre, sink.pre = sink.pre, None
+        if pre is not None:
+            out, done = pre
+            cur.wait_event(done)
+            for g in out:
+                g.record_stream(cur)
+            assert not sink.records
+        else:
+            out = sink.take(cur) or [None] * 9
         for i, g in enumerate(grads):            # uses of the aliases outside NoteDecoderFn (none on the hot path)
             if g is not None:
                 out[i] = g if out[i] is None else out[i] + g
         return (None,) + tuple(out)
 
+
+
+class DecoderEarlyBackward:
+    """Per forward pass of the bar loop: the NoteDecoderFn calls, keyed (staff, bar), whose backward StackLogpFn launches."""
+    def __init__(self):
+        self.calls = {}
+        self.sinks = []         # (DecoderGradSink, side stream): weight-gradient contractions enqueued right behind the last call
+
+
+class StackLogpFn(torch.autograd.Function):
+    """(torch.stack(upper per-bar log-probs, 1), torch.stack(lower ..., 1)) of models.py:313-316.  A note decoder's backward
+    depends on nothing but the loss gradient of its own log-probabilities (its predictions reach the next bar through argmax
+    only), so this node -- the first of the decoder to run in a backward pass -- enqueues ALL (bar, staff) backward kernels on
+    their side streams at once, last bar first.  The two 64-CTA kernels that fit the GPU side by side then run back to back,
+    instead of each bar's pair waiting for the bar chain of the bar after it (autograd's node order)."""
+
+    @staticmethod
+    def forward(ctx, early, n_upper, *logps):
+        ctx.early, ctx.n = early, (n_upper, len(logps) - n_upper)
+        ctx.prec = current_precision()
+        ctx.set_materialize_grads(False)
+        return torch.stack(logps[:n_upper], 1), torch.stack(logps[n_upper:], 1)
+
+    @staticmethod
+    def backward(ctx, d_up, d_lo):
+        nu, nl = ctx.n
+        parts = [[None if d is None else d[:, bar] for bar in range(n)] for d, n in ((d_up, nu), (d_lo, nl))]
+        calls = ctx.early.calls
+        for bar in reversed(range(max(nu, nl))):
+            for si in (0, 1):
+                c = calls.pop((si, bar), None)
+                if c is not None and bar < len(parts[si]) and parts[si][bar] is not None:
+                    c.pre = NoteDecoderFn.launch_backward(c, parts[si][bar])
+        if not calls:               # every call has left its rows: the weight gradients follow on the side streams
+            with use_precision(ctx.prec):
+                for sink, side in ctx.early.sinks:
+                    sink.launch(side)
+        return (None, None) + tuple(parts[0]) + tuple(parts[1])
 
 
 # ----------------------------------------------------------------------------------------------------------------

@@ -28,6 +28,20 @@ def compute_objectives(predictions, ground_truth):
     return parts[0] + parts[1] + parts[2] + parts[3], parts
 
 
+def targets_to_device(ground_truth, device):
+    """`batch.to(device)` of the reference trainer (pretrain.py:39) for the six target tensors, asynchronous when they are
+    pinned.  The host copies are still at hand here, so the number of decoder steps each (staff, bar) executes -- a function
+    of the targets alone (HierarchicalDecoder._steps_from_gt), which the host needs to size and launch the decoder kernels --
+    is counted on the host and travels with the device tensors (attribute `_pa2s_steps`), instead of being read back from the
+    device inside forward().  Plain device tensors without the attribute work too (models.HierarchicalDecoder.prefetch_steps)."""
+    from .models import HierarchicalDecoder
+    out = [t.to(device, non_blocking=True) for t in ground_truth]
+    for i in (2, 4):
+        if not ground_truth[i].is_cuda:
+            out[i]._pa2s_steps = HierarchicalDecoder._steps_from_gt(ground_truth[i]).tolist()
+    return out
+
+
 class FlatAdadelta:
     """All parameters (and their .grad) re-pointed into two flat fp32 buffers; clip_grad_norm_(max_grad_norm) +
     torch.optim.Adadelta(lr, rho, eps) semantics in two kernels (sum of squares, fused update)."""

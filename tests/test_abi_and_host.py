@@ -82,6 +82,11 @@ def test_steps_from_ground_truth():
     full = gt[2].clone()
     full[0, 1, :] = 5                                                 # a row without <eos>: loop never exits early
     assert int(models.HierarchicalDecoder._steps_from_gt(full)[1]) == 14
+    # the loader counts the same numbers on the host and attaches them to the (device) targets
+    from piano_a2s_b200.train import targets_to_device
+    out = targets_to_device(gt, "cpu")
+    assert len(out) == 6 and out[2]._pa2s_steps == s.tolist()
+    assert out[4]._pa2s_steps == [int(gt[5][:, bar].max()) + 1 for bar in range(3)]
 
 
 def test_attention_split_covers_all_frames():

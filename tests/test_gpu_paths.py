@@ -44,10 +44,12 @@ def _ragged_spectrogram(B, T, Fq, seed):
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16x3", "bf16"])
-@pytest.mark.parametrize("B,T", [(3, 24), (1, 19), (5, 33)])
+# 18 clips: two batch chunks in the persistent decoder.  (T = 17 because at T = 16 a key-head pre-activation of the ORACLE is 3e-6 from
+# zero: in the bf16x3 mode its ReLU takes the other branch, which moves that unit's whole weight-gradient row -- see DESIGN.md section 2.)
+@pytest.mark.parametrize("B,T", [(3, 24), (1, 19), (5, 33), (18, 17)])
 def test_training_step_every_precision_and_ragged_batches(cuda, prec, B, T):
     from piano_a2s_b200 import ops, rng
-    from piano_a2s_b200.train import compute_objectives
+    from piano_a2s_b200.train import compute_objectives, targets_to_device
     act_tol, grad_tol, l2_tol = TOL[prec]
     m, sd = _model(cuda, **SMALL)
     m.train()
@@ -64,7 +66,8 @@ def test_training_step_every_precision_and_ragged_batches(cuda, prec, B, T):
     ops.set_precision(train=prec)
     try:
         with rng.use_source(ReplayDeviceSource(rec.coins, rec.masks)):
-            outs = m(x.to(cuda), inference=False, ground_truth=[g.to(cuda) for g in gt], teacher_forcing_ratio=0.6, device=cuda)
+            # loader path: step counts travel with the targets (no device read in forward); test_gpu_parity.py covers plain tensors
+            outs = m(x.to(cuda), inference=False, ground_truth=targets_to_device(gt, cuda), teacher_forcing_ratio=0.6, device=cuda)
         loss, _ = compute_objectives(outs, [g.to(cuda) for g in gt])
         loss.backward()
     finally:
@@ -98,7 +101,7 @@ def test_training_step_every_precision_and_ragged_batches(cuda, prec, B, T):
         assert abs(loss.item() - ref_loss.item()) < 5e-2 * abs(ref_loss.item())
 
 
-@pytest.mark.parametrize("B,T", [(1, 24), (4, 31), (7, 12)])
+@pytest.mark.parametrize("B,T", [(1, 24), (4, 31), (7, 12), (33, 12)])      # 33 clips: three batch chunks, the last with one clip
 def test_greedy_inference_tokens_and_kern_strings_bit_exact(cuda, B, T):
     from piano_a2s_b200 import kern
     import models

@@ -40,6 +40,23 @@ def main():
     with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
         step()
         torch.cuda.synchronize()
+    if os.environ.get("PA2S_HOSTLAUNCH"):
+        # host launch time next to the device start time of every kernel >= 100 us (chrome trace, matched by correlation id):
+        # tells a device-side dependency (launched long before it starts) from a launch-bound stretch (starts when launched)
+        import json
+        import tempfile
+        path = os.path.join(tempfile.mkdtemp(), "trace.json")
+        prof.export_chrome_trace(path)
+        tr = json.load(open(path))["traceEvents"]
+        launch = {e["args"]["correlation"]: e for e in tr if e.get("cat") == "cuda_runtime" and "correlation" in e.get("args", {})}
+        kern = sorted((e for e in tr if e.get("cat") == "kernel"), key=lambda e: e["ts"])
+        t00 = kern[0]["ts"]
+        print("  device start | dur | host launch (ms rel. to first kernel) | stream | kernel")
+        for e in kern:
+            if e["dur"] >= 100:
+                l = launch.get(e["args"].get("correlation"))
+                lt = f"{1e-3 * (l['ts'] - t00):8.3f}" if l else "    n/a"
+                print(f"  t={1e-3 * (e['ts'] - t00):8.3f}  dur={1e-3 * e['dur']:7.3f}  host={lt}  stream={e['args'].get('stream')}  {e['name'][:50]}")
     evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
     if os.environ.get("PA2S_TIMELINE"):
         # coarse timeline: per stream (device_index of a CUDA event = stream id in kineto), kernels >= 100 us, and per-stream busy time
