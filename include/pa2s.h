@@ -198,4 +198,9 @@ PA2S_API int pa2s_adadelta(void* stream, float* p, const float* g, float* sq, fl
  * <eos> token (L if none): `pred = outs.argmax(-1)` + `unpad` of pretrain.py:97-117,245-249 / finetune.py:86-108 for all
  * (clip, bar) sequences of one staff in one launch.  tokens is int64 (nseq, L), lengths int32 (nseq). */
 PA2S_API int pa2s_greedy_tokens(void* stream, const float* logp, long long nseq, int L, int V, int eos, long long* tokens, int* lengths);
+/* ---- batch collation ---------------------------------------------------------------------------------
+ * `pad_spectrogram` of datasets/syn.py:46-58 and datasets/asap.py:338-350 for B clips in one launch: `packed` holds the clips'
+ * (n_b, F) fp32 spectrograms back to back, row_off (B+1 int64, device) their first rows; out (B, 1, Tmax, F) receives the first
+ * min(n_b, Tmax) frames of each clip and zeros after them. */
+PA2S_API int pa2s_pad_spectrograms(void* stream, const float* packed, const long long* row_off, int B, int Tmax, int F, float* out);
 #endif

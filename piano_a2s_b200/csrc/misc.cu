@@ -192,6 +192,40 @@ PA2S_API int pa2s_adadelta(void* stream, float* p, const float* g, float* sq, fl
     return 0;
 }
 
+// pad_spectrogram (datasets/syn.py:46-58, asap.py:338-350) for a whole batch: clip b's frames [row_off[b], row_off[b+1]) of the
+// packed ragged buffer go to out[b][0][0 .. min(n_b, Tmax)) and the remaining frames of the clip are zero.  Pure HBM stream:
+// one float4 per thread (F % 4 == 0) or one float; grid-stride over B*Tmax*F so that 148 x 8 CTAs cover any size.
+template <typename V>
+__global__ void pad_spectrograms_kernel(const V* __restrict__ src, const long long* __restrict__ row_off, V* __restrict__ out,
+                                        long long total, int Tmax, int Fv) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int f = (int)(i % Fv);
+        const long long bt = i / Fv;
+        const int t = (int)(bt % Tmax);
+        const int b = (int)(bt / Tmax);
+        const long long r0 = __ldg(row_off + b), n = __ldg(row_off + b + 1) - r0;
+        V v;
+        if (t < n) v = __ldcs(src + (r0 + t) * Fv + f);
+        else memset(&v, 0, sizeof(V));
+        __stcs(out + i, v);
+    }
+}
+
+PA2S_API int pa2s_pad_spectrograms(void* stream, const float* packed, const long long* row_off, int B, int Tmax, int F, float* out) {
+    if (B < 0 || Tmax <= 0 || F <= 0) return -1;
+    if (B == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool vec = (F % 4 == 0) && ((uintptr_t)packed % 16 == 0) && ((uintptr_t)out % 16 == 0);
+    const int Fv = vec ? F / 4 : F;
+    const long long total = (long long)B * Tmax * Fv;
+    const int grid = (int)min((long long)148 * 8, (total + 255) / 256);
+    if (vec) pad_spectrograms_kernel<float4><<<grid, 256, 0, st>>>((const float4*)packed, row_off, (float4*)out, total, Tmax, Fv);
+    else pad_spectrograms_kernel<float><<<grid, 256, 0, st>>>(packed, row_off, out, total, Tmax, Fv);
+    PA2S_CHECK_LAST();
+    return 0;
+}
+
 PA2S_API int pa2s_greedy_tokens(void* stream, const float* logp, long long nseq, int L, int V, int eos, long long* tokens, int* lengths) {
     if (nseq <= 0 || L <= 0 || V <= 0) return nseq == 0 ? 0 : -1;
     greedy_tokens_kernel<<<(unsigned)nseq, 256, 0, (cudaStream_t)stream>>>(logp, L, V, eos, tokens, lengths);

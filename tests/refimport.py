@@ -30,3 +30,40 @@ def import_reference_models():
         if saved_dp is not None:
             sys.modules["data_processing"] = saved_dp
     return mod
+
+
+def reference_dataset_stub(max_frame_num=1201, device="cpu"):
+    """An instance of the reference's `datasets.syn.SyntheticDataset` WITHOUT running its __init__ (which lists feature folders):
+    only the attributes `pad_spectrogram` / `pad_score` / `pad_single_measure` / `key_to_int` read are set.  The third-party modules
+    datasets/syn.py and utilities.py import at module top but these methods never touch (pretty_midi, librosa, mido, hyperpyyaml,
+    music21) are stubbed when absent."""
+    def stub(name, **attrs):
+        if name not in sys.modules:
+            try:
+                importlib.import_module(name)
+            except Exception:
+                m = types.ModuleType(name)
+                for k, v in attrs.items():
+                    setattr(m, k, v)
+                sys.modules[name] = m
+    for name, attrs in (("music21", {}), ("pretty_midi", {}), ("librosa", {}), ("mido", {"MidiFile": object}),
+                        ("hyperpyyaml", {"load_hyperpyyaml": None})):
+        stub(name, **attrs)
+    saved_path = list(sys.path)
+    saved = {k: sys.modules.pop(k, None) for k in ("data_processing", "datasets", "utilities")}
+    sys.path.insert(0, REF_ROOT)
+    try:
+        spec = importlib.util.spec_from_file_location("ref_syn", os.path.join(REF_ROOT, "datasets", "syn.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        sys.path[:] = saved_path
+        for k in ("data_processing", "datasets", "utilities"):
+            sys.modules.pop(k, None)
+            if saved[k] is not None:
+                sys.modules[k] = saved[k]
+    ds = object.__new__(mod.SyntheticDataset)
+    ds.hparams = {"max_frame_num": max_frame_num}
+    ds.device = device
+    ds.labels = mod.LabelsMultiple(extended=True)
+    return ds
