@@ -183,6 +183,10 @@ PA2S_API int pa2s_note_decoder_fwd_persist(void* stream, const void* args, int s
 PA2S_API int pa2s_dec_dlogits(void* stream, const void* args);
 PA2S_API int pa2s_dec_deferred_blocks(int T);
 PA2S_API int pa2s_note_decoder_bwd_persist(void* stream, const void* args);
+/* the two halves of pa2s_note_decoder_bwd_persist on their own: the sequential chain (cooperative kernel), and the parallel
+ * dEp / dv accumulation, which only reads ds_all / qs / Ep / v and may therefore run on another stream behind the chain. */
+PA2S_API int pa2s_note_decoder_bwd_chain(void* stream, const void* args);
+PA2S_API int pa2s_note_decoder_bwd_deferred(void* stream, const void* args);
 PA2S_API int pa2s_attn_step_fwd(void* stream, const void* args);
 PA2S_API int pa2s_attn_step_bwd(void* stream, const void* args);
 

@@ -1014,7 +1014,9 @@ PA2S_API int pa2s_dec_dlogits(void* stream, const void* args) {
     PA2S_CHECK_LAST();
     return 0;
 }
-PA2S_API int pa2s_note_decoder_bwd_persist(void* stream, const void* args) {
+// The two halves of pa2s_note_decoder_bwd_persist as separate entry points, so that a caller can put the parallel dEp / dv
+// kernel (which only reads ds_all, qs, Ep, v) on another stream than the sequential chain.
+PA2S_API int pa2s_note_decoder_bwd_chain(void* stream, const void* args) {
     DecArgs a = *reinterpret_cast<const DecArgs*>(args);
     cudaStream_t st = (cudaStream_t)stream;
     if (a.B <= 0 || a.S <= 0) return 0;
@@ -1024,7 +1026,17 @@ PA2S_API int pa2s_note_decoder_bwd_persist(void* stream, const void* args) {
     void* kargs[] = {(void*)&a};
     PA2S_TRY(cudaLaunchCooperativeKernel((const void*)dec_persist_bwd_kernel, dim3(PG), dim3(NTB), kargs, smem, st));
     PA2S_COUNT_LAUNCH();
-    dec_attn_deferred_kernel<<<dim3(ceil_div(a.T, DEF_FPB), a.B), DEF_WARPS * 32, 0, st>>>(a);
+    return 0;
+}
+PA2S_API int pa2s_note_decoder_bwd_deferred(void* stream, const void* args) {
+    DecArgs a = *reinterpret_cast<const DecArgs*>(args);
+    if (a.B <= 0 || a.S <= 0) return 0;
+    if (a.ds_all == nullptr || a.dEp == nullptr || a.dv_part == nullptr) return -2;
+    dec_attn_deferred_kernel<<<dim3(ceil_div(a.T, DEF_FPB), a.B), DEF_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
     PA2S_CHECK_LAST();
     return 0;
+}
+PA2S_API int pa2s_note_decoder_bwd_persist(void* stream, const void* args) {
+    const int rc = pa2s_note_decoder_bwd_chain(stream, args);
+    return rc != 0 ? rc : pa2s_note_decoder_bwd_deferred(stream, args);
 }

@@ -11,6 +11,8 @@ from __future__ import annotations
 import hashlib
 import math
 
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -149,6 +151,7 @@ class HierarchicalDecoder(nn.Module):
         self._side_streams = None
         self._aux_stream = None
         self._presunk = None
+        self._defer_stream = None
         self._steps_host = None
         self._steps_pending = None
         self.init_weight()
@@ -209,6 +212,13 @@ class HierarchicalDecoder(nn.Module):
         lower_gt.record_stream(side)
         self._steps_pending = (ev, upper_gt, lower_gt)
 
+    def _make_streams(self):
+        # the persistent note-decoder kernels (64 co-resident CTAs that own their SMs) go ahead of the wide parallel kernels that fill
+        # the remaining SMs: two high-priority streams for the staves, one normal-priority stream for the deferred dEp / dv kernels
+        prio = -1 if os.environ.get("PA2S_SIDE_PRIO", "0") == "1" else 0
+        self._side_streams = (torch.cuda.Stream(priority=prio), torch.cuda.Stream(priority=prio))
+        self._defer_stream = torch.cuda.Stream() if os.environ.get("PA2S_DEFER_STREAM", "0") == "1" else None
+
     def weight_sinks(self):
         """[(DecoderGradSink, weight aliases) or None] for the upper / lower note decoder (ops.DecoderWeightSinkFn).  Autograd runs
         nodes in reverse creation order: ScoreTranscription.forward creates the sinks BEFORE the ConvStack, so their node -- which
@@ -266,7 +276,7 @@ class HierarchicalDecoder(nn.Module):
         early = ops.DecoderEarlyBackward() if (torch.is_grad_enabled() and enc.is_cuda and self.parallel_staves) else None
         if early is not None:
             if self._side_streams is None:
-                self._side_streams = (torch.cuda.Stream(), torch.cuda.Stream())
+                self._make_streams()
             early.sinks = [(sk[0], self._side_streams[si]) for si, sk in enumerate(sunk) if sk is not None]
 
         token = self.get_SOS_token(B)[0].squeeze(1)                      # (B, 4*staff+ts+key)
@@ -289,7 +299,7 @@ class HierarchicalDecoder(nn.Module):
             main = torch.cuda.current_stream() if enc.is_cuda else None
             use_streams = self.parallel_staves and main is not None
             if use_streams and self._side_streams is None:
-                self._side_streams = (torch.cuda.Stream(), torch.cuda.Stream())
+                self._make_streams()
             ready = main.record_event() if use_streams else None
             done = []
             for si, (dec, Ep) in enumerate(((self.upper_decoder, Ep_up), (self.lower_decoder, Ep_lo))):
@@ -301,7 +311,8 @@ class HierarchicalDecoder(nn.Module):
                     for t_ in (enc, Ep, bar_summary) + ((gt_staff,) if gt_staff is not None else ()):
                         t_.record_stream(side)
                     out = dec._decode(enc, Ep, bar_summary, inference, gt_staff, tf_in, steps[si][bar], src, sunk[si],
-                                      side=side, early=(early, (si, bar)) if early is not None else None)
+                                      side=side, early=(early, (si, bar)) if early is not None else None,
+                                      defer_stream=self._defer_stream if early is not None else None)
                     done.append(side.record_event())
                     for t_ in out:
                         t_.record_stream(main)
@@ -378,11 +389,12 @@ class NoteDecoder(nn.Module):
         return (self.attn.attn.weight, self.attn.v.weight, self.embedding.weight, g.weight_ih_l0, g.weight_hh_l0, g.bias_ih_l0,
                 g.bias_hh_l0, self.out.weight, self.out.bias)
 
-    def _decode(self, enc, Ep, h0, inference, gt, tf_ratio, S, src, sunk=None, side=None, early=None):
+    def _decode(self, enc, Ep, h0, inference, gt, tf_ratio, S, src, sunk=None, side=None, early=None, defer_stream=None):
         """All steps of one (bar, staff).  Coins/masks are pre-drawn in the reference's order (models.py:391,404).
         `sunk` = (DecoderGradSink, weight aliases from DecoderWeightSinkFn) when the caller defers the weight gradients;
         `side` = the CUDA stream the call is enqueued on (the caller orders it against the current stream with events);
-        `early` = (ops.DecoderEarlyBackward, key) when the caller launches the backward of all its calls at once."""
+        `early` = (ops.DecoderEarlyBackward, key) when the caller launches the backward of all its calls at once;
+        `defer_stream` = stream for the parallel dEp / dv kernel of the backward (default: the call's own stream)."""
         B = enc.shape[0]
         dev = enc.device
         training = self.training
@@ -397,7 +409,7 @@ class NoteDecoder(nn.Module):
             if training:
                 mask = src.dropout_mask((S, B, self.note_emb_size), 0.1, dev, "note_steps").contiguous()
         cfg = dict(S=S, max_steps=self.max_steps, inference=inference or not have_gt, gt=gt if have_gt else None,
-                   use_gt=use_gt, mask=mask, sos=SOS, eos=EOS, stream=side, early=early)
+                   use_gt=use_gt, mask=mask, sos=SOS, eos=EOS, stream=side, early=early, defer_stream=defer_stream)
         wts = self._weights()
         if sunk is not None:
             cfg["sink"], wts = sunk

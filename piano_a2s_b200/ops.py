@@ -765,6 +765,7 @@ class NoteDecoderFn(torch.autograd.Function):
         # autograd sees a node of the current stream; the caller waits for the side stream before it reads the outputs.
         side = cfg.get("stream")
         ctx.side, ctx.pre = side, None
+        ctx.defer_stream, ctx.defer_done = cfg.get("defer_stream"), None     # stream of the parallel dEp / dv kernel of the backward
         with _on_stream(side):
             return NoteDecoderFn._forward(ctx, enc, Ep, h0, attn_w, attn_v, emb, W_ih, W_hh, b_ih, b_hh, W_out, b_out, cfg)
 
@@ -830,8 +831,8 @@ class NoteDecoderFn(torch.autograd.Function):
         if pre is None:
             pre = NoteDecoderFn.launch_backward(ctx, dlogp)
         grads, done = pre
-        if done is not None:
-            torch.cuda.current_stream().wait_event(done)
+        for ev in done:
+            torch.cuda.current_stream().wait_event(ev)
         return grads
 
     @staticmethod
@@ -841,13 +842,16 @@ class NoteDecoderFn(torch.autograd.Function):
         side = ctx.side
         with use_precision(ctx.prec):
             if side is None:
-                return NoteDecoderFn._backward(ctx, dlogp), None
+                grads = NoteDecoderFn._backward(ctx, dlogp)
+                return grads, [ev for ev in (ctx.defer_done,) if ev is not None]
             cur = torch.cuda.current_stream()
             side.wait_event(cur.record_event())
             dlogp.record_stream(side)
             with torch.cuda.stream(side):
                 grads = NoteDecoderFn._backward(ctx, dlogp)
-                done = side.record_event()
+                done = [side.record_event()]
+            if ctx.defer_done is not None:
+                done.append(ctx.defer_done)
             for g in grads:
                 if torch.is_tensor(g):
                     g.record_stream(cur)
@@ -881,7 +885,20 @@ class NoteDecoderFn(torch.autograd.Function):
             with ktime("note_decoder_bwd"):
                 lib.pa2s_dec_dlogits(st, ctypes.byref(args))
                 gemm(bw["dlogits_all"], W_out, bw["dhc_all"], S * B, 2 * D, V, lda=VP, ldb=2 * D, ldc=2 * D)
-                lib.pa2s_note_decoder_bwd_persist(st, ctypes.byref(args))
+                aux = ctx.defer_stream
+                if aux is None:
+                    lib.pa2s_note_decoder_bwd_persist(st, ctypes.byref(args))
+                else:
+                    # the sequential chain here; the parallel dEp / dv kernel (reads ds_all, qs, Ep, v) on `aux`, so that the next
+                    # persistent kernel of this stream starts right behind the chain
+                    lib.pa2s_note_decoder_bwd_chain(st, ctypes.byref(args))
+                    cur = torch.cuda.current_stream()
+                    aux.wait_event(cur.record_event())
+                    with torch.cuda.stream(aux):
+                        lib.pa2s_note_decoder_bwd_deferred(stream(), ctypes.byref(args))
+                        ctx.defer_done = aux.record_event()
+                    for t_ in (bw["ds_all"], bw["dEp"], bw["dv_part"], qs, Ep, v):
+                        t_.record_stream(aux)
             SYNC_FLAGS.append(bw["sync"])
             dh0 = bw["dhq"]
         else:
@@ -908,6 +925,7 @@ class NoteDecoderFn(torch.autograd.Function):
             # weight gradients of this module are formed once per backward pass, over the rows of ALL its calls (one per bar)
             rec["event"] = torch.cuda.current_stream().record_event()
             rec["stream"] = torch.cuda.current_stream()
+            rec["event2"] = ctx.defer_done                  # dv_part comes from the deferred kernel's stream
             sink.records.append(rec)
             sink.dims = dims
             wg = (None,) * 9
@@ -965,8 +983,11 @@ class DecoderGradSink:
         if not recs:
             return None
         for r in recs:
+            if r.get("event2") is not None:
+                cur.wait_event(r["event2"])
             if r["stream"] != cur:
                 cur.wait_event(r["event"])
+            if r["stream"] != cur or r.get("event2") is not None:
                 for v in r.values():
                     if torch.is_tensor(v):
                         v.record_stream(cur)
