@@ -206,5 +206,13 @@ PA2S_API int pa2s_greedy_tokens(void* stream, const float* logp, long long nseq,
  * `pad_spectrogram` of datasets/syn.py:46-58 and datasets/asap.py:338-350 for B clips in one launch: `packed` holds the clips'
  * (n_b, F) fp32 spectrograms back to back, row_off (B+1 int64, device) their first rows; out (B, 1, Tmax, F) receives the first
  * min(n_b, Tmax) frames of each clip and zeros after them. */
+/* ---- evaluation metric right after the path ------------------------------------------------------------
+ * Per clip, the counts jiwer.wer(target, pred) of `calculate_wer` (pretrain.py:216-227) is made of: hyp / ref are (nclips, bars, L)
+ * int64 token rows (greedy tokens / targets); a row ends at its first `eos`; tokens equal to skip_a / skip_b (the pure-whitespace
+ * labels "\t" and "\n", which jiwer's whitespace collapsing removes) are dropped; `sep` (any id outside the vocabulary) stands for
+ * the "=" word between bars.  dist = Levenshtein distance of the two word sequences, nref / nhyp their lengths (int32 per clip);
+ * wer = dist / nref. */
+PA2S_API int pa2s_wer_counts(void* stream, const long long* hyp, const long long* ref, int nclips, int bars, int Lh, int Lr, int eos,
+                             int skip_a, int skip_b, int sep, int* dist, int* nref, int* nhyp);
 PA2S_API int pa2s_pad_spectrograms(void* stream, const float* packed, const long long* row_off, int B, int Tmax, int F, float* out);
 #endif
