@@ -406,8 +406,8 @@ def algorithmic_work(B, S_total, n_dec_calls):
     px = float(T * F * B)
     ch = [1, 20, 20, 40, 40]
     w = {}
-    w["conv1_fwd"] = ("conv3x3_kernel<1,20> fp32 FFMA (conv1+stats)", 2 * 9 * 1 * 20 * px, px * 4 * (1 + 20))
-    w["conv1_wgrad"] = ("conv3x3_wgrad_kernel<1,20> fp32 FFMA", 2 * 9 * 1 * 20 * px, px * 4 * (1 + 20 + 20))
+    w["conv1_fwd"] = ("conv1_fwd_kernel fp32 stream (conv1 + BatchNorm sums)", 2 * 9 * 1 * 20 * px, px * 4 * (1 + 20))
+    w["conv1_wgrad"] = ("conv1_wgrad_kernel fp32 stream", 2 * 9 * 1 * 20 * px, px * 4 * (1 + 20 + 20))
     for i in (2, 3, 4):
         ci, co = ch[i - 1], ch[i]
         fl = 2.0 * 9 * ci * co * px
