@@ -406,6 +406,10 @@ def algorithmic_work(B, S_total, n_dec_calls):
     px = float(T * F * B)
     ch = [1, 20, 20, 40, 40]
     w = {}
+    # VQT: algorithmic = direct form 4*T*sum(N_k) = 1.313 GFLOP/clip; the kernel contracts the dense 960 x 800 filter bank
+    # (1.84 GFLOP/clip) once per bf16 piece product (x6 for the three-piece split): the tensor pipe sees 8.4x the algorithmic FLOPs
+    w["vqt_filterbank"] = ("tc_gemm_tma_kernel VQT filterbank (+audio split), bf16x6, overlapping frame rows", 1.313e9 * B,
+                           B * (0.77e6 + T * 960 * 4.0))
     w["conv1_fwd"] = ("conv1_fwd_kernel fp32 stream (conv1 + BatchNorm sums)", 2 * 9 * 1 * 20 * px, px * 4 * (1 + 20))
     w["conv1_wgrad"] = ("conv1_wgrad_kernel fp32 stream", 2 * 9 * 1 * 20 * px, px * 4 * (1 + 20 + 20))
     for i in (2, 3, 4):

@@ -214,5 +214,9 @@ PA2S_API int pa2s_greedy_tokens(void* stream, const float* logp, long long nseq,
  * wer = dist / nref. */
 PA2S_API int pa2s_wer_counts(void* stream, const long long* hyp, const long long* ref, int nclips, int bars, int Lh, int Lr, int eos,
                              int skip_a, int skip_b, int sep, int* dist, int* nref, int* nhyp);
+/* ---- audio ingest (the arithmetic of datasets/asap.py:83-86) ---------------------------------------------
+ * audio (channels, n) fp32 -> out (n): mean over channels, then divided by max|mean| (IEEE division; an all-zero clip gives NaN
+ * like the reference's 0/0).  scratch: one uint32 on the device. */
+PA2S_API int pa2s_mono_peak_normalize(void* stream, const float* audio, int channels, long long n, float* out, unsigned int* scratch);
 PA2S_API int pa2s_pad_spectrograms(void* stream, const float* packed, const long long* row_off, int B, int Tmax, int F, float* out);
 #endif

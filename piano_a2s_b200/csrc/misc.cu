@@ -212,6 +212,44 @@ __global__ void pad_spectrograms_kernel(const V* __restrict__ src, const long lo
     }
 }
 
+// Audio ingest in front of the VQT (datasets/asap.py:83-86): mono = mean over channels, then audio / max|audio|.
+// Pass 1 keeps the per-clip maximum of |mono| as the bit pattern of a non-negative float (atomicMax on uint is order-preserving
+// for those; a NaN sample has a larger pattern than every finite value and so survives, like torch.max); pass 2 divides with an
+// IEEE division (__fdiv_rn), so the result is bit-identical to torch's `audio / torch.max(torch.abs(audio))`.
+__global__ void mono_absmax_kernel(const float* __restrict__ in, int C, long long n, float* __restrict__ mono, unsigned int* __restrict__ amax) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const float inv = 1.0f / (float)C;
+    unsigned int m = 0u;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float s = __ldcs(in + i);
+        for (int c = 1; c < C; ++c) s += __ldcs(in + (long long)c * n + i);
+        if (C > 1) s *= inv;
+        mono[i] = s;
+        m = max(m, __float_as_uint(fabsf(s)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m != 0u) atomicMax(amax, m);
+}
+__global__ void peak_divide_kernel(float* __restrict__ mono, long long n, const unsigned int* __restrict__ amax) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const float peak = __uint_as_float(*amax);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) mono[i] = __fdiv_rn(mono[i], peak);
+}
+
+PA2S_API int pa2s_mono_peak_normalize(void* stream, const float* audio, int channels, long long n, float* out, unsigned int* scratch) {
+    if (channels <= 0 || n < 0) return -1;
+    if (n == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    PA2S_TRY(cudaMemsetAsync(scratch, 0, sizeof(unsigned int), st));
+    const int grid = (int)min((long long)148 * 8, (n + 255) / 256);
+    mono_absmax_kernel<<<grid, 256, 0, st>>>(audio, channels, n, out, scratch);
+    PA2S_CHECK_LAST();
+    peak_divide_kernel<<<grid, 256, 0, st>>>(out, n, scratch);
+    PA2S_CHECK_LAST();
+    return 0;
+}
+
 PA2S_API int pa2s_pad_spectrograms(void* stream, const float* packed, const long long* row_off, int B, int Tmax, int F, float* out) {
     if (B < 0 || Tmax <= 0 || F <= 0) return -1;
     if (B == 0) return 0;

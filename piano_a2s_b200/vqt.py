@@ -86,8 +86,9 @@ class VQT(torch.nn.Module):
             if self._fop is None or self._fop[0] != (self.precision, filt.device):
                 self._fop = ((self.precision, filt.device), ops.split_operand(filt, 2 * self.n_bins, K, K, npieces=ops.npieces_for(self.precision)))
             filt = self._fop[1]
-        ops.gemm(ypad, filt, C, T, 2 * self.n_bins, K, transB=True, lda=self.hop, ldb=K, ldc=2 * self.n_bins,
-                 batch=B, strideA=plen, strideB=0, strideC=T * 2 * self.n_bins, a_off=self.j0, precision=self.precision)
+        with ops.ktime("vqt_filterbank"):
+            ops.gemm(ypad, filt, C, T, 2 * self.n_bins, K, transB=True, lda=self.hop, ldb=K, ldc=2 * self.n_bins,
+                     batch=B, strideA=plen, strideB=0, strideC=T * 2 * self.n_bins, a_off=self.j0, precision=self.precision)
         out = torch.empty(B, T, self.n_bins, device=audio.device, dtype=torch.float32)
         cmax = torch.empty(B, device=audio.device, dtype=torch.int32)
         lib.pa2s_vqt_post(stream(), ptr(C), ptr(out), ptr(cmax), B, T, self.n_bins)
