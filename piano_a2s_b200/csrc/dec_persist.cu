@@ -21,9 +21,12 @@ constexpr int PG = 64;                 // CTAs of a persistent decoder grid (two
 #define PA2S_DEC_NT 384
 #endif
 #ifndef PA2S_DEC_PD
-#define PA2S_DEC_PD 2
+#define PA2S_DEC_PD 1
 #endif
-constexpr int PD = PA2S_DEC_PD;        // frames per warp in flight in the attention phases (register ring depth)
+// frames per warp in flight in the attention phases (register ring depth).  Measured (tools/prof_decoder.py, B=16, S=80, forward /
+// backward us per step): PD=1 32.4 / 32.5, PD=2 36.5 / 33.3, PD=3 38.3 / 49.3, PD=4 51.4 / 67.4 -- a second frame costs 24 registers
+// per thread, which at 384 threads x 168 registers spills inside the frame loop (ptxas: 0 / 156 / 496 / 816 bytes of spill stores).
+constexpr int PD = PA2S_DEC_PD;
 constexpr int NT = PA2S_DEC_NT;        // threads per CTA: 12 warps stream the attention memory, the first 8 own the GEMV columns
 constexpr int NW = NT / 32;
 constexpr int UPC = DD / PG;           // hidden units per CTA (8)
@@ -126,6 +129,11 @@ __device__ __forceinline__ int rs_base(int lane) {
     return base;
 }
 
+// phase B: (4 clip groups x 8 warps) x (24 rows x 4 clips); phase C: 32 x 32.  The per-warp partial contexts of phase A (NW x 512
+// floats) live in the CONTEXT columns of xs instead, which are dead between phase C of one step and the staging of phase B of the
+// next (row w of xs = warp w: needs NW <= BT); that keeps 16 warps within the 227 KB of shared memory.
+constexpr int RED_FLOATS = 4 * 8 * GR * 4;
+static_assert(NW <= BT && RED_FLOATS >= 32 * 32, "partial contexts alias xs rows; phase C scratch");
 struct FwdSmem {
     float* Wg;      // [GR][1024]   rows g*8+u: [W_hh row | W_ih row, context columns]
     float* Wc;      // [CR][1024]   W_out rows / W_h rows (zero beyond 512) / zero rows
@@ -133,7 +141,7 @@ struct FwdSmem {
     float* bias;    // [4][8]       b_r (ih+hh), b_z (ih+hh), b_in, b_hn
     float* bc;      // [8]          b_out of the phase-C rows (0 for query rows)
     float* xs;      // [BT][XP]
-    float* red;     // NW*512 floats: cross-warp reduction scratch (B, C) | per-warp partial contexts (A)
+    float* red;     // RED_FLOATS: cross-warp reduction scratch of phases B and C
     float* qv;      // [DA]
     float* vv;      // [DA]
 };
@@ -146,12 +154,12 @@ __device__ __forceinline__ FwdSmem carve(float* sm) {
     s.bias = sm; sm += 32;
     s.bc = sm; sm += 8;
     s.xs = sm; sm += BT * XP;
-    s.red = sm; sm += NW * DD;
+    s.red = sm; sm += RED_FLOATS;
     s.qv = sm; sm += DA;
     s.vv = sm; sm += DA;
     return s;
 }
-constexpr int FWD_SMEM_FLOATS = GR * 2 * DD + CR * 2 * DD + GR * DE + 32 + 8 + BT * XP + NW * DD + 2 * DA;
+constexpr int FWD_SMEM_FLOATS = GR * 2 * DD + CR * 2 * DD + GR * DE + 32 + 8 + BT * XP + RED_FLOATS + 2 * DA;
 
 // ------------------------------------------------------------------------------------------------ phase A
 // Attention for item (clip b, frame range js) of step s in ONE pass over the frames: every warp keeps an online-softmax
@@ -237,9 +245,9 @@ __device__ void attn_item(const DecArgs& a, const FwdSmem& S, int s, int b, int 
         }
     }
     SUB_MARK(9);
-    float* part = S.red;                                        // NW x DD per-warp partial contexts
+    float* part = S.xs + DD;                                    // per-warp partial contexts: context columns of xs row `warp`
 #pragma unroll
-    for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(part + warp * DD + j * 128 + lane * 4) = cacc[j];
+    for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(part + warp * XP + j * 128 + lane * 4) = cacc[j];
     if (lane == 0) { wm[warp] = m; wl[warp] = l; }
     __syncthreads();
     float M = -INFINITY, L = 0.f, c0 = 0.f, c1 = 0.f;
@@ -250,7 +258,7 @@ __device__ void attn_item(const DecArgs& a, const FwdSmem& S, int s, int b, int 
         for (int w = 0; w < NW; ++w) {
             const float wgt = (wm[w] == -INFINITY) ? 0.f : expf(wm[w] - M);
             L = fmaf(wl[w], wgt, L);
-            const float2 pw = *reinterpret_cast<const float2*>(part + w * DD + 2 * tid);
+            const float2 pw = *reinterpret_cast<const float2*>(part + w * XP + 2 * tid);
             c0 = fmaf(pw.x, wgt, c0);
             c1 = fmaf(pw.y, wgt, c1);
         }
