@@ -36,6 +36,7 @@ constexpr int XP = 2 * DD + DE;        // per-clip state row in shared memory: [
 constexpr int XP4 = XP / 4;
 constexpr int KM4 = 2 * DD / 4;        // float4 columns of the main part (256 = one per thread)
 static_assert(KM4 <= NT, "one float4 column of [h|ctx] per thread of the first 8 warps");
+constexpr int TEAMS = NT / KM4;        // groups of 256 threads that split the clip groups of the GEMV phases (1 at 384 threads, 2 at 512)
 
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 
@@ -358,23 +359,24 @@ __device__ void finalize_step(const DecArgs& a, int s, int b, int eos_id) {
 // ------------------------------------------------------------------------------------------------ phase B
 // GRU cell for the CTA's 8 hidden units and the clips [bb0, bb0+nb) staged in xs.
 __device__ void gru_phase(const DecArgs& a, const FwdSmem& S, int s, int bb0, int nb) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int col = tid & (KM4 - 1), warp = col >> 5, team = tid / KM4;      // TEAMS groups of 256 threads share the clip groups
     const float4* xs4 = reinterpret_cast<const float4*>(S.xs);
     const float4* wg4 = reinterpret_cast<const float4*>(S.Wg);
     const int base = rs_base<UPC * 4>(lane);
 #pragma unroll 1
-    for (int cg = 0; cg < BT / 4; ++cg) {
-        if (cg * 4 >= nb || tid >= KM4) break;
+    for (int cg = team; cg < BT / 4; cg += TEAMS) {
+        if (cg * 4 >= nb || team >= TEAMS) break;
         float4 xv[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) xv[c] = xs4[(cg * 4 + c) * XP4 + tid];
+        for (int c = 0; c < 4; ++c) xv[c] = xs4[(cg * 4 + c) * XP4 + col];
         float* dst = S.red + (cg * 8 + warp) * (GR * 4) + base;
 #pragma unroll
         for (int g = 0; g < 3; ++g) {                  // one gate (8 rows x 4 clips) at a time keeps the register tile small
             float acc[UPC * 4];
 #pragma unroll
             for (int u = 0; u < UPC; ++u) {
-                const float4 w = wg4[(g * UPC + u) * KM4 + tid];
+                const float4 w = wg4[(g * UPC + u) * KM4 + col];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) acc[u * 4 + c] = dot4(w, xv[c]);
             }
@@ -422,22 +424,23 @@ __device__ void gru_phase(const DecArgs& a, const FwdSmem& S, int s, int bb0, in
 // ------------------------------------------------------------------------------------------------ phase C
 // logits and next query for the CTA's 7 rows and the clips staged in xs ([h' | ctx]).
 __device__ void out_phase(const DecArgs& a, const FwdSmem& S, int qslot, int bb0, int nb, bool only_q) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int col = tid & (KM4 - 1), warp = col >> 5, team = tid / KM4;
     const float4* xs4 = reinterpret_cast<const float4*>(S.xs);
     const float4* wc4 = reinterpret_cast<const float4*>(S.Wc);
     float4 wr[CR];
 #pragma unroll
-    for (int r = 0; r < CR; ++r) wr[r] = wc4[r * KM4 + (tid & (KM4 - 1))];
+    for (int r = 0; r < CR; ++r) wr[r] = wc4[r * KM4 + col];
     const int base = rs_base<32>(lane);
 #pragma unroll 1
-    for (int cg = 0; cg < BT / 4; ++cg) {
-        if (cg * 4 >= nb || tid >= KM4) break;
+    for (int cg = team; cg < BT / 4; cg += TEAMS) {
+        if (cg * 4 >= nb || team >= TEAMS) break;
         float acc[32];                                 // 8 rows (7 real) x 4 clips
 #pragma unroll
         for (int i = 0; i < 32; ++i) acc[i] = 0.f;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            const float4 x = xs4[(cg * 4 + c) * XP4 + tid];
+            const float4 x = xs4[(cg * 4 + c) * XP4 + col];
 #pragma unroll
             for (int r = 0; r < CR; ++r) acc[r * 4 + c] = dot4(wr[r], x);
         }
