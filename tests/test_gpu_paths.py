@@ -160,3 +160,52 @@ def test_colsum_tall_and_short(cuda, R, N):
     acc = torch.ones(N, device=cuda)
     ops.colsum(x.to(cuda), out=acc, accumulate=True)
     assert rel_err(acc, ref + 1.0) < 1e-6
+
+
+def test_full_size_training_step_properties(cuda):
+    """BASELINE configs[1] at full size (pretrain.yaml model, 16 clips x 1201 frames x 480 bins, targets of 40-80 / 20-50 tokens per
+    bar): size-independent properties of the step -- finite loss and gradients for every parameter, no grid-barrier watchdog,
+    the same loss when the step is replayed with the same coins and masks, executed decoder steps = the count derived from the
+    targets, and a loss that falls when Adadelta is applied to the same batch."""
+    import models
+    from piano_a2s_b200 import ops, train
+    from piano_a2s_b200.synthetic import executed_steps
+    torch.manual_seed(1234)
+    m = models.ScoreTranscription(max_length=(398, 189)).to(cuda).train()
+    gt_h = make_ground_truth(16, 5, 398, 189, seed=1234)
+    gt = train.targets_to_device(gt_h, cuda)
+    g = torch.Generator().manual_seed(5)
+    spec = torch.rand(16, 1, 1201, 480, generator=g).to(cuda)
+
+    def run(seed):
+        torch.manual_seed(seed)
+        random.seed(seed)
+        outs = m(spec, inference=False, ground_truth=gt, teacher_forcing_ratio=0.7, device=cuda)
+        loss, parts = train.compute_objectives(outs, gt)
+        return outs, loss, parts
+
+    outs, loss, parts = run(11)
+    assert [tuple(o.shape) for o in outs] == [(16, 5, 7), (16, 5, 14), (16, 5, 398, 173), (16, 5, 189, 173)]
+    steps = int(torch.stack(m.decoder.last_step_counters)[:, 1].sum().item())
+    assert steps == executed_steps(gt_h)
+    loss.backward()
+    ops.check_sync_flags()
+    assert torch.isfinite(loss).item() and all(torch.isfinite(p).item() for p in parts)
+    for k, p in m.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all().item(), k
+    # rows the decoder did not run stay zero (models.py:372: outputs are zero-initialised)
+    up = outs[2].detach()
+    n_up = int(gt_h[3][:, 0].max()) + 1
+    assert float(up[:, 0, n_up:].abs().max()) == 0.0 and float(up[:, 0, :n_up].abs().max()) > 0.0
+    # replay: same seeds -> same coins / dropout masks -> the same loss (split-K accumulation order may move the last bits)
+    m.zero_grad(set_to_none=True)
+    _, loss2, _ = run(11)
+    assert abs(loss2.item() - loss.item()) < 1e-5 * abs(loss.item())
+    # three Adadelta steps on this batch lower its loss
+    opt = train.FlatAdadelta(m)
+    torch.manual_seed(3)
+    random.seed(3)
+    first = train.fit_batch(m, opt, spec, gt, 0.7).item()
+    for _ in range(3):
+        last = train.fit_batch(m, opt, spec, gt, 0.7).item()
+    assert last < first
