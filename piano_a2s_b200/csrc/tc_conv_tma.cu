@@ -100,6 +100,19 @@ __global__ void __launch_bounds__(128 * ((C + 7) / 8)) planes_kernel(PlaneArgs a
     constexpr bool HALF = (C % 8) != 0;
     const int q = blockIdx.x * 128 + threadIdx.x, grp = threadIdx.y;
     const int tp = blockIdx.y, b = blockIdx.z;
+    // per-channel constants of the backward transform: staged once per CTA (7 x C floats) and read as warp-wide broadcasts instead
+    // of 7 global loads per element (48 -> 32 registers; measured: no change of the 1.03 ms of the 40-channel launch, which is
+    // bound by its three strided 32-byte-per-lane streams, not by these loads)
+    __shared__ float cs[MODE == 1 ? 7 : 1][NGR * 8];
+    if (MODE == 1) {
+        const int i = threadIdx.y * 128 + threadIdx.x;
+        if (i < 7 * NGR * 8) {
+            const int k = i / (NGR * 8), c = i % (NGR * 8);
+            const float* src = k == 0 ? a.c0 : k == 1 ? a.c1 : k == 2 ? a.c2 : k == 3 ? a.c3 : k == 4 ? a.c4 : k == 5 ? a.c5 : a.c6;
+            cs[k][c] = c < C ? __ldg(src + c) : 0.f;
+        }
+        __syncthreads();
+    }
     if (q >= a.g.FP) return;
     const int f = q - 2, t = tp - 1;
     float x[8];
@@ -132,10 +145,10 @@ __global__ void __launch_bounds__(128 * ((C + 7) / 8)) planes_kernel(PlaneArgs a
             for (int e = 0; e < 8; ++e) {
                 const int c = 8 * grp + e;
                 if (c < C) {
-                    const float z = fmaf(yy[e], __ldg(a.c0 + c), __ldg(a.c1 + c));
+                    const float z = fmaf(yy[e], cs[0][c], cs[1][c]);
                     const float gm = z > 0.f ? x[e] : 0.f;
-                    const float xh = (yy[e] - __ldg(a.c2 + c)) * __ldg(a.c3 + c);
-                    x[e] = __ldg(a.c4 + c) * (gm - __ldg(a.c5 + c) - xh * __ldg(a.c6 + c));
+                    const float xh = (yy[e] - cs[2][c]) * cs[3][c];
+                    x[e] = cs[4][c] * (gm - cs[5][c] - xh * cs[6][c]);
                 } else {
                     x[e] = 0.f;
                 }
