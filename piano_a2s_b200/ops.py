@@ -9,6 +9,7 @@ import collections
 import contextlib
 import ctypes
 import os
+import sys
 from typing import Optional
 
 import torch
@@ -433,21 +434,31 @@ class ConvStackFn(torch.autograd.Function):
             lib.pa2s_colstats(st, 1, ptr(Y), ptr(G), ptr(mask), npix, C, ptr(aff[0]), ptr(aff[1]), ptr(aff[2]), ptr(aff[3]),
                               ptr(partial), nct)
             sums = _bn_sums(partial, C)
+            local = None
             if world > 1:
+                # SyncBatchNorm: the input gradient uses the sums over ALL ranks, dgamma / dbeta stay this rank's sums (the gradient
+                # all-reduce averages them afterwards, like torch.nn.SyncBatchNorm under DDP): keep them before the all-reduce
+                local = sums.to(F32)
                 dist.all_reduce(sums)
             dg = torch.zeros(C, device=dev, dtype=F32)
             db = torch.zeros(C, device=dev, dtype=F32)
             k = torch.empty(3, C, device=dev, dtype=F32)
             lib.pa2s_bn_bwd_finalize(st, ptr(sums), float(npix * world), C, ptr(gamma), ptr(aff[3]), ptr(dg), ptr(db),
                                      ptr(k[0]), ptr(k[1]), ptr(k[2]))
-            if world > 1:      # DDP averages parameter gradients afterwards; local grads must be the local sums
-                pass
+            if local is not None:
+                dg, db = local[C:].contiguous(), local[:C].contiguous()
+                if os.environ.get("PA2S_CHECK_LOCAL_BN") == "1":
+                    # debug: a second pass over the tensors must give the same numbers (up to the order of colstats' shared-memory atomics)
+                    dg2, db2 = _local_bn_param_grads(Y, G, mask, aff, npix, C, nct, dev)
+                    err = max(float((dg - dg2).abs().max() / dg2.abs().max().clamp_min(1e-30)),
+                              float((db - db2).abs().max() / db2.abs().max().clamp_min(1e-30)))
+                    print(f"PA2S_CHECK_LOCAL_BN C={C}: max relative difference {err:.2e}", file=sys.stderr)
+                    if not err < 1e-5:
+                        raise RuntimeError("SyncBatchNorm backward: local dgamma/dbeta differ from the recomputed sums")
             return dg, db, k
 
         # out_bn + relu + dropout backward
         dg5, db5, k5 = bn_bwd_consts(z, dout, mk, aff5, gam[4], M, O)
-        if world > 1:
-            dg5, db5 = _local_bn_param_grads(z, dout, mk, aff5, M, O, nct, dev)
         grads[13], grads[14] = dg5, db5
         dz = torch.empty(M, O, device=dev, dtype=F32)
         lib.pa2s_bn_bwd_apply(st, ptr(dout), ptr(z), ptr(mk), M, O, ptr(aff5[0]), ptr(aff5[1]), ptr(aff5[2]), ptr(aff5[3]),
@@ -480,8 +491,6 @@ class ConvStackFn(torch.autograd.Function):
             y, aff = ys[i], affs[i]
             npix = B * T * Fq
             dg, db, k = bn_bwd_consts(y, G, None, aff, gam[i], npix, Cout)
-            if world > 1:
-                dg, db = _local_bn_param_grads(y, G, None, aff, npix, Cout, nct, dev)
             grads[3 * i + 1], grads[3 * i + 2] = dg, db
             xin = ys[i - 1] if i > 0 else spec
             isc = affs[i - 1][0] if i > 0 else None
