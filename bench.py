@@ -130,9 +130,49 @@ def cpu_step_factory(n_clips):
     return step, torch.get_num_threads()
 
 
+def cpu_infer_factory(n_clips):
+    """BASELINE configs[0]: `n_clips` synthetic 12-s clips through the float64 VQT oracle and the oracle's greedy hierarchical decode
+    (eval mode, no_grad), on all host threads torch can use."""
+    import numpy as np
+    import torch
+    import models
+    from oracle import a2s_oracle as O
+    from oracle import vqt_oracle as VO
+    from piano_a2s_b200.synthetic import make_audio
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(1234)
+    sd = {k: v.clone() for k, v in models.ScoreTranscription(**CFG).state_dict().items()}
+    audio = make_audio(n_clips, N_SAMPLES, seed=1234).numpy()
+
+    def step():
+        with torch.no_grad():
+            spec = torch.from_numpy(np.stack([VO.get_vqt(a) for a in audio])).unsqueeze(1)
+            outs = O.score_transcription(sd, spec, CFG)
+            return O.greedy_tokens(outs)
+    return step, torch.get_num_threads()
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
+        return
+    if args.workload == "infer":
+        step, threads = cpu_infer_factory(args.cpu_clips)
+        for _ in range(min(args.warmup, 1)):
+            step()
+        t0 = time.time()
+        for _ in range(args.steps):
+            step()
+        dt = time.time() - t0
+        v = args.cpu_clips * args.steps / dt
+        sample = f"{args.cpu_clips} clip(s)/step, greedy decode of all 5 x (398 + 189) note steps (oracle port of the reference, torch CPU fp32 + float64 numpy VQT)"
+        print(json.dumps({
+            "impl": "reference", "metric": "clips_per_sec_greedy_decode", "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[0]: single synthetic 12-s clip, random-init model, VQT + encoder + greedy hierarchical decode on CPU", "sample": sample},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
         return
     step, threads = cpu_step_factory(args.cpu_clips)
     for _ in range(min(args.warmup, 1)):
@@ -377,6 +417,15 @@ def run_b200_infer(args):
         except Exception:
             pass
         roof, roof_all = roofline({k: v for k, v in ktimes.items() if k.startswith("note_decoder")}, B, peaks, S, n_dec=10)
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cstep, threads = cpu_infer_factory(args.cpu_clips)
+            t0 = time.time()
+            cstep()
+            dt = time.time() - t0
+            cpu = {"value": args.cpu_clips / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": f"{args.cpu_clips} clip(s), greedy decode of the same workload through the oracle port (torch CPU fp32 + float64 "
+                             f"numpy VQT), {dt:.1f} s"}
         print(json.dumps({
             "metric": "clips_per_sec_greedy_decode", "value": clips / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -390,7 +439,7 @@ def run_b200_infer(args):
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "clocks": sampler.summary(w0, w2),
             "roofline": roof, "roofline_all": [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items()} for r in roof_all],
-            "cpu_baseline": None}), flush=True)
+            "cpu_baseline": cpu}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
