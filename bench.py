@@ -6,6 +6,7 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W                         (N>1, NCCL)
     python bench.py --impl reference ...                               (the reference's CPU path: the oracle port)
+    python bench.py --workload infer [--impl reference]                (BASELINE configs[4] / [0]: batched greedy decode; not the headline)
 
 Workload = BASELINE.json configs[1]: pretrain.yaml model (random init, seed 1234), synthetic 12-s clips, batch 16 per
 GPU, fp32, teacher forcing 0.7, targets U[40,80)/U[20,50) tokens per bar.  Weak scaling: per-GPU batch is

@@ -65,6 +65,33 @@ def _worker(rank, world, port, q):
         dist.all_gather(gathered, pad)
         union = torch.cat([gathered[r][: 5 + r] for r in range(world)])
         ok = ok and torch.allclose(mean, union.mean(0)) and torch.allclose(var, union.var(0, unbiased=False))
+        # SyncBatchNorm BACKWARD arithmetic as ops.ConvStackFn does it: every rank forms (sum g, sum g*xhat) with the GLOBAL statistics,
+        # keeps them as ITS dbeta / dgamma (the gradient all-reduce averages them afterwards), all-reduces a copy and uses the global
+        # sums for the input gradient.  Checked against autograd through a plain BatchNorm over the union with loss = mean of the
+        # per-rank losses (DDP semantics): averaged dgamma/dbeta equal the union's, and dx equals world * the union's dx.
+        eps = 1e-5
+        gamma = torch.tensor([0.7, -1.3, 2.0, 0.4], dtype=torch.float64)
+        beta = torch.tensor([0.1, 0.0, -0.2, 0.3], dtype=torch.float64)
+        wgt = torch.randn(6, 4, dtype=torch.float64, generator=torch.Generator().manual_seed(9))       # loss_r = sum(relu(bn(x_r)) * wgt_r)
+        invstd = 1.0 / torch.sqrt(var + eps)
+        xhat = (x - mean) * invstd
+        ypre = xhat * gamma + beta
+        g = wgt[: x.shape[0]] * (ypre > 0)                                       # dloss_r / d bn output (ReLU mask folded in)
+        local = torch.cat([g.sum(0), (g * xhat).sum(0)])
+        glob = local.clone()
+        dist.all_reduce(glob)
+        dx = gamma * invstd * (g - glob[:4] / n - xhat * (glob[4:] / n))
+        grads = local.clone()
+        dist.all_reduce(grads)
+        grads /= world                                                           # what FlatAdadelta.allreduce_mean does to dbeta, dgamma
+        xu = union.clone().requires_grad_(True)
+        gu, bu = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+        yu = torch.relu(torch.nn.functional.batch_norm(xu, None, None, gu, bu, True, 0.0, eps))
+        wu = torch.cat([wgt[: 5 + r] for r in range(world)])
+        ((yu * wu).sum() / world).backward()
+        lo = sum(5 + r for r in range(rank))
+        ok = ok and torch.allclose(grads[:4], bu.grad) and torch.allclose(grads[4:], gu.grad)
+        ok = ok and torch.allclose(dx, world * xu.grad[lo: lo + x.shape[0]])
         # per-rank synthetic shards differ (seed = base + rank, as bench.py does)
         g = make_ground_truth(2, 2, 14, 9, seed=1234 + rank, lo_up=(3, 13), lo_lo=(2, 9))
         tok = [torch.zeros_like(g[2]) for _ in range(world)]
