@@ -81,8 +81,8 @@ class ScoreTranscription(nn.Module):
                 # executed decoder steps per (staff, bar) are a function of the targets alone: fetch them on a side stream now,
                 # so that the one host read the decoder needs does not wait for the ConvStack / encoder kernels queued below
                 self.decoder.prefetch_steps(ground_truth)
-            if torch.is_grad_enabled() and spectrogram.is_cuda:
-                self.decoder._presunk = self.decoder.weight_sinks()
+            # (always reassigned: a forward that raised before the decoder must not leave its aliases to the next graph)
+            self.decoder._presunk = self.decoder.weight_sinks() if (torch.is_grad_enabled() and spectrogram.is_cuda) else None
             conv_outputs = self.convstack(spectrogram)                   # (B, T, conv_feature_size)
             encoder_outputs, hidden = self.encoder(conv_outputs)         # (B, T, 2H), (1, B, 2H)
             return self.decoder(encoder_outputs, hidden, inference, ground_truth, teacher_forcing_ratio, device)
