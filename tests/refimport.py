@@ -67,3 +67,60 @@ def reference_dataset_stub(max_frame_num=1201, device="cpu"):
     ds.device = device
     ds.labels = mod.LabelsMultiple(extended=True)
     return ds
+
+
+def import_reference_trainer(name="pretrain"):
+    """The reference's `pretrain.py` / `finetune.py` as a module, with the packages its top-level imports need but the functions
+    under test never touch replaced by stubs when absent (speechbrain, hyperpyyaml, jiwer, pretty_midi, librosa, mido, music21).
+    `speechbrain.Brain` becomes a plain base class and `speechbrain.Stage` an enum with TRAIN / VALID / TEST."""
+    import enum
+    key = f"ref_{name}"
+    if key in sys.modules:
+        return sys.modules[key]
+
+    def stub(modname, **attrs):
+        if modname in sys.modules:
+            return sys.modules[modname]
+        try:
+            return importlib.import_module(modname)
+        except Exception:
+            m = types.ModuleType(modname)
+            for k, v in attrs.items():
+                setattr(m, k, v)
+            sys.modules[modname] = m
+            return m
+
+    class Stage(enum.Enum):
+        TRAIN, VALID, TEST = 1, 2, 3
+
+    sb = stub("speechbrain", Brain=type("Brain", (), {}), Stage=Stage)
+    utils = stub("speechbrain.utils")
+    distm = stub("speechbrain.utils.distributed", run_on_main=lambda f, *a, **k: f(*a, **k), if_main_process=lambda: True)
+    if not hasattr(sb, "utils"):
+        sb.utils = utils
+    if not hasattr(utils, "distributed"):
+        utils.distributed = distm
+    stub("hyperpyyaml", load_hyperpyyaml=None)
+    stub("jiwer", wer=None)
+    for n, a in (("music21", {}), ("pretty_midi", {}), ("librosa", {}), ("mido", {"MidiFile": object})):
+        stub(n, **a)
+    saved_path = list(sys.path)
+    saved = {k: sys.modules.pop(k, None) for k in ("data_processing", "datasets", "utilities")}
+    sys.path.insert(0, REF_ROOT)
+    # the reference's `datasets/` has no __init__.py: an installed `datasets` distribution would win over the namespace package
+    pkg = types.ModuleType("datasets")
+    pkg.__path__ = [os.path.join(REF_ROOT, "datasets")]
+    sys.modules["datasets"] = pkg
+    try:
+        spec = importlib.util.spec_from_file_location(key, os.path.join(REF_ROOT, f"{name}.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        sys.modules[key] = mod
+    finally:
+        sys.path[:] = saved_path
+        for k in [m for m in sys.modules if m == "datasets" or m.startswith("datasets.")] + ["data_processing", "utilities"]:
+            sys.modules.pop(k, None)
+        for k, v in saved.items():
+            if v is not None:
+                sys.modules[k] = v
+    return mod
