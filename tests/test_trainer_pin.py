@@ -111,3 +111,35 @@ def test_optimizer_step_matches_torch_clip_and_adadelta():
         assert abs(float(total) - float(total_ref)) <= 1e-6 * float(total_ref)
         for i, p in enumerate(ref_params):
             assert torch.allclose(mine[str(i)], p.detach(), rtol=1e-6, atol=1e-7), (step, i)
+
+
+@pytest.mark.parametrize("script", ["pretrain", "finetune"])
+def test_reference_call_site_binds_to_the_drop_in_forward(script):
+    """The keyword arguments the reference's `ASR.compute_forward` passes (pretrain.py:41-53, finetune.py:40-52) bind to the
+    drop-in `models.ScoreTranscription.forward` in both stages, with the values the reference uses."""
+    import inspect
+    import models
+    from refimport import import_reference_trainer
+    mod = import_reference_trainer(script)
+    sb = __import__("speechbrain")
+    calls = []
+
+    def transcription(**kw):
+        calls.append(kw)
+        return tuple(torch.zeros(1) for _ in range(4))
+    asr = object.__new__(mod.ASR)
+    asr.modules = types.SimpleNamespace(transcription=transcription)
+    asr.teacher_forcing_ratio, asr.device = 0.7, "cuda:0"                     # pretrain.py keeps the (decaying) ratio on the Brain,
+    asr.hparams = types.SimpleNamespace(teacher_forcing_ratio=0.7)            # finetune.py reads it from the hparams
+    _, gt, batch = _batch()
+    mod.ASR.compute_forward(asr, batch, sb.Stage.TRAIN)
+    mod.ASR.compute_forward(asr, batch, sb.Stage.VALID)
+    sig = inspect.signature(models.ScoreTranscription.forward)
+    for kw in calls:
+        bound = sig.bind(None, **kw)                                          # raises TypeError on an unknown / missing argument
+        assert set(kw) == {"spectrogram", "inference", "ground_truth", "teacher_forcing_ratio", "device"}
+        assert bound.arguments["device"] == "cuda:0"
+    train, valid = calls
+    assert train["inference"] is False and train["teacher_forcing_ratio"] == 0.7 and len(train["ground_truth"]) == 6
+    assert all(a is b for a, b in zip(train["ground_truth"], gt)) or all(torch.equal(a, b) for a, b in zip(train["ground_truth"], gt))
+    assert valid["inference"] is True and valid["ground_truth"] is None and valid["teacher_forcing_ratio"] == 0.
