@@ -846,8 +846,8 @@ class NoteDecoderFn(torch.autograd.Function):
 
     @staticmethod
     def launch_backward(ctx, dlogp):
-        """Enqueues the whole backward of this call on the stream its forward ran on -> (input gradients, completion event or
-        None).  Called by backward(), or ahead of it by StackLogpFn.backward as soon as the loss gradient exists."""
+        """Enqueues the whole backward of this call on the stream its forward ran on -> (input gradients, [completion events]).
+        Called by backward(), or ahead of it by StackLogpFn.backward as soon as the loss gradient exists."""
         side = ctx.side
         with use_precision(ctx.prec):
             if side is None:
@@ -1013,9 +1013,10 @@ class DecoderGradSink:
 class DecoderWeightSinkFn(torch.autograd.Function):
     """Identity on the nine NoteDecoder weights.  Every NoteDecoderFn call that uses the returned aliases hands its weight
     gradients here as saved rows instead of computing them: autograd runs this node after the last of those calls, and the
-    gradients are then ONE set of contractions over all bars (K = sum of S*B) on the stream the forward ran on.  Besides the
-    5x fewer small GEMMs this keeps parameter-gradient accumulation off the two decoder streams, where autograd's
-    AccumulateGrad (pinned to the stream of a parameter's first use) serialised the two staves of every other bar."""
+    gradients are then ONE set of contractions over all bars (K = sum of S*B) -- enqueued on a side stream by StackLogpFn right
+    behind the last decoder backward kernel (DecoderGradSink.launch), or here on the current stream when nothing was enqueued
+    ahead.  Besides the 5x fewer small GEMMs this keeps parameter-gradient accumulation off the two decoder streams, where
+    autograd's AccumulateGrad (pinned to the stream of a parameter's first use) serialised the two staves of every other bar."""
 
     @staticmethod
     def forward(ctx, sink, *weights):
