@@ -53,9 +53,10 @@ def test_loss_matches_reference_compute_objectives(script):
     assert abs(sum(parts) - float(mine)) < 1e-5
 
 
-def test_validation_records_match_oracle_tokens():
+@pytest.mark.parametrize("script", ["pretrain", "finetune"])
+def test_validation_records_match_oracle_tokens(script):
     from refimport import import_reference_trainer
-    mod = import_reference_trainer("pretrain")
+    mod = import_reference_trainer(script)
     sb = __import__("speechbrain")
     preds, gt, batch = _batch(seed=6)
     # make some predicted rows end early: put <eos> as the argmax at a few positions
@@ -65,7 +66,7 @@ def test_validation_records_match_oracle_tokens():
     mod.ASR.compute_objectives(asr, tuple(preds), batch, sb.Stage.VALID)
     want = O.greedy_tokens(preds)
     for b in range(3):
-        rid = "~".join([str(b), f"song{b}"])
+        rid = "~".join([str(b), f"song{b}"]) if script == "pretrain" else f"song{b}"       # pretrain.py:99 / finetune.py:89
         assert asr.upper_pred[rid] == want["upper"][b] and asr.lower_pred[rid] == want["lower"][b]
         assert asr.key_pred[rid] == want["key"][b] and asr.time_sig_pred[rid] == want["time_sig"][b]
         assert asr.upper_target[rid] == [O.unpad(r) for r in gt[2][b].tolist()]
