@@ -139,6 +139,13 @@ class FlatAdadelta:
         return self.norm
 
 
+def teacher_forcing_schedule(ratio: float, decay: float, epoch: int, training: bool = True) -> float:
+    """`on_stage_start` of pretrain.py:149-153: the ratio decays exponentially with the epoch in training
+    (`teacher_forcing_ratio * teacher_forcing_decay ** epoch`, pretrain.yaml:41-42: 0.7, 0.99) and is 0 in validation / test.
+    finetune.py uses the constant `hparams.teacher_forcing_ratio` (0.6): pass decay = 1."""
+    return ratio * decay ** epoch if training else 0.
+
+
 def fit_batch(model, optimizer: FlatAdadelta, spectrogram, ground_truth, teacher_forcing_ratio):
     """One training step (pretrain.py:121-129).  Returns the detached loss tensor (no host sync)."""
     preds = model(spectrogram=spectrogram, inference=False, ground_truth=ground_truth,

@@ -144,3 +144,21 @@ def test_reference_call_site_binds_to_the_drop_in_forward(script):
     assert train["inference"] is False and train["teacher_forcing_ratio"] == 0.7 and len(train["ground_truth"]) == 6
     assert all(a is b for a, b in zip(train["ground_truth"], gt)) or all(torch.equal(a, b) for a, b in zip(train["ground_truth"], gt))
     assert valid["inference"] is True and valid["ground_truth"] is None and valid["teacher_forcing_ratio"] == 0.
+
+
+def test_teacher_forcing_schedule_matches_reference_on_stage_start():
+    """pretrain.py:149-153, executed live on a stub Brain for a few epochs and both stages."""
+    from refimport import import_reference_trainer
+    from piano_a2s_b200.train import teacher_forcing_schedule
+    mod = import_reference_trainer("pretrain")
+    sb = __import__("speechbrain")
+    asr = _brain(mod)
+    asr.hparams.teacher_forcing_ratio, asr.hparams.teacher_forcing_decay = 0.7, 0.99
+    mod.load = lambda path: []                                                # on_stage_start also reads a metadata json (pretrain.py:148)
+    for epoch in (0, 1, 7, 29):
+        mod.ASR.on_stage_start(asr, sb.Stage.TRAIN, epoch)
+        assert asr.teacher_forcing_ratio == teacher_forcing_schedule(0.7, 0.99, epoch)
+    asr.hparams.output_folder = "/tmp/pa2s_pin_out"
+    mod.mkdirs = lambda *a, **k: None
+    mod.ASR.on_stage_start(asr, sb.Stage.VALID, 3)
+    assert asr.teacher_forcing_ratio == teacher_forcing_schedule(0.7, 0.99, 3, training=False) == 0.
