@@ -5,8 +5,12 @@
     python bench.py --gpus 1 --steps K --warmup W                      (N=1)
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W                         (N>1, NCCL)
-    python bench.py --impl reference ...                               (the reference's CPU path: the oracle port)
+    python bench.py --impl reference ...                               (the reference's own CPU path: oracle/_ref, else the oracle port)
+    python bench.py --impl reference-gpu ...                           (same-box GPU baseline: the unmodified reference module on stock
+                                                                        PyTorch / cuDNN / cuBLAS on the B200; builder-run, profiles/)
     python bench.py --workload infer [--impl reference]                (BASELINE configs[4] / [0]: batched greedy decode; not the headline)
+    python bench.py --workload finetune                                (configs[3]: finetune.yaml, ragged U[4 s,12 s] clips, tf 0.6, bf16)
+    python bench.py --precision bf16                                   (configs[2]: bf16 contractions; default bf16x3 = fp32-accurate split)
 
 Workload = BASELINE.json configs[1]: pretrain.yaml model (random init, seed 1234), synthetic 12-s clips, batch 16 per
 GPU, fp32, teacher forcing 0.7, targets U[40,80)/U[20,50) tokens per bar.  Weak scaling: per-GPU batch is
@@ -36,21 +40,57 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="train", choices=["train", "infer"],
-                    help="train = BASELINE configs[1] (the headline metric); infer = configs[4], batched greedy decode (evaluate path)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference-gpu"])
+    ap.add_argument("--workload", default="train", choices=["train", "finetune", "infer"],
+                    help="train = BASELINE configs[1] (the headline metric); finetune = configs[3] (finetune.yaml: ragged real-audio-shaped "
+                         "clips, teacher forcing 0.6); infer = configs[4], batched greedy decode (evaluate path)")
+    ap.add_argument("--precision", default=None, choices=["fp32", "bf16x3", "bf16"],
+                    help="contraction precision of the training step: bf16x3 (default for train: fp32 operands as two bf16 pieces, fp32 "
+                         "TMEM accumulation, 1e-4 parity) or bf16 (BASELINE configs[2..3]; default for finetune)")
+    ap.add_argument("--also-steps", type=int, default=5, help="steps of the secondary bf16 measurement in the default headline line (0 = off)")
     ap.add_argument("--batch", type=int, default=None, help="clips per GPU per step (default 16 for train, 32 for infer)")
     ap.add_argument("--cpu-clips", type=int, default=1, help="clips per step of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
     if a.batch is None:
-        a.batch = 16 if a.workload == "train" else 32
+        a.batch = 32 if a.workload == "infer" else 16
+    if a.precision is None:
+        a.precision = "bf16" if a.workload == "finetune" else "bf16x3"
     return a
 
 
-def workload_name(batch):
+PRECISION_NOTE = {
+    "bf16x3": "fp32 tensors; contractions on tcgen05 with every fp32 operand split into two bf16 pieces (hi*hi + hi*lo + lo*hi, fp32 TMEM "
+              "accumulation): fp32-level results (1e-4 parity with the fp32 reference)",
+    "bf16": "fp32 master tensors; contractions on tcgen05 with single bf16 operands, fp32 accumulation (BASELINE configs[2..3])",
+    "fp32": "exact-fp32 FFMA kernels (the eval / greedy-decode mode)"}
+DTYPE = {"bf16x3": "f32 (bf16x3 split operands, fp32 accumulate)", "bf16": "bf16", "fp32": "f32"}
+
+
+def tf_ratio(workload):
+    return 0.6 if workload == "finetune" else TF_RATIO          # finetune.yaml: constant 0.6; pretrain.yaml:41: 0.7
+
+
+def workload_name(batch, workload="train", precision="bf16x3"):
+    if workload == "finetune":
+        return (f"BASELINE configs[3]: finetune.yaml model (same architecture as pretrain.yaml), synthetic real-audio-shaped clips: lengths "
+                f"U[4 s,12 s] (asap.py:101), peak-normalised, frames beyond the clip zero-padded to 1201 (asap.py:345-349), batch {batch}/GPU, "
+                f"one fwd+bwd training step + clip + Adadelta, {precision}, teacher_forcing 0.6")
     return (f"pretrain.yaml model, synthetic 12-s clips ({N_SAMPLES} samples @16 kHz -> 1201x480 VQT), batch {batch}/GPU, "
-            f"one fwd+bwd training step + clip + Adadelta, fp32, teacher_forcing {TF_RATIO}")
+            f"one fwd+bwd training step + clip + Adadelta, {precision}, teacher_forcing {TF_RATIO}")
+
+
+def make_ragged_audio(B, seed):
+    """configs[3]: clip lengths U[4 s, 12 s] (the ASAP duration filter, asap.py:100-102), peak-normalised (asap.py:86), zero-padded to the
+    12-s buffer -> (audio (B, N_SAMPLES) float32, n_samples (B,) int64)."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    n = torch.randint(4 * 16000, 12 * 16000 + 1, (B,), generator=g)
+    a = torch.clamp(0.25 * torch.randn(B, N_SAMPLES, generator=g), -1.0, 1.0)
+    for b in range(B):
+        a[b, int(n[b]):] = 0.
+        a[b] /= a[b].abs().max()
+    return a, n
 
 
 # ---------------------------------------------------------------------------------------------- clocks
@@ -101,96 +141,168 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ---------------------------------------------------------------------------------------------- CPU arm (oracle port)
-def cpu_step_factory(n_clips):
-    """One bounded CPU sample of the same workload: `n_clips` clips through the float64 VQT oracle and the oracle's
-    fwd + 4xNLL + backward + clip/Adadelta, on all host threads torch can use."""
+# ---------------------------------------------------------------------------------------------- reference arms
+def _reference_module():
+    """(reference `models` module or None, kind): the unmodified reference compiled into oracle/_ref by oracle/build_ref.py, else None
+    (-> the oracle port)."""
+    from oracle import build_ref
+    if build_ref.available():
+        return build_ref.load(), "reference"
+    return None, "port"
+
+
+def _synthetic_inputs(n_clips, workload, device="cpu", with_vqt=True):
+    """Spectrogram factory + targets of the workload.  The VQT stage of the CPU arms is the float64 numpy restatement of librosa.vqt
+    (librosa / soxr are not installed; the reference computes it offline on the CPU, utilities.py:240-254); the GPU-baseline arm is fed
+    cached spectrograms like the reference's own training loop (datasets/syn.py:99-100)."""
     import numpy as np
+    import torch
+    from oracle import vqt_oracle as VO
+    from piano_a2s_b200.synthetic import make_audio, make_ground_truth
+    gt = make_ground_truth(n_clips, 5, 398, 189, seed=1234)
+    if workload == "finetune":
+        audio, n = make_ragged_audio(n_clips, seed=1234)
+        clips = [audio[b, :int(n[b])].numpy() for b in range(n_clips)]
+    else:
+        clips = list(make_audio(n_clips, N_SAMPLES, seed=1234).numpy())
+
+    def spectrogram():
+        out = torch.zeros(n_clips, 1, 1201, 480)
+        for b, a in enumerate(clips):
+            v = torch.from_numpy(VO.get_vqt(a))
+            out[b, 0, :v.shape[0]] = v
+        return out
+    if not with_vqt:
+        cached = spectrogram().to(device)
+        return (lambda: cached), [t.to(device) for t in gt]
+    return spectrogram, gt
+
+
+def reference_step_factory(n_clips, workload="train", device="cpu", with_vqt=True):
+    """One bounded sample of the training workload through the REFERENCE's own code when oracle/_ref exists: its `ScoreTranscription`
+    (train mode, python-`random` teacher forcing), the 4 NLL losses of pretrain.py:56-93, backward, `clip_grad_norm_(5.0)` and
+    `torch.optim.Adadelta(lr=1, rho=.95, eps=1e-8)` (pretrain.yaml:44-47) -- on `device` ("cpu": all host threads; "cuda": stock
+    PyTorch / cuDNN / cuBLAS, the same-box GPU baseline).  Without oracle/_ref: the oracle port (CPU only).  -> (step, threads, kind)."""
     import torch
     import models
     from oracle import a2s_oracle as O
-    from oracle import vqt_oracle as VO
-    from piano_a2s_b200.synthetic import make_audio, make_ground_truth
     torch.set_num_threads(os.cpu_count() or 1)
+    ref, kind = _reference_module()
+    spectrogram, gt = _synthetic_inputs(n_clips, workload, device, with_vqt)
+    tf = tf_ratio(workload)
+    dev = torch.device(device)
     torch.manual_seed(1234)
+    if ref is not None:
+        model = ref.ScoreTranscription(**CFG).to(dev).train()
+        opt = torch.optim.Adadelta(model.parameters(), lr=1.0, rho=0.95, eps=1e-8)
+
+        def step():
+            outs = model(spectrogram=spectrogram().to(dev), inference=False, ground_truth=gt, teacher_forcing_ratio=tf, device=dev)
+            loss = O.training_loss(outs, gt)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(model.parameters(), 5.0)
+            opt.step()
+            opt.zero_grad()
+            return float(loss.detach())          # the reference reads its losses back every step (pretrain.py:90-93)
+        return step, torch.get_num_threads(), kind
+    if dev.type != "cpu":
+        raise RuntimeError("the GPU baseline needs oracle/_ref (python -m oracle.build_ref where /root/reference exists)")
     sd = {k: v.clone() for k, v in models.ScoreTranscription(**CFG).state_dict().items()}
     params = {k: v.requires_grad_(True) for k, v in sd.items() if v.dtype == torch.float32 and "running" not in k}
     state = {k: (torch.zeros_like(v), torch.zeros_like(v)) for k, v in params.items()}
-    audio = make_audio(n_clips, N_SAMPLES, seed=1234).numpy()
-    gt = make_ground_truth(n_clips, 5, 398, 189, seed=1234)
 
     def step():
-        spec = torch.from_numpy(np.stack([VO.get_vqt(a) for a in audio])).unsqueeze(1)
-        outs = O.score_transcription(sd, spec, CFG, False, gt, TF_RATIO, True)
+        outs = O.score_transcription(sd, spectrogram(), CFG, False, gt, tf, True)
         loss = O.training_loss(outs, gt)
         grads = dict(zip(params.keys(), torch.autograd.grad(loss, list(params.values()), allow_unused=True)))
         grads = {k: (g if g is not None else torch.zeros_like(params[k])) for k, g in grads.items()}
         with torch.no_grad():
             O.adadelta_step(params, grads, state)
         return float(loss.detach())
-    return step, torch.get_num_threads()
+    return step, torch.get_num_threads(), kind
 
 
-def cpu_infer_factory(n_clips):
-    """BASELINE configs[0]: `n_clips` synthetic 12-s clips through the float64 VQT oracle and the oracle's greedy hierarchical decode
-    (eval mode, no_grad), on all host threads torch can use."""
-    import numpy as np
+def reference_infer_factory(n_clips, device="cpu", with_vqt=True):
+    """BASELINE configs[0] / [4]: greedy hierarchical decode (eval mode, no_grad) of `n_clips` synthetic 12-s clips through the reference
+    module (oracle/_ref) or the oracle port, + argmax / unpad token lists on the host.  -> (step, threads, kind)."""
     import torch
     import models
     from oracle import a2s_oracle as O
-    from oracle import vqt_oracle as VO
-    from piano_a2s_b200.synthetic import make_audio
     torch.set_num_threads(os.cpu_count() or 1)
+    ref, kind = _reference_module()
+    spectrogram, _ = _synthetic_inputs(n_clips, "train", device, with_vqt)
+    dev = torch.device(device)
     torch.manual_seed(1234)
+    if ref is not None:
+        model = ref.ScoreTranscription(**CFG).to(dev).eval()
+
+        def step():
+            with torch.no_grad():
+                outs = model(spectrogram=spectrogram().to(dev), inference=True, ground_truth=None, teacher_forcing_ratio=0., device=dev)
+                return O.greedy_tokens([o.cpu() for o in outs])
+        return step, torch.get_num_threads(), kind
+    if dev.type != "cpu":
+        raise RuntimeError("the GPU baseline needs oracle/_ref (python -m oracle.build_ref where /root/reference exists)")
     sd = {k: v.clone() for k, v in models.ScoreTranscription(**CFG).state_dict().items()}
-    audio = make_audio(n_clips, N_SAMPLES, seed=1234).numpy()
 
     def step():
         with torch.no_grad():
-            spec = torch.from_numpy(np.stack([VO.get_vqt(a) for a in audio])).unsqueeze(1)
-            outs = O.score_transcription(sd, spec, CFG)
-            return O.greedy_tokens(outs)
-    return step, torch.get_num_threads()
+            return O.greedy_tokens(O.score_transcription(sd, spectrogram(), CFG))
+    return step, torch.get_num_threads(), kind
+
+
+def _kind_text(kind):
+    return ("the unmodified reference module (oracle/_ref, compiled from /root/reference)" if kind == "reference"
+            else "oracle port of the reference")
 
 
 def run_reference(args):
+    """--impl reference: the reference's CPU path on the box's host cores.  --impl reference-gpu: the same module on the B200 with stock
+    PyTorch kernels (same-box GPU baseline, SURVEY 8d last line)."""
+    import torch
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    if args.workload == "infer":
-        step, threads = cpu_infer_factory(args.cpu_clips)
-        for _ in range(min(args.warmup, 1)):
-            step()
-        t0 = time.time()
-        for _ in range(args.steps):
-            step()
-        dt = time.time() - t0
-        v = args.cpu_clips * args.steps / dt
-        sample = f"{args.cpu_clips} clip(s)/step, greedy decode of all 5 x (398 + 189) note steps (oracle port of the reference, torch CPU fp32 + float64 numpy VQT)"
-        print(json.dumps({
-            "impl": "reference", "metric": "clips_per_sec_greedy_decode", "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "BASELINE configs[0]: single synthetic 12-s clip, random-init model, VQT + encoder + greedy hierarchical decode on CPU", "sample": sample},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
-            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
-        return
-    step, threads = cpu_step_factory(args.cpu_clips)
-    for _ in range(min(args.warmup, 1)):
+    gpu = args.impl == "reference-gpu"
+    device = "cuda" if gpu else "cpu"
+    n = args.batch if gpu else args.cpu_clips
+    infer = args.workload == "infer"
+    if infer:
+        step, threads, kind = reference_infer_factory(n, device, with_vqt=not gpu)
+        metric = "clips_per_sec_greedy_decode"
+        workload = ("BASELINE configs[4]: batched greedy hierarchical decode, eval mode" if gpu else
+                    "BASELINE configs[0]: single synthetic 12-s clip, random-init model, VQT + encoder + greedy hierarchical decode on CPU")
+        what = "greedy decode of all 5 x (398 + 189) note steps"
+    else:
+        step, threads, kind = reference_step_factory(n, args.workload, device, with_vqt=not gpu)
+        metric = METRIC
+        workload = workload_name(args.batch, args.workload, "fp32" if not gpu else "fp32 (stock PyTorch, TF32 off)")
+        what = "one fwd+bwd+clip+Adadelta step of the same workload"
+    sync = torch.cuda.synchronize if gpu else (lambda: None)
+    warm = max(min(args.warmup, 1), 1 if gpu else 0)
+    for _ in range(warm):
         step()
+    sync()
     t0 = time.time()
     for _ in range(args.steps):
         step()
+    sync()
     dt = time.time() - t0
-    v = args.cpu_clips * args.steps / dt
-    sample = f"{args.cpu_clips} clip(s)/step of the same workload (oracle port of the reference, torch CPU fp32 + float64 numpy VQT)"
-    print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+    v = n * args.steps / dt
+    where = "1 x B200, stock PyTorch (cuDNN / cuBLAS / ATen) kernels, cached spectrograms on the device" if gpu else \
+            f"{threads} host threads, torch CPU fp32 + float64 numpy VQT"
+    sample = f"{n} clip(s)/step, {what}, {_kind_text(kind)}, {where}"
+    line = {
+        "impl": args.impl, "metric": metric, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": warm, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.batch), "sample": sample},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
-        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+        "config": {"workload": workload, "sample": sample, "clips_per_step": n},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if gpu:
+        line["gpu_baseline"] = {"value": v, "unit": UNIT, "kind": kind, "sample": sample}
+    else:
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample}
+    print(json.dumps(line), flush=True)
 
 
 # ---------------------------------------------------------------------------------------------- B200 arm
@@ -214,26 +326,35 @@ def run_b200(args):
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
+    finetune = args.workload == "finetune"
+    TF = tf_ratio(args.workload)
+    ops.set_precision(train=args.precision)
     torch.manual_seed(1234)
     model = models.ScoreTranscription(**CFG).to(dev).train()
     model.convstack.sync_batchnorm = world > 1          # speechbrain converts BatchNorm -> SyncBatchNorm under DDP
     opt = train.FlatAdadelta(model)
     vqt = VQT().to(dev)
-    audio_h = make_audio(B, N_SAMPLES, seed=1234 + rank).pin_memory()
+    if finetune:
+        audio_h, n_h = make_ragged_audio(B, seed=1234 + rank)
+        audio_h, n_h = audio_h.pin_memory(), n_h.pin_memory()
+    else:
+        audio_h, n_h = make_audio(B, N_SAMPLES, seed=1234 + rank).pin_memory(), None
     gt_h = [t.pin_memory() for t in make_ground_truth(B, 5, 398, 189, seed=1234 + rank)]
     S = executed_steps(gt_h)
     audio_d = audio_h.to(dev)
+    n_d = n_h.to(dev) if finetune else None
     gt_d = train.targets_to_device(gt_h, dev)
 
     def step_device():
-        spec = vqt(audio_d).unsqueeze(1)
-        return train.fit_batch(model, opt, spec, gt_d, TF_RATIO)
+        spec = vqt(audio_d, n_d).unsqueeze(1)
+        return train.fit_batch(model, opt, spec, gt_d, TF)
 
     def step_e2e():
         a = audio_h.to(dev, non_blocking=True)
+        n = n_h.to(dev, non_blocking=True) if finetune else None
         g = train.targets_to_device(gt_h, dev)
-        spec = vqt(a).unsqueeze(1)
-        return train.fit_batch(model, opt, spec, g, TF_RATIO).item()          # D2H read of the step's loss
+        spec = vqt(a, n).unsqueeze(1)
+        return train.fit_batch(model, opt, spec, g, TF).item()          # D2H read of the step's loss
 
     def barrier():
         if world > 1:
@@ -270,7 +391,7 @@ def run_b200(args):
         sampler.start()
     for _ in range(max(args.warmup, 3) - 1):
         step_device()
-    # the step enqueues ~1 500 launches from Python; a generation-2 garbage collection over torch's heap inside the timed region
+    # the step enqueues ~1 000 launches from Python; a generation-2 garbage collection over torch's heap inside the timed region
     # stalls the launch thread for tens of ms (seen as 64 vs 76 ms/step between otherwise identical runs): collect now and move
     # the survivors out of the collector's reach, as a training loop would after its first iterations
     gc.collect()
@@ -289,12 +410,36 @@ def run_b200(args):
     ops.KernelTimers.reset(False)
     step_e2e()
     ms_e2e, _, w2 = timed(step_e2e, args.steps)
-    if rank == 0:
-        sampler.stop()
+    ops.check_sync_flags()
     clips = B * world * args.steps
     value = clips / (ms / 1e3)
     e2e = clips / (ms_e2e / 1e3)
-    h2d = audio_h.numel() * 4 + sum(t.numel() * 8 for t in gt_h)
+    h2d = audio_h.numel() * 4 + sum(t.numel() * 8 for t in gt_h) + (n_h.numel() * 8 if finetune else 0)
+
+    # secondary measurement in the default headline run: the same step with single-bf16 contractions (BASELINE configs[2])
+    also = None
+    if args.also_steps > 0 and args.precision == "bf16x3" and not finetune:
+        ops.set_precision(train="bf16")
+        for _ in range(3):
+            step_device()
+        ms_b, _, _ = timed(step_device, args.also_steps)
+        ms_be, _, w2 = timed(step_e2e, args.also_steps)
+        ops.set_precision(train=args.precision)
+        cb = B * world * args.also_steps
+        also = {"precision": "bf16", "dtype": DTYPE["bf16"], "steps": args.also_steps, "value": cb / (ms_b / 1e3), "unit": UNIT,
+                "ms_per_step": ms_b / args.also_steps, "e2e_value": cb / (ms_be / 1e3), "note": PRECISION_NOTE["bf16"]}
+    if rank == 0:
+        sampler.stop()
+
+    # data-parallel correctness: after the timed steps every rank must hold bit-identical parameters, optimizer state and BatchNorm
+    # running statistics (they only ever see all-reduced gradients / statistics)
+    rank_consistent = None
+    if world > 1:
+        bn = torch.cat([b.reshape(-1).float() for n_, b in model.named_buffers() if "running" in n_])
+        sums = torch.stack([t.contiguous().view(torch.int32).to(torch.int64).sum() for t in (opt.flat, opt.square_avg, opt.acc_delta, bn)])
+        allsums = [torch.empty_like(sums) for _ in range(world)]
+        dist.all_gather(allsums, sums)
+        rank_consistent = all(bool((a == allsums[0]).all().item()) for a in allsums)
 
     if rank == 0:
         peaks = {}
@@ -310,27 +455,35 @@ def run_b200(args):
         roof, roof_all = roofline(ktimes, B, peaks, S, traffic)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            cstep, threads = cpu_step_factory(args.cpu_clips)
+            cstep, threads, kind = reference_step_factory(args.cpu_clips, args.workload)
             t0 = time.time()
             cstep()
             dt = time.time() - t0
-            cpu = {"value": args.cpu_clips / dt, "unit": UNIT, "cores": threads, "kind": "port",
-                   "sample": f"{args.cpu_clips} clip(s), one fwd+bwd+Adadelta step of the same workload through the oracle port "
+            cpu = {"value": args.cpu_clips / dt, "unit": UNIT, "cores": threads, "kind": kind,
+                   "sample": f"{args.cpu_clips} clip(s), one fwd+bwd+clip+Adadelta step of the same workload through {_kind_text(kind)} "
                              f"(torch CPU fp32 + float64 numpy VQT), {dt:.1f} s"}
-        print(json.dumps({
+        line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE[args.precision],
             "data": "synthetic",
-            "config": {"workload": workload_name(B), "global_batch": B * world, "decoder_steps_per_forward": S,
+            "config": {"workload": workload_name(B, args.workload, args.precision), "precision": PRECISION_NOTE[args.precision],
+                       "global_batch": B * world, "decoder_steps_per_forward": S,
                        "parallelism": f"dp{world}", "l2": "working set >> 126 MB L2 (4.4 GB of conv activations per step), no flush needed",
                        "kernel_ms": {k: round(v[1], 4) for k, v in sorted(ktimes.items())}},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
-            "host_enqueue_ms_per_step": round(host_ms[0], 3), "per_step": {"device_resident": per_step[0], "e2e": per_step[-1]},
+            "host_enqueue_ms_per_step": round(host_ms[0], 3), "per_step": {"device_resident": per_step[0], "e2e": per_step[1]},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(w0, w2),
             "roofline": roof, "roofline_all": [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items()} for r in roof_all],
-            "cpu_baseline": cpu}), flush=True)
+            "cpu_baseline": cpu}
+        if also is not None:
+            line["also"] = also
+        if rank_consistent is not None:
+            line["rank_consistent"] = rank_consistent
+        print(json.dumps(line), flush=True)
     if world > 1:
+        if not rank_consistent:
+            raise RuntimeError("data-parallel ranks diverged: parameters / optimizer state / BatchNorm statistics differ across ranks")
         dist.destroy_process_group()
 
 
@@ -420,13 +573,13 @@ def run_b200_infer(args):
         roof, roof_all = roofline({k: v for k, v in ktimes.items() if k.startswith("note_decoder")}, B, peaks, S, n_dec=10)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            cstep, threads = cpu_infer_factory(args.cpu_clips)
+            cstep, threads, kind = reference_infer_factory(args.cpu_clips)
             t0 = time.time()
             cstep()
             dt = time.time() - t0
-            cpu = {"value": args.cpu_clips / dt, "unit": UNIT, "cores": threads, "kind": "port",
-                   "sample": f"{args.cpu_clips} clip(s), greedy decode of the same workload through the oracle port (torch CPU fp32 + float64 "
-                             f"numpy VQT), {dt:.1f} s"}
+            cpu = {"value": args.cpu_clips / dt, "unit": UNIT, "cores": threads, "kind": kind,
+                   "sample": f"{args.cpu_clips} clip(s), greedy decode of the same workload through {_kind_text(kind)} (torch CPU fp32 + "
+                             f"float64 numpy VQT), {dt:.1f} s"}
         print(json.dumps({
             "metric": "clips_per_sec_greedy_decode", "value": clips / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -523,7 +676,7 @@ def roofline(ktimes, B, peaks, S_total, traffic=None, n_dec=None):
 
 if __name__ == "__main__":
     a = parse()
-    if a.impl == "reference":
+    if a.impl in ("reference", "reference-gpu"):
         run_reference(a)
     elif a.workload == "infer":
         run_b200_infer(a)

@@ -64,8 +64,11 @@ PA2S_API int pa2s_gemm_bf16_tma(void* stream, int M, int N, int K,
 
 /* ---- VQT front end (utilities.py:246-253) -------------------------------------------------------------------
  * C: (nclips*rows_per_clip, 2*nb) filterbank responses (re,im interleaved).  Writes
- * out = amplitude_to_db(|V|, ref=max over the clip, amin=1e-5, top_db=80)/80 + 1 as (nclips, rows_per_clip, nb). */
-PA2S_API int pa2s_vqt_post(void* stream, const float* C, float* out, unsigned int* clip_max, int nclips, int rows_per_clip, int nb);
+ * out = amplitude_to_db(|V|, ref=max over the clip, amin=1e-5, top_db=80)/80 + 1 as (nclips, rows_per_clip, nb).
+ * valid_rows (int32 per clip, or NULL): frames the un-padded clip has; later rows are excluded from the maximum and written as zeros
+ * (the zero padding of pad_spectrogram, datasets/asap.py:345-349). */
+PA2S_API int pa2s_vqt_post(void* stream, const float* C, float* out, unsigned int* clip_max, int nclips, int rows_per_clip, int nb,
+                          const int* valid_rows);
 
 /* ---- ConvStack (models.py:463-543) ---------------------------------------------------------------------------
  * mode 0: Y = conv3x3(relu?(X*in_scale+in_shift)) (in_scale NULL = identity), Wpacked = W.permute(2,3,1,0);
@@ -134,7 +137,9 @@ PA2S_API int pa2s_colsum(void* stream, const float* X, int R, int N, double* scr
 /* per-channel sums over (npix, C): mode 0 [sum x, sum x^2]; mode 1 [sum g, sum g*xhat] (BatchNorm backward). */
 PA2S_API int pa2s_colstats(void* stream, int mode, const float* X, const float* G, const float* mask, long long npix, int C,
                            const float* zs, const float* zb, const float* mean, const float* invstd, float* partial, int nctas);
-/* nn.BatchNorm{1,2}d (models.py:499-505) train-mode statistics -> affine, running buffers updated in place. */
+/* nn.BatchNorm{1,2}d (models.py:499-505) train-mode statistics -> affine, running buffers updated in place.
+ * count <= 0: the element count is read from sums[2*C] (SyncBatchNorm: it was all-reduced together with the sums, so ranks may hold
+ * different batch sizes); the same convention holds for pa2s_bn_bwd_finalize. */
 PA2S_API int pa2s_bn_finalize(void* stream, const double* sums, double count, int C, const float* gamma, const float* beta,
                               float eps, float momentum, float* running_mean, float* running_var,
                               float* scale, float* shift, float* mean, float* invstd);

@@ -12,7 +12,7 @@ including the per-step ``cat`` + ``Linear(1024->256)`` attention recompute, the
 absence of an attention length mask, and "finished sequences keep decoding" --
 so that it is a faithful CPU baseline as well as the parity checker.
 
-Pinning: `tests/test_oracle_vs_reference.py` imports the unmodified reference
+Pinning: `tests/test_oracle_golden.py` imports the unmodified reference
 (`/root/reference/models.py`, with a stub for its top-level `music21` import)
 in the build container and checks this file against it for eval, greedy and
 teacher-forced training forwards and for all parameter gradients; the golden

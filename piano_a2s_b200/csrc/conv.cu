@@ -348,6 +348,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count
                                    float* running_var, float* scale, float* shift, float* mean_out, float* invstd_out) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
+    if (count <= 0.0) count = sums[2 * C];          // SyncBatchNorm: the element count was all-reduced with the sums (uneven rank batches)
     double mean = sums[c] / count;
     double var = sums[C + c] / count - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -381,6 +382,7 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, double c
                                        const float* __restrict__ invstd, float* dgamma, float* dbeta, float* k1, float* k2, float* k3) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
+    if (count <= 0.0) count = sums[2 * C];
     double sg = sums[c], sgx = sums[C + c];
     dbeta[c] += (float)sg;
     dgamma[c] += (float)sgx;

@@ -60,8 +60,10 @@ __device__ __forceinline__ float4 lds4(const float4* p) {
 #endif
 }
 
-// Grid barrier for a co-resident grid: monotonically increasing arrival counter.  A watchdog turns a lost CTA into an
-// error flag instead of a hang.
+// Grid barrier for a co-resident grid: monotonically increasing arrival counter.  A watchdog turns a lost CTA into a
+// LOUD failure instead of a hang: it records the error flag (sync[1], for a post-mortem read) and traps, so the launch
+// fails with a CUDA error at the next synchronisation and no later kernel (Adadelta in particular) consumes the
+// inconsistent state the barrier would otherwise have let through.
 __device__ __forceinline__ void grid_sync(unsigned int* sync, unsigned int& target) {
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -73,7 +75,7 @@ __device__ __forceinline__ void grid_sync(unsigned int* sync, unsigned int& targ
             unsigned int v;
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(sync) : "memory");
             if (v >= target) break;
-            if (++spins > (1u << 24)) { atomicExch(sync + 1, 1u); break; }
+            if (++spins > (1u << 24)) { atomicExch(sync + 1, 1u); __threadfence_system(); __trap(); }
         }
         __threadfence();
     }

@@ -6,16 +6,20 @@
 namespace {
 
 // C: (rows, 2*nb) filterbank responses, (re, im) interleaved per bin.  mag: (rows, nb).  One clip = rows_per_clip rows.
+// valid_rows (or NULL): frames of each clip that exist (1 + n_samples/hop of the un-padded clip); later rows are the zero padding of
+// pad_spectrogram (asap.py:345-349): they do not enter the clip maximum and come out as exact zeros.
 __global__ void vqt_mag_kernel(const float2* __restrict__ C, float* __restrict__ mag, unsigned int* __restrict__ clip_max,
-                               long long n, int nb, int rows_per_clip) {
+                               long long n, int nb, int rows_per_clip, const int* __restrict__ valid_rows) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     float m = 0.f;
     int clip = 0;
     if (i < n) {
         float2 v = __ldg(C + i);
         m = sqrtf(v.x * v.x + v.y * v.y);
+        const long long row = i / nb;
+        clip = (int)(row / rows_per_clip);
+        if (valid_rows != nullptr && (int)(row - (long long)clip * rows_per_clip) >= valid_rows[clip]) m = 0.f;
         mag[i] = m;
-        clip = (int)((i / nb) / rows_per_clip);
     }
     // a warp may straddle two clips only at a clip boundary; reduce when uniform, else fall back to per-lane atomics
     int clip0 = __shfl_sync(0xffffffffu, clip, 0);
@@ -30,10 +34,12 @@ __global__ void vqt_mag_kernel(const float2* __restrict__ C, float* __restrict__
 
 // librosa.amplitude_to_db(|V|, ref=max, amin=1e-5, top_db=80)/80 + 1
 __global__ void vqt_logscale_kernel(float* __restrict__ mag, const unsigned int* __restrict__ clip_max, long long n, int nb,
-                                    int rows_per_clip) {
+                                    int rows_per_clip, const int* __restrict__ valid_rows) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    int clip = (int)((i / nb) / rows_per_clip);
+    const long long row = i / nb;
+    int clip = (int)(row / rows_per_clip);
+    if (valid_rows != nullptr && (int)(row - (long long)clip * rows_per_clip) >= valid_rows[clip]) { mag[i] = 0.f; return; }
     const float amin = 1e-5f;
     float ref = fmaxf(amin, __uint_as_float(clip_max[clip]));
     float db = 20.f * log10f(fmaxf(amin, mag[i])) - 20.f * log10f(ref);
@@ -146,13 +152,14 @@ __global__ void greedy_tokens_kernel(const float* __restrict__ logp, int L, int 
 
 }  // namespace
 
-PA2S_API int pa2s_vqt_post(void* stream, const float* C, float* out, unsigned int* clip_max, int nclips, int rows_per_clip, int nb) {
+PA2S_API int pa2s_vqt_post(void* stream, const float* C, float* out, unsigned int* clip_max, int nclips, int rows_per_clip, int nb,
+                          const int* valid_rows) {
     cudaStream_t st = (cudaStream_t)stream;
     long long n = (long long)nclips * rows_per_clip * nb;
     PA2S_TRY(cudaMemsetAsync(clip_max, 0, sizeof(unsigned int) * nclips, st));
-    vqt_mag_kernel<<<ceil_div(n, 256), 256, 0, st>>>((const float2*)C, out, clip_max, n, nb, rows_per_clip);
+    vqt_mag_kernel<<<ceil_div(n, 256), 256, 0, st>>>((const float2*)C, out, clip_max, n, nb, rows_per_clip, valid_rows);
     PA2S_CHECK_LAST();
-    vqt_logscale_kernel<<<ceil_div(n, 256), 256, 0, st>>>(out, clip_max, n, nb, rows_per_clip);
+    vqt_logscale_kernel<<<ceil_div(n, 256), 256, 0, st>>>(out, clip_max, n, nb, rows_per_clip, valid_rows);
     PA2S_CHECK_LAST();
     return 0;
 }

@@ -19,9 +19,6 @@ import torch.nn.functional as F
 
 from . import ops, rng
 
-# the two staves run on two CUDA streams; their gradients meet in AccumulateGrad nodes of the default stream by design
-torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
-
 # ---------------------------------------------------------------------------------------------------------------
 # Vocabulary (data_processing/humdrum.py:70-131 `LabelsMultiple(extended=True)`): 148 + 25 = 173 symbols.
 # ---------------------------------------------------------------------------------------------------------------
@@ -100,6 +97,10 @@ class Encoder(nn.Module):
         init_layer(self.fc)
 
     def forward(self, x):
+        with ops.module_precision(self):
+            return self._forward(x)
+
+    def _forward(self, x):
         g = self.gru
         B = x.shape[0]
         bg = 4 if B >= 4 else (2 if B >= 2 else 1)
@@ -216,6 +217,9 @@ class HierarchicalDecoder(nn.Module):
         # the persistent note-decoder kernels (64 co-resident CTAs that own their SMs) go ahead of the wide parallel kernels that fill
         # the remaining SMs: two high-priority streams for the staves, one normal-priority stream for the deferred dEp / dv kernels
         prio = -1 if os.environ.get("PA2S_SIDE_PRIO", "0") == "1" else 0
+        # the two staves run on two CUDA streams; their gradients meet in AccumulateGrad nodes of the default stream by design, so
+        # autograd's stream-mismatch warning is switched off -- here, when the two-stream decoder is first used, not at import
+        torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
         self._side_streams = (torch.cuda.Stream(priority=prio), torch.cuda.Stream(priority=prio))
         self._defer_stream = torch.cuda.Stream() if os.environ.get("PA2S_DEFER_STREAM", "0") == "1" else None
 
@@ -361,11 +365,12 @@ class HierarchicalDecoder(nn.Module):
     def forward(self, encoder_outputs, hidden, inference=True, ground_truth=None, teacher_forcing_ratio=0,
                 device=torch.device("cuda" if torch.cuda.is_available() else "cpu")):
         self.device = device
-        if inference:
-            assert teacher_forcing_ratio == 0
-            assert ground_truth is None
-            return self.decode_bars(encoder_outputs, hidden, True, None, 0.)
-        return self.decode_bars(encoder_outputs, hidden, False, ground_truth, teacher_forcing_ratio)
+        with ops.module_precision(self):
+            if inference:
+                assert teacher_forcing_ratio == 0
+                assert ground_truth is None
+                return self.decode_bars(encoder_outputs, hidden, True, None, 0.)
+            return self.decode_bars(encoder_outputs, hidden, False, ground_truth, teacher_forcing_ratio)
 
 
 class NoteDecoder(nn.Module):
@@ -435,11 +440,12 @@ class NoteDecoder(nn.Module):
     def forward(self, encoder_outputs, hidden, inference=True, ground_truth=None, teacher_forcing_ratio=0,
                 device=torch.device("cuda" if torch.cuda.is_available() else "cpu")):
         self.device = device
-        if inference:
-            assert teacher_forcing_ratio == 0
-            assert ground_truth is None
-            return self.decode_notes(encoder_outputs, hidden, True, None, 0.)
-        return self.decode_notes(encoder_outputs, hidden, False, ground_truth, teacher_forcing_ratio)
+        with ops.module_precision(self):
+            if inference:
+                assert teacher_forcing_ratio == 0
+                assert ground_truth is None
+                return self.decode_notes(encoder_outputs, hidden, True, None, 0.)
+            return self.decode_notes(encoder_outputs, hidden, False, ground_truth, teacher_forcing_ratio)
 
 
 class AttentionLayer(nn.Module):
@@ -456,10 +462,11 @@ class AttentionLayer(nn.Module):
     def forward(self, hidden, encoder_output):
         """(1,B,2H), (B,T,2H) -> softmax attention weights (B,T) (models.py:452-461)."""
         B, T, D = encoder_output.shape
-        Ep = ops.linear(encoder_output.reshape(B * T, D), self.attn.weight[:, D:], self.attn.bias).view(B, T, -1)
-        q = ops.linear(hidden[0], self.attn.weight[:, :D], None)
-        energy = torch.tanh(q.unsqueeze(1) + Ep)
-        return F.softmax(ops.linear(energy, self.v.weight, None).squeeze(2), dim=1)
+        with ops.module_precision(self):
+            Ep = ops.linear(encoder_output.reshape(B * T, D), self.attn.weight[:, D:], self.attn.bias).view(B, T, -1)
+            q = ops.linear(hidden[0], self.attn.weight[:, :D], None)
+            energy = torch.tanh(q.unsqueeze(1) + Ep)
+            return F.softmax(ops.linear(energy, self.v.weight, None).squeeze(2), dim=1)
 
 
 class ConvStack(nn.Module):
@@ -500,7 +507,8 @@ class ConvStack(nn.Module):
         for c, b in zip((self.conv1, self.conv2, self.conv3, self.conv4), bns[:4]):
             params += [c.weight, b.weight, b.bias]
         params += [self.out.weight, self.out_bn.weight, self.out_bn.bias]
-        y = ops.ConvStackFn.apply(x, mask, bufs, training, sync, float(self.bn1.eps), float(self.bn1.momentum), *params)
+        with ops.module_precision(self):
+            y = ops.ConvStackFn.apply(x, mask, bufs, training, sync, float(self.bn1.eps), float(self.bn1.momentum), *params)
         if training:
             with torch.no_grad():
                 for b in bns:

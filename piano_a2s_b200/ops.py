@@ -79,6 +79,7 @@ def _dist_on() -> bool:
 PRECISION = {"train": "bf16x3", "eval": "fp32"}
 TC_MIN_FLOP = 2.0e8
 _CURRENT = ["bf16x3"]
+_DEPTH = [0]                # > 0 inside a use_precision scope
 
 
 def set_precision(train=None, eval=None):
@@ -104,9 +105,11 @@ class use_precision:
     def __enter__(self):
         self.old = _CURRENT[0]
         _CURRENT[0] = self.prec
+        _DEPTH[0] += 1
 
     def __exit__(self, *exc):
         _CURRENT[0] = self.old
+        _DEPTH[0] -= 1
 
 
 def _bwd_precision(fn):
@@ -118,6 +121,12 @@ def _bwd_precision(fn):
 
 
 def module_precision(module):
+    """Scope entered by EVERY public module forward (ScoreTranscription and the sub-modules the reference exposes: ConvStack, Encoder,
+    HierarchicalDecoder, NoteDecoder, AttentionLayer): `PRECISION["train" | "eval"]` by the module's mode, so that a sub-module called
+    on its own in eval() runs the exact-fp32 kernels too.  An enclosing scope (the parent module's, or an explicit `use_precision`)
+    wins."""
+    if _DEPTH[0] > 0:
+        return contextlib.nullcontext()
     return use_precision(PRECISION["train" if module.training else "eval"])
 
 
@@ -294,8 +303,12 @@ def _tc_pack(W, Cout, Cin, dgrad):
     return buf
 
 
-def _bn_sums(partial, C):
-    sums = torch.empty(2 * C, device=partial.device, dtype=torch.float64)
+def _bn_sums(partial, C, count=None):
+    """fp64 column sums of the per-CTA partials; with `count` the vector gets a third part [local element count], so that one
+    all-reduce carries sums AND count (torch.nn.SyncBatchNorm gathers per-rank counts: ranks may hold different batch sizes)."""
+    sums = torch.empty(2 * C + (1 if count is not None else 0), device=partial.device, dtype=torch.float64)
+    if count is not None:
+        sums[2 * C:].fill_(float(count))
     lib.pa2s_reduce_rows(stream(), ptr(partial), partial.shape[0], 2 * C, ptr(sums), None, 0)
     return sums
 
@@ -356,11 +369,11 @@ class ConvStackFn(torch.autograd.Function):
                                      ptr(in_scale), ptr(in_shift), 1, None, None, None, None, None, None, None, None)
             aff = torch.empty(4, Cout, device=dev, dtype=F32)      # scale, shift, mean, invstd
             if training:
-                sums = _bn_sums(partial, Cout)
+                sums = _bn_sums(partial, Cout, B * T * Fq if world > 1 else None)
                 if world > 1:
                     dist.all_reduce(sums)
                 rm, rv = bufs[i]
-                lib.pa2s_bn_finalize(st, ptr(sums), float(B * T * Fq * world), Cout, ptr(gam[i]), ptr(bet[i]), eps, momentum,
+                lib.pa2s_bn_finalize(st, ptr(sums), -1.0 if world > 1 else float(B * T * Fq), Cout, ptr(gam[i]), ptr(bet[i]), eps, momentum,
                                      ptr(rm), ptr(rv), ptr(aff[0]), ptr(aff[1]), ptr(aff[2]), ptr(aff[3]))
             else:
                 rm, rv = bufs[i]
@@ -397,11 +410,11 @@ class ConvStackFn(torch.autograd.Function):
             nct = 4 * N_SM
             partial = torch.empty(nct, 2 * O, device=dev, dtype=F32)
             lib.pa2s_colstats(st, 0, ptr(z), None, None, M, O, None, None, None, None, ptr(partial), nct)
-            sums = _bn_sums(partial, O)
+            sums = _bn_sums(partial, O, M if world > 1 else None)
             if world > 1:
                 dist.all_reduce(sums)
             rm, rv = bufs[4]
-            lib.pa2s_bn_finalize(st, ptr(sums), float(M * world), O, ptr(gam[4]), ptr(bet[4]), eps, momentum,
+            lib.pa2s_bn_finalize(st, ptr(sums), -1.0 if world > 1 else float(M), O, ptr(gam[4]), ptr(bet[4]), eps, momentum,
                                  ptr(rm), ptr(rv), ptr(aff5[0]), ptr(aff5[1]), ptr(aff5[2]), ptr(aff5[3]))
         else:
             rm, rv = bufs[4]
@@ -433,17 +446,17 @@ class ConvStackFn(torch.autograd.Function):
             partial = torch.empty(nct, 2 * C, device=dev, dtype=F32)
             lib.pa2s_colstats(st, 1, ptr(Y), ptr(G), ptr(mask), npix, C, ptr(aff[0]), ptr(aff[1]), ptr(aff[2]), ptr(aff[3]),
                               ptr(partial), nct)
-            sums = _bn_sums(partial, C)
+            sums = _bn_sums(partial, C, npix if world > 1 else None)
             local = None
             if world > 1:
                 # SyncBatchNorm: the input gradient uses the sums over ALL ranks, dgamma / dbeta stay this rank's sums (the gradient
                 # all-reduce averages them afterwards, like torch.nn.SyncBatchNorm under DDP): keep them before the all-reduce
-                local = sums.to(F32)
+                local = sums[:2 * C].to(F32)
                 dist.all_reduce(sums)
             dg = torch.zeros(C, device=dev, dtype=F32)
             db = torch.zeros(C, device=dev, dtype=F32)
             k = torch.empty(3, C, device=dev, dtype=F32)
-            lib.pa2s_bn_bwd_finalize(st, ptr(sums), float(npix * world), C, ptr(gamma), ptr(aff[3]), ptr(dg), ptr(db),
+            lib.pa2s_bn_bwd_finalize(st, ptr(sums), -1.0 if world > 1 else float(npix), C, ptr(gamma), ptr(aff[3]), ptr(dg), ptr(db),
                                      ptr(k[0]), ptr(k[1]), ptr(k[2]))
             if local is not None:
                 dg, db = local[C:].contiguous(), local[:C].contiguous()

@@ -5,9 +5,10 @@ averaging, gradient clipping and the Adadelta update (pretrain.yaml:44-47), all 
 Data parallelism: one process per GPU, batch-sharded; BatchNorm statistics are reduced across
 ranks inside ConvStackFn (SyncBatchNorm semantics) and parameter gradients are averaged by NCCL all-reduces over
 contiguous buckets of a flat fp32 gradient buffer (16.36 M elements = 65.4 MB).  A bucket is reduced as soon as
-autograd has accumulated its last gradient (post-accumulate hooks), on NCCL's own stream, so the decoder and
-encoder buckets travel over NVLink while the ConvStack backward is still running (what torch DDP does for the
-reference under speechbrain).
+autograd has accumulated its last gradient (post-accumulate hooks), on NCCL's own stream, so the bar-level decoder,
+encoder and `convstack.out` buckets travel over NVLink while the ConvStack backward is still running (what torch DDP
+does for the reference under speechbrain); the note decoders' weights, whose gradients autograd hands over last
+(ops.DecoderWeightSinkFn), form buckets of their own that are reduced at the end of backward.
 """
 from __future__ import annotations
 
@@ -47,7 +48,12 @@ class FlatAdadelta:
     torch.optim.Adadelta(lr, rho, eps) semantics in two kernels (sum of squares, fused update)."""
 
     def __init__(self, model, lr=1.0, rho=0.95, eps=1e-8, max_grad_norm=5.0, bucket_bytes=24 << 20, overlap=True):
-        self.params = [p for p in model.parameters() if p.requires_grad]
+        named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+        self.params = [p for _, p in named]
+        # gradients of the two NoteDecoder modules are handed over by ops.DecoderWeightSinkFn, the LAST node of a backward pass
+        # (models.HierarchicalDecoder.weight_sinks): they get buckets of their own, so that every other bucket -- bar-level decoder,
+        # encoder, convstack.out -- is reduced while the ConvStack backward is still running
+        late = [("upper_decoder." in n or "lower_decoder." in n) for n, _ in named]
         # every parameter starts on a 256-byte boundary: the kernels read weight rows with 128-bit loads
         al = lambda k: (k + 63) // 64 * 64
         n = sum(al(p.numel()) for p in self.params)
@@ -75,7 +81,7 @@ class FlatAdadelta:
         hi, members = n, []
         for i in range(len(self.params) - 1, -1, -1):
             members.append(i)
-            if (hi - self.offsets[i]) * 4 >= bucket_bytes or i == 0:
+            if (hi - self.offsets[i]) * 4 >= bucket_bytes or i == 0 or late[i] != late[i - 1]:
                 self.buckets.append((self.offsets[i], hi, members))
                 hi, members = self.offsets[i], []
         self.bucket_of = [0] * len(self.params)

@@ -68,7 +68,10 @@ class VQT(torch.nn.Module):
         self._fop = None
 
     @torch.no_grad()
-    def forward(self, audio):
+    def forward(self, audio, n_samples=None):
+        """`n_samples` (B,) int tensor on the device, or None: true length of each zero-padded clip.  Frames a clip does not have
+        (t >= 1 + n_b // hop) come out as zeros and stay out of the clip maximum, i.e. the result equals get_VQT of the un-padded clip
+        followed by pad_spectrogram (datasets/asap.py:345-349, 383)."""
         if not audio.is_cuda:
             raise RuntimeError("VQT runs on CUDA only")
         audio = audio.float()
@@ -91,7 +94,10 @@ class VQT(torch.nn.Module):
                      batch=B, strideA=plen, strideB=0, strideC=T * 2 * self.n_bins, a_off=self.j0, precision=self.precision)
         out = torch.empty(B, T, self.n_bins, device=audio.device, dtype=torch.float32)
         cmax = torch.empty(B, device=audio.device, dtype=torch.int32)
-        lib.pa2s_vqt_post(stream(), ptr(C), ptr(out), ptr(cmax), B, T, self.n_bins)
+        valid = None
+        if n_samples is not None:
+            valid = (1 + torch.div(n_samples.to(audio.device), self.hop, rounding_mode="floor")).to(torch.int32).contiguous()
+        lib.pa2s_vqt_post(stream(), ptr(C), ptr(out), ptr(cmax), B, T, self.n_bins, ptr(valid))
         return out
 
 

@@ -8,7 +8,14 @@ REF_ROOT = "/root/reference"
 
 
 def have_reference():
-    return os.path.isfile(os.path.join(REF_ROOT, "models.py"))
+    """The reference model is importable: from /root/reference (build container) or from the compiled oracle/_ref (GPU box)."""
+    from oracle import build_ref
+    return os.path.isfile(os.path.join(REF_ROOT, "models.py")) or build_ref.available()
+
+
+def have_reference_tree():
+    """The whole reference tree (datasets/, pretrain.py, ...) is mounted: build container only."""
+    return os.path.isfile(os.path.join(REF_ROOT, "pretrain.py"))
 
 
 def import_reference_models():
@@ -16,6 +23,9 @@ def import_reference_models():
     at module top but the model never uses it)."""
     if "ref_models" in sys.modules:
         return sys.modules["ref_models"]
+    if not os.path.isfile(os.path.join(REF_ROOT, "models.py")):
+        from oracle import build_ref
+        return build_ref.load()
     sys.modules.setdefault("music21", types.ModuleType("music21"))
     saved_path = list(sys.path)
     saved_dp = sys.modules.pop("data_processing", None)

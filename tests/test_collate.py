@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from oracle import collate_oracle as CO
-from refimport import have_reference
+from refimport import have_reference_tree as have_reference
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden", "collate_golden.npz")
 PAD_, EOS_ = 147, 146

@@ -12,7 +12,7 @@ import torch
 from helpers import make_ground_truth
 from oracle import a2s_oracle as O
 from oracle import metrics_oracle as MO
-from refimport import have_reference
+from refimport import have_reference_tree as have_reference
 
 pytestmark = pytest.mark.skipif(not have_reference(), reason="/root/reference is only mounted in the build container")
 
