@@ -4,7 +4,7 @@ TEST / BASELINE INFRASTRUCTURE ONLY (see oracle/a2s_oracle.py): nothing under pi
 
 The reference's hot path is two Python files (`/root/reference/models.py`, which imports `LabelsMultiple` from
 `/root/reference/data_processing/humdrum.py`).  They are byte-compiled from `/root/reference` -- no source is copied into
-this repository -- and only the compiled `.pyc` files are written to `oracle/_ref/` (git-ignored, NOT gpurun-ignored, so
+this repository -- and only the compiled bytecode files (`*.pyc.bin`) are written to `oracle/_ref/` (git-ignored, NOT gpurun-ignored, so
 they travel to the GPU box like our own `.so`; same image => same CPython => the bytecode loads there).  `load()` imports
 the result as module `ref_models` with `music21` stubbed (humdrum.py:4 imports it at module top; the model never uses
 it).  With it
@@ -23,7 +23,8 @@ import types
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SRC = "/root/reference"
 OUT = os.path.join(HERE, "_ref")
-FILES = (("models.py", "models.pyc"), (os.path.join("data_processing", "humdrum.py"), os.path.join("data_processing", "humdrum.pyc")))
+# (the compiled files are named *.bin: the gpurun snapshot skips *.pyc)
+FILES = (("models.py", "models.pyc.bin"), (os.path.join("data_processing", "humdrum.py"), os.path.join("data_processing", "humdrum.pyc.bin")))
 
 
 def build(verbose=False):
