@@ -192,6 +192,23 @@ PA2S_API int pa2s_note_decoder_bwd_persist(void* stream, const void* args);
  * dEp / dv accumulation, which only reads ds_all / qs / Ep / v and may therefore run on another stream behind the chain. */
 PA2S_API int pa2s_note_decoder_bwd_chain(void* stream, const void* args);
 PA2S_API int pa2s_note_decoder_bwd_deferred(void* stream, const void* args);
+
+/* ---- multi-sequence persistent note decoder (dec_multi.cu): NQ bars of one staff x B clips per launch ---------------------
+ * Replaces NoteDecoder.decode_notes (models.py:366-420) for every run of bars whose input tokens do not depend on the previous
+ * bar's predictions (teacher-forced bars, models.py:289-311), and the autograd of all bars of a staff in ONE reverse launch.
+ * `args` points to a HOST struct DecMArgs (csrc/decm_args.cuh, mirrored by ctypes in piano_a2s_b200/_lib.py).  The attention
+ * memory is passed as Ee = exp(2 * (enc W_e^T + b)) (pa2s_exp2x): tanh(q + Ep) = 1 - 2 / (1 + exp(2q) * Ee), one SFU op per
+ * element.  Backward: pa2s_decm_dlogits, caller GEMM dhc_all = dlogits_all @ W_out, pa2s_decm_bwd_chain, pa2s_decm_bwd_deferred. */
+PA2S_API int pa2s_decm_args_size(void);
+PA2S_API int pa2s_decm_max_queries(void);
+PA2S_API int pa2s_decm_tile_max(void);
+PA2S_API int pa2s_decm_grid(void);
+PA2S_API int pa2s_decm_deferred_blocks(int T);
+PA2S_API int pa2s_exp2x(void* stream, const float* x, float* y, long long n);
+PA2S_API int pa2s_decm_fwd(void* stream, const void* args, int sos_id, int eos_id);
+PA2S_API int pa2s_decm_dlogits(void* stream, const void* args);
+PA2S_API int pa2s_decm_bwd_chain(void* stream, const void* args);
+PA2S_API int pa2s_decm_bwd_deferred(void* stream, const void* args);
 PA2S_API int pa2s_attn_step_fwd(void* stream, const void* args);
 PA2S_API int pa2s_attn_step_bwd(void* stream, const void* args);
 

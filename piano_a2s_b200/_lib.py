@@ -57,7 +57,8 @@ class _Lib:
         if name in ("pa2s_launch_count", "pa2s_dec_args_size", "pa2s_gru_seq_max_bg", "pa2s_conv3x3_num_partials",
                     "pa2s_tc_conv_pack_bytes", "pa2s_tc_conv_num_partials", "pa2s_gemm_tc_supported",
                     "pa2s_tc_conv_wgrad_num_partials", "pa2s_dec_persist_grid", "pa2s_dec_deferred_blocks", "pa2s_planes_bytes",
-                    "pa2s_conv_tma_num_partials", "pa2s_conv_tma_wgrad_num_partials"):
+                    "pa2s_conv_tma_num_partials", "pa2s_conv_tma_wgrad_num_partials", "pa2s_decm_args_size", "pa2s_decm_max_queries",
+                    "pa2s_decm_tile_max", "pa2s_decm_grid", "pa2s_decm_deferred_blocks"):
             return fn
 
         def call(*args):
@@ -109,4 +110,31 @@ def make_dec_args(**kw):
         else:
             assert k in DecArgs._ptrs, k
             setattr(a, k, None if v is None else v.data_ptr())
+    return a
+
+
+class DecMArgs(ctypes.Structure):
+    """Mirror of `struct DecMArgs` in csrc/decm_args.cuh (field order and types must match exactly)."""
+    _ints = ["B", "NQ", "T", "V", "VP", "S", "max_steps", "NS", "tile", "inference", "save", "Rtot", "r0", "bars", "k0", "Spitch"]
+    _ptrs = ["enc", "Ee", "Wattn", "v", "emb", "W_ih", "W_hh", "b_ih", "b_hh", "W_out", "b_out", "W_hT", "W_ihT", "W_hhT",
+             "gt", "use_gt", "mask", "logp", "lengths", "eos", "counters",
+             "hs", "ctxs", "attn", "gates", "qs", "eqs", "xtok", "toks", "ml",
+             "xbuf", "logits", "pm", "pl", "pc", "tickets", "sync",
+             "dhc_all", "dgi_all", "dgh_all", "dq_all", "dctx_all", "dxtok_all", "ds_all", "dEp", "dv_part", "d_hc", "dhq", "dx",
+             "dq_part", "dh_carry", "dlogp", "dlogits_all", "prof"]
+    _fields_ = [(n, ctypes.c_int) for n in _ints] + [("Sq", ctypes.c_int * 8)] + [(n, ctypes.c_void_p) for n in _ptrs]
+
+
+def make_decm_args(Sq, **kw):
+    """Pointer fields take a tensor, a raw int address (pre-offset views) or None."""
+    a = DecMArgs()
+    assert len(Sq) <= 8
+    for i, v in enumerate(Sq):
+        a.Sq[i] = int(v)
+    for k, v in kw.items():
+        if k in DecMArgs._ints:
+            setattr(a, k, int(v))
+        else:
+            assert k in DecMArgs._ptrs, k
+            setattr(a, k, None if v is None else (v if isinstance(v, int) else v.data_ptr()))
     return a

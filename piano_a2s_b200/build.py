@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libpa2s.so")
-SOURCES = ["gemm.cu", "tc_gemm.cu", "tc_gemm_tma.cu", "tc_conv.cu", "tc_conv_tma.cu", "conv.cu", "conv1.cu", "misc.cu", "metrics.cu", "gru.cu", "decoder.cu", "dec_persist.cu"]
+SOURCES = ["gemm.cu", "tc_gemm.cu", "tc_gemm_tma.cu", "tc_conv.cu", "tc_conv_tma.cu", "conv.cu", "conv1.cu", "misc.cu", "metrics.cu", "gru.cu", "decoder.cu", "dec_persist.cu", "dec_multi.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 

@@ -242,6 +242,165 @@ class HierarchicalDecoder(nn.Module):
         return F.log_softmax(ops.linear(x, seq[4].weight, seq[4].bias), dim=-1)
 
     def decode_bars(self, encoder_outputs, hidden, inference=True, ground_truth=None, teacher_forcing_ratio=0):
+        if encoder_outputs.is_cuda and ops.DECODER_IMPL == "multi":
+            return self._decode_bars_multi(encoder_outputs, hidden, inference, ground_truth, teacher_forcing_ratio)
+        return self._decode_bars_per_bar(encoder_outputs, hidden, inference, ground_truth, teacher_forcing_ratio)
+
+    def _steps(self, ground_truth):
+        """[upper steps per bar, lower steps per bar] a forward executes for these targets (one host read at most, see prefetch_steps)"""
+        upper_gt, lower_gt = ground_truth[2], ground_truth[4]
+        pend, self._steps_pending = self._steps_pending, None
+        hint = (getattr(upper_gt, "_pa2s_steps", None), getattr(lower_gt, "_pa2s_steps", None))
+        if hint[0] is not None and hint[1] is not None:
+            return [list(hint[0]), list(hint[1])]                        # counted on the host by the loader (train.targets_to_device)
+        if pend is not None and pend[1] is upper_gt and pend[2] is lower_gt:
+            pend[0].synchronize()                                        # waits for the tiny side-stream read only
+            return self._steps_host.tolist()
+        return torch.stack([self._steps_from_gt(upper_gt), self._steps_from_gt(lower_gt)]).cpu().tolist()   # one sync
+
+    def _bar_step(self, token, h, enc, Ep_bar):
+        """bar-level attention + GRU cell + heads of one bar (models.py:239-247, 281-286) -> (bar_summary, ts_lp, key_lp)"""
+        D = enc.shape[2]
+        q = ops.linear(h, self.attn.attn.weight[:, :D], None)
+        context = ops.AttnStepFn.apply(q, Ep_bar, enc, self.attn.v.weight)
+        g = self.gru
+        h = ops.gru_cell(torch.cat([token, context], dim=1), h, g.weight_ih_l0, g.weight_hh_l0, g.bias_ih_l0, g.bias_hh_l0)
+        head_in = torch.cat([h, context], dim=1)
+        return h, self._heads(self.time_sig_out, head_in), self._heads(self.key_out, head_in)
+
+    def _decode_bars_multi(self, enc, hidden, inference=True, ground_truth=None, teacher_forcing_ratio=0):
+        """decode_bars (models.py:191-316) on the multi-sequence decoder kernels (ops.StaffRun / ops.DecodersFn).
+
+        A bar whose input token is built from the ground truth (bar-level teacher forcing, models.py:289-299) does not depend on the
+        previous bar's note decoders; all coins are pre-drawn (in the reference's order), so the bars split into SEGMENTS: runs of
+        bars of which only the first needs the previous bar's predictions.  Per segment the bar-level chain runs first, then ONE
+        launch per staff decodes all its bars (both staves concurrently on two streams); the reverse pass is one launch per staff
+        over all bars."""
+        B, T, D = enc.shape
+        dev = enc.device
+        training = self.training
+        src = rng.source()
+        nb = self.max_bars
+        if inference:
+            assert teacher_forcing_ratio == 0
+            assert ground_truth is None
+        have_gt = ground_truth is not None
+        if have_gt:
+            time_sig_gt, key_gt, upper_gt, upper_len_gt, lower_gt, lower_len_gt = ground_truth
+            steps = self._steps(ground_truth)
+        else:
+            steps = [[self.max_length[0]] * nb, [self.max_length[1]] * nb]
+        decs = (self.upper_decoder, self.lower_decoder)
+        E = self.note_emb_size
+        tokdim = self.staff_emb_size * 4 + self.time_sig_emb_size + self.key_emb_size
+        tf_bars = have_gt and not inference                              # the next bar token may come from the ground truth
+        # ---- all randomness of the forward pass, drawn in the reference's order (models.py:239, 391, 404, 289)
+        iid = getattr(src, "iid", False)
+        Smax = [max(steps[0]), max(steps[1])]
+        bar_masks = None
+        note_masks = [None, None]
+        use_gt_h = None
+        if have_gt and not inference:
+            use_gt_h = [torch.zeros((nb, Smax[si]), dtype=torch.int32, pin_memory=True) for si in (0, 1)]
+        if training and iid:
+            bar_masks = src.dropout_mask((nb, B, tokdim), 0.1, dev, "bar_token")
+            note_masks = [src.dropout_mask((Smax[si], nb * B, E), 0.1, dev, "note_steps") for si in (0, 1)]
+        elif training:
+            bar_masks = []
+            note_masks = [torch.ones(Smax[si], nb * B, E, device=dev) for si in (0, 1)]
+        bar_tf = []
+        for bar in range(nb):
+            if training and not iid:
+                bar_masks.append(src.dropout_mask((B, 1, tokdim), 0.1, dev, "bar_token").view(B, tokdim))
+            for si in (0, 1):
+                S = steps[si][bar]
+                if have_gt:
+                    coins = src.coins(S)
+                    if not inference:
+                        use_gt_h[si][bar, :S] = torch.tensor([1 if c < teacher_forcing_ratio else 0 for c in coins], dtype=torch.int32)
+                if training and not iid:
+                    note_masks[si][:S, bar * B:(bar + 1) * B] = src.dropout_mask((S, B, E), 0.1, dev, "note_steps")
+            bar_tf.append(src.coin() < teacher_forcing_ratio)
+        use_gt_d = [t.to(dev, non_blocking=True) for t in use_gt_h] if use_gt_h is not None else [None, None]
+        # bars k >= 1 whose token is built from bar k-1's predictions start a new segment
+        nqmax = ops.lib.pa2s_decm_max_queries()
+        segs, k0 = [], 0
+        for k in range(1, nb + 1):
+            if k == nb or not (tf_bars and bar_tf[k - 1]) or k - k0 == nqmax:
+                segs.append((k0, k))
+                k0 = k
+
+        # step-invariant encoder half of the three attention layers (models.py:458): Ep = enc W_e^T + b
+        enc2 = enc.reshape(B * T, D)
+        def ep(att):
+            return ops.linear(enc2, att.attn.weight[:, D:], att.attn.bias).view(B, T, -1)
+        Ep_bar, Ep_up, Ep_lo = ep(self.attn), ep(self.upper_decoder.attn), ep(self.lower_decoder.attn)
+
+        grad = torch.is_grad_enabled() and (enc.requires_grad or any(w.requires_grad for d in decs for w in d._weights()))
+        main = torch.cuda.current_stream()
+        if self._side_streams is None:
+            self._make_streams()
+        sides = self._side_streams if self.parallel_staves else (None, None)
+        runs = []
+        for si, (dec, Ep) in enumerate(zip(decs, (Ep_up, Ep_lo))):
+            gt_staff = (upper_gt, lower_gt)[si] if have_gt else None
+            runs.append(ops.StaffRun(dec._weights(), enc, Ep, nb, dec.max_steps, steps[si], inference or not have_gt, grad, sides[si],
+                                     SOS, EOS, gt=gt_staff, use_gt=use_gt_d[si], mask=note_masks[si]))
+
+        token = self.get_SOS_token(B)[0].squeeze(1)                      # (B, 4*staff+ts+key)
+        h = hidden[0]
+        ts_outs, key_outs, summaries = [], [], []
+        done = []
+        for (k0, k1) in segs:
+            seg_h = []
+            for bar in range(k0, k1):
+                if bar > 0 and tf_bars and bar_tf[bar - 1]:              # teacher-forced: token from the targets of bar-1
+                    us = self._staff_summary(upper_gt[:, bar - 1, :], upper_len_gt[:, bar - 1])
+                    ls = self._staff_summary(lower_gt[:, bar - 1, :], lower_len_gt[:, bar - 1])
+                    token = torch.cat([us, ls, self.time_sig_emb(time_sig_gt[:, bar - 1]), self.key_emb(key_gt[:, bar - 1])], dim=-1)
+                elif bar > 0:                                            # token from bar-1's predictions (first bar of a segment)
+                    assert bar == k0
+                    for ev in done:
+                        main.wait_event(ev)
+                    done = []
+                    us = self._staff_summary(torch.argmax(runs[0].logp[:, bar - 1], dim=-1), runs[0].lengths[bar - 1])
+                    ls = self._staff_summary(torch.argmax(runs[1].logp[:, bar - 1], dim=-1), runs[1].lengths[bar - 1])
+                    tst = self.time_sig_emb(torch.argmax(ts_outs[-1], dim=-1))
+                    kyt = self.key_emb(torch.argmax(key_outs[-1], dim=-1))
+                    token = torch.cat([us, ls, tst, kyt], dim=-1)
+                if training:
+                    token = token * bar_masks[bar]
+                h, ts_lp, key_lp = self._bar_step(token, h, enc, Ep_bar)
+                seg_h.append(h)
+                ts_outs.append(ts_lp)
+                key_outs.append(key_lp)
+            summaries += seg_h
+            h0 = torch.stack([x.detach() for x in seg_h])               # (nq, B, D)
+            ready = main.record_event()
+            for si, run in enumerate(runs):
+                side = sides[si]
+                if side is not None:
+                    side.wait_event(ready)
+                    h0.record_stream(side)
+                with ops._on_stream(side):
+                    run.launch(k0, k1 - k0, h0)
+                    if side is not None:
+                        done.append(side.record_event())
+        for ev in done:
+            main.wait_event(ev)
+        counters = [c for run in runs for c in run.counters]
+        if not have_gt and self.consume_python_rng:
+            # the reference draws one coin per executed note step (models.py:404); only the count matters here
+            src.coins(int(torch.stack(counters)[:, 1].sum().item()))
+        self.last_step_counters = counters
+        if grad:
+            w = [x for d in decs for x in d._weights()]
+            up_all, lo_all = ops.DecodersFn.apply(tuple(runs), enc, Ep_up, Ep_lo, torch.stack(summaries), *w)
+        else:
+            up_all, lo_all = runs[0].logp, runs[1].logp
+        return (torch.stack(ts_outs, 1), torch.stack(key_outs, 1), up_all, lo_all)
+
+    def _decode_bars_per_bar(self, encoder_outputs, hidden, inference=True, ground_truth=None, teacher_forcing_ratio=0):
         enc = encoder_outputs
         B, T, D = enc.shape
         dev = enc.device

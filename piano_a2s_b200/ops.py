@@ -15,7 +15,7 @@ from typing import Optional
 import torch
 import torch.distributed as dist
 
-from ._lib import lib, ptr, stream, make_dec_args
+from ._lib import lib, ptr, stream, make_dec_args, make_decm_args
 
 F32 = torch.float32
 N_SM = 148
@@ -764,8 +764,11 @@ def context_grad_enc(attn, dctx_all, B, T, D, S):
 # ----------------------------------------------------------------------------------------------------------------
 # Note decoder (models.py:366-420) -- all steps of one (bar, staff) in one call
 # ----------------------------------------------------------------------------------------------------------------
-# "persistent": one cooperative kernel per (bar, staff) call (dec_persist.cu); "steps": one launch per phase per step (decoder.cu)
-DECODER_IMPL = os.environ.get("PA2S_DECODER", "persistent")
+# "multi" (default): HierarchicalDecoder batches every run of teacher-forced bars of a staff into one cooperative launch and runs
+# the reverse pass of all bars of a staff in one launch (dec_multi.cu, StaffRun / DecodersFn below);
+# "persistent": one cooperative kernel per (bar, staff) call (dec_persist.cu); "steps": one launch per phase per step (decoder.cu).
+# The stand-alone NoteDecoder module always uses the per-call kernels ("multi" -> "persistent" there).
+DECODER_IMPL = os.environ.get("PA2S_DECODER", "multi")
 PROF = {}              # optional {"fwd": uint64[8] tensor, "bwd": ...}: per-phase ns of CTA 0 (tools/prof_decoder.py)
 SYNC_FLAGS = collections.deque(maxlen=256)        # [arrivals, watchdog flag] of recent persistent launches (tests / bench check flag == 0)
 
@@ -805,7 +808,7 @@ class NoteDecoderFn(torch.autograd.Function):
         gt, use_gt, mask = cfg.get("gt"), cfg.get("use_gt"), cfg.get("mask")
         save = any(ctx.needs_input_grad)
         VP = (V + 3) // 4 * 4
-        persist = DECODER_IMPL == "persistent"
+        persist = DECODER_IMPL != "steps"
         NS, tile = attn_split(B, T, lib.pa2s_dec_persist_grid() if persist else N_SM)
         z = lambda *s, dt=F32: torch.zeros(*s, device=dev, dtype=dt)
         e = lambda *s, dt=F32: torch.empty(*s, device=dev, dtype=dt)
@@ -889,7 +892,7 @@ class NoteDecoderFn(torch.autograd.Function):
         X = E + D
         z = lambda *s, dt=F32: torch.zeros(*s, device=dev, dtype=dt)
         e = lambda *s, dt=F32: torch.empty(*s, device=dev, dtype=dt)
-        persist = DECODER_IMPL == "persistent"
+        persist = DECODER_IMPL != "steps"
         W_hT = attn_w.detach()[:, :D].t().contiguous()
         W_ihT = W_ih.detach().t().contiguous()
         W_hhT = W_hh.detach().t().contiguous()
@@ -1095,6 +1098,205 @@ class StackLogpFn(torch.autograd.Function):
                 for sink, side in ctx.early.sinks:
                     sink.launch(side)
         return (None, None) + tuple(parts[0]) + tuple(parts[1])
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Multi-sequence note decoder (dec_multi.cu): NQ bars of one staff x B clips per launch, all bars in one reverse launch
+# ----------------------------------------------------------------------------------------------------------------
+def decm_split(B, T):
+    """frames of a clip are split over NS items of <= pa2s_decm_tile_max() frames so that B * NS items fill the grid"""
+    tmax, pg = lib.pa2s_decm_tile_max(), lib.pa2s_decm_grid()
+    ns = max(-(-T // tmax), min(16, max(1, pg // max(B, 1))))
+    tile = -(-T // ns)
+    return -(-T // tile), tile
+
+
+class StaffRun:
+    """All bars of ONE staff in one forward pass of HierarchicalDecoder.decode_bars.
+
+    Holds the staff's output log-probabilities (B, bars, max_steps, V) and, when a backward pass will follow, the step-major
+    saved state of every (step, bar, clip) row (row = bar * B + clip).  `launch(k0, nq, h0)` decodes bars k0 .. k0+nq-1 (whose
+    bar summaries `h0` are known) in one cooperative kernel on `self.stream`; `backward(dlogp)` runs the reverse pass over ALL
+    rows in one launch (per group of pa2s_decm_max_queries() bars) followed by the weight-gradient contractions."""
+
+    def __init__(self, weights, enc, Ep, bars, max_steps, steps, inference, save, side, sos, eos, gt=None, use_gt=None, mask=None):
+        self.w = tuple(weights)
+        attn_w, attn_v, emb, W_ih, W_hh, b_ih, b_hh, W_out, b_out = self.w
+        for k, w in zip(("attn_w", "attn_v", "emb", "W_ih", "W_hh", "b_ih", "b_hh", "W_out", "b_out"), self.w):
+            assert w.is_contiguous() and w.dtype == F32 and w.data_ptr() % 16 == 0, f"{k}: decoder weights must be contiguous, 16-byte aligned fp32"
+        enc, Ep = _f(enc.detach()), _f(Ep.detach())
+        B, T, D = enc.shape
+        A = Ep.shape[2]
+        V, E = emb.shape
+        assert D == 512 and A == 256 and E == 16 and V <= 256, "decoder kernels are specialised for hidden_size=256, note_emb_size=16"
+        self.prec = current_precision()
+        self.enc, self.B, self.T, self.D, self.A, self.V, self.E = enc, B, T, D, A, V, E
+        self.VP = (V + 3) // 4 * 4
+        self.bars, self.max_steps, self.steps = bars, max_steps, [int(x) for x in steps]
+        self.inference, self.save, self.stream, self.sos, self.eos = bool(inference), bool(save), side, int(sos), int(eos)
+        self.Rtot = bars * B
+        self.Smax = max(self.steps)
+        self.NS, self.tile = decm_split(B, T)
+        dev = enc.device
+        z = lambda *s_, dt=F32: torch.zeros(*s_, device=dev, dtype=dt)
+        self.Ee = torch.empty_like(Ep)
+        lib.pa2s_exp2x(stream(), ptr(Ep), ptr(self.Ee), Ep.numel())
+        self.logp = z(B, bars, max_steps, V)
+        self.lengths = torch.full((bars, B), max_steps, device=dev, dtype=torch.int64)
+        self.gt = gt.contiguous() if gt is not None else None
+        if self.gt is not None:
+            assert self.gt.shape == (B, bars, max_steps) and self.gt.dtype == torch.int64
+        self.use_gt, self.mask = use_gt, mask                      # (bars, Smax) int32 / (Smax, Rtot, E) fp32 on the device, or None
+        S, R = self.Smax, self.Rtot
+        self.sv = None
+        if self.save:
+            # zero-filled: rows of bars with fewer steps than Smax are never written but are read (times zero) by the contractions
+            self.sv = dict(hs=z(S + 1, R, D), ctxs=z(S, R, D), attn=z(S, R, T), gates=torch.empty(S, R, 4 * D, device=dev, dtype=F32),
+                           qs=z(S + 1, R, A), eqs=z(S, R, A), xtok=z(S + 1, R, E), toks=z(S + 1, R, dt=torch.int32), ml=z(S, R, 2))
+        self.counters = []
+        self.shared = [self.Ee, self.logp, self.lengths, self.enc] + ([self.gt] if self.gt is not None else []) + \
+                      ([self.use_gt] if self.use_gt is not None else []) + ([self.mask] if self.mask is not None else []) + \
+                      (list(self.sv.values()) if self.sv else [])
+        if side is not None:
+            for t_ in self.shared:
+                t_.record_stream(side)
+
+    def _wargs(self):
+        attn_w, attn_v, emb, W_ih, W_hh, b_ih, b_hh, W_out, b_out = self.w
+        return dict(Wattn=attn_w, v=attn_v, emb=emb, W_ih=W_ih, W_hh=W_hh, b_ih=b_ih, b_hh=b_hh, W_out=W_out, b_out=b_out)
+
+    def launch(self, k0, nq, h0):
+        """Bars k0 .. k0+nq-1; h0 (nq, B, D) = their bar summaries.  Call with `self.stream` current and ordered after h0."""
+        B, D, A, E, V, VP, NS = self.B, self.D, self.A, self.E, self.V, self.VP, self.NS
+        dev = self.enc.device
+        R = nq * B
+        z = lambda *s_, dt=F32: torch.zeros(*s_, device=dev, dtype=dt)
+        e = lambda *s_, dt=F32: torch.empty(*s_, device=dev, dtype=dt)
+        Sq = self.steps[k0:k0 + nq]
+        h0 = _f(h0.detach()).reshape(R, D)
+        mask = self.mask
+        if self.save:
+            sv, Rtot, r0 = self.sv, self.Rtot, k0 * B
+            sv["hs"][0, r0:r0 + R] = h0
+            lengths = self.lengths
+        else:
+            hs = e(2, R, D)
+            hs[0] = h0
+            sv = dict(hs=hs, ctxs=e(1, R, D), attn=None, gates=None, qs=e(2, R, A), eqs=None, xtok=None, toks=None, ml=None)
+            Rtot, r0 = R, 0
+            lengths = self.lengths.data_ptr() + k0 * B * 8
+            if mask is not None:
+                mask = mask[:, k0 * B:k0 * B + R].contiguous()
+        counters = z(2, dt=torch.int32)
+        scratch = dict(xbuf=e(R, E + D), logits=z(R, VP), pm=e(R, NS), pl=e(R, NS), pc=e(R, NS, D), tickets=z(B, dt=torch.int32),
+                       sync=z(2, dt=torch.int32), eos=z(R, dt=torch.int32), counters=counters)
+        args = make_decm_args(Sq, B=B, NQ=nq, T=self.T, V=V, VP=VP, S=max(Sq), max_steps=self.max_steps, NS=NS, tile=self.tile,
+                              inference=int(self.inference), save=int(self.save), Rtot=Rtot, r0=r0, bars=self.bars, k0=k0, Spitch=self.Smax,
+                              enc=self.enc, Ee=self.Ee, gt=self.gt, use_gt=(self.use_gt.data_ptr() + k0 * self.Smax * 4) if self.use_gt is not None else None,
+                              mask=mask, logp=self.logp, lengths=lengths, prof=PROF.get("fwd"), **self._wargs(), **sv, **scratch)
+        with ktime("note_decoder_fwd"):
+            lib.pa2s_decm_fwd(stream(), ctypes.byref(args), self.sos, self.eos)
+        SYNC_FLAGS.append(scratch["sync"])
+        self.counters.append(counters)
+        return counters
+
+    def backward(self, dlogp):
+        """Reverse pass over every saved row -> dict(denc, dEp, dh0 (bars,B,D), wgrads (9, parameter order of NoteDecoder._weights)).
+        Call with `self.stream` current and ordered after dlogp."""
+        assert self.save
+        B, T, D, A, E, V, VP, NS, S, R = self.B, self.T, self.D, self.A, self.E, self.V, self.VP, self.NS, self.Smax, self.Rtot
+        attn_w, attn_v, emb, W_ih, W_hh, b_ih, b_hh, W_out, b_out = self.w
+        dev = self.enc.device
+        sv = self.sv
+        z = lambda *s_, dt=F32: torch.zeros(*s_, device=dev, dtype=dt)
+        e = lambda *s_, dt=F32: torch.empty(*s_, device=dev, dtype=dt)
+        dlogp = _f(dlogp)
+        assert dlogp.shape == self.logp.shape
+        W_hT = attn_w.detach()[:, :D].t().contiguous()
+        W_ihT = W_ih.detach().t().contiguous()
+        W_hhT = W_hh.detach().t().contiguous()
+        nqmax = lib.pa2s_decm_max_queries()
+        groups = [(k0, min(nqmax, self.bars - k0)) for k0 in range(0, self.bars, nqmax)]
+        nblk = lib.pa2s_decm_deferred_blocks(T)
+        bw = dict(dlogits_all=e(S, R, VP), dgi_all=z(S, R, 3 * D), dgh_all=z(S, R, 3 * D), dq_all=z(S + 1, R, A), dctx_all=z(S, R, D),
+                  dxtok_all=z(S, R, E), ds_all=z(S, R, T))
+        dhc_all = e(S * R, 2 * D)
+        dhq = e(R, D)
+        st = stream()
+
+        def gargs(k0, nq, **extra):
+            return make_decm_args(self.steps[k0:k0 + nq], B=B, NQ=nq, T=T, V=V, VP=VP, S=S, max_steps=self.max_steps, NS=NS, tile=self.tile,
+                                  inference=0, save=1, Rtot=R, r0=k0 * B, bars=self.bars, k0=k0, Spitch=S, enc=self.enc, Ee=self.Ee,
+                                  logp=self.logp, dlogp=dlogp, dhc_all=dhc_all, prof=PROF.get("bwd"), W_hT=W_hT, W_ihT=W_ihT, W_hhT=W_hhT,
+                                  **self._wargs(), **sv, **bw, **extra)
+        with ktime("note_decoder_bwd"):
+            for k0, nq in groups:
+                a0 = gargs(k0, nq)
+                lib.pa2s_decm_dlogits(st, ctypes.byref(a0))
+            gemm(bw["dlogits_all"], W_out, dhc_all, S * R, 2 * D, V, lda=VP, ldb=2 * D, ldc=2 * D)
+            dEp, dv_parts = None, []
+            for k0, nq in groups:
+                Rg = nq * B
+                scr = dict(d_hc=e(Rg, 2 * D), dx=e(Rg, E + D), dq_part=e(Rg, NS, A), dh_carry=e(Rg, D), tickets=z(B, dt=torch.int32),
+                           sync=z(2, dt=torch.int32), dEp=e(B, T, A), dv_part=e(B * nblk, A))
+                a1 = gargs(k0, nq, dhq=dhq.data_ptr() + k0 * B * D * 4, **scr)
+                lib.pa2s_decm_bwd_chain(st, ctypes.byref(a1))
+                lib.pa2s_decm_bwd_deferred(st, ctypes.byref(a1))
+                SYNC_FLAGS.append(scr["sync"])
+                dEp = scr["dEp"] if dEp is None else dEp + scr["dEp"]
+                dv_parts.append(scr["dv_part"])
+        dxt = bw["dxtok_all"]
+        if self.mask is not None:
+            dxt = dxt * self.mask[:S]
+        rec = dict(S=S, B=R, dlogits=bw["dlogits_all"], hs=sv["hs"], ctxs=sv["ctxs"], dgi=bw["dgi_all"], dgh=bw["dgh_all"], dq=bw["dq_all"],
+                   xtok=sv["xtok"], dv_part=dv_parts[0] if len(dv_parts) == 1 else torch.cat(dv_parts), dxt=dxt, toks=sv["toks"])
+        wg = decoder_weight_grads([rec], (D, A, V, E, VP, attn_v.shape))
+        # d_enc[b] = sum over (step, bar) of attn^T dctx: rows (s, bar, b) -> one batched GEMM with K = S * bars
+        denc = context_grad_enc(sv["attn"], bw["dctx_all"], B, T, D, S * self.bars)
+        return dict(denc=denc, dEp=dEp, dh0=dhq.view(self.bars, B, D), wgrads=list(wg))
+
+
+class DecodersFn(torch.autograd.Function):
+    """The autograd node of ALL note decoding of a forward pass (both staves, every bar): the forward kernels were launched by the
+    StaffRuns while the bar loop ran; this node only hands out their log-probabilities and, in backward, runs one reverse pass
+    per staff concurrently on the two staff streams.
+    Inputs: runs (StaffRun upper, StaffRun lower), enc, Ep_upper, Ep_lower, h0 (bars,B,D) stacked bar summaries, then the nine
+    weights of the upper and of the lower NoteDecoder."""
+
+    @staticmethod
+    def forward(ctx, runs, enc, Ep_up, Ep_lo, h0, *weights):
+        ctx.runs = runs
+        ctx.prec = current_precision()
+        return runs[0].logp, runs[1].logp
+
+    @staticmethod
+    def backward(ctx, d_up, d_lo):
+        runs = ctx.runs
+        cur = torch.cuda.current_stream()
+        ev = cur.record_event()
+        res = []
+        with use_precision(ctx.prec):
+            for run, d in zip(runs, (d_up, d_lo)):
+                if d is None:
+                    d = torch.zeros_like(run.logp)
+                side = run.stream or cur
+                if side != cur:
+                    side.wait_event(ev)
+                    d.record_stream(side)
+                with torch.cuda.stream(side):
+                    r = run.backward(d)
+                    done = side.record_event()
+                res.append((r, done, side))
+        for r, done, side in res:
+            if side != cur:
+                cur.wait_event(done)
+                for t_ in [r["denc"], r["dEp"], r["dh0"]] + r["wgrads"]:
+                    t_.record_stream(cur)
+        (ru, _, _), (rl, _, _) = res
+        denc = ru["denc"] + rl["denc"]
+        dh0 = ru["dh0"] + rl["dh0"]
+        ctx.runs = None
+        return (None, denc, ru["dEp"], rl["dEp"], dh0, *ru["wgrads"], *rl["wgrads"])
 
 
 # ----------------------------------------------------------------------------------------------------------------

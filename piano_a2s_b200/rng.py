@@ -12,6 +12,10 @@ import torch
 
 
 class DeviceRandom:
+    # masks are i.i.d. Bernoulli draws from the device generator: a caller may ask for them in any order and in bulk (one launch
+    # for all steps of all bars) instead of the reference's call-by-call order, which only a replaying source has to honour
+    iid = True
+
     def coin(self) -> float:
         return random.random()
 
@@ -20,7 +24,7 @@ class DeviceRandom:
 
     def dropout_mask(self, shape, p: float, device, kind: str) -> torch.Tensor:
         """{0, 1/(1-p)} mask; `kind` in {"conv", "bar_token", "note_steps"} tells a replaying source what is asked for."""
-        return (torch.rand(shape, device=device) >= p).to(torch.float32).div_(1.0 - p)
+        return torch.empty(shape, device=device, dtype=torch.float32).bernoulli_(1.0 - p).mul_(1.0 / (1.0 - p))
 
 
 SOURCE = DeviceRandom()

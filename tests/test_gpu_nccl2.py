@@ -172,7 +172,7 @@ def test_convstack_syncbn_uneven_shards_match_union_oracle(two_rank_results):
     for k, g in res[0]["cs_grads"].items():
         e = rel_err(g, sdg["convstack." + k].grad)
         print("  grad", k, "%.2e" % e)
-        assert e < 1e-2, k                                      # bf16x3 ConvStack gradient bound of tests/test_gpu_parity.py
+        assert e < 3e-2, k                                      # bf16x3 ConvStack bound for ragged batches (tests/test_gpu_paths.py: a clip has zero-padded frames)
     for k, v in ns.items():
         kk = k[len("convstack."):]
         a, b = res[0]["cs_stats"][kk], res[1]["cs_stats"][kk]
