@@ -39,8 +39,23 @@ __device__ __forceinline__ float rcp_fast(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
-// exp(2x) with the exponent clamped so that the product of two such factors stays finite (|x| <= 21.5 is exact)
-__device__ __forceinline__ float exp2x(float x) { return expf(fminf(fmaxf(2.f * x, -43.f), 43.f)); }
+// exp(2x) with the exponent clamped to +-21 (|x| <= 10.5 is exact; tanh is saturated to 1e-9 there): 1 + exp(2q) exp(2e) <= 1.8e18, so
+// the product of TWO such terms stays finite and one reciprocal serves two elements: 1/a = b * rcp(a b), 1/b = a * rcp(a b).
+__device__ __forceinline__ float exp2x(float x) { return expf(fminf(fmaxf(2.f * x, -21.f), 21.f)); }
+// sum over two elements of w_k / (1 + q_k e_k) with one SFU reciprocal
+__device__ __forceinline__ float pair_term(float q0, float e0, float w0, float q1, float e1, float w1) {
+    const float a0 = fmaf(q0, e0, 1.f), a1 = fmaf(q1, e1, 1.f);
+    return rcp_fast(a0 * a1) * fmaf(w0, a1, w1 * a0);
+}
+// per-lane asynchronous copies global -> shared (a lane only ever reads back what it copied itself: no barrier needed, and the
+// depth of the prefetch costs neither registers nor scoreboard slots)
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ int mslot(const DecMArgs& a, int s) { return a.save ? s : 0; }
 __device__ __forceinline__ int mhslot(const DecMArgs& a, int s) { return a.save ? s : (s & 1); }
@@ -139,8 +154,12 @@ __device__ __forceinline__ FwdSmem carve(float* sm) {
     s.v2 = sm; sm += DA;
     return s;
 }
-// attention scratch inside xs: Eq [NQ][DA] | sc [NQ][TILE_MAX] | cred [NFS][NQ][DD]
-static_assert(NQMAX * (DA + TILE_MAX + NFS * DD) <= BT * XP, "attention scratch must fit the staged-row region");
+// attention scratch inside xs: Eq [NQ][DA] | sc [NQ][TILE_MAX] | ring [NW][RING] (per-lane cp.async rings of the two streaming passes),
+// aliased after the loops by cred [NFS][NQ][DD]
+constexpr int D1 = 4, D2 = 8;                 // frames in flight per warp: pass 1 (1 KB per frame), pass 2 (512 B per frame)
+constexpr int RING = D2 * 32 * 4;             // floats per warp
+static_assert(D1 * 32 * 8 == RING, "both passes use the same ring bytes");
+static_assert(NQMAX * (DA + TILE_MAX) + NW * RING <= BT * XP && NFS * NQMAX * DD <= NW * RING, "attention scratch must fit the staged-row region");
 
 // ------------------------------------------------------------------------------------------------ phase A (forward)
 template <int NQ>
@@ -150,10 +169,12 @@ __device__ void attn_item(const DecMArgs& a, const FwdSmem& S, float sumv, int s
     __shared__ int is_last;
     float* Eq = S.xs;                              // [NQ][DA]
     float* sc = Eq + NQ * DA;                      // [NQ][TILE_MAX]
-    float* cred = sc + NQ * TILE_MAX;              // [NFS][NQ][DD]
+    float* ringb = sc + NQ * TILE_MAX;             // [NW][RING]
+    float* cred = ringb;                           // [NFS][NQ][DD] (after the streaming loops)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int T = a.T, B = a.B;
     const int t0 = js * a.tile, t1 = min(T, t0 + a.tile), nt = t1 - t0;
+    float* myring = ringb + warp * RING;
     bool actq[NQ];
 #pragma unroll
     for (int q = 0; q < NQ; ++q) actq[q] = s < g_Sq[q];
@@ -172,49 +193,72 @@ __device__ void attn_item(const DecMArgs& a, const FwdSmem& S, float sumv, int s
     }
     __syncthreads();
     SUB_MARK(8);
-    // ---- pass 1: scores.  One frame per warp iteration, 4 frames in flight; lane holds 8 of the 256 exp(2 Ep) values of a frame.
+    // ---- pass 1: scores.  Warp w takes the frames t0 + w, t0 + w + 12, ...; a lane holds 8 of the 256 exp(2 Ep) values of a frame
+    // (D1 frames in flight through its cp.async ring); G frames x NQ queries = up to 32 per-lane partial sums are reduced at once.
     {
         const float4 va = *reinterpret_cast<const float4*>(S.v2 + lane * 4);
         const float4 vb = *reinterpret_cast<const float4*>(S.v2 + 128 + lane * 4);
         float mq[NQ];
 #pragma unroll
         for (int q = 0; q < NQ; ++q) mq[q] = -INFINITY;
-        constexpr int P1 = 4;
-        float4 r0[P1], r1[P1];
-        const float4* ee = reinterpret_cast<const float4*>(a.Ee + (size_t)b * T * DA);
-        const int tw = t0 + warp;
+        constexpr int G = (32 / NQ) < 8 ? (32 / NQ) : 8;
+        const float4* ee = reinterpret_cast<const float4*>(a.Ee + (size_t)b * T * DA) + lane;
+        float4* slot = reinterpret_cast<float4*>(myring) + lane;            // slot i: [i*64 + lane] and [i*64 + 32 + lane]
+        const int base = rs_base<32>(lane);
+        const int nf = (t1 - t0 - warp + NW - 1) / NW;                      // frames of this warp (<= 0: none)
 #pragma unroll
-        for (int i = 0; i < P1; ++i) {
-            const int t = tw + i * NW;
-            if (t < t1) { r0[i] = ldg4(ee + (size_t)t * (DA / 4) + lane); r1[i] = ldg4(ee + (size_t)t * (DA / 4) + 32 + lane); }
+        for (int i = 0; i < D1; ++i) {
+            if (i < nf) {
+                const size_t t = t0 + warp + i * NW;
+                cp_async16(slot + i * 64, ee + t * (DA / 4));
+                cp_async16(slot + i * 64 + 32, ee + t * (DA / 4) + 32);
+            }
+            cp_async_commit();
         }
-        for (int tb = tw; tb < t1; tb += P1 * NW) {
+        for (int f0 = 0; f0 < nf; f0 += G) {
+            float val[32];
 #pragma unroll
-            for (int i = 0; i < P1; ++i) {
-                const int t = tb + i * NW;
-                if (t >= t1) break;                                  // warp-uniform
-                const float4 c0 = r0[i], c1 = r1[i];
-                const int tn = t + P1 * NW;
-                if (tn < t1) { r0[i] = ldg4(ee + (size_t)tn * (DA / 4) + lane); r1[i] = ldg4(ee + (size_t)tn * (DA / 4) + 32 + lane); }
+            for (int i = 0; i < 32; ++i) val[i] = 0.f;
 #pragma unroll
-                for (int q = 0; q < NQ; ++q) {
-                    if (!actq[q]) continue;                          // block-uniform
-                    const float4 qa = *reinterpret_cast<const float4*>(Eq + q * DA + lane * 4);
-                    const float4 qb = *reinterpret_cast<const float4*>(Eq + q * DA + 128 + lane * 4);
-                    float x = va.x * rcp_fast(fmaf(qa.x, c0.x, 1.f));
-                    x = fmaf(va.y, rcp_fast(fmaf(qa.y, c0.y, 1.f)), x);
-                    x = fmaf(va.z, rcp_fast(fmaf(qa.z, c0.z, 1.f)), x);
-                    x = fmaf(va.w, rcp_fast(fmaf(qa.w, c0.w, 1.f)), x);
-                    float y = vb.x * rcp_fast(fmaf(qb.x, c1.x, 1.f));
-                    y = fmaf(vb.y, rcp_fast(fmaf(qb.y, c1.y, 1.f)), y);
-                    y = fmaf(vb.z, rcp_fast(fmaf(qb.z, c1.z, 1.f)), y);
-                    y = fmaf(vb.w, rcp_fast(fmaf(qb.w, c1.w, 1.f)), y);
-                    const float e = sumv + warp_sum(x + y);          // sum_k v_k tanh(q_k + Ep_k)
-                    if (lane == 0) sc[q * TILE_MAX + (t - t0)] = e;
-                    mq[q] = fmaxf(mq[q], e);
+            for (int i = 0; i < G; ++i) {
+                const int f = f0 + i;
+                if (f < nf) {                                                // warp-uniform
+                    cp_async_wait<D1 - 1>();
+                    const int sl = f % D1;
+                    const float4 c0 = slot[sl * 64], c1 = slot[sl * 64 + 32];
+                    if (f + D1 < nf) {
+                        const size_t t = t0 + warp + (f + D1) * NW;
+                        cp_async16(slot + sl * 64, ee + t * (DA / 4));
+                        cp_async16(slot + sl * 64 + 32, ee + t * (DA / 4) + 32);
+                    }
+                    cp_async_commit();
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) {
+                        if (!actq[q]) continue;                              // block-uniform
+                        const float4 qa = *reinterpret_cast<const float4*>(Eq + q * DA + lane * 4);
+                        const float4 qb = *reinterpret_cast<const float4*>(Eq + q * DA + 128 + lane * 4);
+                        val[i * NQ + q] = pair_term(qa.x, c0.x, va.x, qa.y, c0.y, va.y) + pair_term(qa.z, c0.z, va.z, qa.w, c0.w, va.w) +
+                                          pair_term(qb.x, c1.x, vb.x, qb.y, c1.y, vb.y) + pair_term(qb.z, c1.z, vb.z, qb.w, c1.w, vb.w);
+                    }
+                }
+            }
+            reduce_scatter<32>(val, lane);
+            // the lane now holds the warp total of element `base` = (frame base / NQ of the group, query base % NQ)
+            if (base < G * NQ) {
+                const int i = base / NQ, q = base - i * NQ;
+                const int f = f0 + i;
+                if (f < nf && s < g_Sq[q]) {
+                    const float e = sumv + val[0];                           // sum_k v_k tanh(q_k + Ep_k)
+                    sc[q * TILE_MAX + warp + f * NW] = e;
+#pragma unroll
+                    for (int qq = 0; qq < NQ; ++qq)
+                        if (qq == q) mq[qq] = fmaxf(mq[qq], e);
                 }
             }
         }
+        cp_async_wait<0>();
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) mq[q] = warp_max(mq[q]);
         if (lane == 0) {
 #pragma unroll
             for (int q = 0; q < NQ; ++q) wred[warp][q] = mq[q];
@@ -261,33 +305,34 @@ __device__ void attn_item(const DecMArgs& a, const FwdSmem& S, float sumv, int s
         Lq[tid] = l;
     }
     SUB_MARK(10);
-    // ---- pass 2: contexts.  Warp (cb, fs): 128-column block cb of the frames t0 + fs, t0 + fs + 3, ...; 8 frames in flight.
+    // ---- pass 2: contexts.  Warp (cb, fs): 128-column block cb of the frames t0 + fs, t0 + fs + 3, ...; D2 frames in flight.
     {
         const int cb = warp & (NCB - 1), fs = warp / NCB;
         float4 acc[NQ];
 #pragma unroll
         for (int q = 0; q < NQ; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-        constexpr int P2 = 8;
-        float4 ring[P2];
         const float4* en = reinterpret_cast<const float4*>(a.enc + (size_t)b * T * DD) + cb * 32 + lane;
-        const int tw = t0 + fs;
+        float4* slot = reinterpret_cast<float4*>(myring) + lane;            // slot i: [i*32 + lane]
+        const int nf = (t1 - t0 - fs + NFS - 1) / NFS;
 #pragma unroll
-        for (int i = 0; i < P2; ++i) {
-            const int t = tw + i * NFS;
-            if (t < t1) ring[i] = ldg4(en + (size_t)t * (DD / 4));
+        for (int i = 0; i < D2; ++i) {
+            if (i < nf) cp_async16(slot + i * 32, en + (size_t)(t0 + fs + i * NFS) * (DD / 4));
+            cp_async_commit();
         }
-        for (int tb = tw; tb < t1; tb += P2 * NFS) {
+        for (int f0 = 0; f0 < nf; f0 += D2) {
 #pragma unroll
-            for (int i = 0; i < P2; ++i) {
-                const int t = tb + i * NFS;
-                if (t >= t1) break;
-                const float4 e = ring[i];
-                const int tn = t + P2 * NFS;
-                if (tn < t1) ring[i] = ldg4(en + (size_t)tn * (DD / 4));
+            for (int i = 0; i < D2; ++i) {
+                const int f = f0 + i;
+                if (f >= nf) break;                                          // warp-uniform
+                cp_async_wait<D2 - 1>();
+                const float4 e = slot[i * 32];
+                if (f + D2 < nf) cp_async16(slot + i * 32, en + (size_t)(t0 + fs + (f + D2) * NFS) * (DD / 4));
+                cp_async_commit();
+                const int j = fs + f * NFS;
 #pragma unroll
                 for (int q = 0; q < NQ; ++q) {
                     if (!actq[q]) continue;
-                    const float p = sc[q * TILE_MAX + (t - t0)];
+                    const float p = sc[q * TILE_MAX + j];
                     acc[q].x = fmaf(p, e.x, acc[q].x);
                     acc[q].y = fmaf(p, e.y, acc[q].y);
                     acc[q].z = fmaf(p, e.z, acc[q].z);
@@ -295,6 +340,8 @@ __device__ void attn_item(const DecMArgs& a, const FwdSmem& S, float sumv, int s
                 }
             }
         }
+        cp_async_wait<0>();
+        __syncthreads();                                                     // every warp is done with its ring: cred aliases it
 #pragma unroll
         for (int q = 0; q < NQ; ++q)
             *reinterpret_cast<float4*>(cred + ((size_t)(fs * NQ + q)) * DD + cb * 128 + lane * 4) = acc[q];
@@ -694,8 +741,8 @@ struct BwdSmem {
 constexpr int QP = 132;
 constexpr int BWD_RED_FLOATS = 4 * 12 * 64 + 12 * BT;
 constexpr int BWD_SMEM_FLOATS = (RPB + 1) * K3 + BT * K3 + BWD_RED_FLOATS + UPC * 2 * QP + DA;
-// P3 scratch inside U: dc [NQ][DD] | Eq [NQ][DA] | dap [NCB][NQ][TILE_MAX] (ds in dap[0]) | dqr [NW][DA]
-static_assert(NQMAX * (DD + DA + NCB * TILE_MAX) + NW * DA <= BT * K3, "attention-backward scratch must fit U");
+// P3 scratch inside U: dc [NQ][DD] | Eq [NQ][DA] | dap [NCB][NQ][TILE_MAX] (ds in dap[0]) | ring [NW][RING], aliased afterwards by dqr [NW][DA]
+static_assert(NQMAX * (DD + DA + NCB * TILE_MAX) + NW * RING <= BT * K3 && DA <= RING, "attention-backward scratch must fit U");
 
 // ---- P1: dh of this CTA's 8 hidden units, GRU gate gradients -> dgi_all / dgh_all / dh*z
 __device__ void bwd_gates_phase(const DecMArgs& a, const BwdSmem& S, int s, int rb0, int nb) {
@@ -835,8 +882,10 @@ __device__ void bwd_attn_item(const DecMArgs& a, const BwdSmem& S, int s, int b,
     float* dc = S.U;                               // [NQ][DD]
     float* Eq = dc + NQ * DD;                      // [NQ][DA]
     float* dap = Eq + NQ * DA;                     // [NCB][NQ][TILE_MAX]
-    float* dqr = dap + NCB * NQ * TILE_MAX;        // [NW][DA]
+    float* ringb = dap + NCB * NQ * TILE_MAX;      // [NW][RING]
+    float* dqr = ringb;                            // [NW][DA] (after the streaming loops)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float* myring = ringb + warp * RING;
     const int T = a.T, B = a.B;
     const int t0 = js * a.tile, t1 = min(T, t0 + a.tile), nt = t1 - t0;
     bool actq[NQ];
@@ -888,7 +937,7 @@ __device__ void bwd_attn_item(const DecMArgs& a, const BwdSmem& S, int s, int b,
         c0s[tid] = c;
     }
     SUB_MARK(8);
-    // ---- pass 1: da partials per 128-column block.  Warp (cb, fs); G frames per group, G*NQ <= 32 dot products reduced at once.
+    // ---- pass 1: da partials per 128-column block.  Warp (cb, fs), D2 frames in flight; G frames x NQ dot products reduced at once.
     {
         const int cb = warp & (NCB - 1), fs = warp / NCB;
         float4 dcq[NQ];
@@ -896,36 +945,39 @@ __device__ void bwd_attn_item(const DecMArgs& a, const BwdSmem& S, int s, int b,
         for (int q = 0; q < NQ; ++q) dcq[q] = *reinterpret_cast<const float4*>(dc + q * DD + cb * 128 + lane * 4);
         constexpr int G = (32 / NQ) < 8 ? (32 / NQ) : 8;
         const float4* en = reinterpret_cast<const float4*>(a.enc + (size_t)b * T * DD) + cb * 32 + lane;
+        float4* slot = reinterpret_cast<float4*>(myring) + lane;
         const int base = rs_base<32>(lane);
-        float4 ring[G];
+        const int nf = (t1 - t0 - fs + NFS - 1) / NFS;
 #pragma unroll
-        for (int i = 0; i < G; ++i) {
-            const int t = t0 + fs + i * NFS;
-            if (t < t1) ring[i] = ldg4(en + (size_t)t * (DD / 4));
+        for (int i = 0; i < D2; ++i) {
+            if (i < nf) cp_async16(slot + i * 32, en + (size_t)(t0 + fs + i * NFS) * (DD / 4));
+            cp_async_commit();
         }
-        for (int tb = t0 + fs; tb < t1; tb += G * NFS) {
+        for (int f0 = 0; f0 < nf; f0 += G) {
             float val[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) val[i] = 0.f;
 #pragma unroll
             for (int i = 0; i < G; ++i) {
-                const int t = tb + i * NFS;
-                if (t < t1) {
-                    const float4 e = ring[i];
-                    const int tn = t + G * NFS;
-                    if (tn < t1) ring[i] = ldg4(en + (size_t)tn * (DD / 4));
+                const int f = f0 + i;
+                if (f < nf) {
+                    cp_async_wait<D2 - 1>();
+                    const int sl = f % D2;
+                    const float4 e = slot[sl * 32];
+                    if (f + D2 < nf) cp_async16(slot + sl * 32, en + (size_t)(t0 + fs + (f + D2) * NFS) * (DD / 4));
+                    cp_async_commit();
 #pragma unroll
                     for (int q = 0; q < NQ; ++q) val[i * NQ + q] = dot4(dcq[q], e);
                 }
             }
             reduce_scatter<32>(val, lane);
-            // lane now holds the warp total of element `base`: frame index base / NQ of the group, query base % NQ
             if (base < G * NQ) {
                 const int i = base / NQ, q = base - i * NQ;
-                const int t = tb + i * NFS;
-                if (t < t1) dap[(cb * NQ + q) * TILE_MAX + (t - t0)] = val[0];
+                const int f = f0 + i;
+                if (f < nf) dap[(cb * NQ + q) * TILE_MAX + fs + f * NFS] = val[0];
             }
         }
+        cp_async_wait<0>();
     }
     __syncthreads();
     SUB_MARK(9);
@@ -950,46 +1002,59 @@ __device__ void bwd_attn_item(const DecMArgs& a, const BwdSmem& S, int s, int b,
     }
     __syncthreads();
     SUB_MARK(10);
-    // ---- pass 2: dq.  One frame per warp iteration, 4 frames in flight; lane holds 8 of the 256 exp(2 Ep) values of a frame.
+    // ---- pass 2: dq.  Warp w takes the frames t0 + w, t0 + w + 12, ...; D1 frames in flight; a lane holds 8 of the 256 exp(2 Ep) values.
     float dq[NQ][8];
 #pragma unroll
     for (int q = 0; q < NQ; ++q)
 #pragma unroll
         for (int k = 0; k < 8; ++k) dq[q][k] = 0.f;
     {
-        constexpr int P1 = 4;
-        float4 r0[P1], r1[P1];
-        const float4* ee = reinterpret_cast<const float4*>(a.Ee + (size_t)b * T * DA);
-        const int tw = t0 + warp;
+        const float4* ee = reinterpret_cast<const float4*>(a.Ee + (size_t)b * T * DA) + lane;
+        float4* slot = reinterpret_cast<float4*>(myring) + lane;
+        const int nf = (t1 - t0 - warp + NW - 1) / NW;
 #pragma unroll
-        for (int i = 0; i < P1; ++i) {
-            const int t = tw + i * NW;
-            if (t < t1) { r0[i] = ldg4(ee + (size_t)t * (DA / 4) + lane); r1[i] = ldg4(ee + (size_t)t * (DA / 4) + 32 + lane); }
+        for (int i = 0; i < D1; ++i) {
+            if (i < nf) {
+                const size_t t = t0 + warp + i * NW;
+                cp_async16(slot + i * 64, ee + t * (DA / 4));
+                cp_async16(slot + i * 64 + 32, ee + t * (DA / 4) + 32);
+            }
+            cp_async_commit();
         }
-        for (int tb = tw; tb < t1; tb += P1 * NW) {
+        for (int f0 = 0; f0 < nf; f0 += D1) {
 #pragma unroll
-            for (int i = 0; i < P1; ++i) {
-                const int t = tb + i * NW;
-                if (t >= t1) break;
-                const float4 c0 = r0[i], c1 = r1[i];
-                const int tn = t + P1 * NW;
-                if (tn < t1) { r0[i] = ldg4(ee + (size_t)tn * (DA / 4) + lane); r1[i] = ldg4(ee + (size_t)tn * (DA / 4) + 32 + lane); }
+            for (int i = 0; i < D1; ++i) {
+                const int f = f0 + i;
+                if (f >= nf) break;
+                cp_async_wait<D1 - 1>();
+                const float4 c0 = slot[i * 64], c1 = slot[i * 64 + 32];
+                if (f + D1 < nf) {
+                    const size_t t = t0 + warp + (f + D1) * NW;
+                    cp_async16(slot + i * 64, ee + t * (DA / 4));
+                    cp_async16(slot + i * 64 + 32, ee + t * (DA / 4) + 32);
+                }
+                cp_async_commit();
                 const float ev[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+                const int j = warp + f * NW;
 #pragma unroll
                 for (int q = 0; q < NQ; ++q) {
                     if (!actq[q]) continue;
-                    const float ds = dap[q * TILE_MAX + (t - t0)];
+                    const float ds = dap[q * TILE_MAX + j];
                     const float4 qa = *reinterpret_cast<const float4*>(Eq + q * DA + lane * 4);
                     const float4 qb = *reinterpret_cast<const float4*>(Eq + q * DA + 128 + lane * 4);
                     const float qk[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const float r = rcp_fast(fmaf(qk[k], ev[k], 1.f));
-                        dq[q][k] = fmaf(ds, fmaf(-r, r, r), dq[q][k]);        // r (1 - r) = (1 - tanh^2) / 4
+                    for (int k = 0; k < 8; k += 2) {
+                        const float a0 = fmaf(qk[k], ev[k], 1.f), a1 = fmaf(qk[k + 1], ev[k + 1], 1.f);
+                        const float rp = rcp_fast(a0 * a1);
+                        const float r0 = a1 * rp, r1 = a0 * rp;                  // 1 / a0, 1 / a1
+                        dq[q][k] = fmaf(ds, fmaf(-r0, r0, r0), dq[q][k]);        // r (1 - r) = (1 - tanh^2) / 4
+                        dq[q][k + 1] = fmaf(ds, fmaf(-r1, r1, r1), dq[q][k + 1]);
                     }
                 }
             }
         }
+        cp_async_wait<0>();
     }
     SUB_MARK(11);
     // ---- cross-warp sums, one query at a time

@@ -248,11 +248,26 @@ __global__ void __launch_bounds__(256) gemm_skinny_nn_kernel(GemmArgs g) {
 #pragma unroll
     for (int m = 0; m < MR; ++m) acc[m] = 0.f;
     if (n < g.N) {
-        for (int k = kb; k < ke; ++k) {
-            const float b = __ldg(g.B + (long long)k * g.ldb + n);
+        // 8 rows of B in flight per thread (the loop is a chain of dependent L2 round trips otherwise: 75 us for 16 x 1024 x 1024)
+        for (int k0 = kb; k0 < ke; k0 += 8) {
+            float b[8];
 #pragma unroll
-            for (int m = 0; m < MR; ++m)
-                if (m < g.M) acc[m] = fmaf(__ldg(g.A + (long long)m * g.lda + k), b, acc[m]);
+            for (int j = 0; j < 8; ++j) b[j] = (k0 + j < ke) ? __ldg(g.B + (long long)(k0 + j) * g.ldb + n) : 0.f;
+#pragma unroll
+            for (int m = 0; m < MR; ++m) {
+                if (m < g.M) {
+                    const float* arow = g.A + (long long)m * g.lda + k0;
+                    if (k0 + 8 <= ke && (g.lda & 3) == 0 && (k0 & 3) == 0 && ((size_t)g.A & 15) == 0) {
+                        const float4 a0 = __ldg(reinterpret_cast<const float4*>(arow)), a1 = __ldg(reinterpret_cast<const float4*>(arow) + 1);
+                        acc[m] = fmaf(a0.x, b[0], fmaf(a0.y, b[1], fmaf(a0.z, b[2], fmaf(a0.w, b[3], acc[m]))));
+                        acc[m] = fmaf(a1.x, b[4], fmaf(a1.y, b[5], fmaf(a1.z, b[6], fmaf(a1.w, b[7], acc[m]))));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (k0 + j < ke) acc[m] = fmaf(__ldg(arow + j), b[j], acc[m]);
+                    }
+                }
+            }
         }
     }
 #pragma unroll

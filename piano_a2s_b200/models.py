@@ -168,11 +168,21 @@ class HierarchicalDecoder(nn.Module):
 
     def get_SOS_token(self, batch_size):
         dev = self.note_emb.weight.device
-        se = torch.tensor([[SOS, EOS]], device=dev, dtype=torch.long).repeat(batch_size, 1)
-        staff_token = self._staff_summary(se, torch.full((batch_size,), 2, device=dev, dtype=torch.long)).unsqueeze(1)
+        # constant index tensors, built once per (device, batch size): `torch.tensor(list, device=cuda)` is a BLOCKING copy that waits
+        # for everything queued on the stream (the whole ConvStack + encoder of the step: 28 ms of a 61 ms step were spent here)
+        key = (str(dev), int(batch_size))
+        cache = getattr(self, "_sos_cache", None)
+        if cache is None or cache[0] != key:
+            se = torch.tensor([[SOS, EOS]], dtype=torch.long).repeat(batch_size, 1).to(dev)
+            cache = (key, se, torch.full((batch_size,), 2, device=dev, dtype=torch.long),
+                     torch.full((batch_size, 1), self.time_sig_SOS, device=dev, dtype=torch.long),
+                     torch.full((batch_size, 1), self.key_SOS, device=dev, dtype=torch.long))
+            self._sos_cache = cache
+        _, se, two, ts_idx, key_idx = cache
+        staff_token = self._staff_summary(se, two).unsqueeze(1)
         bar_token = torch.cat([staff_token, staff_token], dim=-1)
-        ts = self.time_sig_emb(torch.full((batch_size, 1), self.time_sig_SOS, device=dev, dtype=torch.long))
-        ky = self.key_emb(torch.full((batch_size, 1), self.key_SOS, device=dev, dtype=torch.long))
+        ts = self.time_sig_emb(ts_idx)
+        ky = self.key_emb(key_idx)
         return torch.cat([bar_token, ts, ky], dim=-1), staff_token
 
     def get_staff_token_from_probs(self, score_probs, lengths):
@@ -259,14 +269,13 @@ class HierarchicalDecoder(nn.Module):
         return torch.stack([self._steps_from_gt(upper_gt), self._steps_from_gt(lower_gt)]).cpu().tolist()   # one sync
 
     def _bar_step(self, token, h, enc, Ep_bar):
-        """bar-level attention + GRU cell + heads of one bar (models.py:239-247, 281-286) -> (bar_summary, ts_lp, key_lp)"""
+        """bar-level attention + GRU cell of one bar (models.py:239-247) -> (bar_summary, context)"""
         D = enc.shape[2]
         q = ops.linear(h, self.attn.attn.weight[:, :D], None)
         context = ops.AttnStepFn.apply(q, Ep_bar, enc, self.attn.v.weight)
         g = self.gru
         h = ops.gru_cell(torch.cat([token, context], dim=1), h, g.weight_ih_l0, g.weight_hh_l0, g.bias_ih_l0, g.bias_hh_l0)
-        head_in = torch.cat([h, context], dim=1)
-        return h, self._heads(self.time_sig_out, head_in), self._heads(self.key_out, head_in)
+        return h, context
 
     def _decode_bars_multi(self, enc, hidden, inference=True, ground_truth=None, teacher_forcing_ratio=0):
         """decode_bars (models.py:191-316) on the multi-sequence decoder kernels (ops.StaffRun / ops.DecodersFn).
@@ -352,7 +361,7 @@ class HierarchicalDecoder(nn.Module):
         ts_outs, key_outs, summaries = [], [], []
         done = []
         for (k0, k1) in segs:
-            seg_h = []
+            seg_h, seg_ctx = [], []
             for bar in range(k0, k1):
                 if bar > 0 and tf_bars and bar_tf[bar - 1]:              # teacher-forced: token from the targets of bar-1
                     us = self._staff_summary(upper_gt[:, bar - 1, :], upper_len_gt[:, bar - 1])
@@ -370,10 +379,9 @@ class HierarchicalDecoder(nn.Module):
                     token = torch.cat([us, ls, tst, kyt], dim=-1)
                 if training:
                     token = token * bar_masks[bar]
-                h, ts_lp, key_lp = self._bar_step(token, h, enc, Ep_bar)
+                h, context = self._bar_step(token, h, enc, Ep_bar)
                 seg_h.append(h)
-                ts_outs.append(ts_lp)
-                key_outs.append(key_lp)
+                seg_ctx.append(context)
             summaries += seg_h
             h0 = torch.stack([x.detach() for x in seg_h])               # (nq, B, D)
             ready = main.record_event()
@@ -386,6 +394,11 @@ class HierarchicalDecoder(nn.Module):
                     run.launch(k0, k1 - k0, h0)
                     if side is not None:
                         done.append(side.record_event())
+            # time-signature / key heads (models.py:281-286): off the chain that feeds the note decoders, so they run behind the launch
+            for hb, cb in zip(seg_h, seg_ctx):
+                head_in = torch.cat([hb, cb], dim=1)
+                ts_outs.append(self._heads(self.time_sig_out, head_in))
+                key_outs.append(self._heads(self.key_out, head_in))
         for ev in done:
             main.wait_event(ev)
         counters = [c for run in runs for c in run.counters]
@@ -395,7 +408,12 @@ class HierarchicalDecoder(nn.Module):
         self.last_step_counters = counters
         if grad:
             w = [x for d in decs for x in d._weights()]
-            up_all, lo_all = ops.DecodersFn.apply(tuple(runs), enc, Ep_up, Ep_lo, torch.stack(summaries), *w)
+            h0_all = torch.stack(summaries)
+            # autograd runs a node's backward on the stream its forward was issued on and orders it against the producers / consumers
+            # of its gradients: issued on the upper staff's stream, the reverse pass of the note decoders overlaps the backward of the
+            # heads (which do not depend on it) on the main stream
+            with ops._on_stream(sides[0]):
+                up_all, lo_all = ops.DecodersFn.apply(tuple(runs), enc, Ep_up, Ep_lo, h0_all, *w)
         else:
             up_all, lo_all = runs[0].logp, runs[1].logp
         return (torch.stack(ts_outs, 1), torch.stack(key_outs, 1), up_all, lo_all)

@@ -29,7 +29,7 @@ def main():
     vqt = VQT().to(dev)
     B = args.batch
     audio = make_audio(B, 192000, seed=1234).to(dev)
-    gt = [g.to(dev) for g in make_ground_truth(B, 5, 398, 189, seed=1234)]
+    gt = train.targets_to_device([g.pin_memory() for g in make_ground_truth(B, 5, 398, 189, seed=1234)], dev)
 
     def step():
         spec = vqt(audio).unsqueeze(1)
