@@ -358,15 +358,19 @@ class HierarchicalDecoder(nn.Module):
 
         token = self.get_SOS_token(B)[0].squeeze(1)                      # (B, 4*staff+ts+key)
         h = hidden[0]
-        ts_outs, key_outs, summaries = [], [], []
+        tok_gt = None
+        if tf_bars and any(bar_tf[:nb - 1]):
+            # tokens built from the targets (models.py:290-299), for all bars in ONE staff-summariser call per staff: row (b, bar)
+            us = self._staff_summary(upper_gt.reshape(B * nb, -1), upper_len_gt.reshape(-1)).view(B, nb, -1)
+            ls = self._staff_summary(lower_gt.reshape(B * nb, -1), lower_len_gt.reshape(-1)).view(B, nb, -1)
+            tok_gt = torch.cat([us, ls, self.time_sig_emb(time_sig_gt), self.key_emb(key_gt)], dim=-1)       # [:, k] = token of bar k+1
+        summaries, contexts = [], []
         done = []
         for (k0, k1) in segs:
             seg_h, seg_ctx = [], []
             for bar in range(k0, k1):
                 if bar > 0 and tf_bars and bar_tf[bar - 1]:              # teacher-forced: token from the targets of bar-1
-                    us = self._staff_summary(upper_gt[:, bar - 1, :], upper_len_gt[:, bar - 1])
-                    ls = self._staff_summary(lower_gt[:, bar - 1, :], lower_len_gt[:, bar - 1])
-                    token = torch.cat([us, ls, self.time_sig_emb(time_sig_gt[:, bar - 1]), self.key_emb(key_gt[:, bar - 1])], dim=-1)
+                    token = tok_gt[:, bar - 1]
                 elif bar > 0:                                            # token from bar-1's predictions (first bar of a segment)
                     assert bar == k0
                     for ev in done:
@@ -374,15 +378,18 @@ class HierarchicalDecoder(nn.Module):
                     done = []
                     us = self._staff_summary(torch.argmax(runs[0].logp[:, bar - 1], dim=-1), runs[0].lengths[bar - 1])
                     ls = self._staff_summary(torch.argmax(runs[1].logp[:, bar - 1], dim=-1), runs[1].lengths[bar - 1])
-                    tst = self.time_sig_emb(torch.argmax(ts_outs[-1], dim=-1))
-                    kyt = self.key_emb(torch.argmax(key_outs[-1], dim=-1))
-                    token = torch.cat([us, ls, tst, kyt], dim=-1)
+                    with torch.no_grad():                                # (the differentiable heads of all bars are formed at the end)
+                        head_in = torch.cat([summaries[-1], contexts[-1]], dim=1)
+                        ts_pred = torch.argmax(self._heads(self.time_sig_out, head_in), dim=-1)
+                        key_pred = torch.argmax(self._heads(self.key_out, head_in), dim=-1)
+                    token = torch.cat([us, ls, self.time_sig_emb(ts_pred), self.key_emb(key_pred)], dim=-1)
                 if training:
                     token = token * bar_masks[bar]
                 h, context = self._bar_step(token, h, enc, Ep_bar)
                 seg_h.append(h)
                 seg_ctx.append(context)
             summaries += seg_h
+            contexts += seg_ctx
             h0 = torch.stack([x.detach() for x in seg_h])               # (nq, B, D)
             ready = main.record_event()
             for si, run in enumerate(runs):
@@ -394,11 +401,6 @@ class HierarchicalDecoder(nn.Module):
                     run.launch(k0, k1 - k0, h0)
                     if side is not None:
                         done.append(side.record_event())
-            # time-signature / key heads (models.py:281-286): off the chain that feeds the note decoders, so they run behind the launch
-            for hb, cb in zip(seg_h, seg_ctx):
-                head_in = torch.cat([hb, cb], dim=1)
-                ts_outs.append(self._heads(self.time_sig_out, head_in))
-                key_outs.append(self._heads(self.key_out, head_in))
         for ev in done:
             main.wait_event(ev)
         counters = [c for run in runs for c in run.counters]
@@ -416,7 +418,13 @@ class HierarchicalDecoder(nn.Module):
                 up_all, lo_all = ops.DecodersFn.apply(tuple(runs), enc, Ep_up, Ep_lo, h0_all, *w)
         else:
             up_all, lo_all = runs[0].logp, runs[1].logp
-        return (torch.stack(ts_outs, 1), torch.stack(key_outs, 1), up_all, lo_all)
+        # time-signature / key heads (models.py:281-286) of all bars in one pass, rows (b, bar).  They are off the chain that feeds the
+        # note decoders, and -- created last -- their backward is the first thing autograd enqueues on the main stream, where it runs
+        # while the note decoders' reverse pass occupies the staff streams
+        head_in = torch.cat([torch.stack(summaries, 1), torch.stack(contexts, 1)], dim=-1).view(B * nb, -1)
+        ts_all = self._heads(self.time_sig_out, head_in).view(B, nb, -1)
+        key_all = self._heads(self.key_out, head_in).view(B, nb, -1)
+        return (ts_all, key_all, up_all, lo_all)
 
     def _decode_bars_per_bar(self, encoder_outputs, hidden, inference=True, ground_truth=None, teacher_forcing_ratio=0):
         enc = encoder_outputs
