@@ -115,7 +115,7 @@ def make_dec_args(**kw):
 
 class DecMArgs(ctypes.Structure):
     """Mirror of `struct DecMArgs` in csrc/decm_args.cuh (field order and types must match exactly)."""
-    _ints = ["B", "NQ", "T", "V", "VP", "S", "max_steps", "NS", "tile", "inference", "save", "Rtot", "r0", "bars", "k0", "Spitch"]
+    _ints = ["B", "NQ", "T", "V", "VP", "S", "max_steps", "NS", "tile", "inference", "save", "Rtot", "r0", "bars", "k0", "Spitch", "tc"]
     _ptrs = ["enc", "Ee", "Wattn", "v", "emb", "W_ih", "W_hh", "b_ih", "b_hh", "W_out", "b_out", "W_hT", "W_ihT", "W_hhT",
              "gt", "use_gt", "mask", "logp", "lengths", "eos", "counters",
              "hs", "ctxs", "attn", "gates", "qs", "eqs", "xtok", "toks", "ml",

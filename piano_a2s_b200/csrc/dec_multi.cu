@@ -16,6 +16,7 @@
 // The reverse kernel has the same shape (P1 gate gradients | P2 W^T products | P3 attention backward, two passes).
 #include "decm_args.cuh"
 #include <cooperative_groups.h>
+#include <cuda_bf16.h>
 
 namespace {
 
@@ -25,7 +26,7 @@ constexpr int NW = NT / 32;            // 12 warps
 constexpr int UPC = DD / PG;           // hidden units per CTA (8)
 constexpr int GR = 3 * UPC;            // gate rows per CTA (24)
 constexpr int CR = 7;                  // phase-C rows per CTA: PG*CR = 448 >= V + DA
-constexpr int XP = 2 * DD + DE;        // per-row state in shared memory: [h (512) | ctx (512) | tok (16)]
+constexpr int XP = 2 * DD + DE + 8;    // per-row state in shared memory: [h (512) | ctx (512) | tok (16)] (+8: pitch = 24 mod 32 banks, see mma_a_frag)
 constexpr int XP4 = XP / 4;
 constexpr int KM4 = 2 * DD / 4;        // 256 float4 columns of [h | ctx]
 constexpr int TILE_MAX = 320;          // frames per attention item (host: NS >= ceil(T / TILE_MAX))
@@ -126,27 +127,76 @@ __device__ __forceinline__ int rs_base(int lane) {
     return base;
 }
 
+// ---- tensor-core path of the weight-stationary products (precision modes bf16x3 / bf16) ---------------------------------------
+// A chunk of 16 staged rows is ONE m16 tile: C[16 x 8n] += A[16 x K] W^T, mma.sync.m16n8k16 bf16 with fp32 accumulation, the K range
+// split over the 12 warps.  fp32 operands are split into bf16 hi + lo on the fly (activations) / at kernel start (weights) and
+// hi*hi + lo*hi + hi*lo is accumulated (the bf16x3 scheme of the tcgen05 GEMMs: ~5e-6 relative).  Replaces the FFMA products and
+// their warp-shuffle reductions (10x fewer instructions per chunk); the exact-fp32 mode (eval / greedy decode) keeps the FFMA path.
+__device__ __forceinline__ void split2(float x0, float x1, unsigned int& hi, unsigned int& lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+    const float2 hf = __bfloat1622float2(h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - hf.x, x1 - hf.y);
+    hi = *reinterpret_cast<const unsigned int*>(&h);
+    lo = *reinterpret_cast<const unsigned int*>(&l);
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const unsigned int (&a)[4], unsigned int b0, unsigned int b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// A fragment of k-step `col0` (16 columns) from fp32 rows of pitch `pitch` floats: rows g / g+8, columns 2tg,2tg+1 / +8.  With
+// pitch = 8 or 24 (mod 32) the 64-bit loads of a half warp hit 32 distinct banks.
+__device__ __forceinline__ void mma_a_frag(const float* x, int pitch, int col0, int g, int tg, unsigned int (&hi)[4], unsigned int (&lo)[4]) {
+    const float2 v0 = *reinterpret_cast<const float2*>(x + g * pitch + col0 + 2 * tg);
+    const float2 v1 = *reinterpret_cast<const float2*>(x + (g + 8) * pitch + col0 + 2 * tg);
+    const float2 v2 = *reinterpret_cast<const float2*>(x + g * pitch + col0 + 8 + 2 * tg);
+    const float2 v3 = *reinterpret_cast<const float2*>(x + (g + 8) * pitch + col0 + 8 + 2 * tg);
+    split2(v0.x, v0.y, hi[0], lo[0]);
+    split2(v1.x, v1.y, hi[1], lo[1]);
+    split2(v2.x, v2.y, hi[2], lo[2]);
+    split2(v3.x, v3.y, hi[3], lo[3]);
+}
+// acc[j] += A (hi, lo) x rows j*8 .. j*8+7 of the packed weights (bf16x2 words, row pitch wp words), k-step ks
+template <int NTILES>
+__device__ __forceinline__ void mma_kstep(float (&acc)[NTILES][4], const unsigned int (&ahi)[4], const unsigned int (&alo)[4],
+                                          const unsigned int* whi, const unsigned int* wlo, int wp, int ks, int g, int tg) {
+#pragma unroll
+    for (int j = 0; j < NTILES; ++j) {
+        const int o = (j * 8 + g) * wp + ks * 8 + tg;
+        const unsigned int bh0 = whi[o], bh1 = whi[o + 4], bl0 = wlo[o], bl1 = wlo[o + 4];
+        mma16816(acc[j], ahi, bh0, bh1);
+        mma16816(acc[j], alo, bh0, bh1);
+        mma16816(acc[j], ahi, bl0, bl1);
+    }
+}
+constexpr int WGP = (2 * DD + DE) / 2 + 4;   // packed row pitch of the gate weights (524 words = 12 mod 32: conflict-free B fragments)
+constexpr int WCP = DD + 4;                  // ... of the phase-C rows (K = 1024 -> 512 words + 4)
+constexpr int WTP = 3 * DD / 2 + 4;          // ... of the reverse kernel's W^T rows (K = 1536 -> 768 words + 4)
+
 // per-query step counts, copied to shared memory at kernel start (dynamic indexing of the kernel-parameter array would force a
 // local-memory copy of the whole argument block)
 __shared__ int g_Sq[8];
 
-constexpr int RED_FLOATS = 4 * 8 * GR * 4;             // phase B: (4 clip groups x 8 warps) x (24 rows x 4 clips); phase C: 32 x 32
+constexpr int RED_FLOATS = NW * BT * GR;               // FFMA path: (4 clip groups x 8 warps) x (24 rows x 4 clips) = 3072; MMA path: 12 warps x 16 x 24
+constexpr int WG_WORDS = 2 * GR * WGP;                 // >= GR * 2 * DD + GR * DE (fp32 layout of the FFMA path)
+constexpr int WC_WORDS = 2 * 8 * WCP;                  // >= CR * 2 * DD
+static_assert(WG_WORDS >= GR * 2 * DD + GR * DE && WC_WORDS >= CR * 2 * DD, "the packed layouts must cover the fp32 ones");
 struct FwdSmem {
-    float* Wg;      // [GR][1024]   rows g*8+u: [W_hh row | W_ih row, context columns]
-    float* Wc;      // [CR][1024]   W_out rows / W_h rows (zero beyond 512) / zero rows
-    float* Wtok;    // [GR][16]
+    float* Wg;      // FFMA: [GR][1024] rows g*8+u: [W_hh row | W_ih row, context columns], then Wtok [GR][16]
+                    // MMA:  hi [GR][WGP] | lo [GR][WGP] bf16x2 words over k = [h | ctx | tok]
+    float* Wc;      // FFMA: [CR][1024] W_out rows / W_h rows (zero beyond 512) / zero rows;  MMA: hi [8][WCP] | lo [8][WCP]
+    float* Wtok;    // [GR][16] (FFMA path)
     float* bias;    // [4][8]       b_r (ih+hh), b_z (ih+hh), b_in, b_hn
     float* bc;      // [8]
     float* xs;      // [BT][XP]     staged rows of phases B / C; attention scratch of phase A
     float* red;     // RED_FLOATS
     float* v2;      // [DA]         -2 v
 };
-constexpr int FWD_SMEM_FLOATS = GR * 2 * DD + CR * 2 * DD + GR * DE + 32 + 8 + BT * XP + RED_FLOATS + DA;
+constexpr int FWD_SMEM_FLOATS = WG_WORDS + WC_WORDS + 32 + 8 + BT * XP + RED_FLOATS + DA;
 __device__ __forceinline__ FwdSmem carve(float* sm) {
     FwdSmem s;
-    s.Wg = sm; sm += GR * 2 * DD;
-    s.Wc = sm; sm += CR * 2 * DD;
-    s.Wtok = sm; sm += GR * DE;
+    s.Wg = sm; s.Wtok = sm + GR * 2 * DD; sm += WG_WORDS;
+    s.Wc = sm; sm += WC_WORDS;
     s.bias = sm; sm += 32;
     s.bc = sm; sm += 8;
     s.xs = sm; sm += BT * XP;
@@ -593,6 +643,96 @@ __device__ void out_phase(const DecMArgs& a, const FwdSmem& S, int s, int qslot,
     }
 }
 
+// ------------------------------------------------------------------------------------------------ phases B / C on the tensor cores
+// B: the staged chunk [h | ctx | tok] (16 rows x 1040) times this CTA's 24 gate rows.  Warps 0-5 take the hidden-state k-steps
+// (W_hh h), warps 6-11 the input k-steps (W_ih [ctx, tok]): the n gate needs the two sums apart.
+__device__ void gru_phase_tc(const DecMArgs& a, const FwdSmem& S, int s, int rb0, int nb) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tg = lane & 3;
+    const unsigned int* whi = reinterpret_cast<const unsigned int*>(S.Wg);
+    const unsigned int* wlo = whi + GR * WGP;
+    float acc[3][4];
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
+    const int half = warp / 6, wi = warp - half * 6;
+    const int ks1 = half ? (2 * DD + DE) / 16 : DD / 16;
+    for (int ks = half * (DD / 16) + wi; ks < ks1; ks += 6) {
+        unsigned int ahi[4], alo[4];
+        mma_a_frag(S.xs, XP, ks * 16, g, tg, ahi, alo);
+        mma_kstep<3>(acc, ahi, alo, whi, wlo, WGP, ks, g, tg);
+    }
+    float* dst = S.red + warp * (BT * GR);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        *reinterpret_cast<float2*>(dst + g * GR + j * 8 + 2 * tg) = make_float2(acc[j][0], acc[j][1]);
+        *reinterpret_cast<float2*>(dst + (g + 8) * GR + j * 8 + 2 * tg) = make_float2(acc[j][2], acc[j][3]);
+    }
+    __syncthreads();
+    if (tid < UPC * BT) {
+        const int br = tid >> 3, u = tid & 7;
+        const int r = rb0 + br;
+        if (br < nb && s < g_Sq[r / a.B]) {
+            float g3[3], nh = 0.f;
+#pragma unroll
+            for (int gi = 0; gi < 3; ++gi) {
+                const int idx = br * GR + gi * 8 + u;
+                float lo = 0.f, hi = 0.f;
+#pragma unroll
+                for (int w = 0; w < 6; ++w) lo += S.red[w * (BT * GR) + idx];             // W_hh h
+#pragma unroll
+                for (int w = 6; w < 12; ++w) hi += S.red[w * (BT * GR) + idx];            // W_ih [ctx, tok]
+                if (gi < 2) g3[gi] = lo + hi;
+                else { g3[2] = hi; nh = lo; }
+            }
+            const int j = blockIdx.x * UPC + u;
+            const size_t gr = (size_t)a.r0 + r;
+            const float rr = sigmoidf_(g3[0] + S.bias[u]);
+            const float z = sigmoidf_(g3[1] + S.bias[8 + u]);
+            const float hnl = nh + S.bias[24 + u];
+            const float n = tanhf(g3[2] + S.bias[16 + u] + rr * hnl);
+            const float hp = S.xs[br * XP + j];
+            const float hn = (1.f - z) * n + z * hp;
+            a.hs[((size_t)mhslot(a, s + 1) * a.Rtot + gr) * DD + j] = hn;
+            if (a.save) {
+                float* gs = a.gates + ((size_t)s * a.Rtot + gr) * 4 * DD + j;
+                gs[0] = rr; gs[DD] = z; gs[2 * DD] = n; gs[3 * DD] = hnl;
+            }
+        }
+    }
+}
+// C: [h' | ctx] (16 rows x 1024) times this CTA's 7 (+1 zero) logit / query rows
+__device__ void out_phase_tc(const DecMArgs& a, const FwdSmem& S, int s, int qslot, int rb0, int nb) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tg = lane & 3;
+    const unsigned int* whi = reinterpret_cast<const unsigned int*>(S.Wc);
+    const unsigned int* wlo = whi + 8 * WCP;
+    float acc[1][4] = {{0.f, 0.f, 0.f, 0.f}};
+    for (int ks = warp; ks < 2 * DD / 16; ks += NW) {
+        unsigned int ahi[4], alo[4];
+        mma_a_frag(S.xs, XP, ks * 16, g, tg, ahi, alo);
+        mma_kstep<1>(acc, ahi, alo, whi, wlo, WCP, ks, g, tg);
+    }
+    float* dst = S.red + warp * (BT * 8);
+    *reinterpret_cast<float2*>(dst + g * 8 + 2 * tg) = make_float2(acc[0][0], acc[0][1]);
+    *reinterpret_cast<float2*>(dst + (g + 8) * 8 + 2 * tg) = make_float2(acc[0][2], acc[0][3]);
+    __syncthreads();
+    if (tid < CR * BT) {
+        const int rr = tid >> 4, br = tid & 15;
+        const int rg = blockIdx.x * CR + rr;
+        const int r = rb0 + br;
+        if (br < nb && rg < a.V + DA && (s < 0 || s < g_Sq[r / a.B])) {
+            float v = 0.f;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) v += S.red[w * (BT * 8) + br * 8 + rr];
+            if (rg < a.V) {
+                if (s >= 0) a.logits[(size_t)r * a.VP + rg] = v + S.bc[rr];
+            } else {
+                a.qs[((size_t)qslot * a.Rtot + a.r0 + r) * DA + (rg - a.V)] = v;
+            }
+        }
+    }
+}
+
 __device__ __forceinline__ bool chunk_active(const DecMArgs& a, int s, int rb0, int nb) {
     // rows are q-major: the chunk covers queries rb0 / B .. (rb0 + nb - 1) / B
     for (int q = rb0 / a.B; q <= (rb0 + nb - 1) / a.B; ++q)
@@ -600,7 +740,7 @@ __device__ __forceinline__ bool chunk_active(const DecMArgs& a, int s, int rb0, 
     return false;
 }
 
-template <int NQ>
+template <int NQ, bool TC>
 __global__ void __launch_bounds__(NT, 1) decm_fwd_kernel(DecMArgs a, int eos_id) {
     extern __shared__ __align__(16) float smem_f[];
     __shared__ float s_sumv;
@@ -610,6 +750,28 @@ __global__ void __launch_bounds__(NT, 1) decm_fwd_kernel(DecMArgs a, int eos_id)
     if (tid < 8) g_Sq[tid] = tid == 0 ? a.Sq[0] : tid == 1 ? a.Sq[1] : tid == 2 ? a.Sq[2] : tid == 3 ? a.Sq[3] : tid == 4 ? a.Sq[4] : tid == 5 ? a.Sq[5] : tid == 6 ? a.Sq[6] : a.Sq[7];
 
     // ---- one-time: this CTA's weight slices -> shared memory
+    if (TC) {
+        unsigned int* ghi = reinterpret_cast<unsigned int*>(S.Wg);
+        unsigned int* glo = ghi + GR * WGP;
+        constexpr int KW = (2 * DD + DE) / 2;                       // 520 bf16x2 words per gate row: k = [h | ctx | tok]
+        for (int i = tid; i < GR * KW; i += NT) {
+            const int r = i / KW, pw = i - r * KW, k = 2 * pw;
+            const int row = (r / UPC) * DD + cta * UPC + (r % UPC);
+            const float* src = k < DD ? a.W_hh + (size_t)row * DD + k
+                             : k < 2 * DD ? a.W_ih + (size_t)row * DX + DE + (k - DD) : a.W_ih + (size_t)row * DX + (k - 2 * DD);
+            split2(__ldg(src), __ldg(src + 1), ghi[r * WGP + pw], glo[r * WGP + pw]);
+        }
+        unsigned int* chi = reinterpret_cast<unsigned int*>(S.Wc);
+        unsigned int* clo = chi + 8 * WCP;
+        for (int i = tid; i < 8 * DD; i += NT) {
+            const int rr = i / DD, pw = i - rr * DD, k = 2 * pw;
+            const int rg = cta * CR + rr;
+            float w0 = 0.f, w1 = 0.f;
+            if (rr < CR && rg < a.V) { w0 = __ldg(a.W_out + (size_t)rg * 2 * DD + k); w1 = __ldg(a.W_out + (size_t)rg * 2 * DD + k + 1); }
+            else if (rr < CR && rg < a.V + DA && k < DD) { w0 = __ldg(a.Wattn + (size_t)(rg - a.V) * 2 * DD + k); w1 = __ldg(a.Wattn + (size_t)(rg - a.V) * 2 * DD + k + 1); }
+            split2(w0, w1, chi[rr * WCP + pw], clo[rr * WCP + pw]);
+        }
+    } else {
     for (int i = tid; i < GR * KM4; i += NT) {
         const int r = i / KM4, k4 = i % KM4;
         const int row = (r / UPC) * DD + cta * UPC + (r % UPC);
@@ -630,6 +792,8 @@ __global__ void __launch_bounds__(NT, 1) decm_fwd_kernel(DecMArgs a, int eos_id)
         else if (rg < a.V + DA && k4 < 128) w = __ldg(reinterpret_cast<const float4*>(a.Wattn + (size_t)(rg - a.V) * 2 * DD) + k4);
         reinterpret_cast<float4*>(S.Wc)[i] = w;
     }
+    }
+    for (int i = tid; i < BT * XP; i += NT) S.xs[i] = 0.f;           // rows beyond a partial chunk must hold finite values
     if (tid < UPC) {
         const int j = cta * UPC + tid;
         S.bias[tid] = a.b_ih[j] + a.b_hh[j];
@@ -659,7 +823,8 @@ __global__ void __launch_bounds__(NT, 1) decm_fwd_kernel(DecMArgs a, int eos_id)
         __syncthreads();
         stage_xs(a, S, rb0, nb, 1, mhslot(a, 0), 0);
         __syncthreads();
-        out_phase(a, S, -1, mhslot(a, 0), rb0, nb);
+        if (TC) out_phase_tc(a, S, -1, mhslot(a, 0), rb0, nb);
+        else out_phase(a, S, -1, mhslot(a, 0), rb0, nb);
     }
     grid_sync(a.sync, target);
     PROF_MARK(6);
@@ -686,7 +851,8 @@ __global__ void __launch_bounds__(NT, 1) decm_fwd_kernel(DecMArgs a, int eos_id)
             __syncthreads();
             stage_xs(a, S, rb0, nb, 7, mhslot(a, s), mslot(a, s));
             __syncthreads();
-            gru_phase(a, S, s, rb0, nb);
+            if (TC) gru_phase_tc(a, S, s, rb0, nb);
+            else gru_phase(a, S, s, rb0, nb);
         }
         PROF_MARK(2);
         grid_sync(a.sync, target);
@@ -698,7 +864,8 @@ __global__ void __launch_bounds__(NT, 1) decm_fwd_kernel(DecMArgs a, int eos_id)
             __syncthreads();
             stage_xs(a, S, rb0, nb, 3, mhslot(a, s + 1), mslot(a, s));
             __syncthreads();
-            out_phase(a, S, s, mhslot(a, s + 1), rb0, nb);
+            if (TC) out_phase_tc(a, S, s, mhslot(a, s + 1), rb0, nb);
+            else out_phase(a, S, s, mhslot(a, s + 1), rb0, nb);
         }
         PROF_MARK(4);
         grid_sync(a.sync, target);
@@ -731,18 +898,22 @@ constexpr int K3 = 3 * DD;
 constexpr int RPB = 16;                // W^T rows per CTA (+1 token row on the first 16 CTAs)
 static_assert(K3 / 4 == NTB, "one float4 column of the gate gradients per thread");
 static_assert(PG == 64 && RPB * (PG / 2) == DD, "row slicing of the reverse kernel");
+constexpr int UP = K3 + 8;             // pitch of the staged gate-gradient rows (8 mod 32 banks: conflict-free A fragments)
+constexpr int UP4 = UP / 4;
 struct BwdSmem {
-    float* WT;      // [RPB+1][K3]
-    float* U;       // [BT][K3]     gate gradients of the staged rows (P2) | scratch of P1 and P3
-    float* red;     // [4][12][64] + [12][BT]
+    float* WT;      // FFMA: [RPB+1][K3] fp32;  MMA: hi [RPB][WTP] | lo [RPB][WTP] bf16x2 words, then the token row [K3] fp32
+    float* U;       // [BT][UP]     gate gradients of the staged rows (P2) | scratch of P1 and P3
+    float* red;     // FFMA: [4][12][64] + [12][BT];  MMA: [12][16][16] + [12][BT]
     float* Wq;      // [UPC*2][QP]
     float* v4;      // [DA]         4 v
 };
 constexpr int QP = 132;
 constexpr int BWD_RED_FLOATS = 4 * 12 * 64 + 12 * BT;
-constexpr int BWD_SMEM_FLOATS = (RPB + 1) * K3 + BT * K3 + BWD_RED_FLOATS + UPC * 2 * QP + DA;
+constexpr int WT_WORDS = 2 * RPB * WTP + K3;           // >= (RPB + 1) * K3
+static_assert(WT_WORDS >= (RPB + 1) * K3 && NW * BT * RPB + 12 * BT <= BWD_RED_FLOATS, "packed W^T layout / MMA partials");
+constexpr int BWD_SMEM_FLOATS = WT_WORDS + BT * UP + BWD_RED_FLOATS + UPC * 2 * QP + DA;
 // P3 scratch inside U: dc [NQ][DD] | Eq [NQ][DA] | dap [NCB][NQ][TILE_MAX] (ds in dap[0]) | ring [NW][RING], aliased afterwards by dqr [NW][DA]
-static_assert(NQMAX * (DD + DA + NCB * TILE_MAX) + NW * RING <= BT * K3 && DA <= RING, "attention-backward scratch must fit U");
+static_assert(NQMAX * (DD + DA + NCB * TILE_MAX) + NW * RING <= BT * UP && DA <= RING, "attention-backward scratch must fit U");
 
 // ---- P1: dh of this CTA's 8 hidden units, GRU gate gradients -> dgi_all / dgh_all / dh*z
 __device__ void bwd_gates_phase(const DecMArgs& a, const BwdSmem& S, int s, int rb0, int nb) {
@@ -792,6 +963,7 @@ __device__ void bwd_gates_phase(const DecMArgs& a, const BwdSmem& S, int s, int 
 }
 
 // ---- P2: dx = dgi W_ih (CTAs < 32; 16 context columns + 1 token column), dh_prev = dgh W_hh + dh*z (CTAs >= 32)
+template <bool TC>
 __device__ void bwd_gemv_phase(const DecMArgs& a, const BwdSmem& S, int s, int rb0, int nb) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, cta = blockIdx.x;
     const bool is_dx = cta < PG / 2;
@@ -808,20 +980,52 @@ __device__ void bwd_gemv_phase(const DecMArgs& a, const BwdSmem& S, int s, int r
                 if (b0 + j < nb) v[j] = ldcg4(src + ((size_t)(b0 + j) * (K3 / 4) + tid) * 4);
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-                if (b0 + j < nb) u4[(b0 + j) * (K3 / 4) + tid] = v[j];
+                if (b0 + j < nb) u4[(b0 + j) * UP4 + tid] = v[j];
         }
     }
     __syncthreads();
     const float4* x4 = reinterpret_cast<const float4*>(S.U);
+    float* tokred = S.red + 4 * 12 * 64;
+    if (TC) {
+        const int g = lane >> 2, tg = lane & 3;
+        const unsigned int* whi = reinterpret_cast<const unsigned int*>(S.WT);
+        const unsigned int* wlo = whi + RPB * WTP;
+        float acc[2][4];
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
+        for (int ks = warp; ks < K3 / 16; ks += NW) {
+            unsigned int ahi[4], alo[4];
+            mma_a_frag(S.U, UP, ks * 16, g, tg, ahi, alo);
+            mma_kstep<2>(acc, ahi, alo, whi, wlo, WTP, ks, g, tg);
+        }
+        float* dst = S.red + warp * (BT * RPB);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            *reinterpret_cast<float2*>(dst + g * RPB + j * 8 + 2 * tg) = make_float2(acc[j][0], acc[j][1]);
+            *reinterpret_cast<float2*>(dst + (g + 8) * RPB + j * 8 + 2 * tg) = make_float2(acc[j][2], acc[j][3]);
+        }
+        if (has_tok) {                                         // the one token row stays an FFMA row product
+            const float4 w = reinterpret_cast<const float4*>(S.WT + 2 * RPB * WTP)[tid];
+#pragma unroll 1
+            for (int cg = 0; cg < BT / 4; ++cg) {
+                if (cg * 4 >= nb) break;
+                float tk[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) tk[c] = warp_sum(dot4(w, x4[(cg * 4 + c) * UP4 + tid]));
+                if (lane < 4) tokred[warp * BT + cg * 4 + lane] = lane == 0 ? tk[0] : lane == 1 ? tk[1] : lane == 2 ? tk[2] : tk[3];
+            }
+        }
+    } else {
     const float4* w4 = reinterpret_cast<const float4*>(S.WT);
     const int base = rs_base<32>(lane);
-    float* tokred = S.red + 4 * 12 * 64;
 #pragma unroll 1
     for (int cg = 0; cg < BT / 4; ++cg) {
         if (cg * 4 >= nb) break;
         float4 xv[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) xv[c] = x4[(cg * 4 + c) * (K3 / 4) + tid];
+        for (int c = 0; c < 4; ++c) xv[c] = x4[(cg * 4 + c) * UP4 + tid];
         float* dst = S.red + (cg * 12 + warp) * 64 + base;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -843,15 +1047,21 @@ __device__ void bwd_gemv_phase(const DecMArgs& a, const BwdSmem& S, int s, int r
         }
         if (has_tok && lane < 4) tokred[warp * BT + cg * 4 + lane] = lane == 0 ? tk[0] : lane == 1 ? tk[1] : lane == 2 ? tk[2] : tk[3];
     }
+    }
     __syncthreads();
     if (tid < RPB * BT) {
         const int rr = tid >> 4, br = tid & 15;
         const int r = rb0 + br;
         if (br < nb && s < g_Sq[r / a.B]) {
-            const int cg = br >> 2, c = br & 3;
             float v = 0.f;
+            if (TC) {
 #pragma unroll
-            for (int w = 0; w < 12; ++w) v += S.red[(cg * 12 + w) * 64 + rr * 4 + c];
+                for (int w = 0; w < NW; ++w) v += S.red[w * (BT * RPB) + br * RPB + rr];
+            } else {
+                const int cg = br >> 2, c = br & 3;
+#pragma unroll
+                for (int w = 0; w < 12; ++w) v += S.red[(cg * 12 + w) * 64 + rr * 4 + c];
+            }
             if (is_dx) {
                 a.dx[(size_t)r * DX + DE + cta * RPB + rr] = v;
             } else {
@@ -1093,13 +1303,13 @@ __device__ void bwd_attn_item(const DecMArgs& a, const BwdSmem& S, int s, int b,
     }
 }
 
-template <int NQ>
+template <int NQ, bool TC>
 __global__ void __launch_bounds__(NTB, 1) decm_bwd_kernel(DecMArgs a) {
     extern __shared__ __align__(16) float smem_f[];
     BwdSmem S;
     S.WT = smem_f;
-    S.U = S.WT + (RPB + 1) * K3;
-    S.red = S.U + BT * K3;
+    S.U = S.WT + WT_WORDS;
+    S.red = S.U + BT * UP;
     S.Wq = S.red + BWD_RED_FLOATS;
     S.v4 = S.Wq + UPC * 2 * QP;
     const int tid = threadIdx.x, cta = blockIdx.x;
@@ -1107,6 +1317,18 @@ __global__ void __launch_bounds__(NTB, 1) decm_bwd_kernel(DecMArgs a) {
     if (tid < 8) g_Sq[tid] = tid == 0 ? a.Sq[0] : tid == 1 ? a.Sq[1] : tid == 2 ? a.Sq[2] : tid == 3 ? a.Sq[3] : tid == 4 ? a.Sq[4] : tid == 5 ? a.Sq[5] : tid == 6 ? a.Sq[6] : a.Sq[7];
     {
         const bool is_dx = cta < PG / 2;
+        if (TC) {
+            unsigned int* whi = reinterpret_cast<unsigned int*>(S.WT);
+            unsigned int* wlo = whi + RPB * WTP;
+            for (int i = tid; i < RPB * (K3 / 2); i += NTB) {
+                const int r = i / (K3 / 2), pw = i - r * (K3 / 2);
+                const float* row = is_dx ? a.W_ihT + (size_t)(DE + cta * RPB + r) * K3 : a.W_hhT + (size_t)((cta - PG / 2) * RPB + r) * K3;
+                split2(__ldg(row + 2 * pw), __ldg(row + 2 * pw + 1), whi[r * WTP + pw], wlo[r * WTP + pw]);
+            }
+            for (int i = tid; i < K3 / 4; i += NTB)
+                reinterpret_cast<float4*>(S.WT + 2 * RPB * WTP)[i] =
+                    cta < DE ? __ldg(reinterpret_cast<const float4*>(a.W_ihT + (size_t)cta * K3) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
         for (int i = tid; i < (RPB + 1) * (K3 / 4); i += NTB) {
             const int r = i / (K3 / 4), k4 = i % (K3 / 4);
             float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1118,6 +1340,8 @@ __global__ void __launch_bounds__(NTB, 1) decm_bwd_kernel(DecMArgs a) {
             }
             reinterpret_cast<float4*>(S.WT)[i] = w;
         }
+        }
+        for (int i = tid; i < BT * UP; i += NTB) S.U[i] = 0.f;
         for (int i = tid; i < UPC * DA; i += NTB)
             S.Wq[(i >> 7) * QP + (i & 127)] = a.W_hT[(size_t)cta * UPC * DA + i];
         if (tid < DA) S.v4[tid] = 4.f * a.v[tid];
@@ -1137,7 +1361,7 @@ __global__ void __launch_bounds__(NTB, 1) decm_bwd_kernel(DecMArgs a) {
         PROF_MARK(1);
         for (int ch = 0; ch < nchunks; ++ch) {
             const int rb0 = ch * BT, nb = min(BT, R - rb0);
-            if (chunk_active(a, s, rb0, nb)) bwd_gemv_phase(a, S, s, rb0, nb);
+            if (chunk_active(a, s, rb0, nb)) bwd_gemv_phase<TC>(a, S, s, rb0, nb);
         }
         PROF_MARK(2);
         grid_sync(a.sync, target);
@@ -1278,23 +1502,31 @@ int check_args(const DecMArgs& a) {
     return 0;
 }
 
+template <int NQ, bool TC>
+int launch_fwd2(DecMArgs& a, int eos_id, cudaStream_t st) {
+    const size_t smem = (size_t)FWD_SMEM_FLOATS * sizeof(float);
+    PA2S_TRY(cudaFuncSetAttribute(decm_fwd_kernel<NQ, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    void* kargs[] = {(void*)&a, (void*)&eos_id};
+    PA2S_TRY(cudaLaunchCooperativeKernel((const void*)decm_fwd_kernel<NQ, TC>, dim3(PG), dim3(NT), kargs, smem, st));
+    PA2S_COUNT_LAUNCH();
+    return 0;
+}
 template <int NQ>
 int launch_fwd(DecMArgs& a, int eos_id, cudaStream_t st) {
-    const size_t smem = (size_t)FWD_SMEM_FLOATS * sizeof(float);
-    PA2S_TRY(cudaFuncSetAttribute(decm_fwd_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    void* kargs[] = {(void*)&a, (void*)&eos_id};
-    PA2S_TRY(cudaLaunchCooperativeKernel((const void*)decm_fwd_kernel<NQ>, dim3(PG), dim3(NT), kargs, smem, st));
+    return a.tc ? launch_fwd2<NQ, true>(a, eos_id, st) : launch_fwd2<NQ, false>(a, eos_id, st);
+}
+template <int NQ, bool TC>
+int launch_bwd2(DecMArgs& a, cudaStream_t st) {
+    const size_t smem = (size_t)BWD_SMEM_FLOATS * sizeof(float);
+    PA2S_TRY(cudaFuncSetAttribute(decm_bwd_kernel<NQ, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    void* kargs[] = {(void*)&a};
+    PA2S_TRY(cudaLaunchCooperativeKernel((const void*)decm_bwd_kernel<NQ, TC>, dim3(PG), dim3(NTB), kargs, smem, st));
     PA2S_COUNT_LAUNCH();
     return 0;
 }
 template <int NQ>
 int launch_bwd(DecMArgs& a, cudaStream_t st) {
-    const size_t smem = (size_t)BWD_SMEM_FLOATS * sizeof(float);
-    PA2S_TRY(cudaFuncSetAttribute(decm_bwd_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    void* kargs[] = {(void*)&a};
-    PA2S_TRY(cudaLaunchCooperativeKernel((const void*)decm_bwd_kernel<NQ>, dim3(PG), dim3(NTB), kargs, smem, st));
-    PA2S_COUNT_LAUNCH();
-    return 0;
+    return a.tc ? launch_bwd2<NQ, true>(a, st) : launch_bwd2<NQ, false>(a, st);
 }
 
 }  // namespace

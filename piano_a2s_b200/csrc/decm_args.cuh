@@ -14,6 +14,7 @@ constexpr int NQMAX = 5;
 
 struct DecMArgs {
     int B, NQ, T, V, VP, S, max_steps, NS, tile, inference, save, Rtot, r0, bars, k0, Spitch;
+    int tc;                  // 1: weight-stationary products on the tensor cores (bf16 hi/lo split, fp32 accumulate); 0: exact fp32 FFMA
     int Sq[8];               // executed steps of query q (1 <= Sq[q] <= S = max_q Sq[q])
     // encoder memory and attention module
     const float* enc;        // (B,T,DD)

@@ -242,8 +242,11 @@ __global__ void __launch_bounds__(256) gemm_skinny_nn_kernel(GemmArgs g) {
     __shared__ float red[8][MR][33];
     const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
     const int n = blockIdx.x * 32 + lane;
-    const int kper = (g.K + 7) / 8;
-    const int kb = slice * kper, ke = min(g.K, kb + kper);
+    // gridDim.y CTAs split K (their partial sums meet in C through atomics: the launcher zero-fills C and sets g.atomic), 8 warps split a CTA's range
+    const int kcta = (g.K + gridDim.y - 1) / gridDim.y;
+    const int k_lo = blockIdx.y * kcta, k_hi = min(g.K, k_lo + kcta);
+    const int kper = (k_hi - k_lo + 7) / 8;
+    const int kb = k_lo + slice * kper, ke = min(k_hi, kb + kper);
     float acc[MR];
 #pragma unroll
     for (int m = 0; m < MR; ++m) acc[m] = 0.f;
@@ -277,7 +280,7 @@ __global__ void __launch_bounds__(256) gemm_skinny_nn_kernel(GemmArgs g) {
         float v = 0.f;
 #pragma unroll
         for (int s = 0; s < 8; ++s) v += red[s][m][lane];
-        if (n < g.N) skinny_store(g.C + (long long)m * g.ldc + n, v + (g.bias ? __ldg(g.bias + n) : 0.f), g.atomic, g.accumulate);
+        if (n < g.N) skinny_store(g.C + (long long)m * g.ldc + n, v + ((g.bias && blockIdx.y == 0) ? __ldg(g.bias + n) : 0.f), g.atomic, g.accumulate);
     }
 }
 
@@ -334,7 +337,15 @@ bool launch_skinny(const GemmArgs& g0, int transA, int transB, cudaStream_t st) 
             if (g.M <= 16) gemm_skinny_nt_kernel<16><<<grid, 256, 0, st>>>(g);
             else gemm_skinny_nt_kernel<32><<<grid, 256, 0, st>>>(g);
         } else {
-            const int grid = ceil_div(g.N, 32);
+            // few column blocks (N / 32) and a long K: split K over gridDim.y so that ~150 CTAs share the weight matrix
+            const int nblk = ceil_div(g.N, 32);
+            int ks = 1;
+            if (!g.atomic && !g.accumulate && g.K >= 512) ks = max(1, min(g.K / 128, 160 / nblk));
+            if (ks > 1) {
+                if (cudaMemset2DAsync(g.C, (size_t)g.ldc * sizeof(float), 0, (size_t)g.N * sizeof(float), (size_t)g.M, st) != cudaSuccess) ks = 1;
+                else g.atomic = 1;
+            }
+            const dim3 grid(nblk, ks);
             if (g.M <= 16) gemm_skinny_nn_kernel<16><<<grid, 256, 0, st>>>(g);
             else gemm_skinny_nn_kernel<32><<<grid, 256, 0, st>>>(g);
         }

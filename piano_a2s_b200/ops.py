@@ -1130,6 +1130,8 @@ class StaffRun:
         V, E = emb.shape
         assert D == 512 and A == 256 and E == 16 and V <= 256, "decoder kernels are specialised for hidden_size=256, note_emb_size=16"
         self.prec = current_precision()
+        # weight-stationary products of the kernels: tensor cores (bf16 hi/lo split, ~5e-6) in the training precisions, exact FFMA in fp32
+        self.tc = int(self.prec != "fp32" and os.environ.get("PA2S_DECM_TC", "1") == "1")
         self.enc, self.B, self.T, self.D, self.A, self.V, self.E = enc, B, T, D, A, V, E
         self.VP = (V + 3) // 4 * 4
         self.bars, self.max_steps, self.steps = bars, max_steps, [int(x) for x in steps]
@@ -1191,7 +1193,7 @@ class StaffRun:
         scratch = dict(xbuf=e(R, E + D), logits=z(R, VP), pm=e(R, NS), pl=e(R, NS), pc=e(R, NS, D), tickets=z(B, dt=torch.int32),
                        sync=z(2, dt=torch.int32), eos=z(R, dt=torch.int32), counters=counters)
         args = make_decm_args(Sq, B=B, NQ=nq, T=self.T, V=V, VP=VP, S=max(Sq), max_steps=self.max_steps, NS=NS, tile=self.tile,
-                              inference=int(self.inference), save=int(self.save), Rtot=Rtot, r0=r0, bars=self.bars, k0=k0, Spitch=self.Smax,
+                              inference=int(self.inference), save=int(self.save), Rtot=Rtot, r0=r0, bars=self.bars, k0=k0, Spitch=self.Smax, tc=self.tc,
                               enc=self.enc, Ee=self.Ee, gt=self.gt, use_gt=(self.use_gt.data_ptr() + k0 * self.Smax * 4) if self.use_gt is not None else None,
                               mask=mask, logp=self.logp, lengths=lengths, prof=PROF.get("fwd"), **self._wargs(), **sv, **scratch)
         with ktime("note_decoder_fwd"):
@@ -1226,7 +1228,7 @@ class StaffRun:
 
         def gargs(k0, nq, **extra):
             return make_decm_args(self.steps[k0:k0 + nq], B=B, NQ=nq, T=T, V=V, VP=VP, S=S, max_steps=self.max_steps, NS=NS, tile=self.tile,
-                                  inference=0, save=1, Rtot=R, r0=k0 * B, bars=self.bars, k0=k0, Spitch=S, enc=self.enc, Ee=self.Ee,
+                                  inference=0, save=1, Rtot=R, r0=k0 * B, bars=self.bars, k0=k0, Spitch=S, tc=self.tc, enc=self.enc, Ee=self.Ee,
                                   logp=self.logp, dlogp=dlogp, dhc_all=dhc_all, prof=PROF.get("bwd"), W_hT=W_hT, W_ihT=W_ihT, W_hhT=W_hhT,
                                   **self._wargs(), **sv, **bw, **extra)
         with ktime("note_decoder_bwd"):
