@@ -504,28 +504,17 @@ __device__ void finalize_row(const DecMArgs& a, int s, int q, int b, int eos_id)
 __device__ void stage_xs(const DecMArgs& a, const FwdSmem& S, int rb0, int nb, int parts, int hs_slot, int ctx_slot) {
     float4* xs4 = reinterpret_cast<float4*>(S.xs);
     const int tid = threadIdx.x;
-    constexpr int NLD = (BT * (DD / 4) + NT - 1) / NT;
     const int n4 = nb * (DD / 4);
-    float4 tk = make_float4(0.f, 0.f, 0.f, 0.f);
-    const bool has_tk = (parts & 4) && tid < nb * (DE / 4);
-    if (has_tk) tk = ldcg4(a.xbuf + (size_t)(rb0 + (tid >> 2)) * DX + (tid & 3) * 4);
+    // every part with asynchronous 16-byte copies (L2 -> shared memory, no registers): ONE L2 round trip for the whole chunk
+    if ((parts & 4) && tid < nb * (DE / 4)) cp_async16(xs4 + (tid >> 2) * XP4 + 256 + (tid & 3), a.xbuf + (size_t)(rb0 + (tid >> 2)) * DX + (tid & 3) * 4);
 #pragma unroll
     for (int part = 0; part < 2; ++part) {
         if (!(parts & (1 << part))) continue;
         const float* src = part == 0 ? a.hs + ((size_t)hs_slot * a.Rtot + a.r0 + rb0) * DD : a.ctxs + ((size_t)ctx_slot * a.Rtot + a.r0 + rb0) * DD;
-        float4 v[NLD];
-#pragma unroll
-        for (int j = 0; j < NLD; ++j) {
-            const int i = tid + j * NT;
-            if (i < n4) v[j] = ldcg4(src + (size_t)i * 4);
-        }
-#pragma unroll
-        for (int j = 0; j < NLD; ++j) {
-            const int i = tid + j * NT;
-            if (i < n4) xs4[(i >> 7) * XP4 + part * 128 + (i & 127)] = v[j];
-        }
+        for (int i = tid; i < n4; i += NT) cp_async16(xs4 + (i >> 7) * XP4 + part * 128 + (i & 127), src + (size_t)i * 4);
     }
-    if (has_tk) xs4[(tid >> 2) * XP4 + 256 + (tid & 3)] = tk;
+    cp_async_commit();
+    cp_async_wait<0>();
 }
 
 // ------------------------------------------------------------------------------------------------ phase B
@@ -915,49 +904,66 @@ constexpr int BWD_SMEM_FLOATS = WT_WORDS + BT * UP + BWD_RED_FLOATS + UPC * 2 * 
 // P3 scratch inside U: dc [NQ][DD] | Eq [NQ][DA] | dap [NCB][NQ][TILE_MAX] (ds in dap[0]) | ring [NW][RING], aliased afterwards by dqr [NW][DA]
 static_assert(NQMAX * (DD + DA + NCB * TILE_MAX) + NW * RING <= BT * UP && DA <= RING, "attention-backward scratch must fit U");
 
-// ---- P1: dh of this CTA's 8 hidden units, GRU gate gradients -> dgi_all / dgh_all / dh*z
-__device__ void bwd_gates_phase(const DecMArgs& a, const BwdSmem& S, int s, int rb0, int nb) {
+// ---- P1: dh of this CTA's 8 hidden units, GRU gate gradients -> dgi_all / dgh_all / dh*z; ALL rows in one pass (blocks of P1R rows)
+constexpr int P1R = 80;
+static_assert(P1R * 2 * QP <= BT * UP, "dq rows of a P1 block must fit U");
+__device__ void bwd_gates_all(const DecMArgs& a, const BwdSmem& S, int s, int R) {
     const int tid = threadIdx.x, cta = blockIdx.x;
-    float* dqs = S.U;                                 // [BT][2][QP]
-    __syncthreads();
-    for (int i = tid; i < nb * (DA / 4); i += NTB) {
-        const int br = i >> 6;
-        const int r = rb0 + br;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (s + 1 < g_Sq[r / a.B]) v = ldcg4(a.dq_all + ((size_t)(s + 1) * a.Rtot + a.r0 + rb0) * DA + (size_t)i * 4);
-        *reinterpret_cast<float4*>(dqs + (i >> 5) * QP + (i & 31) * 4) = v;
-    }
-    __syncthreads();
-    if (tid < 2 * UPC * BT) {
-        const int br = tid >> 4, u = (tid >> 1) & 7, half = tid & 1;
-        const int r = rb0 + br;
-        const int Sr = br < nb ? g_Sq[r / a.B] : 0;
-        const bool on = br < nb && s < Sr;
-        const bool last_step = (s == Sr - 1);
-        float dhq = 0.f;
-        if (on && !last_step) {
-            const float4* w4 = reinterpret_cast<const float4*>(S.Wq + (u * 2 + half) * QP);
-            const float4* d4 = reinterpret_cast<const float4*>(dqs + (br * 2 + half) * QP);
-#pragma unroll 8
-            for (int i = 0; i < 32; ++i) dhq += dot4(w4[i], d4[i]);
+    float* dqs = S.U;                                 // [P1R][2][QP]
+    for (int rblk = 0; rblk < R; rblk += P1R) {
+        const int nr = min(P1R, R - rblk);
+        __syncthreads();
+        for (int i = tid; i < nr * (DA / 4); i += NTB) {
+            const int br = i >> 6;
+            const int r = rblk + br;
+            float* dst = dqs + (i >> 5) * QP + (i & 31) * 4;
+            if (s + 1 < g_Sq[r / a.B]) cp_async16(dst, a.dq_all + ((size_t)(s + 1) * a.Rtot + a.r0 + rblk) * DA + (size_t)i * 4);
+            else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        dhq += __shfl_xor_sync(0xffffffffu, dhq, 1);
-        if (half == 0 && on) {
+        cp_async_commit();
+        const int nitems = nr * 2 * UPC;
+        for (int base = 0; base < nitems; base += NTB) {
+            const int it = base + tid;
+            const bool valid = it < nitems;
+            const int br = it >> 4, u = (it >> 1) & 7, half = it & 1;
+            const int r = rblk + br;
+            const int Sr = valid ? g_Sq[r / a.B] : 0;
+            const bool on = valid && s < Sr;
+            const bool last_step = (s == Sr - 1);
             const int j = cta * UPC + u;
             const size_t sb = (size_t)s * a.Rtot + a.r0 + r;
-            float dh = __ldg(a.dhc_all + sb * 2 * DD + j);
-            if (!last_step) dh += dhq + __ldcg(a.dh_carry + (size_t)r * DD + j);
-            const float* gs = a.gates + sb * 4 * DD + j;
-            const float rr = gs[0], z = gs[DD], n = gs[2 * DD], hnl = gs[3 * DD];
-            const float hp = a.hs[sb * DD + j];
-            const float dn_pre = dh * (1.f - z) * (1.f - n * n);
-            const float dr_pre = dn_pre * hnl * rr * (1.f - rr);
-            const float dz_pre = dh * (hp - n) * z * (1.f - z);
-            float* gi = a.dgi_all + sb * K3 + j;
-            float* gh = a.dgh_all + sb * K3 + j;
-            gi[0] = dr_pre; gi[DD] = dz_pre; gi[2 * DD] = dn_pre;
-            gh[0] = dr_pre; gh[DD] = dz_pre; gh[2 * DD] = dn_pre * rr;
-            a.d_hc[(size_t)r * 2 * DD + j] = dh * z;
+            // the step's saved values first (their L2 latency overlaps the wait for the dq rows and the dot product)
+            float dh = 0.f, carry = 0.f, rr = 0.f, z = 0.f, n = 0.f, hnl = 0.f, hp = 0.f;
+            if (on && half == 0) {
+                dh = __ldg(a.dhc_all + sb * 2 * DD + j);
+                if (!last_step) carry = __ldcg(a.dh_carry + (size_t)r * DD + j);
+                const float* gs = a.gates + sb * 4 * DD + j;
+                rr = gs[0]; z = gs[DD]; n = gs[2 * DD]; hnl = gs[3 * DD];
+                hp = a.hs[sb * DD + j];
+            }
+            if (base == 0) {
+                cp_async_wait<0>();
+                __syncthreads();
+            }
+            float dhq = 0.f;
+            if (on && !last_step) {
+                const float4* w4 = reinterpret_cast<const float4*>(S.Wq + (u * 2 + half) * QP);
+                const float4* d4 = reinterpret_cast<const float4*>(dqs + (br * 2 + half) * QP);
+#pragma unroll 8
+                for (int i = 0; i < 32; ++i) dhq += dot4(w4[i], d4[i]);
+            }
+            dhq += __shfl_xor_sync(0xffffffffu, dhq, 1);
+            if (half == 0 && on) {
+                if (!last_step) dh += dhq + carry;
+                const float dn_pre = dh * (1.f - z) * (1.f - n * n);
+                const float dr_pre = dn_pre * hnl * rr * (1.f - rr);
+                const float dz_pre = dh * (hp - n) * z * (1.f - z);
+                float* gi = a.dgi_all + sb * K3 + j;
+                float* gh = a.dgh_all + sb * K3 + j;
+                gi[0] = dr_pre; gi[DD] = dz_pre; gi[2 * DD] = dn_pre;
+                gh[0] = dr_pre; gh[DD] = dz_pre; gh[2 * DD] = dn_pre * rr;
+                a.d_hc[(size_t)r * 2 * DD + j] = dh * z;
+            }
         }
     }
 }
@@ -972,16 +978,9 @@ __device__ void bwd_gemv_phase(const DecMArgs& a, const BwdSmem& S, int s, int r
     __syncthreads();
     {
         float4* u4 = reinterpret_cast<float4*>(S.U);
-#pragma unroll
-        for (int b0 = 0; b0 < BT; b0 += 8) {
-            float4 v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (b0 + j < nb) v[j] = ldcg4(src + ((size_t)(b0 + j) * (K3 / 4) + tid) * 4);
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (b0 + j < nb) u4[(b0 + j) * UP4 + tid] = v[j];
-        }
+        for (int br = 0; br < nb; ++br) cp_async16(u4 + br * UP4 + tid, src + ((size_t)br * (K3 / 4) + tid) * 4);
+        cp_async_commit();
+        cp_async_wait<0>();
     }
     __syncthreads();
     const float4* x4 = reinterpret_cast<const float4*>(S.U);
@@ -1352,10 +1351,7 @@ __global__ void __launch_bounds__(NTB, 1) decm_bwd_kernel(DecMArgs a) {
     const int nitems = B * a.NS;
     unsigned long long prof_t = gtimer();
     for (int s = a.S - 1; s >= 0; --s) {
-        for (int ch = 0; ch < nchunks; ++ch) {
-            const int rb0 = ch * BT, nb = min(BT, R - rb0);
-            if (chunk_active(a, s, rb0, nb)) bwd_gates_phase(a, S, s, rb0, nb);
-        }
+        bwd_gates_all(a, S, s, R);
         PROF_MARK(0);
         grid_sync(a.sync, target);
         PROF_MARK(1);

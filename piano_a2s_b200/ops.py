@@ -1149,7 +1149,10 @@ class StaffRun:
         if self.gt is not None:
             assert self.gt.shape == (B, bars, max_steps) and self.gt.dtype == torch.int64
         self.use_gt, self.mask = use_gt, mask                      # (bars, Smax) int32 / (Smax, Rtot, E) fp32 on the device, or None
-        S, R = self.Smax, self.Rtot
+        # buffers are sized for Smax rounded up to a multiple of 16 steps: the sizes then repeat from step to step and the caching
+        # allocator serves them from its pool (a fresh cudaMalloc in the middle of a step stalls the launch thread for tens of ms)
+        self.Salloc = (self.Smax + 15) // 16 * 16
+        S, R = self.Salloc, self.Rtot
         self.sv = None
         if self.save:
             # zero-filled: rows of bars with fewer steps than Smax are never written but are read (times zero) by the contractions
@@ -1220,9 +1223,10 @@ class StaffRun:
         nqmax = lib.pa2s_decm_max_queries()
         groups = [(k0, min(nqmax, self.bars - k0)) for k0 in range(0, self.bars, nqmax)]
         nblk = lib.pa2s_decm_deferred_blocks(T)
-        bw = dict(dlogits_all=e(S, R, VP), dgi_all=z(S, R, 3 * D), dgh_all=z(S, R, 3 * D), dq_all=z(S + 1, R, A), dctx_all=z(S, R, D),
-                  dxtok_all=z(S, R, E), ds_all=z(S, R, T))
-        dhc_all = e(S * R, 2 * D)
+        Sa = self.Salloc
+        bw = dict(dlogits_all=e(Sa, R, VP), dgi_all=z(Sa, R, 3 * D), dgh_all=z(Sa, R, 3 * D), dq_all=z(Sa + 1, R, A), dctx_all=z(Sa, R, D),
+                  dxtok_all=z(Sa, R, E), ds_all=z(Sa, R, T))
+        dhc_all = e(Sa * R, 2 * D)
         dhq = e(R, D)
         st = stream()
 
@@ -1247,7 +1251,7 @@ class StaffRun:
                 SYNC_FLAGS.append(scr["sync"])
                 dEp = scr["dEp"] if dEp is None else dEp + scr["dEp"]
                 dv_parts.append(scr["dv_part"])
-        dxt = bw["dxtok_all"]
+        dxt = bw["dxtok_all"][:S]
         if self.mask is not None:
             dxt = dxt * self.mask[:S]
         rec = dict(S=S, B=R, dlogits=bw["dlogits_all"], hs=sv["hs"], ctxs=sv["ctxs"], dgi=bw["dgi_all"], dgh=bw["dgh_all"], dq=bw["dq_all"],
