@@ -62,6 +62,20 @@ PA2S_API int pa2s_gemm_bf16_tma(void* stream, int M, int N, int K,
                                 const void* B, long long b_ld, long long b_piece_stride, long long b_batch_stride, int b_pieces, int b_mn,
                                 float* C, long long ldc, long long strideC, const float* bias, int atomic, int batch, int splitk);
 
+/* the same contraction with the VQT epilogue fused: N columns = (re, im) pairs; writes mag (batch, M, N/2) = |.| and folds each batch's
+ * maximum into clip_max[batch] (uint32 view of a non-negative float, zeroed by the caller); rows >= valid_rows[batch] (or all rows when
+ * NULL) ... are zeros and stay out of the maximum.  Replaces librosa.vqt + np.abs + the `ref=np.max` reduction of utilities.py:246-253. */
+PA2S_API int pa2s_gemm_bf16_tma_mag(void* stream, int M, int N, int K,
+                                    const void* A, long long a_ld, long long a_piece_stride, long long a_batch_stride, int a_pieces, int a_mn,
+                                    const void* B, long long b_ld, long long b_piece_stride, long long b_batch_stride, int b_pieces, int b_mn,
+                                    float* mag, long long strideMag, unsigned int* clip_max, const int* valid_rows, int batch);
+
+/* ---- audio ingest (utilities.py:241-242 `librosa.load(sr=16000)`, datasets/asap.py:80-86) ---------------------------------
+ * y[c][m] = sum_i x[c][i] * h[taps/2 + m*down - i*up]: rational resampling with a host-designed odd-length FIR (scaled by `up`);
+ * n_out = ceil(n_in * up / down).  x: (channels, n_in), y: (channels, n_out). */
+PA2S_API int pa2s_resample_poly(void* stream, const float* x, int channels, long long n_in, int up, int down, const float* h, int taps,
+                                float* y, long long n_out);
+
 /* ---- VQT front end (utilities.py:246-253) -------------------------------------------------------------------
  * C: (nclips*rows_per_clip, 2*nb) filterbank responses (re,im interleaved).  Writes
  * out = amplitude_to_db(|V|, ref=max over the clip, amin=1e-5, top_db=80)/80 + 1 as (nclips, rows_per_clip, nb).
@@ -69,6 +83,9 @@ PA2S_API int pa2s_gemm_bf16_tma(void* stream, int M, int N, int K,
  * (the zero padding of pad_spectrogram, datasets/asap.py:345-349). */
 PA2S_API int pa2s_vqt_post(void* stream, const float* C, float* out, unsigned int* clip_max, int nclips, int rows_per_clip, int nb,
                           const int* valid_rows);
+/* the dB / scale half alone, in place on magnitudes written by pa2s_gemm_bf16_tma_mag */
+PA2S_API int pa2s_vqt_logscale(void* stream, float* mag, const unsigned int* clip_max, int nclips, int rows_per_clip, int nb,
+                              const int* valid_rows);
 
 /* ---- ConvStack (models.py:463-543) ---------------------------------------------------------------------------
  * mode 0: Y = conv3x3(relu?(X*in_scale+in_shift)) (in_scale NULL = identity), Wpacked = W.permute(2,3,1,0);

@@ -150,6 +150,26 @@ __global__ void greedy_tokens_kernel(const float* __restrict__ logp, int L, int 
     if (threadIdx.x == 0) lengths[seq] = first_eos;
 }
 
+// Rational resampling up/down with a polyphase FIR (audio ingest, utilities.py:242 `librosa.load(sr=16000)`):
+//   y[c][m] = sum_i x[c][i] * h[half + m*down - i*up],   0 <= half + m*down - i*up < L
+// h (L = 2*half+1 taps, already scaled by `up`) is designed on the host.  One thread per output sample; x is read through L1 (the
+// windows of neighbouring outputs overlap almost entirely), h through the read-only cache.
+__global__ void resample_poly_kernel(const float* __restrict__ x, int C, long long n_in, int up, int down, const float* __restrict__ h,
+                                     int L, int half, float* __restrict__ y, long long n_out) {
+    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.y;
+    if (m >= n_out) return;
+    const long long t = m * down + half;
+    long long i_lo = (t - (L - 1) + up - 1) / up;            // ceil((t - (L-1)) / up), t - (L-1) may be negative
+    if (t - (L - 1) < 0) i_lo = 0;
+    long long i_hi = t / up;
+    if (i_hi > n_in - 1) i_hi = n_in - 1;
+    const float* xc = x + (long long)c * n_in;
+    double acc = 0.0;                                        // fp64 accumulation: ~20..60 taps per output, keeps 1e-7 parity with the fp64 oracle
+    for (long long i = i_lo; i <= i_hi; ++i) acc += (double)__ldg(xc + i) * (double)__ldg(h + (t - i * up));
+    y[(long long)c * n_out + m] = (float)acc;
+}
+
 }  // namespace
 
 PA2S_API int pa2s_vqt_post(void* stream, const float* C, float* out, unsigned int* clip_max, int nclips, int rows_per_clip, int nb,
@@ -160,6 +180,15 @@ PA2S_API int pa2s_vqt_post(void* stream, const float* C, float* out, unsigned in
     vqt_mag_kernel<<<ceil_div(n, 256), 256, 0, st>>>((const float2*)C, out, clip_max, n, nb, rows_per_clip, valid_rows);
     PA2S_CHECK_LAST();
     vqt_logscale_kernel<<<ceil_div(n, 256), 256, 0, st>>>(out, clip_max, n, nb, rows_per_clip, valid_rows);
+    PA2S_CHECK_LAST();
+    return 0;
+}
+
+// second half of the VQT epilogue on magnitudes the filterbank GEMM has already written (pa2s_gemm_bf16_tma_mag), in place
+PA2S_API int pa2s_vqt_logscale(void* stream, float* mag, const unsigned int* clip_max, int nclips, int rows_per_clip, int nb,
+                              const int* valid_rows) {
+    long long n = (long long)nclips * rows_per_clip * nb;
+    vqt_logscale_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(mag, clip_max, n, nb, rows_per_clip, valid_rows);
     PA2S_CHECK_LAST();
     return 0;
 }
@@ -274,6 +303,16 @@ PA2S_API int pa2s_pad_spectrograms(void* stream, const float* packed, const long
 PA2S_API int pa2s_greedy_tokens(void* stream, const float* logp, long long nseq, int L, int V, int eos, long long* tokens, int* lengths) {
     if (nseq <= 0 || L <= 0 || V <= 0) return nseq == 0 ? 0 : -1;
     greedy_tokens_kernel<<<(unsigned)nseq, 256, 0, (cudaStream_t)stream>>>(logp, L, V, eos, tokens, lengths);
+    PA2S_CHECK_LAST();
+    return 0;
+}
+
+PA2S_API int pa2s_resample_poly(void* stream, const float* x, int channels, long long n_in, int up, int down, const float* h, int taps,
+                                float* y, long long n_out) {
+    if (channels <= 0 || n_out <= 0) return 0;
+    if (up < 1 || down < 1 || taps < 1 || (taps & 1) == 0) return -1;
+    resample_poly_kernel<<<dim3(ceil_div(n_out, 256), channels), 256, 0, (cudaStream_t)stream>>>(x, channels, n_in, up, down, h, taps,
+                                                                                               taps / 2, y, n_out);
     PA2S_CHECK_LAST();
     return 0;
 }

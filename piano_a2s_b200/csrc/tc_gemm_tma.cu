@@ -37,6 +37,9 @@ struct TmaGemmArgs {
     int nA, nB, a_mn, b_mn, nstage;
     int a_bz, b_bz;                 // 0: the operand is shared by all batches
     uint32_t stage_bytes, b_piece_bytes;
+    // complex-magnitude epilogue (the VQT filterbank, utilities.py:246-253): columns are (re, im) pairs; instead of C the kernel writes
+    // mag[bz][m][n/2] = |re + i im| and folds the per-batch maximum into clip_max[bz] (bit pattern of a non-negative float)
+    float* mag; unsigned int* clip_max; const int* valid_rows; long long sMag;
 };
 
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
@@ -105,6 +108,37 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_tma_kernel(const __grid_c
             float* crow = g.C + (long long)c.bz * g.sC + (long long)m * g.ldc;
             const bool use_atomic = g.atomic || g.splitk > 1;
             const bool vec = !use_atomic && (g.ldc % 4 == 0) && (g.sC % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
+            if (g.mag != nullptr) {
+                // fused |.| + per-clip maximum: rows past the clip's own frames (valid_rows) are written as zeros and stay out of the max
+                const bool row_ok = m < g.M && (g.valid_rows == nullptr || m < __ldg(g.valid_rows + c.bz));
+                float* mrow = g.mag + (long long)c.bz * g.sMag + (long long)m * (g.N / 2);
+                float rmax = 0.f;
+                for (int c0 = 0; c0 < BN; c0 += 16) {
+                    const int n0 = c.tn * BN + c0;
+                    if (n0 >= g.N) break;                               // warp-uniform
+                    float v[16];
+                    tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BNMAX + c0), v);
+                    if (m >= g.M) continue;
+                    float mg[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        mg[i] = row_ok ? sqrtf(v[2 * i] * v[2 * i] + v[2 * i + 1] * v[2 * i + 1]) : 0.f;
+                        if (n0 + 2 * i < g.N) rmax = fmaxf(rmax, mg[i]);
+                    }
+                    if (n0 + 15 < g.N) {
+                        reinterpret_cast<float4*>(mrow + n0 / 2)[0] = make_float4(mg[0], mg[1], mg[2], mg[3]);
+                        reinterpret_cast<float4*>(mrow + n0 / 2)[1] = make_float4(mg[4], mg[5], mg[6], mg[7]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) if (n0 + 2 * i < g.N) mrow[n0 / 2 + i] = mg[i];
+                    }
+                }
+                rmax = warp_max(rmax);                                  // (a tile never straddles two batches: bz is tile-uniform)
+                if (lane == 0 && rmax > 0.f) atomicMax(g.clip_max + c.bz, __float_as_uint(rmax));
+                tc_fence_before();
+                mbar_arrive(&tempty_bar[acc]);
+                continue;
+            }
             for (int c0 = 0; c0 < BN; c0 += 16) {
                 const int n0 = c.tn * BN + c0;
                 if (n0 >= g.N) break;                                   // warp-uniform
@@ -321,13 +355,16 @@ PA2S_API int pa2s_split_bf16(void* stream, const float* src, long long rows, lon
 // Operand X (A: rows of C, B: columns of C): bf16 pieces at x + piece * x_piece_stride + batch * x_batch_stride (elements);
 // x_mn = 0: stored [mn][k] with row pitch x_ld (K-major); x_mn = 1: stored [k][mn] (MN-major).  Pitches are multiples of 8
 // elements, base pointers 16-byte aligned; x_batch_stride = 0 shares the operand between batches.  `atomic` (or splitk > 1) accumulates into C with atomicAdd.
-PA2S_API int pa2s_gemm_bf16_tma(void* stream, int M, int N, int K,
-                                const void* A, long long a_ld, long long a_piece_stride, long long a_batch_stride, int a_pieces, int a_mn,
-                                const void* B, long long b_ld, long long b_piece_stride, long long b_batch_stride, int b_pieces, int b_mn,
-                                float* C, long long ldc, long long strideC, const float* bias, int atomic, int batch, int splitk) {
+static int launch_tma_gemm(void* stream, int M, int N, int K,
+                           const void* A, long long a_ld, long long a_piece_stride, long long a_batch_stride, int a_pieces, int a_mn,
+                           const void* B, long long b_ld, long long b_piece_stride, long long b_batch_stride, int b_pieces, int b_mn,
+                           float* C, long long ldc, long long strideC, const float* bias, int atomic, int batch, int splitk,
+                           float* mag, unsigned int* clip_max, const int* valid_rows, long long strideMag) {
     if (M <= 0 || N <= 0 || batch <= 0) return 0;
     if (K <= 0 || a_pieces < 1 || a_pieces > 3 || b_pieces < 1 || b_pieces > 3) return -1;
     TmaGemmArgs g;
+    g.mag = mag; g.clip_max = clip_max; g.valid_rows = valid_rows; g.sMag = strideMag;
+    if (mag != nullptr && (splitk > 1 || atomic || (N & 15) != 0 || ((uintptr_t)mag & 15) != 0 || (strideMag & 3) != 0)) return -1;
     g.C = C; g.bias = bias; g.M = M; g.N = N; g.K = K; g.ldc = ldc; g.sC = strideC; g.batch = batch;
     g.nA = a_pieces; g.nB = b_pieces; g.a_mn = a_mn ? 1 : 0; g.b_mn = b_mn ? 1 : 0;
     // UMMA N: multiple of 16 (64 for an MN-major B, whose boxes are 64 columns wide), shrunk until two stages fit
@@ -368,4 +405,24 @@ PA2S_API int pa2s_gemm_bf16_tma(void* stream, int M, int N, int K,
     tc_gemm_tma_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, g);
     PA2S_CHECK_LAST();
     return 0;
+}
+
+PA2S_API int pa2s_gemm_bf16_tma(void* stream, int M, int N, int K,
+                                const void* A, long long a_ld, long long a_piece_stride, long long a_batch_stride, int a_pieces, int a_mn,
+                                const void* B, long long b_ld, long long b_piece_stride, long long b_batch_stride, int b_pieces, int b_mn,
+                                float* C, long long ldc, long long strideC, const float* bias, int atomic, int batch, int splitk) {
+    return launch_tma_gemm(stream, M, N, K, A, a_ld, a_piece_stride, a_batch_stride, a_pieces, a_mn, B, b_ld, b_piece_stride, b_batch_stride,
+                           b_pieces, b_mn, C, ldc, strideC, bias, atomic, batch, splitk, nullptr, nullptr, nullptr, 0);
+}
+
+// The same contraction with the VQT epilogue fused (utilities.py:246-253): the N columns are (re, im) pairs of N/2 bins; writes
+// mag[batch][m][N/2] = |.| and atomically folds each batch's maximum into clip_max[batch] (zero it first).  valid_rows (int32 per batch or
+// NULL): rows >= valid_rows[batch] are written as zeros and excluded from the maximum (frames the un-padded clip does not have).
+PA2S_API int pa2s_gemm_bf16_tma_mag(void* stream, int M, int N, int K,
+                                    const void* A, long long a_ld, long long a_piece_stride, long long a_batch_stride, int a_pieces, int a_mn,
+                                    const void* B, long long b_ld, long long b_piece_stride, long long b_batch_stride, int b_pieces, int b_mn,
+                                    float* mag, long long strideMag, unsigned int* clip_max, const int* valid_rows, int batch) {
+    if (mag == nullptr || clip_max == nullptr) return -1;
+    return launch_tma_gemm(stream, M, N, K, A, a_ld, a_piece_stride, a_batch_stride, a_pieces, a_mn, B, b_ld, b_piece_stride, b_batch_stride,
+                           b_pieces, b_mn, nullptr, 0, 0, nullptr, 0, batch, 1, mag, clip_max, valid_rows, strideMag);
 }

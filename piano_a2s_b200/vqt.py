@@ -82,22 +82,33 @@ class VQT(torch.nn.Module):
         plen = ((half + n + half + self.hop + 3) // 4) * 4
         ypad = torch.zeros(B, plen, device=audio.device, dtype=torch.float32)
         ypad[:, half:half + n] = audio
-        C = torch.empty(B, T, 2 * self.n_bins, device=audio.device, dtype=torch.float32)
-        # frames[t, j] = ypad[t*hop + j0 + j]: overlapping rows, lda = hop
-        filt = self.filters
-        if self.precision != "fp32":                 # the filter bank is constant: split it into bf16 pieces once
-            if self._fop is None or self._fop[0] != (self.precision, filt.device):
-                self._fop = ((self.precision, filt.device), ops.split_operand(filt, 2 * self.n_bins, K, K, npieces=ops.npieces_for(self.precision)))
-            filt = self._fop[1]
-        with ops.ktime("vqt_filterbank"):
-            ops.gemm(ypad, filt, C, T, 2 * self.n_bins, K, transB=True, lda=self.hop, ldb=K, ldc=2 * self.n_bins,
-                     batch=B, strideA=plen, strideB=0, strideC=T * 2 * self.n_bins, a_off=self.j0, precision=self.precision)
-        out = torch.empty(B, T, self.n_bins, device=audio.device, dtype=torch.float32)
-        cmax = torch.empty(B, device=audio.device, dtype=torch.int32)
         valid = None
         if n_samples is not None:
             valid = (1 + torch.div(n_samples.to(audio.device), self.hop, rounding_mode="floor")).to(torch.int32).contiguous()
-        lib.pa2s_vqt_post(stream(), ptr(C), ptr(out), ptr(cmax), B, T, self.n_bins, ptr(valid))
+        out = torch.empty(B, T, self.n_bins, device=audio.device, dtype=torch.float32)
+        cmax = torch.zeros(B, device=audio.device, dtype=torch.int32)
+        # frames[t, j] = ypad[t*hop + j0 + j]: overlapping rows, lda = hop
+        if self.precision == "fp32":
+            C = torch.empty(B, T, 2 * self.n_bins, device=audio.device, dtype=torch.float32)
+            with ops.ktime("vqt_filterbank"):
+                ops.gemm(ypad, self.filters, C, T, 2 * self.n_bins, K, transB=True, lda=self.hop, ldb=K, ldc=2 * self.n_bins,
+                         batch=B, strideA=plen, strideB=0, strideC=T * 2 * self.n_bins, a_off=self.j0, precision="fp32")
+            lib.pa2s_vqt_post(stream(), ptr(C), ptr(out), ptr(cmax), B, T, self.n_bins, ptr(valid))
+            return out
+        # tensor-core path: the filter bank is constant (split into bf16 pieces once); |.| and the per-clip maximum are the EPILOGUE of
+        # the contraction (the (B, T, 960) complex responses never reach HBM), the dB / scale pass then works in place on the magnitudes
+        npc = ops.npieces_for(self.precision)
+        if self._fop is None or self._fop[0] != (self.precision, self.filters.device):
+            self._fop = ((self.precision, self.filters.device), ops.split_operand(self.filters, 2 * self.n_bins, K, K, npieces=npc))
+        Bop = self._fop[1]
+        none = dict(t_scale=None, t_shift=None, t_period=1, t_relu=False)
+        with ops.ktime("vqt_filterbank"):
+            Aop, a_mn, a_ld = ops._operand(ypad, False, T, K, self.hop, self.j0, B, plen, npc, none)
+            lib.pa2s_gemm_bf16_tma_mag(stream(), T, 2 * self.n_bins, K,
+                                       ptr(Aop.buf), a_ld or Aop.ld, Aop.piece_stride, Aop.batch_stride, Aop.npieces, int(a_mn),
+                                       ptr(Bop.buf), Bop.ld, Bop.piece_stride, Bop.batch_stride, Bop.npieces, 0,
+                                       ptr(out), T * self.n_bins, ptr(cmax), ptr(valid), B)
+        lib.pa2s_vqt_logscale(stream(), ptr(out), ptr(cmax), B, T, self.n_bins, ptr(valid))
         return out
 
 
@@ -105,11 +116,14 @@ _CACHE = {}
 
 
 def get_VQT(audio_or_path, hparams):
-    """Same signature as utilities.get_VQT: (frames, n_bins) float32 numpy for one clip."""
-    if isinstance(audio_or_path, str):
-        raise NotImplementedError("file decoding/resampling (librosa.load) is outside the hot path; pass a 16 kHz mono array")
+    """Same signature as utilities.get_VQT: a 16 kHz mono array or the path of a .wav file -> (frames, n_bins) float32 numpy."""
     key = (hparams["sample_rate"], hparams["hop_length"], hparams["bins_per_octave"], hparams["n_octaves"], hparams["gamma"])
     if key not in _CACHE:
         _CACHE[key] = VQT(*key).cuda()
-    y = torch.as_tensor(np.asarray(audio_or_path), dtype=torch.float32).cuda().reshape(1, -1)
+    if isinstance(audio_or_path, (str, os.PathLike)):
+        # `librosa.load(audio, sr=hparams['sample_rate'])` of utilities.py:241-242: WAVE decode + mono + resampling (audio.load)
+        from .audio import load
+        y = load(os.fspath(audio_or_path), sr=hparams["sample_rate"]).reshape(1, -1)
+    else:
+        y = torch.as_tensor(np.asarray(audio_or_path), dtype=torch.float32).cuda().reshape(1, -1)
     return _CACHE[key](y)[0].cpu().numpy()
