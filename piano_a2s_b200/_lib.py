@@ -117,20 +117,26 @@ class DecMArgs(ctypes.Structure):
     """Mirror of `struct DecMArgs` in csrc/decm_args.cuh (field order and types must match exactly)."""
     _ints = ["B", "NQ", "T", "V", "VP", "S", "max_steps", "NS", "tile", "inference", "save", "Rtot", "r0", "bars", "k0", "Spitch", "tc"]
     _ptrs = ["enc", "Ee", "Wattn", "v", "emb", "W_ih", "W_hh", "b_ih", "b_hh", "W_out", "b_out", "W_hT", "W_ihT", "W_hhT",
-             "gt", "use_gt", "mask", "logp", "lengths", "eos", "counters",
+             "gt", "mask", "logp", "lengths", "eos", "counters",
              "hs", "ctxs", "attn", "gates", "qs", "eqs", "xtok", "toks", "ml",
              "xbuf", "logits", "pm", "pl", "pc", "tickets", "sync",
              "dhc_all", "dgi_all", "dgh_all", "dq_all", "dctx_all", "dxtok_all", "ds_all", "dEp", "dv_part", "d_hc", "dhq", "dx",
              "dq_part", "dh_carry", "dlogp", "dlogits_all", "prof"]
-    _fields_ = [(n, ctypes.c_int) for n in _ints] + [("Sq", ctypes.c_int * 8)] + [(n, ctypes.c_void_p) for n in _ptrs]
+    _fields_ = [(n, ctypes.c_int) for n in _ints] + [("Sq", ctypes.c_int * 8), ("tf_bits", ctypes.c_uint * 64), ("has_tf", ctypes.c_int),
+                                                     ("pad_", ctypes.c_int)] + [(n, ctypes.c_void_p) for n in _ptrs]
 
 
-def make_decm_args(Sq, **kw):
-    """Pointer fields take a tensor, a raw int address (pre-offset views) or None."""
+def make_decm_args(Sq, tf_bits=None, **kw):
+    """Pointer fields take a tensor, a raw int address (pre-offset views) or None.  tf_bits: python int bit mask (bit q * Spitch + s) or None."""
     a = DecMArgs()
     assert len(Sq) <= 8
     for i, v in enumerate(Sq):
         a.Sq[i] = int(v)
+    if tf_bits is not None:
+        assert tf_bits >> 2048 == 0, "teacher-forcing mask of a launch is limited to 2048 (query, step) pairs"
+        a.has_tf = 1
+        for i in range(64):
+            a.tf_bits[i] = (tf_bits >> (32 * i)) & 0xFFFFFFFF
     for k, v in kw.items():
         if k in DecMArgs._ints:
             setattr(a, k, int(v))

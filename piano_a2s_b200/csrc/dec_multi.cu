@@ -176,6 +176,7 @@ constexpr int WTP = 3 * DD / 2 + 4;          // ... of the reverse kernel's W^T 
 // per-query step counts, copied to shared memory at kernel start (dynamic indexing of the kernel-parameter array would force a
 // local-memory copy of the whole argument block)
 __shared__ int g_Sq[8];
+__shared__ unsigned int g_tf[64];      // teacher-forcing coins of the launch (same reason)
 
 constexpr int RED_FLOATS = NW * BT * GR;               // FFMA path: (4 clip groups x 8 warps) x (24 rows x 4 clips) = 3072; MMA path: 12 warps x 16 x 24
 constexpr int WG_WORDS = 2 * GR * WGP;                 // >= GR * 2 * DD + GR * DE (fp32 layout of the FFMA path)
@@ -480,7 +481,8 @@ __device__ void finalize_row(const DecMArgs& a, int s, int q, int b, int eos_id)
     int tok = 0;
     if (lane == 0) {
         const long long gtv = a.gt != nullptr ? a.gt[ro] : -1;
-        const bool tf = (!a.inference) && a.use_gt != nullptr && a.gt != nullptr && a.use_gt[q * a.Spitch + s] != 0;
+        const int tb = q * a.Spitch + s;
+        const bool tf = (!a.inference) && a.has_tf && a.gt != nullptr && ((g_tf[tb >> 5] >> (tb & 31)) & 1u);
         tok = tf ? (int)gtv : idx;
         const bool hit = a.gt != nullptr ? (gtv == eos_id) : (idx == eos_id);
         if (hit) {
@@ -737,6 +739,10 @@ __global__ void __launch_bounds__(NT, 1) decm_fwd_kernel(DecMArgs a, int eos_id)
     const int tid = threadIdx.x, cta = blockIdx.x, warp = tid >> 5;
     unsigned int target = 0;
     if (tid < 8) g_Sq[tid] = tid == 0 ? a.Sq[0] : tid == 1 ? a.Sq[1] : tid == 2 ? a.Sq[2] : tid == 3 ? a.Sq[3] : tid == 4 ? a.Sq[4] : tid == 5 ? a.Sq[5] : tid == 6 ? a.Sq[6] : a.Sq[7];
+    if (tid == 32) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) g_tf[i] = a.tf_bits[i];        // (compile-time indices: read straight from the parameter bank)
+    }
 
     // ---- one-time: this CTA's weight slices -> shared memory
     if (TC) {

@@ -16,6 +16,8 @@ struct DecMArgs {
     int B, NQ, T, V, VP, S, max_steps, NS, tile, inference, save, Rtot, r0, bars, k0, Spitch;
     int tc;                  // 1: weight-stationary products on the tensor cores (bf16 hi/lo split, fp32 accumulate); 0: exact fp32 FFMA
     int Sq[8];               // executed steps of query q (1 <= Sq[q] <= S = max_q Sq[q])
+    unsigned int tf_bits[64];// note-level teacher-forcing coins (models.py:404) of this launch, bit q * Spitch + s (NQ * Spitch <= 2048)
+    int has_tf, pad_;        // 1: tf_bits is valid (training with targets); 0: every next token is the arg-max
     // encoder memory and attention module
     const float* enc;        // (B,T,DD)
     const float* Ee;         // (B,T,DA)  exp(2 * (enc W_e^T + b)): tanh(q + Ep) = 1 - 2 / (1 + exp(2q) * Ee)
@@ -30,7 +32,6 @@ struct DecMArgs {
     const float* W_hhT;      // (DD, 3DD)
     // teacher forcing / dropout
     const long long* gt;     // (B, bars, max_steps) or null; row (q,b) reads bar k0+q
-    const int* use_gt;       // (NQ, Spitch) or null
     const float* mask;       // (S, Rtot, DE) or null: dropout mask of the input embedding of (step, global row), like xtok
     // outputs
     float* logp;             // (B, bars, max_steps, V), pre-zeroed; row (q,b) writes bar k0+q

@@ -308,9 +308,7 @@ class HierarchicalDecoder(nn.Module):
         Smax = [max(steps[0]), max(steps[1])]
         bar_masks = None
         note_masks = [None, None]
-        use_gt_h = None
-        if have_gt and not inference:
-            use_gt_h = [torch.zeros((nb, Smax[si]), dtype=torch.int32, pin_memory=True) for si in (0, 1)]
+        tf_bits = [[0] * nb, [0] * nb] if (have_gt and not inference) else [None, None]
         if training and iid:
             bar_masks = src.dropout_mask((nb, B, tokdim), 0.1, dev, "bar_token")
             note_masks = [src.dropout_mask((Smax[si], nb * B, E), 0.1, dev, "note_steps") for si in (0, 1)]
@@ -326,11 +324,14 @@ class HierarchicalDecoder(nn.Module):
                 if have_gt:
                     coins = src.coins(S)
                     if not inference:
-                        use_gt_h[si][bar, :S] = torch.tensor([1 if c < teacher_forcing_ratio else 0 for c in coins], dtype=torch.int32)
+                        bits = 0
+                        for st_, c in enumerate(coins):
+                            if c < teacher_forcing_ratio:
+                                bits |= 1 << st_
+                        tf_bits[si][bar] = bits
                 if training and not iid:
                     note_masks[si][:S, bar * B:(bar + 1) * B] = src.dropout_mask((S, B, E), 0.1, dev, "note_steps")
             bar_tf.append(src.coin() < teacher_forcing_ratio)
-        use_gt_d = [t.to(dev, non_blocking=True) for t in use_gt_h] if use_gt_h is not None else [None, None]
         # bars k >= 1 whose token is built from bar k-1's predictions start a new segment
         nqmax = ops.lib.pa2s_decm_max_queries()
         segs, k0 = [], 0
@@ -354,7 +355,7 @@ class HierarchicalDecoder(nn.Module):
         for si, (dec, Ep) in enumerate(zip(decs, (Ep_up, Ep_lo))):
             gt_staff = (upper_gt, lower_gt)[si] if have_gt else None
             runs.append(ops.StaffRun(dec._weights(), enc, Ep, nb, dec.max_steps, steps[si], inference or not have_gt, grad, sides[si],
-                                     SOS, EOS, gt=gt_staff, use_gt=use_gt_d[si], mask=note_masks[si]))
+                                     SOS, EOS, gt=gt_staff, tf_bits=tf_bits[si], mask=note_masks[si]))
 
         token = self.get_SOS_token(B)[0].squeeze(1)                      # (B, 4*staff+ts+key)
         h = hidden[0]

@@ -1119,7 +1119,7 @@ class StaffRun:
     bar summaries `h0` are known) in one cooperative kernel on `self.stream`; `backward(dlogp)` runs the reverse pass over ALL
     rows in one launch (per group of pa2s_decm_max_queries() bars) followed by the weight-gradient contractions."""
 
-    def __init__(self, weights, enc, Ep, bars, max_steps, steps, inference, save, side, sos, eos, gt=None, use_gt=None, mask=None):
+    def __init__(self, weights, enc, Ep, bars, max_steps, steps, inference, save, side, sos, eos, gt=None, tf_bits=None, mask=None):
         self.w = tuple(weights)
         attn_w, attn_v, emb, W_ih, W_hh, b_ih, b_hh, W_out, b_out = self.w
         for k, w in zip(("attn_w", "attn_v", "emb", "W_ih", "W_hh", "b_ih", "b_hh", "W_out", "b_out"), self.w):
@@ -1148,7 +1148,9 @@ class StaffRun:
         self.gt = gt.contiguous() if gt is not None else None
         if self.gt is not None:
             assert self.gt.shape == (B, bars, max_steps) and self.gt.dtype == torch.int64
-        self.use_gt, self.mask = use_gt, mask                      # (bars, Smax) int32 / (Smax, Rtot, E) fp32 on the device, or None
+        # tf_bits: per bar, a python int whose bit s says 'step s takes its next token from the targets' (the pre-drawn coins of
+        # models.py:404; they travel in the kernel's argument block: no device tensor, no H2D copy); mask: (Smax, Rtot, E) fp32 or None
+        self.tf_bits, self.mask = tf_bits, mask
         # buffers are sized for Smax rounded up to a multiple of 16 steps: the sizes then repeat from step to step and the caching
         # allocator serves them from its pool (a fresh cudaMalloc in the middle of a step stalls the launch thread for tens of ms)
         self.Salloc = (self.Smax + 15) // 16 * 16
@@ -1160,7 +1162,7 @@ class StaffRun:
                            qs=z(S + 1, R, A), eqs=z(S, R, A), xtok=z(S + 1, R, E), toks=z(S + 1, R, dt=torch.int32), ml=z(S, R, 2))
         self.counters = []
         self.shared = [self.Ee, self.logp, self.lengths, self.enc] + ([self.gt] if self.gt is not None else []) + \
-                      ([self.use_gt] if self.use_gt is not None else []) + ([self.mask] if self.mask is not None else []) + \
+                      ([self.mask] if self.mask is not None else []) + \
                       (list(self.sv.values()) if self.sv else [])
         if side is not None:
             for t_ in self.shared:
@@ -1195,9 +1197,14 @@ class StaffRun:
         counters = z(2, dt=torch.int32)
         scratch = dict(xbuf=e(R, E + D), logits=z(R, VP), pm=e(R, NS), pl=e(R, NS), pc=e(R, NS, D), tickets=z(B, dt=torch.int32),
                        sync=z(2, dt=torch.int32), eos=z(R, dt=torch.int32), counters=counters)
-        args = make_decm_args(Sq, B=B, NQ=nq, T=self.T, V=V, VP=VP, S=max(Sq), max_steps=self.max_steps, NS=NS, tile=self.tile,
+        bits = None
+        if self.tf_bits is not None:
+            bits = 0
+            for q in range(nq):
+                bits |= self.tf_bits[k0 + q] << (q * self.Smax)
+        args = make_decm_args(Sq, bits, B=B, NQ=nq, T=self.T, V=V, VP=VP, S=max(Sq), max_steps=self.max_steps, NS=NS, tile=self.tile,
                               inference=int(self.inference), save=int(self.save), Rtot=Rtot, r0=r0, bars=self.bars, k0=k0, Spitch=self.Smax, tc=self.tc,
-                              enc=self.enc, Ee=self.Ee, gt=self.gt, use_gt=(self.use_gt.data_ptr() + k0 * self.Smax * 4) if self.use_gt is not None else None,
+                              enc=self.enc, Ee=self.Ee, gt=self.gt,
                               mask=mask, logp=self.logp, lengths=lengths, prof=PROF.get("fwd"), **self._wargs(), **sv, **scratch)
         with ktime("note_decoder_fwd"):
             lib.pa2s_decm_fwd(stream(), ctypes.byref(args), self.sos, self.eos)
@@ -1231,7 +1238,7 @@ class StaffRun:
         st = stream()
 
         def gargs(k0, nq, **extra):
-            return make_decm_args(self.steps[k0:k0 + nq], B=B, NQ=nq, T=T, V=V, VP=VP, S=S, max_steps=self.max_steps, NS=NS, tile=self.tile,
+            return make_decm_args(self.steps[k0:k0 + nq], None, B=B, NQ=nq, T=T, V=V, VP=VP, S=S, max_steps=self.max_steps, NS=NS, tile=self.tile,
                                   inference=0, save=1, Rtot=R, r0=k0 * B, bars=self.bars, k0=k0, Spitch=S, tc=self.tc, enc=self.enc, Ee=self.Ee,
                                   logp=self.logp, dlogp=dlogp, dhc_all=dhc_all, prof=PROF.get("bwd"), W_hT=W_hT, W_ihT=W_ihT, W_hhT=W_hhT,
                                   **self._wargs(), **sv, **bw, **extra)

@@ -19,14 +19,14 @@ Ep = torch.randn(B, T, 256, device=dev)
 for NQ in [int(x) for x in os.environ.get("PQ", "1,2,3,5").split(",")]:
     bars = NQ
     gt = torch.randint(0, 144, (B, bars, 398), device=dev)
-    use_gt = torch.ones(bars, S, dtype=torch.int32, device=dev)
+    use_gt = [(1 << S) - 1] * bars
     mask = (torch.rand(S, bars * B, 16, device=dev) > 0.1).float() / 0.9
     h0 = torch.randn(bars, B, 512, device=dev)
     dl = torch.randn(B, bars, 398, 173, device=dev) * 1e-3
 
     def run():
         with ops.use_precision(os.environ.get("PPREC", "bf16x3")):
-            r = ops.StaffRun(dec._weights(), enc, Ep, bars, 398, [S] * bars, False, True, None, models.SOS, models.EOS, gt=gt, use_gt=use_gt, mask=mask)
+            r = ops.StaffRun(dec._weights(), enc, Ep, bars, 398, [S] * bars, False, True, None, models.SOS, models.EOS, gt=gt, tf_bits=use_gt, mask=mask)
             r.launch(0, NQ, h0)
             return r.backward(dl)
 

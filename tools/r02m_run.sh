@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r02m_tests.log 2>&1; echo "tests exit $?" >> gpurun_out/r02m_tests.log
+tail -25 gpurun_out/r02m_tests.log
+bash tools/r02f_run.sh
