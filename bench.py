@@ -328,6 +328,11 @@ def run_b200(args):
     B = args.batch
     finetune = args.workload == "finetune"
     TF = tf_ratio(args.workload)
+    # One large block for the caching allocator to carve from.  The launch thread runs several steps ahead of the device, so buffers that
+    # were used on the decoder's side streams cannot be recycled until those streams have caught up, and the allocator would otherwise
+    # meet the shortfall with cudaMalloc calls in the middle of a step (each one a multi-ms stall of the launch thread; seen as
+    # 100 ms outlier steps).  A training script does the same once at start-up (train.reserve_memory).
+    train.reserve_memory(int(os.environ.get("PA2S_RESERVE_GB", "24")))
     ops.set_precision(train=args.precision)
     torch.manual_seed(1234)
     model = models.ScoreTranscription(**CFG).to(dev).train()
@@ -398,6 +403,7 @@ def run_b200(args):
     gc.freeze()
     step_device()                                # last warm-up step, after the collection (the first step after it is the slow one)
     n0 = lib.pa2s_launch_count()
+    seg0 = torch.cuda.memory_stats(dev).get("segment.all.allocated", 0)
     ops.KernelTimers.reset(rank == 0)
     prof = os.environ.get("PA2S_PROFILE_RANGE") == "1"      # ncu --profile-from-start off: capture the timed steps only
     if prof:
@@ -406,11 +412,19 @@ def run_b200(args):
     if prof:
         torch.cuda.profiler.stop()
     launches = lib.pa2s_launch_count() - n0
+    mallocs = torch.cuda.memory_stats(dev).get("segment.all.allocated", 0) - seg0
     ktimes = ops.KernelTimers.summary() if rank == 0 else {}
     ops.KernelTimers.reset(False)
     step_e2e()
     ms_e2e, _, w2 = timed(step_e2e, args.steps)
     ops.check_sync_flags()
+    # host time to enqueue ONE step on an idle device (in the timed loop the host runs ahead until the launch queue is full and is
+    # then paced by the device, so `host_enqueue_ms_per_step` ~ device time there): the launch-bound floor of the step
+    barrier()
+    t_h = time.time()
+    step_device()
+    host_unblocked = (time.time() - t_h) * 1e3
+    barrier()
     clips = B * world * args.steps
     value = clips / (ms / 1e3)
     e2e = clips / (ms_e2e / 1e3)
@@ -471,8 +485,8 @@ def run_b200(args):
                        "parallelism": f"dp{world}", "l2": "working set >> 126 MB L2 (4.4 GB of conv activations per step), no flush needed",
                        "kernel_ms": {k: round(v[1], 4) for k, v in sorted(ktimes.items())}},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
-            "host_enqueue_ms_per_step": round(host_ms[0], 3), "per_step": {"device_resident": per_step[0], "e2e": per_step[1]},
-            "gpu_launches": int(launches),
+            "host_enqueue_ms_per_step": round(host_ms[0], 3), "host_enqueue_ms_idle_device": round(host_unblocked, 3), "per_step": {"device_resident": per_step[0], "e2e": per_step[1]},
+            "gpu_launches": int(launches), "cuda_mallocs_in_timed_region": int(mallocs),
             "clocks": sampler.summary(w0, w2),
             "roofline": roof, "roofline_all": [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items()} for r in roof_all],
             "cpu_baseline": cpu}
@@ -601,7 +615,7 @@ def run_b200_infer(args):
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}     # B200_PROFILING.md fallback
 
 
-def algorithmic_work(B, S_total, n_dec_calls):
+def algorithmic_work(B, S_total, n_dec_calls, n_dec_bwd_calls=None):
     """{timer name: (kernel, FLOP per launch, compulsory HBM bytes per launch)} at T=1201, F=480 -- SURVEY 8(d)'s per-clip
     figures x the B clips one launch processes.  Activations count as 4 B/element (fp32, or the two
     bf16 pieces the bf16x3 contractions read); FLOPs are the single-precision-equivalent 2*MAC count, NOT x3 for the split."""
@@ -635,8 +649,10 @@ def algorithmic_work(B, S_total, n_dec_calls):
     w["encoder_gru_bwd"] = ("gru_seq_bwd_kernel", 2 * 2 * T * B * 2.0 * 768 * 256, B * T * 2 * (768 + 256 + 1024 + 768) * 4.0)
     # note decoder: per executed step and clip 6.27 MFLOP and 3.69 MB streamed (enc 2.46 MB + Ep 1.23 MB; L2-resident at B=16)
     steps = S_total / max(n_dec_calls, 1)
-    w["note_decoder_fwd"] = ("dec_persist_fwd_kernel (all steps of one (bar, staff), cooperative)", 6.27e6 * B * steps, 3.69e6 * B * steps)
-    w["note_decoder_bwd"] = ("dec_persist_bwd_kernel (+dlogits, out-projection GEMM, deferred dEp/dv)", 2 * 6.27e6 * B * steps, 3.69e6 * B * steps)
+    steps_bwd = S_total / max(n_dec_bwd_calls or n_dec_calls, 1)
+    # (`steps` = executed (bar, step) pairs per launch: a launch of the multi-sequence kernel decodes several bars of a staff)
+    w["note_decoder_fwd"] = ("decm_fwd_kernel (all steps of the teacher-forced bars of one staff segment, cooperative)", 6.27e6 * B * steps, 3.69e6 * B * steps)
+    w["note_decoder_bwd"] = ("decm_bwd_kernel (all bars of a staff; +dlogits, out-projection GEMM, deferred dEp/dv)", 2 * 6.27e6 * B * steps_bwd, 3.69e6 * B * steps_bwd)
     return w
 
 
@@ -649,9 +665,11 @@ def roofline(ktimes, B, peaks, S_total, traffic=None, n_dec=None):
     hbm = float(pk.get("hbm_gbs") or FALLBACK_PEAKS["hbm_gbs"])
     tf = float(pk.get("bf16_tflops_sustained") or pk.get("bf16_tflops") or FALLBACK_PEAKS["bf16_tflops_sustained"])
     src = "MEASURED_PEAKS.json (hbm_gbs, bf16_tflops_sustained)" if measured else "fallback of B200_PROFILING.md (6.65 TB/s, 1.4 PFLOP/s sustained)"
+    nsteps = max(ktimes.get("conv1_fwd", (1, 0))[0], 1)
     if n_dec is None:
-        n_dec = ktimes.get("note_decoder_fwd", (10, 0))[0] // max(ktimes.get("conv1_fwd", (1, 0))[0], 1)
-    work = algorithmic_work(B, S_total, n_dec)
+        n_dec = ktimes.get("note_decoder_fwd", (10, 0))[0] / nsteps          # launches per step (average: it depends on the bar coins)
+    n_dec_bwd = ktimes.get("note_decoder_bwd", (0, 0))[0] / nsteps or None
+    work = algorithmic_work(B, S_total, n_dec, n_dec_bwd)
     rows = []
     for name, (n, ms) in ktimes.items():
         if name not in work or ms <= 0:

@@ -20,10 +20,13 @@ transform, in float64 and in direct (time-domain) form:
   V /= sqrt(N_k) amount to     V[k,t] = sqrt(N_k) * | sum_o b_k[o] * y[t*hop - o] |        (y zero outside the clip)
   librosa/core/spectrum.py::amplitude_to_db(|V|, ref=max, amin=1e-5, top_db=80), then /80 + 1, transposed.
 
-librosa itself evaluates the same filters octave by octave on a soxr-decimated signal and keeps only
-99 % of each filter's spectral energy (sparsity=0.01); its output therefore deviates from this definition
-by ~1e-2 relative in amplitude (~1e-3 absolute after the /80 dB scaling).  That deviation is a property of
-librosa's approximation, not of this oracle, and is out of reach without librosa.
+librosa itself evaluates the same filters octave by octave on a decimated signal and keeps only 99 % of
+each filter's spectral L1 mass (sparsity=0.01).  `oracle/vqt_recursive_oracle.py` restates THAT computation
+(with scipy's decimator in place of soxr) and is what `get_vqt` returns by default; measured against it
+(tests/test_vqt_oracles.py) this direct form agrees to 0.2-0.5 % at spectral peaks but reads up to 0.38 (of the
+0..1 scale) higher in quiet low-octave bins: without the recursion's anti-aliasing low-passes the 787-tap
+low-octave filters pick up Hann side-lobe leakage of strong components at -45..-55 dB, which librosa's
+low-passes remove.  The product therefore implements the recursion (composed into one filter bank).
 """
 from __future__ import annotations
 
@@ -83,7 +86,14 @@ def amplitude_to_db(mag, amin=1e-5, top_db=80.0):
     return np.maximum(log_spec, log_spec.max() - top_db)
 
 
-def get_vqt(y, params=DEFAULT_PARAMS):
-    """utilities.get_VQT for an in-memory mono clip: (frames, n_bins) float32 in [0, 1]."""
+def get_vqt(y, params=DEFAULT_PARAMS, algorithm=None):
+    """utilities.get_VQT for an in-memory mono clip: (frames, n_bins) float32 in [0, 1].
+    algorithm "librosa" (default, like the product's VQT module; env PA2S_VQT_ALGO): the octave-recursive computation librosa actually
+    performs (oracle/vqt_recursive_oracle.py); "direct": this file's time-domain definition (no decimation, no sparsification)."""
+    import os
+    algorithm = algorithm or os.environ.get("PA2S_VQT_ALGO", "librosa")
+    if algorithm == "librosa":
+        from . import vqt_recursive_oracle as VR
+        return VR.get_vqt(y, params)
     log_vqt = amplitude_to_db(vqt_magnitude(y, params)) / 80.0 + 1.0
     return log_vqt.T.astype(np.float32)

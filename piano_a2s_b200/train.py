@@ -145,6 +145,19 @@ class FlatAdadelta:
         return self.norm
 
 
+def reserve_memory(gigabytes: int, device=None):
+    """Hands the caching allocator ONE large segment to carve every later request from (allocate + free).  The launch thread of a
+    training loop runs ahead of the device; blocks that were used on the decoder's side streams stay unavailable until those streams
+    have passed the point of their last use, and without spare cached memory the allocator answers the next request with a
+    `cudaMalloc` -- a multi-millisecond stall of the launch thread, per call.  Call once after the model has been moved to the GPU."""
+    if gigabytes > 0:
+        free, _ = torch.cuda.mem_get_info(device)
+        n = min(int(gigabytes) << 30, int(free * 0.5))
+        if n > 0:
+            del_me = torch.empty(n, dtype=torch.uint8, device=device or "cuda")
+            del del_me
+
+
 def teacher_forcing_schedule(ratio: float, decay: float, epoch: int, training: bool = True) -> float:
     """`on_stage_start` of pretrain.py:149-153: the ratio decays exponentially with the epoch in training
     (`teacher_forcing_ratio * teacher_forcing_decay ** epoch`, pretrain.yaml:41-42: 0.7, 0.99) and is 0 in validation / test.
