@@ -394,7 +394,9 @@ def run_b200(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    for _ in range(max(args.warmup, 3) - 1):
+    # (under NCCL the first steps after start-up still grow NCCL's and the allocator's pools: at least 5 untimed steps there)
+    n_warm = max(args.warmup, 5 if world > 1 else 3)
+    for _ in range(n_warm - 1):
         step_device()
     # the step enqueues ~1 000 launches from Python; a generation-2 garbage collection over torch's heap inside the timed region
     # stalls the launch thread for tens of ms (seen as 64 vs 76 ms/step between otherwise identical runs): collect now and move
@@ -477,7 +479,7 @@ def run_b200(args):
                    "sample": f"{args.cpu_clips} clip(s), one fwd+bwd+clip+Adadelta step of the same workload through {_kind_text(kind)} "
                              f"(torch CPU fp32 + float64 numpy VQT), {dt:.1f} s"}
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": n_warm,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE[args.precision],
             "data": "synthetic",
             "config": {"workload": workload_name(B, args.workload, args.precision), "precision": PRECISION_NOTE[args.precision],

