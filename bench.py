@@ -328,17 +328,17 @@ def run_b200(args):
     B = args.batch
     finetune = args.workload == "finetune"
     TF = tf_ratio(args.workload)
-    # One large block for the caching allocator to carve from.  The launch thread runs several steps ahead of the device, so buffers that
-    # were used on the decoder's side streams cannot be recycled until those streams have caught up, and the allocator would otherwise
-    # meet the shortfall with cudaMalloc calls in the middle of a step (each one a multi-ms stall of the launch thread; seen as
-    # 100 ms outlier steps).  A training script does the same once at start-up (train.reserve_memory).
-    train.reserve_memory(int(os.environ.get("PA2S_RESERVE_GB", "24")))
     ops.set_precision(train=args.precision)
     torch.manual_seed(1234)
     model = models.ScoreTranscription(**CFG).to(dev).train()
     model.convstack.sync_batchnorm = world > 1          # speechbrain converts BatchNorm -> SyncBatchNorm under DDP
     opt = train.FlatAdadelta(model)
     vqt = VQT().to(dev)
+    # Pre-filled allocator pools (main stream + the decoder's two staff streams).  The launch thread runs several steps ahead of the
+    # device, so buffers that were used on the side streams cannot be recycled until those streams have caught up, and the allocator
+    # would otherwise meet the shortfall with cudaMalloc calls in the middle of a step, which can wait for the device to drain (seen
+    # as 100-150 ms outlier steps).  A training script does the same once at start-up (train.reserve_memory).
+    train.reserve_memory(float(os.environ.get("PA2S_RESERVE_GB", "16")), dev, streams=model.decoder.streams(), stream_gigabytes=6.0)
     if finetune:
         audio_h, n_h = make_ragged_audio(B, seed=1234 + rank)
         audio_h, n_h = audio_h.pin_memory(), n_h.pin_memory()
@@ -374,11 +374,18 @@ def run_b200(args):
         w0 = time.time()
         e0.record()
         marks, hmarks = [e0], [w0]
+        dbg = os.environ.get("PA2S_BENCH_DEBUG") == "1"
         for _ in range(k):
             fn()
             marks.append(torch.cuda.Event(enable_timing=True))
             marks[-1].record()
             hmarks.append(time.time())
+            if dbg:
+                st = torch.cuda.memory_stats(dev)
+                print("dbg step host_ms %.1f gc %s seg_alloc %d seg_free %d reserved %.2f GB active %.2f GB retries %d" % (
+                    1e3 * (hmarks[-1] - hmarks[-2]), gc.get_count(), st.get("segment.all.allocated", 0), st.get("segment.all.freed", 0),
+                    st.get("reserved_bytes.all.current", 0) / 2 ** 30, st.get("active_bytes.all.current", 0) / 2 ** 30,
+                    st.get("num_alloc_retries", 0)), file=sys.stderr, flush=True)
         e1 = marks[-1]
         host_ms.append((time.time() - w0) * 1e3 / k)        # host time to ENQUEUE one step (launch-bound if ~= the device time)
         barrier()

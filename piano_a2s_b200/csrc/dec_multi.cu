@@ -48,6 +48,41 @@ __device__ __forceinline__ float pair_term(float q0, float e0, float w0, float q
     const float a0 = fmaf(q0, e0, 1.f), a1 = fmaf(q1, e1, 1.f);
     return rcp_fast(a0 * a1) * fmaf(w0, a1, w1 * a0);
 }
+// Packed fp32 pairs (Blackwell FFMA2 / FMUL2: two fp32 operations per instruction on a register pair).  The attention passes are
+// bound by instruction issue + latency at 12 warps per SM, so halving the FP instruction count of their inner loops is a direct gain.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b),
+                       rc = *reinterpret_cast<unsigned long long*>(&c), rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rd;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2*>(&rd);
+}
+// acc += sum over the four elements of w_k / (1 + q_k e_k), two SFU reciprocals: elements (x, z) and (y, w) share one each
+// (1/a = b rcp(ab)), everything else on register pairs (xy, zw)
+__device__ __forceinline__ float2 quad_term(float4 q, float4 e, float4 w, float2 acc) {
+    const float2 one = make_float2(1.f, 1.f);
+    const float2 axy = ffma2(make_float2(q.x, q.y), make_float2(e.x, e.y), one);
+    const float2 azw = ffma2(make_float2(q.z, q.w), make_float2(e.z, e.w), one);
+    const float2 pr = fmul2(axy, azw);                                           // (a0 a2, a1 a3)
+    const float2 r = make_float2(rcp_fast(pr.x), rcp_fast(pr.y));
+    const float2 t = ffma2(make_float2(w.x, w.y), azw, fmul2(make_float2(w.z, w.w), axy));   // (w0 a2 + w2 a0, w1 a3 + w3 a1)
+    return ffma2(r, t, acc);
+}
+// the reverse pass: (dxy, dzw) += ds * r (1 - r) for the four elements, r = 1 / (1 + q e)
+__device__ __forceinline__ void quad_grad(float4 q, float4 e, float ds, float2& dxy, float2& dzw) {
+    const float2 one = make_float2(1.f, 1.f), mone = make_float2(-1.f, -1.f), ds2 = make_float2(ds, ds);
+    const float2 axy = ffma2(make_float2(q.x, q.y), make_float2(e.x, e.y), one);
+    const float2 azw = ffma2(make_float2(q.z, q.w), make_float2(e.z, e.w), one);
+    const float2 pr = fmul2(axy, azw);
+    const float2 rp = make_float2(rcp_fast(pr.x), rcp_fast(pr.y));
+    const float2 rxy = fmul2(azw, rp), rzw = fmul2(axy, rp);                     // 1 / a_xy, 1 / a_zw
+    dxy = ffma2(fmul2(ds2, rxy), ffma2(rxy, mone, one), dxy);
+    dzw = ffma2(fmul2(ds2, rzw), ffma2(rzw, mone, one), dzw);
+}
 // per-lane asynchronous copies global -> shared (a lane only ever reads back what it copied itself: no barrier needed, and the
 // depth of the prefetch costs neither registers nor scoreboard slots)
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -288,8 +323,8 @@ __device__ void attn_item(const DecMArgs& a, const FwdSmem& S, float sumv, int s
                         if (!actq[q]) continue;                              // block-uniform
                         const float4 qa = *reinterpret_cast<const float4*>(Eq + q * DA + lane * 4);
                         const float4 qb = *reinterpret_cast<const float4*>(Eq + q * DA + 128 + lane * 4);
-                        val[i * NQ + q] = pair_term(qa.x, c0.x, va.x, qa.y, c0.y, va.y) + pair_term(qa.z, c0.z, va.z, qa.w, c0.w, va.w) +
-                                          pair_term(qb.x, c1.x, vb.x, qb.y, c1.y, vb.y) + pair_term(qb.z, c1.z, vb.z, qb.w, c1.w, vb.w);
+                        const float2 acc2 = quad_term(qb, c1, vb, quad_term(qa, c0, va, make_float2(0.f, 0.f)));
+                        val[i * NQ + q] = acc2.x + acc2.y;
                     }
                 }
             }
@@ -1234,11 +1269,11 @@ __device__ void bwd_attn_item(const DecMArgs& a, const BwdSmem& S, int s, int b,
     __syncthreads();
     SUB_MARK(10);
     // ---- pass 2: dq.  Warp w takes the frames t0 + w, t0 + w + 12, ...; D1 frames in flight; a lane holds 8 of the 256 exp(2 Ep) values.
-    float dq[NQ][8];
+    float2 dq[NQ][4];                                            // per query: elements (0,1) (2,3) (128,129) (130,131) of the lane's columns
 #pragma unroll
     for (int q = 0; q < NQ; ++q)
 #pragma unroll
-        for (int k = 0; k < 8; ++k) dq[q][k] = 0.f;
+        for (int k = 0; k < 4; ++k) dq[q][k] = make_float2(0.f, 0.f);
     {
         const float4* ee = reinterpret_cast<const float4*>(a.Ee + (size_t)b * T * DA) + lane;
         float4* slot = reinterpret_cast<float4*>(myring) + lane;
@@ -1265,7 +1300,6 @@ __device__ void bwd_attn_item(const DecMArgs& a, const BwdSmem& S, int s, int b,
                     cp_async16(slot + i * 64 + 32, ee + t * (DA / 4) + 32);
                 }
                 cp_async_commit();
-                const float ev[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
                 const int j = warp + f * NW;
 #pragma unroll
                 for (int q = 0; q < NQ; ++q) {
@@ -1273,15 +1307,8 @@ __device__ void bwd_attn_item(const DecMArgs& a, const BwdSmem& S, int s, int b,
                     const float ds = dap[q * TILE_MAX + j];
                     const float4 qa = *reinterpret_cast<const float4*>(Eq + q * DA + lane * 4);
                     const float4 qb = *reinterpret_cast<const float4*>(Eq + q * DA + 128 + lane * 4);
-                    const float qk[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
-#pragma unroll
-                    for (int k = 0; k < 8; k += 2) {
-                        const float a0 = fmaf(qk[k], ev[k], 1.f), a1 = fmaf(qk[k + 1], ev[k + 1], 1.f);
-                        const float rp = rcp_fast(a0 * a1);
-                        const float r0 = a1 * rp, r1 = a0 * rp;                  // 1 / a0, 1 / a1
-                        dq[q][k] = fmaf(ds, fmaf(-r0, r0, r0), dq[q][k]);        // r (1 - r) = (1 - tanh^2) / 4
-                        dq[q][k + 1] = fmaf(ds, fmaf(-r1, r1, r1), dq[q][k + 1]);
-                    }
+                    quad_grad(qa, c0, ds, dq[q][0], dq[q][1]);           // r (1 - r) = (1 - tanh^2) / 4
+                    quad_grad(qb, c1, ds, dq[q][2], dq[q][3]);
                 }
             }
         }
@@ -1294,7 +1321,10 @@ __device__ void bwd_attn_item(const DecMArgs& a, const BwdSmem& S, int s, int b,
         if (!actq[q]) continue;
         __syncthreads();
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { dqr[warp * DA + lane * 4 + i] = dq[q][i]; dqr[warp * DA + 128 + lane * 4 + i] = dq[q][4 + i]; }
+        for (int i = 0; i < 2; ++i) {
+            *reinterpret_cast<float2*>(dqr + warp * DA + lane * 4 + 2 * i) = dq[q][i];
+            *reinterpret_cast<float2*>(dqr + warp * DA + 128 + lane * 4 + 2 * i) = dq[q][2 + i];
+        }
         __syncthreads();
         if (tid < DA) {
             float t = 0.f;

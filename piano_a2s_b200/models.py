@@ -233,6 +233,12 @@ class HierarchicalDecoder(nn.Module):
         self._side_streams = (torch.cuda.Stream(priority=prio), torch.cuda.Stream(priority=prio))
         self._defer_stream = torch.cuda.Stream() if os.environ.get("PA2S_DEFER_STREAM", "0") == "1" else None
 
+    def streams(self):
+        """The CUDA streams the note decoders of the two staves run on (created on first use): for train.reserve_memory."""
+        if self._side_streams is None:
+            self._make_streams()
+        return tuple(self._side_streams)
+
     def weight_sinks(self):
         """[(DecoderGradSink, weight aliases) or None] for the upper / lower note decoder (ops.DecoderWeightSinkFn).  Autograd runs
         nodes in reverse creation order: ScoreTranscription.forward creates the sinks BEFORE the ConvStack, so their node -- which
@@ -409,22 +415,22 @@ class HierarchicalDecoder(nn.Module):
             # the reference draws one coin per executed note step (models.py:404); only the count matters here
             src.coins(int(torch.stack(counters)[:, 1].sum().item()))
         self.last_step_counters = counters
+        # Order of creation = reverse order of execution in backward.  h0_all (whose backward feeds the bar-level GRU chain and has to wait
+        # for the note decoders' reverse pass) first; then the time-signature / key heads (models.py:281-286) of all bars in one pass,
+        # rows (b, bar) -- they are off the chain that feeds the note decoders; LAST the node of all note decoding, so that its backward
+        # is the first thing autograd runs: the two reverse kernels are enqueued at once and the heads' backward overlaps them.
+        h0_all = torch.stack(summaries) if grad else None
+        head_in = torch.cat([torch.stack(summaries, 1), torch.stack(contexts, 1)], dim=-1).view(B * nb, -1)
+        ts_all = self._heads(self.time_sig_out, head_in).view(B, nb, -1)
+        key_all = self._heads(self.key_out, head_in).view(B, nb, -1)
         if grad:
             w = [x for d in decs for x in d._weights()]
-            h0_all = torch.stack(summaries)
             # autograd runs a node's backward on the stream its forward was issued on and orders it against the producers / consumers
-            # of its gradients: issued on the upper staff's stream, the reverse pass of the note decoders overlaps the backward of the
-            # heads (which do not depend on it) on the main stream
+            # of its gradients: issued on the upper staff's stream, the reverse pass does not hold up the main stream
             with ops._on_stream(sides[0]):
                 up_all, lo_all = ops.DecodersFn.apply(tuple(runs), enc, Ep_up, Ep_lo, h0_all, *w)
         else:
             up_all, lo_all = runs[0].logp, runs[1].logp
-        # time-signature / key heads (models.py:281-286) of all bars in one pass, rows (b, bar).  They are off the chain that feeds the
-        # note decoders, and -- created last -- their backward is the first thing autograd enqueues on the main stream, where it runs
-        # while the note decoders' reverse pass occupies the staff streams
-        head_in = torch.cat([torch.stack(summaries, 1), torch.stack(contexts, 1)], dim=-1).view(B * nb, -1)
-        ts_all = self._heads(self.time_sig_out, head_in).view(B, nb, -1)
-        key_all = self._heads(self.key_out, head_in).view(B, nb, -1)
         return (ts_all, key_all, up_all, lo_all)
 
     def _decode_bars_per_bar(self, encoder_outputs, hidden, inference=True, ground_truth=None, teacher_forcing_ratio=0):

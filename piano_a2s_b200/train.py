@@ -145,17 +145,27 @@ class FlatAdadelta:
         return self.norm
 
 
-def reserve_memory(gigabytes: int, device=None):
-    """Hands the caching allocator ONE large segment to carve every later request from (allocate + free).  The launch thread of a
-    training loop runs ahead of the device; blocks that were used on the decoder's side streams stay unavailable until those streams
-    have passed the point of their last use, and without spare cached memory the allocator answers the next request with a
-    `cudaMalloc` -- a multi-millisecond stall of the launch thread, per call.  Call once after the model has been moved to the GPU."""
-    if gigabytes > 0:
-        free, _ = torch.cuda.mem_get_info(device)
-        n = min(int(gigabytes) << 30, int(free * 0.5))
-        if n > 0:
-            del_me = torch.empty(n, dtype=torch.uint8, device=device or "cuda")
-            del del_me
+def reserve_memory(gigabytes: float, device=None, streams=(), stream_gigabytes: float = 4.0, small_megabytes: int = 128):
+    """Pre-fills the caching allocator's pools (allocate + free), so that a training loop never calls `cudaMalloc` in the middle of a
+    step.  The launch thread runs ahead of the device; blocks that were used on the decoder's side streams stay unavailable until
+    those streams have passed the point of their last use, and without spare cached memory the allocator answers the next request
+    with a `cudaMalloc` -- which can wait for the device to drain (seen as 100 ms outlier steps when the host is two steps ahead).
+    The allocator keeps separate pools per stream and per size class, hence: ONE large segment on the current stream (`gigabytes`),
+    one per stream in `streams` (`stream_gigabytes`: the decoder's two staff streams, `model.decoder.streams()`), and
+    `small_megabytes` of 2 MB segments for the < 1 MB requests of each.  Call once after the first step (the side streams exist then)."""
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    free, _ = torch.cuda.mem_get_info(dev)
+    budget = int(free * 0.5)
+    for st, gb in [(None, gigabytes)] + [(s_, stream_gigabytes) for s_ in streams if s_ is not None]:
+        ctx = torch.cuda.stream(st) if st is not None else torch.cuda.stream(torch.cuda.current_stream(dev))
+        with ctx:
+            n = min(int(gb * (1 << 30)), budget)
+            keep = []
+            if n > 0:
+                keep.append(torch.empty(n, dtype=torch.uint8, device=dev))
+                budget -= n
+            keep += [torch.empty(512 << 10, dtype=torch.uint8, device=dev) for _ in range(2 * small_megabytes)]
+            del keep
 
 
 def teacher_forcing_schedule(ratio: float, decay: float, epoch: int, training: bool = True) -> float:
