@@ -79,7 +79,12 @@ class ScoreTranscription(nn.Module):
                 # so that the one host read the decoder needs does not wait for the ConvStack / encoder kernels queued below
                 self.decoder.prefetch_steps(ground_truth)
             # (always reassigned: a forward that raised before the decoder must not leave its aliases to the next graph)
-            self.decoder._presunk = self.decoder.weight_sinks() if (torch.is_grad_enabled() and spectrogram.is_cuda) else None
+            grad_cuda = torch.is_grad_enabled() and spectrogram.is_cuda
+            if ops.DECODER_IMPL == "multi":
+                self.decoder._bar_lins = self.decoder.bar_linears() if grad_cuda else None
+                self.decoder._presunk = None
+            else:
+                self.decoder._presunk = self.decoder.weight_sinks() if grad_cuda else None
             conv_outputs = self.convstack(spectrogram)                   # (B, T, conv_feature_size)
             encoder_outputs, hidden = self.encoder(conv_outputs)         # (B, T, 2H), (1, B, 2H)
             return self.decoder(encoder_outputs, hidden, inference, ground_truth, teacher_forcing_ratio, device)
@@ -152,6 +157,7 @@ class HierarchicalDecoder(nn.Module):
         self._side_streams = None
         self._aux_stream = None
         self._presunk = None
+        self._bar_lins = None
         self._defer_stream = None
         self._steps_host = None
         self._steps_pending = None
@@ -274,13 +280,20 @@ class HierarchicalDecoder(nn.Module):
             return self._steps_host.tolist()
         return torch.stack([self._steps_from_gt(upper_gt), self._steps_from_gt(lower_gt)]).cpu().tolist()   # one sync
 
-    def _bar_step(self, token, h, enc, Ep_bar):
-        """bar-level attention + GRU cell of one bar (models.py:239-247) -> (bar_summary, context)"""
-        D = enc.shape[2]
-        q = ops.linear(h, self.attn.attn.weight[:, :D], None)
-        context = ops.AttnStepFn.apply(q, Ep_bar, enc, self.attn.v.weight)
+    def bar_linears(self, D=None):
+        """The three Linear maps applied once per bar (attention query, bar GRU input / hidden) with deferred weight gradients
+        (ops.DeferredLinear).  ScoreTranscription.forward creates them BEFORE the ConvStack, so that their gradient nodes run at the very
+        end of a backward pass instead of between the note decoders' reverse pass and the encoder's."""
+        D = D or 2 * self.hidden_size
         g = self.gru
-        h = ops.gru_cell(torch.cat([token, context], dim=1), h, g.weight_ih_l0, g.weight_hh_l0, g.bias_ih_l0, g.bias_hh_l0)
+        return (ops.DeferredLinear(self.attn.attn.weight[:, :D], None), ops.DeferredLinear(g.weight_ih_l0, g.bias_ih_l0),
+                ops.DeferredLinear(g.weight_hh_l0, g.bias_hh_l0))
+
+    def _bar_step(self, token, h, enc, Ep_bar, lins):
+        """bar-level attention + GRU cell of one bar (models.py:239-247) -> (bar_summary, context)"""
+        lin_q, lin_ih, lin_hh = lins
+        context = ops.AttnStepFn.apply(lin_q(h), Ep_bar, enc, self.attn.v.weight)
+        h = ops.GRUGatesFn.apply(lin_ih(torch.cat([token, context], dim=1)), lin_hh(h), h)
         return h, context
 
     def _decode_bars_multi(self, enc, hidden, inference=True, ground_truth=None, teacher_forcing_ratio=0):
@@ -363,6 +376,9 @@ class HierarchicalDecoder(nn.Module):
             runs.append(ops.StaffRun(dec._weights(), enc, Ep, nb, dec.max_steps, steps[si], inference or not have_gt, grad, sides[si],
                                      SOS, EOS, gt=gt_staff, tf_bits=tf_bits[si], mask=note_masks[si]))
 
+        lins, self._bar_lins = self._bar_lins, None
+        if lins is None:
+            lins = self.bar_linears(D)
         token = self.get_SOS_token(B)[0].squeeze(1)                      # (B, 4*staff+ts+key)
         h = hidden[0]
         tok_gt = None
@@ -392,7 +408,7 @@ class HierarchicalDecoder(nn.Module):
                     token = torch.cat([us, ls, self.time_sig_emb(ts_pred), self.key_emb(key_pred)], dim=-1)
                 if training:
                     token = token * bar_masks[bar]
-                h, context = self._bar_step(token, h, enc, Ep_bar)
+                h, context = self._bar_step(token, h, enc, Ep_bar, lins)
                 seg_h.append(h)
                 seg_ctx.append(context)
             summaries += seg_h

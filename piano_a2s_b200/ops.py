@@ -288,6 +288,94 @@ def linear(x, W, b=None):
     return LinearFn.apply(x, W, b)
 
 
+# ---- Linear layers that are applied once per bar (bar-level GRU cell, attention query): deferred weight gradients ------------------
+class LinearSink:
+    """Rows (x, dy) left behind by the backward of every use of one Linear in a forward pass."""
+    def __init__(self):
+        self.rows = []
+
+
+class LinearSinkFn(torch.autograd.Function):
+    """Identity on (W[, b]).  Every LinearDeferFn call that uses the returned aliases only forms its INPUT gradient (the part that is on
+    the bar-level chain) and leaves (x, dy) in the sink; autograd runs this node after the last of them, and the weight / bias gradient
+    is then ONE contraction over the rows of all bars: 5x fewer small GEMMs, zero fills and gradient-accumulation adds between the
+    note decoders' reverse pass and the encoder's."""
+
+    @staticmethod
+    def forward(ctx, sink, W, b):
+        ctx.sink, ctx.prec, ctx.has_bias = sink, current_precision(), b is not None
+        ctx.wshape = W.shape
+        ctx.set_materialize_grads(False)
+        return (W.view_as(W), b.view_as(b)) if b is not None else (W.view_as(W), None)
+
+    @staticmethod
+    @_bwd_precision
+    def backward(ctx, gW, gb):
+        rows, ctx.sink.rows = ctx.sink.rows, []
+        dW, db = gW, gb
+        if rows:
+            X = rows[0][0] if len(rows) == 1 else torch.cat([r[0] for r in rows])
+            DY = rows[0][1] if len(rows) == 1 else torch.cat([r[1] for r in rows])
+            M, K = X.shape
+            N = DY.shape[1]
+            d = torch.zeros(N, K, device=X.device, dtype=F32)
+            gemm(DY, X, d, N, K, M, transA=True, lda=N, ldb=K, ldc=K, zeroed=True)
+            dW = d if dW is None else dW + d
+            if ctx.has_bias:
+                c = colsum(DY)
+                db = c if db is None else db + c
+        return None, dW, (db if ctx.has_bias else None)
+
+
+class LinearDeferFn(torch.autograd.Function):
+    """y = x W^T + b like LinearFn, with W / b aliases from LinearSinkFn: backward returns dx only and hands (x, dy) to the sink."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, sink):
+        ctx.prec = current_precision()
+        x2 = _f(x).reshape(-1, x.shape[-1])
+        assert W.stride(1) == 1 and W.dtype == F32
+        M, K = x2.shape
+        N = W.shape[0]
+        y = torch.empty(M, N, device=x.device, dtype=F32)
+        gemm(x2, W, y, M, N, K, transB=True, lda=K, ldb=W.stride(0), ldc=N, bias=b)
+        ctx.save_for_backward(x2, W)
+        ctx.sink, ctx.xshape = sink, x.shape
+        return y.reshape(*x.shape[:-1], N)
+
+    @staticmethod
+    @_bwd_precision
+    def backward(ctx, dy):
+        x2, W = ctx.saved_tensors
+        M, K = x2.shape
+        N = W.shape[0]
+        dy2 = _f(dy).reshape(M, N)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(M, K, device=dy.device, dtype=F32)
+            gemm(dy2, W, dx, M, K, N, lda=N, ldb=W.stride(0), ldc=K)
+            dx = dx.reshape(ctx.xshape)
+        ctx.sink.rows.append((x2, dy2))
+        return dx, None, None, None
+
+
+class DeferredLinear:
+    """One Linear of the bar-level chain for one forward pass: `lin(x)` = F.linear(x, W, b) with the weight gradient deferred."""
+
+    def __init__(self, W, b=None):
+        self.sink = LinearSink()
+        self.defer = torch.is_grad_enabled() and W.requires_grad
+        if self.defer:
+            self.W, self.b = LinearSinkFn.apply(self.sink, W, b)
+        else:
+            self.W, self.b = W, b
+
+    def __call__(self, x):
+        if self.defer:
+            return LinearDeferFn.apply(x, self.W, self.b, self.sink)
+        return LinearFn.apply(x, self.W, self.b)
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # ConvStack (models.py:463-543) as one fused group
 # ----------------------------------------------------------------------------------------------------------------
