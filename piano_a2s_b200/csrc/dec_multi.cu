@@ -253,9 +253,10 @@ __device__ void attn_item(const DecMArgs& a, const FwdSmem& S, float sumv, int s
     __shared__ float wred[NW][NQMAX];
     __shared__ float Mq[NQMAX], Lq[NQMAX];
     __shared__ int is_last;
+    constexpr int TS = TILE_MAX * (NQMAX / NQ);    // frames per item the score table holds: 320 (NQ >= 3), 800 (NQ = 2), 1600 (NQ = 1)
     float* Eq = S.xs;                              // [NQ][DA]
-    float* sc = Eq + NQ * DA;                      // [NQ][TILE_MAX]
-    float* ringb = sc + NQ * TILE_MAX;             // [NW][RING]
+    float* sc = Eq + NQ * DA;                      // [NQ][TS]
+    float* ringb = sc + NQ * TS;                   // [NW][RING]
     float* cred = ringb;                           // [NFS][NQ][DD] (after the streaming loops)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int T = a.T, B = a.B;
@@ -335,7 +336,7 @@ __device__ void attn_item(const DecMArgs& a, const FwdSmem& S, float sumv, int s
                 const int f = f0 + i;
                 if (f < nf && s < g_Sq[q]) {
                     const float e = sumv + val[0];                           // sum_k v_k tanh(q_k + Ep_k)
-                    sc[q * TILE_MAX + warp + f * NW] = e;
+                    sc[q * TS + warp + f * NW] = e;
 #pragma unroll
                     for (int qq = 0; qq < NQ; ++qq)
                         if (qq == q) mq[qq] = fmaxf(mq[qq], e);
@@ -369,10 +370,10 @@ __device__ void attn_item(const DecMArgs& a, const FwdSmem& S, float sumv, int s
             const float m = Mq[q];
             float* araw = a.save ? a.attn + ((size_t)s * a.Rtot + a.r0 + q * B + b) * T + t0 : nullptr;
             for (int j = tid; j < nt; j += NT) {
-                const float e = sc[q * TILE_MAX + j];
+                const float e = sc[q * TS + j];
                 if (araw != nullptr) araw[j] = e;
                 const float p = expf(e - m);
-                sc[q * TILE_MAX + j] = p;
+                sc[q * TS + j] = p;
                 ls[q] += p;
             }
             ls[q] = warp_sum(ls[q]);
@@ -418,7 +419,7 @@ __device__ void attn_item(const DecMArgs& a, const FwdSmem& S, float sumv, int s
 #pragma unroll
                 for (int q = 0; q < NQ; ++q) {
                     if (!actq[q]) continue;
-                    const float p = sc[q * TILE_MAX + j];
+                    const float p = sc[q * TS + j];
                     acc[q].x = fmaf(p, e.x, acc[q].x);
                     acc[q].y = fmaf(p, e.y, acc[q].y);
                     acc[q].z = fmaf(p, e.z, acc[q].z);
@@ -1557,10 +1558,11 @@ __global__ void decm_exp2x_kernel(const float4* __restrict__ x, float4* __restri
     y[i] = make_float4(exp2x(v.x), exp2x(v.y), exp2x(v.z), exp2x(v.w));
 }
 
-int check_args(const DecMArgs& a) {
+int check_args(const DecMArgs& a, bool bwd) {
     if (a.NQ < 1 || a.NQ > NQMAX || a.NQ > 8) return -2;
     if (a.V + DA > PG * CR || a.V > 256 || a.sync == nullptr) return -2;
-    if (a.tile > TILE_MAX || a.NS * a.tile < a.T || a.NS < 1) return -3;
+    // frames per attention item: the forward's score table holds TILE_MAX * (NQMAX / NQ) per query, the reverse pass TILE_MAX
+    if (a.tile > TILE_MAX * (bwd ? 1 : NQMAX / a.NQ) || a.NS * a.tile < a.T || a.NS < 1) return -3;
     for (int q = 0; q < a.NQ; ++q)
         if (a.Sq[q] < 1 || a.Sq[q] > a.S) return -4;
     return 0;
@@ -1613,7 +1615,7 @@ PA2S_API int pa2s_decm_fwd(void* stream, const void* args, int sos_id, int eos_i
     DecMArgs a = *reinterpret_cast<const DecMArgs*>(args);
     cudaStream_t st = (cudaStream_t)stream;
     if (a.B <= 0 || a.S <= 0) return 0;
-    const int rc = check_args(a);
+    const int rc = check_args(a, false);
     if (rc != 0) return rc;
     decm_init_kernel<<<ceil_div(a.NQ * a.B * DE, 128), 128, 0, st>>>(a, sos_id);
     PA2S_CHECK_LAST();
@@ -1641,7 +1643,7 @@ PA2S_API int pa2s_decm_bwd_chain(void* stream, const void* args) {
     DecMArgs a = *reinterpret_cast<const DecMArgs*>(args);
     cudaStream_t st = (cudaStream_t)stream;
     if (a.B <= 0 || a.S <= 0) return 0;
-    const int rc = check_args(a);
+    const int rc = check_args(a, true);
     if (rc != 0) return rc;
     if (a.dhc_all == nullptr || a.ds_all == nullptr || a.eqs == nullptr || a.ml == nullptr) return -2;
     switch (a.NQ) {

@@ -77,6 +77,7 @@ def _dist_on() -> bool:
 #                        "bf16"   tcgen05, bf16 operands, fp32 accumulation (BASELINE configs[2..3]).
 # Small contractions stay on the FFMA kernel (a 128-row UMMA tile would be mostly padding).
 PRECISION = {"train": "bf16x3", "eval": "fp32"}
+EVAL_LINEAR = os.environ.get("PA2S_EVAL_LINEAR", "bf16x6")     # the 19200 -> 256 projection in eval(): "bf16x6" (tensor cores, fp32-level) or "fp32" (FFMA)
 TC_MIN_FLOP = 2.0e8
 _CURRENT = ["bf16x3"]
 _DEPTH = [0]                # > 0 inside a use_precision scope
@@ -477,7 +478,16 @@ class ConvStackFn(torch.autograd.Function):
         M = B * T
         z = torch.zeros(M, O, device=dev, dtype=F32)
         ctx.lin_ops = None
-        if ctx.prec == "fp32":
+        if ctx.prec == "fp32" and not training and EVAL_LINEAR == "bf16x6" and 2.0 * M * O * Kf >= TC_MIN_FLOP:
+            # eval / greedy decode: the one large contraction of the exact-fp32 mode on the tensor cores with THREE bf16 pieces per
+            # operand (3 x 8 mantissa bits = an fp32 value exactly; the six leading piece products, fp32 TMEM accumulation: ~2^-24
+            # relative, the accuracy of an fp32 FMA chain) instead of 15 ms of FFMA at B = 32
+            with ktime("out_linear_split"):
+                a4op = split_operand(ys[3], M, Kf, Kf, npieces=3, t_scale=affs[3][0], t_shift=affs[3][1], t_period=C4, t_relu=True)
+                Wop = split_operand(Wp_out, O, Kf, Kf, npieces=3)
+            with ktime("out_linear_fwd"):
+                gemm(a4op, Wop, z, M, O, Kf, transB=True, ldc=O, zeroed=True, precision="bf16x6")
+        elif ctx.prec == "fp32":
             with ktime("out_linear_fwd"):
                 gemm(ys[3], Wp_out, z, M, O, Kf, transB=True, lda=Kf, ldb=Kf, ldc=O,
                      t_scale=affs[3][0], t_shift=affs[3][1], t_period=C4, t_relu=True, zeroed=True)
@@ -1191,9 +1201,12 @@ class StackLogpFn(torch.autograd.Function):
 # ----------------------------------------------------------------------------------------------------------------
 # Multi-sequence note decoder (dec_multi.cu): NQ bars of one staff x B clips per launch, all bars in one reverse launch
 # ----------------------------------------------------------------------------------------------------------------
-def decm_split(B, T):
-    """frames of a clip are split over NS items of <= pa2s_decm_tile_max() frames so that B * NS items fill the grid"""
+def decm_split(B, T, nq=None):
+    """frames of a clip are split over NS items so that B * NS items fill the grid; an item holds at most pa2s_decm_tile_max() frames
+    (x 5 // nq in forward-only runs, whose launches decode nq bars: the score table of the kernel is shared by the queries)"""
     tmax, pg = lib.pa2s_decm_tile_max(), lib.pa2s_decm_grid()
+    if nq is not None:
+        tmax *= lib.pa2s_decm_max_queries() // nq
     ns = max(-(-T // tmax), min(16, max(1, pg // max(B, 1))))
     tile = -(-T // ns)
     return -(-T // tile), tile
@@ -1226,7 +1239,8 @@ class StaffRun:
         self.inference, self.save, self.stream, self.sos, self.eos = bool(inference), bool(save), side, int(sos), int(eos)
         self.Rtot = bars * B
         self.Smax = max(self.steps)
-        self.NS, self.tile = decm_split(B, T)
+        # (greedy inference decodes bar by bar -- one query per launch -- and has no reverse pass: longer frame ranges, fewer items)
+        self.NS, self.tile = decm_split(B, T, 1 if (self.inference and not self.save) else None)
         dev = enc.device
         z = lambda *s_, dt=F32: torch.zeros(*s_, device=dev, dtype=dt)
         self.Ee = torch.empty_like(Ep)
