@@ -173,6 +173,8 @@ PA2S_API int pa2s_bn_bwd_apply(void* stream, const float* G, const float* Yraw, 
 
 /* ---- Encoder BiGRU recurrence (models.py:63-67,77): gi = x W_ih^T + b_ih for all directions, H = 256 ----------- */
 PA2S_API int pa2s_gru_seq_max_bg(void);
+/* state exchange of the encoder recurrences: 1 (default) st.async + mbarrier, 0 DSMEM stores + cluster barrier */
+PA2S_API int pa2s_gru_seq_set_exchange(int async_exchange);
 PA2S_API int pa2s_gru_seq_fwd(void* stream, int B, int T, int ND, int H, int bg, const float* gi, const float* Whh, const float* bhh,
                               float* out, float* gates, float* hN);
 PA2S_API int pa2s_gru_seq_bwd(void* stream, int B, int T, int ND, int H, int bg, const float* Whh, const float* out, const float* gates,

@@ -43,6 +43,42 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 constexpr int EPF = 4;           // stages of per-step operands in flight (encoder recurrences)
 
+// ---- state exchange of the recurrences without a cluster barrier --------------------------------------------------------------
+// Every CTA of a cluster needs the 256 (fwd) / 768 (bwd) new values of all 8 CTAs before its next step.  Plain DSMEM stores +
+// barrier.cluster cost ~215 cycles (store) + ~490 cycles (UCGABAR wait) per step; `st.async` delivers the value AND signals the
+// destination CTA's mbarrier (complete_tx), so the consumer wakes as soon as the last byte has landed (try_wait: ~60-90 cycles).
+// Double-buffered state + one mbarrier per buffer; a CTA can only start step t+1 once every peer has sent step t, and a peer sends
+// only after it has finished reading the buffer of step t, so a buffer is never overwritten while it is being read.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned mapa_u32(unsigned addr, unsigned rank) {
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned spins = 0;
+    while (!mbar_try_wait(bar, parity))
+        if (++spins > (1u << 20)) __trap();           // a lost peer becomes a launch failure, not a hang
+}
+__device__ __forceinline__ void st_async_v4(unsigned raddr, float4 v, unsigned rmbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                 ::"r"(raddr), "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)), "r"(__float_as_uint(v.w)), "r"(rmbar)
+                 : "memory");
+}
+
+
 constexpr int CPT = 4;           // hidden units per warp (8 warps x 4 = the CTA's 32 units); a warp's 32 lanes are 32 k-slices
 
 // Sum NV (power of two <= 32) per-lane values across the warp: lane L returns the warp total of value index L >> (5 - log2 NV).
@@ -74,7 +110,7 @@ template <int NV> struct LaneShift { static constexpr int value = NV == 16 ? 1 :
 // Each shared-memory read of the state vector is then a conflict-free 512-byte row shared by 12 (fwd) / 4 (bwd) weight rows,
 // instead of the same 128 bytes re-read by every quarter warp.  After the reduce-scatter the total for (unit c, sample bb)
 // sits in lanes (c*BG+bb) << SH, which do the gate math for that (unit, sample).
-template <int BG>
+template <int BG, bool ASYNC>
 __global__ void __launch_bounds__(ENT, 1) gru_seq_fwd_kernel(GruSeqArgs a) {
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
@@ -107,7 +143,22 @@ __global__ void __launch_bounds__(ENT, 1) gru_seq_fwd_kernel(GruSeqArgs a) {
     const bool gate_thread = ((lane & ((1 << SH) - 1)) == 0) && (b < a.B);
     const float bhr = a.bhh[dir * 3 * H + j], bhz = a.bhh[dir * 3 * H + H + j], bhn = a.bhh[dir * 3 * H + 2 * H + j];
     for (int i = tid; i < 2 * BG * EH; i += ENT) (&hbuf[0][0][0])[i] = 0.f;
+    __shared__ __align__(8) unsigned long long xbar[2];
+    if (ASYNC && tid == 0) {
+        mbar_init(&xbar[0], 1);
+        mbar_init(&xbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     cluster.sync();
+    // async exchange: a warp's 4 units of a clip travel as one 16-byte st.async per destination CTA (lane of unit 0 sends)
+    const int nbv = min(BG, a.B - b0);                               // clips of this cluster that exist
+    const unsigned xbytes = (unsigned)(ECL * EU * nbv * sizeof(float));
+    const bool send_thread = gate_thread && (idx / BG == 0);
+    unsigned rbuf[ECL], rbar[ECL];
+    if (ASYNC) {
+#pragma unroll
+        for (int c = 0; c < ECL; ++c) { rbuf[c] = mapa_u32(smem_u32(&hbuf[0][0][0]), c); rbar[c] = mapa_u32(smem_u32(&xbar[0]), c); }
+    }
 
     int p = 0;
     // Input pre-activations (gi: a 118 MB stream) are staged EPF-1 steps ahead with asynchronous copies, so their DRAM latency
@@ -131,6 +182,11 @@ __global__ void __launch_bounds__(ENT, 1) gru_seq_fwd_kernel(GruSeqArgs a) {
     for (int step = 0; step < T; ++step) {
         const int t = dir == 0 ? step : T - 1 - step;
         issue(step + EPF - 1);
+        if (ASYNC) {
+            // arm the mbarrier of the buffer this step's results go to, then wait for the previous step's values of all 8 CTAs
+            if (tid == 0 && step + 1 < T) mbar_arrive_expect_tx(&xbar[p ^ 1], xbytes);
+            if (step > 0) mbar_wait(&xbar[p], (unsigned)(((step - 1) >> 1) & 1));
+        }
         float acc[3][NV];
 #pragma unroll
         for (int g = 0; g < 3; ++g)
@@ -165,14 +221,32 @@ __global__ void __launch_bounds__(ENT, 1) gru_seq_fwd_kernel(GruSeqArgs a) {
             float n = tanhf(gin + r * ghn);
             float hp = hbuf[p][gb][j];
             hn = (1.f - z) * n + z * hp;
-            const int off = ((p ^ 1) * BG + gb) * EH + j;
+            if (!ASYNC) {
+                const int off = ((p ^ 1) * BG + gb) * EH + j;
 #pragma unroll
-            for (int c = 0; c < ECL; ++c) remote[c][off] = hn;
+                for (int c = 0; c < ECL; ++c) remote[c][off] = hn;
+            }
             sv_r = r; sv_z = z; sv_n = n; sv_hn = ghn;
         }
-        // split barrier: the new state is on its way to the 8 CTAs; the global stores of this step (off the sequential chain)
-        // are issued while the arrivals propagate
-        cluster.barrier_arrive();
+        if (ASYNC) {
+            // gather the warp's 4 units of each clip into the lane of unit 0 (lanes (c*BG+bb) << SH) and send 16 bytes per peer
+            const int src0 = (gb << SH);
+            float4 v4;
+            v4.x = hn;
+            v4.y = __shfl_sync(0xffffffffu, hn, ((1 * BG) << SH) + src0);
+            v4.z = __shfl_sync(0xffffffffu, hn, ((2 * BG) << SH) + src0);
+            v4.w = __shfl_sync(0xffffffffu, hn, ((3 * BG) << SH) + src0);
+            if (send_thread && step + 1 < T) {
+                const unsigned off = (unsigned)((((p ^ 1) * BG + gb) * EH + rank * EU + warp * CPT) * sizeof(float));
+                const unsigned boff = (unsigned)((p ^ 1) * sizeof(unsigned long long));
+#pragma unroll
+                for (int c = 0; c < ECL; ++c) st_async_v4(rbuf[c] + off, v4, rbar[c] + boff);
+            }
+        } else {
+            // split barrier: the new state is on its way to the 8 CTAs; the global stores of this step (off the sequential chain)
+            // are issued while the arrivals propagate
+            cluster.barrier_arrive();
+        }
         if (gate_thread) {
             a.out[((size_t)b * T + t) * ND * H + dir * H + j] = hn;
             if (a.gates != nullptr) {
@@ -182,12 +256,14 @@ __global__ void __launch_bounds__(ENT, 1) gru_seq_fwd_kernel(GruSeqArgs a) {
             if (step == T - 1) a.hN[((size_t)dir * a.B + b) * H + j] = hn;
         }
         cp_async_wait<EPF - 2>();          // the stage of step+1 has landed (made visible CTA-wide by the barrier)
-        cluster.barrier_wait();
+        if (ASYNC) __syncthreads();
+        else cluster.barrier_wait();
         p ^= 1;
     }
+    if (ASYNC) cluster.sync();             // no CTA leaves while a peer could still address its shared memory
 }
 
-template <int BG>
+template <int BG, bool ASYNC>
 __global__ void __launch_bounds__(ENT, 1) gru_seq_bwd_kernel(GruSeqArgs a) {
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
@@ -219,7 +295,21 @@ __global__ void __launch_bounds__(ENT, 1) gru_seq_bwd_kernel(GruSeqArgs a) {
     float dhc = 0.f;
     if (gate_thread && a.dhN != nullptr) dhc = a.dhN[((size_t)dir * a.B + b) * H + j];
     for (int i = tid; i < 2 * BG * 3 * EH; i += ENT) (&dbuf[0][0][0])[i] = 0.f;
+    __shared__ __align__(8) unsigned long long xbar[2];
+    if (ASYNC && tid == 0) {
+        mbar_init(&xbar[0], 1);
+        mbar_init(&xbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     cluster.sync();
+    const int nbv = min(BG, a.B - b0);
+    const unsigned xbytes = (unsigned)(ECL * EU * nbv * 3 * sizeof(float));
+    const bool send_thread = gate_thread && (idx / BG == 0);
+    unsigned rbuf[ECL], rbar[ECL];
+    if (ASYNC) {
+#pragma unroll
+        for (int c = 0; c < ECL; ++c) { rbuf[c] = mapa_u32(smem_u32(&dbuf[0][0][0]), c); rbar[c] = mapa_u32(smem_u32(&xbar[0]), c); }
+    }
 
     int p = 0;
     // Saved gates (157 MB per layer), previous state and upstream gradient of each step are staged EPF-1 steps ahead with
@@ -249,6 +339,8 @@ __global__ void __launch_bounds__(ENT, 1) gru_seq_bwd_kernel(GruSeqArgs a) {
         const int t = dir == 0 ? step : T - 1 - step;
         float dh_direct = 0.f, g_r = 0.f, g_z = 0.f, g_n = 0.f, g_hn = 0.f;
         issue(step - (EPF - 1));
+        const int it = T - 1 - step;                                     // iteration count: buffer / mbarrier it & 1, use it >> 1
+        if (ASYNC && tid == 0) mbar_arrive_expect_tx(&xbar[p], xbytes);
         if (gate_thread) {
             const int sl = step % EPF;
             const float r = stg[sl][0][gb][u], z = stg[sl][1][gb][u], n = stg[sl][2][gb][u], hnl = stg[sl][3][gb][u];
@@ -260,14 +352,39 @@ __global__ void __launch_bounds__(ENT, 1) gru_seq_bwd_kernel(GruSeqArgs a) {
             float dhn_lin = dn_pre * r;
             float dz_pre = dzv * z * (1.f - z);
             dh_direct = dh * z;
-            const int off = (p * BG + gb) * 3 * EH + j;
+            if (!ASYNC) {
+                const int off = (p * BG + gb) * 3 * EH + j;
 #pragma unroll
-            for (int c = 0; c < ECL; ++c) {
-                remote[c][off] = dr_pre; remote[c][off + H] = dz_pre; remote[c][off + 2 * H] = dhn_lin;
+                for (int c = 0; c < ECL; ++c) {
+                    remote[c][off] = dr_pre; remote[c][off + H] = dz_pre; remote[c][off + 2 * H] = dhn_lin;
+                }
             }
             g_r = dr_pre; g_z = dz_pre; g_n = dn_pre; g_hn = dhn_lin;
         }
-        cluster.barrier_arrive();          // split barrier: the global stores below overlap the arrival latency
+        if (ASYNC) {
+            // the warp's 4 units of a clip as three 16-byte st.async per destination CTA (lane of unit 0 sends)
+            const int src0 = (gb << SH);
+            float4 vr, vz, vn;
+            vr.x = g_r; vz.x = g_z; vn.x = g_hn;
+            vr.y = __shfl_sync(0xffffffffu, g_r, ((1 * BG) << SH) + src0); vz.y = __shfl_sync(0xffffffffu, g_z, ((1 * BG) << SH) + src0);
+            vn.y = __shfl_sync(0xffffffffu, g_hn, ((1 * BG) << SH) + src0);
+            vr.z = __shfl_sync(0xffffffffu, g_r, ((2 * BG) << SH) + src0); vz.z = __shfl_sync(0xffffffffu, g_z, ((2 * BG) << SH) + src0);
+            vn.z = __shfl_sync(0xffffffffu, g_hn, ((2 * BG) << SH) + src0);
+            vr.w = __shfl_sync(0xffffffffu, g_r, ((3 * BG) << SH) + src0); vz.w = __shfl_sync(0xffffffffu, g_z, ((3 * BG) << SH) + src0);
+            vn.w = __shfl_sync(0xffffffffu, g_hn, ((3 * BG) << SH) + src0);
+            if (send_thread) {
+                const unsigned off = (unsigned)(((p * BG + gb) * 3 * EH + rank * EU + warp * CPT) * sizeof(float));
+                const unsigned boff = (unsigned)(p * sizeof(unsigned long long));
+#pragma unroll
+                for (int c = 0; c < ECL; ++c) {
+                    st_async_v4(rbuf[c] + off, vr, rbar[c] + boff);
+                    st_async_v4(rbuf[c] + off + H * (unsigned)sizeof(float), vz, rbar[c] + boff);
+                    st_async_v4(rbuf[c] + off + 2 * H * (unsigned)sizeof(float), vn, rbar[c] + boff);
+                }
+            }
+        } else {
+            cluster.barrier_arrive();          // split barrier: the global stores below overlap the arrival latency
+        }
         if (gate_thread) {
             const size_t bt = (size_t)b * T + t;
             float* gi = a.dgi + bt * ND * 3 * H + dir * 3 * H + j;
@@ -276,7 +393,8 @@ __global__ void __launch_bounds__(ENT, 1) gru_seq_bwd_kernel(GruSeqArgs a) {
             gh[0] = g_r; gh[H] = g_z; gh[2 * H] = g_hn;
         }
         cp_async_wait<EPF - 2>();          // the stage of step-1 has landed; the barrier makes it visible CTA-wide
-        cluster.barrier_wait();
+        if (ASYNC) mbar_wait(&xbar[p], (unsigned)((it >> 1) & 1));
+        else cluster.barrier_wait();
         float acc[NV];
 #pragma unroll
         for (int i = 0; i < NV; ++i) acc[i] = 0.f;
@@ -298,8 +416,10 @@ __global__ void __launch_bounds__(ENT, 1) gru_seq_bwd_kernel(GruSeqArgs a) {
         }
         const float tot = reduce_scatter_nv<NV>(acc, lane);
         if (gate_thread) dhc = dh_direct + tot;
+        if (ASYNC) __syncthreads();        // the staged operands of the next step (cp.async by other threads) are visible CTA-wide
         p ^= 1;
     }
+    if (ASYNC) cluster.sync();             // no CTA leaves while a peer could still address its shared memory
 }
 
 template <typename K>
@@ -495,6 +615,10 @@ __global__ void gru_gates_bwd_kernel(const float* __restrict__ dh, const float* 
 
 PA2S_API int pa2s_gru_seq_max_bg(void) { return 4; }
 
+// 1 (default): the recurrences exchange their state with st.async + mbarrier; 0: DSMEM stores + cluster barrier (round 1)
+static int g_gru_async = 1;
+PA2S_API int pa2s_gru_seq_set_exchange(int async_exchange) { g_gru_async = async_exchange ? 1 : 0; return 0; }
+
 // Encoder recurrence forward.  H must be 256.  `bg` in {1,2,4} = samples per cluster.
 PA2S_API int pa2s_gru_seq_fwd(void* stream, int B, int T, int ND, int H, int bg, const float* gi, const float* Whh, const float* bhh,
                               float* out, float* gates, float* hN) {
@@ -505,9 +629,15 @@ PA2S_API int pa2s_gru_seq_fwd(void* stream, int B, int T, int ND, int H, int bg,
     a.G = ceil_div(B, bg);
     int nblocks = ND * a.G * ECL;
     cudaStream_t st = (cudaStream_t)stream;
-    if (bg == 1) return launch_cluster(gru_seq_fwd_kernel<1>, st, nblocks, a);
-    if (bg == 2) return launch_cluster(gru_seq_fwd_kernel<2>, st, nblocks, a);
-    if (bg == 4) return launch_cluster(gru_seq_fwd_kernel<4>, st, nblocks, a);
+    if (g_gru_async) {
+        if (bg == 1) return launch_cluster(gru_seq_fwd_kernel<1, true>, st, nblocks, a);
+        if (bg == 2) return launch_cluster(gru_seq_fwd_kernel<2, true>, st, nblocks, a);
+        if (bg == 4) return launch_cluster(gru_seq_fwd_kernel<4, true>, st, nblocks, a);
+        return -1;
+    }
+    if (bg == 1) return launch_cluster(gru_seq_fwd_kernel<1, false>, st, nblocks, a);
+    if (bg == 2) return launch_cluster(gru_seq_fwd_kernel<2, false>, st, nblocks, a);
+    if (bg == 4) return launch_cluster(gru_seq_fwd_kernel<4, false>, st, nblocks, a);
     return -1;
 }
 
@@ -521,9 +651,15 @@ PA2S_API int pa2s_gru_seq_bwd(void* stream, int B, int T, int ND, int H, int bg,
     a.G = ceil_div(B, bg);
     int nblocks = ND * a.G * ECL;
     cudaStream_t st = (cudaStream_t)stream;
-    if (bg == 1) return launch_cluster(gru_seq_bwd_kernel<1>, st, nblocks, a);
-    if (bg == 2) return launch_cluster(gru_seq_bwd_kernel<2>, st, nblocks, a);
-    if (bg == 4) return launch_cluster(gru_seq_bwd_kernel<4>, st, nblocks, a);
+    if (g_gru_async) {
+        if (bg == 1) return launch_cluster(gru_seq_bwd_kernel<1, true>, st, nblocks, a);
+        if (bg == 2) return launch_cluster(gru_seq_bwd_kernel<2, true>, st, nblocks, a);
+        if (bg == 4) return launch_cluster(gru_seq_bwd_kernel<4, true>, st, nblocks, a);
+        return -1;
+    }
+    if (bg == 1) return launch_cluster(gru_seq_bwd_kernel<1, false>, st, nblocks, a);
+    if (bg == 2) return launch_cluster(gru_seq_bwd_kernel<2, false>, st, nblocks, a);
+    if (bg == 4) return launch_cluster(gru_seq_bwd_kernel<4, false>, st, nblocks, a);
     return -1;
 }
 

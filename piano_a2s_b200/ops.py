@@ -659,6 +659,16 @@ def _local_bn_param_grads(Y, G, mask, aff, npix, C, nct, dev):
     return s[C:].contiguous(), s[:C].contiguous()
 
 
+_GRU_EXCHANGE_SET = [False]
+
+
+def _gru_exchange():
+    """PA2S_GRU_EXCHANGE=barrier selects round 1's DSMEM stores + cluster barrier for the encoder recurrences (default: st.async + mbarrier)"""
+    if not _GRU_EXCHANGE_SET[0]:
+        lib.pa2s_gru_seq_set_exchange(0 if os.environ.get("PA2S_GRU_EXCHANGE", "async") == "barrier" else 1)
+        _GRU_EXCHANGE_SET[0] = True
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # Encoder BiGRU layer (models.py:63-67,77)
 # ----------------------------------------------------------------------------------------------------------------
@@ -682,6 +692,7 @@ class BiGRULayerFn(torch.autograd.Function):
         need = any(ctx.needs_input_grad)
         gates = torch.empty(B, T, 2, 4 * H, device=dev, dtype=F32) if need else None
         hN = torch.empty(2, B, H, device=dev, dtype=F32)
+        _gru_exchange()
         with ktime("encoder_gru_fwd"):
             lib.pa2s_gru_seq_fwd(stream(), B, T, 2, H, bg, ptr(gi), ptr(Whh), ptr(bhh), ptr(out), ptr(gates), ptr(hN))
         if need:
