@@ -173,8 +173,9 @@ PA2S_API int pa2s_bn_bwd_apply(void* stream, const float* G, const float* Yraw, 
 
 /* ---- Encoder BiGRU recurrence (models.py:63-67,77): gi = x W_ih^T + b_ih for all directions, H = 256 ----------- */
 PA2S_API int pa2s_gru_seq_max_bg(void);
-/* state exchange of the encoder recurrences: 1 (default) st.async + mbarrier, 0 DSMEM stores + cluster barrier */
-PA2S_API int pa2s_gru_seq_set_exchange(int async_exchange);
+/* state exchange of the encoder recurrences: 0 DSMEM stores + cluster barrier (round 1); 1 (default) st.async + mbarrier with the
+ * row-owner reverse kernel (4 KB instead of 12 KB exchanged per CTA and step); 3 st.async + mbarrier with the column-owner reverse kernel */
+PA2S_API int pa2s_gru_seq_set_exchange(int mode);
 PA2S_API int pa2s_gru_seq_fwd(void* stream, int B, int T, int ND, int H, int bg, const float* gi, const float* Whh, const float* bhh,
                               float* out, float* gates, float* hN);
 PA2S_API int pa2s_gru_seq_bwd(void* stream, int B, int T, int ND, int H, int bg, const float* Whh, const float* out, const float* gates,

@@ -422,6 +422,130 @@ __global__ void __launch_bounds__(ENT, 1) gru_seq_bwd_kernel(GruSeqArgs a) {
     if (ASYNC) cluster.sync();             // no CTA leaves while a peer could still address its shared memory
 }
 
+// Reverse recurrence, second formulation.  dh_prev[k] = sum over the 768 gate rows j of W_hh[j][k] * dgate[j].  The kernel above gives
+// each CTA the columns k of its 32 units and therefore needs ALL 768 gate gradients of a step from the 8 CTAs (12 KB per CTA and
+// step through DSMEM, whose ~21 B/cycle makes that 585 cycles) plus a 16-way shuffle reduction.  Here a CTA keeps the ROWS of its
+// own 32 units (96 x 256 weights, thread k holds column k in registers): it multiplies its own 96 gate gradients (broadcast reads
+// from shared memory, no cross-lane reduction) into partial sums for all 256 k and sends each partial to the CTA that owns unit k --
+// one 16-byte st.async per thread and step, 4 KB per CTA -- where the 8 partials are added.
+template <int BG>
+__global__ void __launch_bounds__(ENT, 1) gru_seq_bwd2_kernel(GruSeqArgs a) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int cid = blockIdx.x / ECL;
+    const int dir = cid / a.G, grp = cid % a.G;
+    const int b0 = grp * BG;
+    const int tid = threadIdx.x;
+    const int H = EH, T = a.T, ND = a.ND;
+    static_assert(ENT == EH, "one thread per state column");
+
+    __shared__ __align__(16) float gsm[3 * EU][BG];            // gate gradients of this CTA's units: row g*32 + u
+    __shared__ __align__(16) float pbuf[2][ECL][EU][BG];       // partial sums received: [buffer][source CTA][unit][clip]
+    __shared__ __align__(16) float stg[EPF][6][BG][EU];
+    __shared__ __align__(8) unsigned long long xbar[2];
+
+    // rows g*H + rank*32 + u of W_hh, column tid
+    float w[3 * EU];
+#pragma unroll
+    for (int jr = 0; jr < 3 * EU; ++jr)
+        w[jr] = __ldg(a.Whh + ((size_t)dir * 3 * H + (jr / EU) * H + rank * EU + (jr % EU)) * H + tid);
+
+    const int u = tid / BG, gb = tid % BG, j = rank * EU + u, b = b0 + gb;
+    const bool gate_thread = tid < EU * BG && b < a.B;
+    float dhc = 0.f;
+    if (gate_thread && a.dhN != nullptr) dhc = a.dhN[((size_t)dir * a.B + b) * H + j];
+    for (int i = tid; i < 3 * EU * BG; i += ENT) (&gsm[0][0])[i] = 0.f;
+    if (tid == 0) {
+        mbar_init(&xbar[0], 1);
+        mbar_init(&xbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    cluster.sync();
+    const unsigned xbytes = (unsigned)(ECL * EU * BG * sizeof(float));
+    const unsigned dst_cta = (unsigned)(tid / EU);                      // owner of unit k = tid
+    const unsigned rdst = mapa_u32(smem_u32(&pbuf[0][rank][tid % EU][0]), dst_cta);
+    const unsigned rbar = mapa_u32(smem_u32(&xbar[0]), dst_cta);
+
+    auto issue = [&](int step_) {          // step_ counts DOWN from T-1; slot = step_ % EPF
+        if (step_ >= 0 && tid < BG * 6 * 8) {
+            const int seg = tid >> 3, q = tid & 7, bb = seg / 6, c = seg % 6;
+            if (b0 + bb < a.B) {
+                const int t_ = dir == 0 ? step_ : T - 1 - step_;
+                const size_t bt_ = (size_t)(b0 + bb) * T + t_;
+                float* dst = &stg[step_ % EPF][c][bb][q * 4];
+                const int col = rank * EU + q * 4;
+                if (c < 4) cp_async16(dst, a.gates + (bt_ * ND + dir) * 4 * H + c * H + col);
+                else if (c == 5) cp_async16(dst, a.dOut + bt_ * ND * H + dir * H + col);
+                else if (step_ > 0) cp_async16(dst, a.out + ((size_t)(b0 + bb) * T + (dir == 0 ? t_ - 1 : t_ + 1)) * ND * H + dir * H + col);
+                else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int i = 0; i < EPF - 1; ++i) issue(T - 1 - i);
+    cp_async_wait<EPF - 2>();
+    __syncthreads();
+    int p = 0;
+    for (int step = T - 1; step >= 0; --step) {
+        const int t = dir == 0 ? step : T - 1 - step;
+        const int it = T - 1 - step;
+        issue(step - (EPF - 1));
+        if (tid == 0) mbar_arrive_expect_tx(&xbar[p], xbytes);
+        float dh_direct = 0.f;
+        if (gate_thread) {
+            const int sl = step % EPF;
+            const float r = stg[sl][0][gb][u], z = stg[sl][1][gb][u], n = stg[sl][2][gb][u], hnl = stg[sl][3][gb][u];
+            const float hp = stg[sl][4][gb][u], dout_t = stg[sl][5][gb][u];
+            const float dh = dout_t + dhc;
+            const float dn = dh * (1.f - z), dzv = dh * (hp - n);
+            const float dn_pre = dn * (1.f - n * n);
+            const float dr_pre = dn_pre * hnl * r * (1.f - r);
+            const float dhn_lin = dn_pre * r;
+            const float dz_pre = dzv * z * (1.f - z);
+            dh_direct = dh * z;
+            gsm[u][gb] = dr_pre; gsm[EU + u][gb] = dz_pre; gsm[2 * EU + u][gb] = dhn_lin;
+            const size_t bt = (size_t)b * T + t;
+            float* gi = a.dgi + bt * ND * 3 * H + dir * 3 * H + j;
+            gi[0] = dr_pre; gi[H] = dz_pre; gi[2 * H] = dn_pre;
+            float* gh = a.dgh + bt * ND * 3 * H + dir * 3 * H + j;
+            gh[0] = dr_pre; gh[H] = dz_pre; gh[2 * H] = dhn_lin;
+        }
+        cp_async_wait<EPF - 2>();          // the stage of step-1 has landed; the barrier below makes it (and gsm) visible CTA-wide
+        __syncthreads();
+        // partial dh_prev[tid] of every clip from this CTA's 96 gate rows
+        float acc[BG];
+#pragma unroll
+        for (int bb = 0; bb < BG; ++bb) acc[bb] = 0.f;
+#pragma unroll
+        for (int jr = 0; jr < 3 * EU; ++jr) {
+#pragma unroll
+            for (int bb = 0; bb < BG; ++bb) acc[bb] = fmaf(w[jr], gsm[jr][bb], acc[bb]);
+        }
+        {
+            const unsigned off = (unsigned)(p * ECL * EU * BG * sizeof(float));
+            const unsigned boff = (unsigned)(p * sizeof(unsigned long long));
+            if (BG == 4) {
+                st_async_v4(rdst + off, make_float4(acc[0], acc[BG > 1 ? 1 : 0], acc[BG > 2 ? 2 : 0], acc[BG > 3 ? 3 : 0]), rbar + boff);
+            } else {
+#pragma unroll
+                for (int bb = 0; bb < BG; ++bb)
+                    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+                                 ::"r"(rdst + off + (unsigned)(bb * sizeof(float))), "r"(__float_as_uint(acc[bb])), "r"(rbar + boff) : "memory");
+            }
+        }
+        mbar_wait(&xbar[p], (unsigned)((it >> 1) & 1));
+        if (gate_thread) {
+            float tot = 0.f;
+#pragma unroll
+            for (int c = 0; c < ECL; ++c) tot += pbuf[p][c][u][gb];
+            dhc = dh_direct + tot;
+        }
+        p ^= 1;
+    }
+    cluster.sync();                        // no CTA leaves while a peer could still address its shared memory
+}
+
 template <typename K>
 int launch_cluster(K kernel, cudaStream_t st, int nblocks, GruSeqArgs a) {
     cudaLaunchConfig_t cfg = {};
@@ -616,8 +740,10 @@ __global__ void gru_gates_bwd_kernel(const float* __restrict__ dh, const float* 
 PA2S_API int pa2s_gru_seq_max_bg(void) { return 4; }
 
 // 1 (default): the recurrences exchange their state with st.async + mbarrier; 0: DSMEM stores + cluster barrier (round 1)
-static int g_gru_async = 1;
-PA2S_API int pa2s_gru_seq_set_exchange(int async_exchange) { g_gru_async = async_exchange ? 1 : 0; return 0; }
+static int g_gru_async = 1, g_gru_bwd2 = 1;
+// 0: DSMEM stores + cluster barrier; 1 (default): st.async + mbarrier, reverse pass in the row-owner formulation (gru_seq_bwd2_kernel);
+// 3: st.async + mbarrier with the column-owner reverse kernel
+PA2S_API int pa2s_gru_seq_set_exchange(int mode) { g_gru_async = mode ? 1 : 0; g_gru_bwd2 = (mode == 1); return 0; }
 
 // Encoder recurrence forward.  H must be 256.  `bg` in {1,2,4} = samples per cluster.
 PA2S_API int pa2s_gru_seq_fwd(void* stream, int B, int T, int ND, int H, int bg, const float* gi, const float* Whh, const float* bhh,
@@ -651,6 +777,12 @@ PA2S_API int pa2s_gru_seq_bwd(void* stream, int B, int T, int ND, int H, int bg,
     a.G = ceil_div(B, bg);
     int nblocks = ND * a.G * ECL;
     cudaStream_t st = (cudaStream_t)stream;
+    if (g_gru_async == 2 || (g_gru_async == 1 && g_gru_bwd2)) {
+        if (bg == 1) return launch_cluster(gru_seq_bwd2_kernel<1>, st, nblocks, a);
+        if (bg == 2) return launch_cluster(gru_seq_bwd2_kernel<2>, st, nblocks, a);
+        if (bg == 4) return launch_cluster(gru_seq_bwd2_kernel<4>, st, nblocks, a);
+        return -1;
+    }
     if (g_gru_async) {
         if (bg == 1) return launch_cluster(gru_seq_bwd_kernel<1, true>, st, nblocks, a);
         if (bg == 2) return launch_cluster(gru_seq_bwd_kernel<2, true>, st, nblocks, a);

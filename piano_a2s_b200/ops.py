@@ -665,7 +665,7 @@ _GRU_EXCHANGE_SET = [False]
 def _gru_exchange():
     """PA2S_GRU_EXCHANGE=barrier selects round 1's DSMEM stores + cluster barrier for the encoder recurrences (default: st.async + mbarrier)"""
     if not _GRU_EXCHANGE_SET[0]:
-        lib.pa2s_gru_seq_set_exchange(0 if os.environ.get("PA2S_GRU_EXCHANGE", "async") == "barrier" else 1)
+        lib.pa2s_gru_seq_set_exchange({"barrier": 0, "async": 1, "async_cols": 3}[os.environ.get("PA2S_GRU_EXCHANGE", "async")])
         _GRU_EXCHANGE_SET[0] = True
 
 

@@ -2,7 +2,7 @@
 mkdir -p gpurun_out
 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "encoder" > gpurun_out/r02aa_enc.log 2>&1; echo "enc tests exit $?" >> gpurun_out/r02aa_enc.log; tail -3 gpurun_out/r02aa_enc.log
 timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/r02aa_tests.log 2>&1; echo "tests exit $?" >> gpurun_out/r02aa_tests.log; tail -3 gpurun_out/r02aa_tests.log
-for mode in async barrier; do
+for mode in async async_cols; do
 PA2S_GRU_EXCHANGE=$mode timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --also-steps 0 > gpurun_out/r02aa_bench_$mode.json 2> gpurun_out/r02aa_bench_$mode.err
 python - <<PY
 import json
