@@ -355,25 +355,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(ConvArgs2 a) {
 // The reduction runs over pixels, so BOTH operands are MN-major UMMA operands (K = position at a 16-byte pitch):
 //   A = dy   (M = 64 >= COUT)  window of row t,  entries 1..128
 //   B = a_in (N = CINP)        windows of rows t-1, t, t+1 (shared between consecutive tiles); tap kx = start + kx*16 bytes
-// Nine accumulators (one per tap, CINP columns, 64 lanes) stay in TMEM for ALL tiles of the persistent CTA and are read out
+// Nine accumulators (one per tap, CINP columns, 64 or 128 lanes) stay in TMEM for ALL tiles of the persistent CTA and are read out
 // once at the end into a per-CTA partial (summed by pa2s_reduce_rows).
 // ====================================================================================================================
 constexpr int NASLOT = 3;
 struct WgradArgs2 {
     const uint4* Pin;      // a_in planes (CIN channels)
     const uint4* Pdy;      // dy planes (COUT channels)
-    float* partial;        // [gridDim.x][COUT*CIN*9]
+    float* partial;        // [2 * gridDim.x][COUT*CIN*9]
     Geom g;
 };
+
+template <int CIN> struct WgradCat { static constexpr bool value = 2 * ((CIN + 7) / 8) * 8 * 9 <= 512; };
 
 template <int CIN, int COUT>
 __global__ void __launch_bounds__(NTHREADS, 1) conv_wgrad_tma_kernel(WgradArgs2 a) {
     constexpr int CINP = (CIN + 15) / 16 * 16;
-    constexpr int NGB = CINP / 8, NGRB = (CIN + 7) / 8;
-    constexpr int NGA = 8, NGRA = (COUT + 7) / 8;                 // dy planes: M = 64
+    constexpr int NGRB = (CIN + 7) / 8;
+    // NCATB (20 input channels): the lo planes of a_in follow its 3 hi planes directly, so that ONE N = 48 operand [x_hi | x_lo]
+    // meets the stacked A = [dy_hi ; dy_lo]: all four piece products in a single M = 128 instruction per tap and k-step.  The
+    // kernel is bound by the shared-memory operand reads (A = 4 KB per instruction), so instructions are what counts:
+    // 5.5 KB per (tap, k-step) instead of 3 x 3 KB.  Nine taps x 2 x CINP columns do not fit TMEM for 40 channels.
+    constexpr bool NCATB = WgradCat<CIN>::value;
+    constexpr int NGB = NCATB ? NGRB : CINP / 8;
+    constexpr int NACC = NCATB ? 2 * NGRB * 8 : CINP;             // accumulator columns per tap
+    constexpr int NGA = 8, NGRA = (COUT + 7) / 8;                 // dy planes: M = 64 per piece
     constexpr int SLOT_BYTES = 2 * NGB * PLANE_BYTES, ASLOT_BYTES = 2 * NGA * PLANE_BYTES;
     constexpr int TM_COLS = 512;
-    static_assert(9 * CINP <= TM_COLS && COUT <= 64, "accumulators must fit TMEM");
+    static_assert(9 * NACC <= TM_COLS && COUT <= 64 && NACC % 16 == 0, "accumulators must fit TMEM");
 
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* win = smem;
@@ -408,25 +417,48 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_wgrad_tma_kernel(WgradArgs2 
         mbar_wait(&done_bar, 0);
         tc_fence_after();
         const bool has_tiles = walk.pos < walk.end;                // a CTA without tiles never initialised its accumulators
-        const int co = 16 * warp + lane;                           // M = 64: row r lives in lane (r%16) + 32*(r/16)
-        float* out = a.partial + (size_t)blockIdx.x * COUT * CIN * 9;
+        // one piece: M = 64, row r lives in lane (r%16) + 32*(r/16), the second partial row of this CTA is zero.
+        // two pieces: M = 128, lane = row; rows 0..63 hold dy_hi * a_in, rows 64..127 dy_lo * a_in -> the two partial rows of this CTA
+        const bool stacked = NP > 1;
+        const int row = 32 * warp + lane;
+        const int co = stacked ? (row & 63) : 16 * warp + lane;
+        const bool writer = stacked ? true : lane < 16;
+        float* out = a.partial + ((size_t)blockIdx.x * 2 + (stacked ? (row >> 6) : 0)) * COUT * CIN * 9;
+        if (!stacked) {
+            float* z = a.partial + ((size_t)blockIdx.x * 2 + 1) * COUT * CIN * 9;
+            for (int i = tid; i < COUT * CIN * 9; i += 128) z[i] = 0.f;
+        }
 #pragma unroll 1
         for (int tap = 0; tap < 9; ++tap) {
+            if (NCATB && stacked) {                                // columns [0, 24) = x_hi products, [24, 48) = x_lo products
+                float v[NACC];
 #pragma unroll
-            for (int c0 = 0; c0 < CINP; c0 += 16) {
-                float v[16];
-                tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(tap * CINP + c0), v);
-                if (lane < 16 && co < COUT) {
+                for (int c0 = 0; c0 < NACC; c0 += 16)
+                    tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(tap * NACC + c0), *reinterpret_cast<float(*)[16]>(&v[c0]));
+                if (co < COUT) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        if (c0 + i < CIN) out[((size_t)co * CIN + c0 + i) * 9 + tap] = has_tiles ? v[i] : 0.f;
+                    for (int i = 0; i < CIN; ++i) out[((size_t)co * CIN + i) * 9 + tap] = has_tiles ? v[i] + v[NACC / 2 + i] : 0.f;
+                }
+            } else {
+#pragma unroll
+                for (int c0 = 0; c0 < CINP; c0 += 16) {
+                    float v[16];
+                    tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(tap * NACC + c0), v);
+                    if (writer && co < COUT) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (c0 + i < CIN) out[((size_t)co * CIN + c0 + i) * 9 + tap] = has_tiles ? v[i] : 0.f;
+                    }
                 }
             }
         }
         tc_fence_before();
     } else if (warp == 4) {
         // ================================================================================= MMA issuer (warp-uniform)
-        const uint32_t idesc = make_idesc(64, CINP, 1, 1);
+        // two pieces: A = [dy_hi ; dy_lo] stacked along M (the lo planes follow the hi planes in the slot), so that ONE M = 128
+        // instruction per a_in piece yields dy_hi * x (rows 0..63) and dy_lo * x (rows 64..127): 2 full-rate MMAs per k-step
+        // instead of 3 half-rate M = 64 ones (the lo * lo term comes for free).
+        const uint32_t idesc = make_idesc(NP > 1 ? 128 : 64, (NCATB && NP > 1) ? NACC : CINP, 1, 1);
         const uint32_t win_base = smem_u32(win), a_base0 = smem_u32(asm_);
         uint32_t it = 0, wbase = 0;
         bool any = false;
@@ -437,7 +469,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_wgrad_tma_kernel(WgradArgs2 
                 mbar_wait(&afull_bar[aslot], (it / NASLOT) & 1);
                 tc_fence_after();
                 const uint64_t dah0 = make_desc(a_base0 + aslot * ASLOT_BYTES + 16, 128, PLANE_BYTES);     // entries 1..128
-                const uint64_t dal0 = desc_advance(dah0, NGA * PLANE_BYTES);
                 const bool last = (k == ch.n - 1);
                 for (int ky = 0; ky < 3; ++ky) {
                     const uint32_t wi = wbase + k + ky;
@@ -451,16 +482,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_wgrad_tma_kernel(WgradArgs2 
                     if (elect_one()) {
 #pragma unroll
                         for (int kx = 0; kx < 3; ++kx) {
-                            const uint32_t d_tmem = tmem_base + (uint32_t)((ky * 3 + kx) * CINP);
+                            const uint32_t d_tmem = tmem_base + (uint32_t)((ky * 3 + kx) * NACC);
 #pragma unroll
                             for (int ks = 0; ks < BM / 16; ++ks) {
-                                const uint64_t dah = desc_advance(dah0, ks * 256), dal = desc_advance(dal0, ks * 256);
+                                const uint64_t dah = desc_advance(dah0, ks * 256);
                                 const uint64_t dbh = desc_advance(dbh0, (kx + 16 * ks) * 16), dbl = desc_advance(dbl0, (kx + 16 * ks) * 16);
                                 tc_mma(d_tmem, dah, dbh, idesc, (it | (uint32_t)ks) != 0);
-                                if (NP > 1) {
-                                    tc_mma(d_tmem, dah, dbl, idesc, 1);
-                                    tc_mma(d_tmem, dal, dbh, idesc, 1);
-                                }
+                                if (NP > 1 && !NCATB) tc_mma(d_tmem, dah, dbl, idesc, 1);
                             }
                         }
                         if (ky == 0 || last) tc_commit(&empty_bar[slot]);
@@ -535,7 +563,8 @@ int launch_conv(cudaStream_t st, const ConvArgs2& a) {
 template <int CIN, int COUT>
 int launch_wgrad(cudaStream_t st, const WgradArgs2& a) {
     constexpr int CINP = (CIN + 15) / 16 * 16;
-    constexpr int SMEM = NWIN * (2 * (CINP / 8) * PLANE_BYTES) + NASLOT * (2 * 8 * PLANE_BYTES) + 1024;
+    constexpr int NGB = WgradCat<CIN>::value ? (CIN + 7) / 8 : CINP / 8;
+    constexpr int SMEM = NWIN * (2 * NGB * PLANE_BYTES) + NASLOT * (2 * 8 * PLANE_BYTES) + 1024;
     static_assert(SMEM <= 227 * 1024, "shared memory");
     PA2S_TRY(cudaFuncSetAttribute(conv_wgrad_tma_kernel<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     conv_wgrad_tma_kernel<CIN, COUT><<<conv_grid(a.g.B, a.g.T, a.g.F), NTHREADS, SMEM, st>>>(a);
@@ -576,7 +605,7 @@ PA2S_API int pa2s_planes_bwd(void* stream, int B, int T, int F, int C, const flo
     return -1;
 }
 PA2S_API int pa2s_conv_tma_num_partials(int B, int T, int F) { return conv_grid(B, T, F) * 4; }
-PA2S_API int pa2s_conv_tma_wgrad_num_partials(int B, int T, int F) { return conv_grid(B, T, F); }
+PA2S_API int pa2s_conv_tma_wgrad_num_partials(int B, int T, int F) { return 2 * conv_grid(B, T, F); }   // two rows per CTA
 // Y (B,T,F,Cout) = conv3x3 of the planes tensor (Cin channels) with Wpack (pa2s_tc_conv_pack: dgrad = 0 the forward filter,
 // dgrad = 1 the flipped / transposed filter, which makes this the data gradient: planes = dy, Cin = channels of dy).
 // partial (or NULL): pa2s_conv_tma_num_partials rows of [sum y, sum y^2].
