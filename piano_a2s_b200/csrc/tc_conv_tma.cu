@@ -275,6 +275,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(ConvArgs2 a) {
         }
     } else if (warp == 4) {
         // ================================================================================= MMA issuer (warp-uniform)
+        // All waits of a tile come first, then ONE elected block issues its 9 * KS * (2 or 3) instructions.  (An elected block per ky
+        // cost a divergence + reconvergence and ~120 setup instructions three times per tile, during which the tensor pipe ran dry:
+        // ~1000 of the 2670 cycles of a tile.  Everything stays warp-uniform so that the descriptors live in uniform registers --
+        // a single-lane role makes the compiler wrap every tcgen05.mma in a waterfall loop.)
         const uint32_t idesc = make_idesc(BM, COUTP, 0, 0), idesc2 = make_idesc(BM, 2 * COUTP, 0, 0);
         const uint32_t w_base = smem_u32(wsm), win_base = smem_u32(win);
         const uint64_t wdesc0 = make_desc(w_base, 2 * COUTP * 16, 128);      // k-group pitch: hi rows + lo rows
@@ -283,20 +287,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(ConvArgs2 a) {
             for (int k = 0; k < ch.n; ++k, ++it) {
                 const int acc = it & 1;
                 mbar_wait(&tempty_bar[acc], ((it >> 1) & 1) ^ 1);
+                const uint32_t wi0 = wbase + k;                       // windows wi0 + ky = input rows t0 + k + ky - 1
+                if (k == 0) {                                         // the two older windows were awaited by the previous tile
+                    mbar_wait(&full_bar[wi0 % NWIN], (wi0 / NWIN) & 1);
+                    mbar_wait(&full_bar[(wi0 + 1) % NWIN], ((wi0 + 1) / NWIN) & 1);
+                }
+                mbar_wait(&full_bar[(wi0 + 2) % NWIN], ((wi0 + 2) / NWIN) & 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TM_COLS);
                 const bool last = (k == ch.n - 1);
+                // everything that varies at run time is formed OUTSIDE the elected block (warp-uniform -> uniform registers)
+                uint32_t sl[3];
+                uint64_t dA[3];
+#pragma unroll
                 for (int ky = 0; ky < 3; ++ky) {
-                    const uint32_t wi = wbase + k + ky;               // window of input row t0 + k + ky - 1
-                    const int slot = wi % NWIN;
-                    if (k == 0 || ky == 2) {                          // the two older windows were awaited by the previous tile
-                        mbar_wait(&full_bar[slot], (wi / NWIN) & 1);
-                        tc_fence_after();
-                    }
-                    const uint64_t dah0 = make_desc(win_base + slot * SLOT_BYTES, PLANE_BYTES, 128);
-                    const uint64_t dal0 = desc_advance(dah0, NG * PLANE_BYTES);
-                    const uint64_t dbw = desc_advance(wdesc0, (uint32_t)(ky * 3 * KS * 2 * WBLK_BYTES));
-                    if (elect_one()) {
+                    sl[ky] = (wi0 + ky) % NWIN;
+                    dA[ky] = make_desc(win_base + sl[ky] * SLOT_BYTES, PLANE_BYTES, 128);
+                }
+                if (elect_one()) {
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky) {
+                        const uint32_t slot = sl[ky];
+                        const uint64_t dah0 = dA[ky];
+                        const uint64_t dal0 = desc_advance(dah0, NG * PLANE_BYTES);
+                        const uint64_t dbw = desc_advance(wdesc0, (uint32_t)(ky * 3 * KS * 2 * WBLK_BYTES));
 #pragma unroll
                         for (int kx = 0; kx < 3; ++kx) {
 #pragma unroll
@@ -320,8 +334,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(ConvArgs2 a) {
                         if (ky == 0 || last) tc_commit(&empty_bar[slot]);
                         if (ky == 2) tc_commit(&tfull_bar[acc]);
                     }
-                    __syncwarp();
                 }
+                __syncwarp();
             }
             wbase += ch.n + 2;
         }
@@ -460,26 +474,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_wgrad_tma_kernel(WgradArgs2 
         // instead of 3 half-rate M = 64 ones (the lo * lo term comes for free).
         const uint32_t idesc = make_idesc(NP > 1 ? 128 : 64, (NCATB && NP > 1) ? NACC : CINP, 1, 1);
         const uint32_t win_base = smem_u32(win), a_base0 = smem_u32(asm_);
-        uint32_t it = 0, wbase = 0;
-        bool any = false;
+        uint32_t it = 0, wbase = 0;                                   // all waits of a tile first, then one elected block (see conv_tma_kernel)
         while (walk.next(ch)) {
-            any = true;
             for (int k = 0; k < ch.n; ++k, ++it) {
                 const int aslot = it % NASLOT;
                 mbar_wait(&afull_bar[aslot], (it / NASLOT) & 1);
+                const uint32_t wi0 = wbase + k;
+                if (k == 0) {
+                    mbar_wait(&full_bar[wi0 % NWIN], (wi0 / NWIN) & 1);
+                    mbar_wait(&full_bar[(wi0 + 1) % NWIN], ((wi0 + 1) / NWIN) & 1);
+                }
+                mbar_wait(&full_bar[(wi0 + 2) % NWIN], ((wi0 + 2) / NWIN) & 1);
                 tc_fence_after();
                 const uint64_t dah0 = make_desc(a_base0 + aslot * ASLOT_BYTES + 16, 128, PLANE_BYTES);     // entries 1..128
                 const bool last = (k == ch.n - 1);
+                uint32_t sl[3];
+                uint64_t dB[3];
+#pragma unroll
                 for (int ky = 0; ky < 3; ++ky) {
-                    const uint32_t wi = wbase + k + ky;
-                    const int slot = wi % NWIN;
-                    if (k == 0 || ky == 2) {
-                        mbar_wait(&full_bar[slot], (wi / NWIN) & 1);
-                        tc_fence_after();
-                    }
-                    const uint64_t dbh0 = make_desc(win_base + slot * SLOT_BYTES, 128, PLANE_BYTES);
-                    const uint64_t dbl0 = desc_advance(dbh0, NGB * PLANE_BYTES);
-                    if (elect_one()) {
+                    sl[ky] = (wi0 + ky) % NWIN;
+                    dB[ky] = make_desc(win_base + sl[ky] * SLOT_BYTES, 128, PLANE_BYTES);
+                }
+                if (elect_one()) {
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky) {
+                        const uint32_t slot = sl[ky];
+                        const uint64_t dbh0 = dB[ky];
+                        const uint64_t dbl0 = desc_advance(dbh0, NGB * PLANE_BYTES);
 #pragma unroll
                         for (int kx = 0; kx < 3; ++kx) {
                             const uint32_t d_tmem = tmem_base + (uint32_t)((ky * 3 + kx) * NACC);
@@ -494,12 +515,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_wgrad_tma_kernel(WgradArgs2 
                         if (ky == 0 || last) tc_commit(&empty_bar[slot]);
                         if (ky == 2) tc_commit(&aempty_bar[aslot]);
                     }
-                    __syncwarp();
                 }
+                __syncwarp();
             }
             wbase += ch.n + 2;
         }
-        (void)any;
         if (elect_one()) tc_commit(&done_bar);
         __syncwarp();
     } else if (lane == 0) {
