@@ -126,6 +126,9 @@ PA2S_API int pa2s_planes_fwd(void* stream, int B, int T, int F, int C, const flo
 PA2S_API int pa2s_planes_bwd(void* stream, int B, int T, int F, int C, const float* G, const float* Yraw, const float* zs, const float* zb,
                              const float* mean, const float* invstd, const float* k1, const float* k2, const float* k3,
                              void* planes, int npieces);
+/* 1 (default): conv_tma3_kernel, the three kx taps share one read of the activation window (126 outputs per tile);
+ * 0: conv_tma_kernel, one instruction group per tap.  Same results up to fp32 summation order. */
+PA2S_API int pa2s_conv_tma_set_impl(int impl);
 PA2S_API int pa2s_conv_tma_num_partials(int B, int T, int F);
 PA2S_API int pa2s_conv_tma_wgrad_num_partials(int B, int T, int F);
 PA2S_API int pa2s_conv_tma(void* stream, int B, int T, int F, int Cin, int Cout, const void* planes, int npieces, const void* Wpack,

@@ -31,6 +31,10 @@ constexpr int WENT = 130;                    // window entries: 128 output posit
 constexpr int PLANE_BYTES = WENT * 16;       // 2080
 constexpr int NWIN = 5;                      // window ring: three rows in use by the MMAs + two in flight
 constexpr int NTHREADS = 192;
+__host__ __device__ constexpr int conv3_nwin(int w_bytes, int slot_bytes) {      // window ring of conv_tma3_kernel: what fits, 5..8
+    const int n = (227 * 1024 - 2048 - ((w_bytes + 127) / 128) * 128) / slot_bytes;
+    return n > 8 ? 8 : n;
+}
 
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -42,9 +46,16 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 
 struct Geom {
     int B, T, F, nfb, FP, NP;                // FP = plane row pitch in positions, NP = pieces (1 or 2)
+    int nfbc;                                // strips per row of conv_tma3_kernel
 };
 __host__ __device__ inline int geom_nfb(int F) { return (F + 2 + BM - 1) / BM; }
-__host__ __device__ inline int geom_fp(int F) { return geom_nfb(F) * BM + 8; }
+// conv_tma3_kernel: a tile = the 128 window entries q0 .. q0+127, q0 = fb*OT, and produces OT = 126 outputs f = q0-1 .. q0+124
+constexpr int OT = 126;
+__host__ __device__ inline int geom_nfbc(int F) { return (F + 1 + OT - 1) / OT; }
+__host__ __device__ inline int geom_fp(int F) {
+    const int a = geom_nfb(F) * BM + 8, b = ((geom_nfbc(F) - 1) * OT + WENT + 7) / 8 * 8;      // every window read stays inside its plane row
+    return a > b ? a : b;
+}
 // 16-byte unit index of (b, t', piece, g, q) in a plane tensor with NGR stored channel groups
 __device__ __forceinline__ size_t plane_unit(const Geom& g, int NGR, int b, int tp, int piece, int grp, int q) {
     return ((((size_t)b * (g.T + 2) + tp) * g.NP + piece) * NGR + grp) * g.FP + q;
@@ -55,8 +66,8 @@ __device__ __forceinline__ size_t plane_unit(const Geom& g, int NGR, int b, int 
 struct Chunk { int b, fb, t0, n; };
 struct Walk {
     long long pos, end; int T, nfb;
-    __device__ __forceinline__ void init(const Geom& g) {
-        T = g.T; nfb = g.nfb;
+    __device__ __forceinline__ void init(const Geom& g, int nfb_ = 0) {
+        T = g.T; nfb = nfb_ > 0 ? nfb_ : g.nfb;
         const long long total = (long long)g.B * nfb * T;
         const long long per = (total + gridDim.x - 1) / gridDim.x;
         pos = (long long)blockIdx.x * per;
@@ -74,8 +85,8 @@ struct Walk {
     }
 };
 // number of CTAs such that every CTA owns at least one tile under Walk's ceil-division
-static int conv_grid(int B, int T, int F) {
-    const long long total = (long long)B * geom_nfb(F) * T;
+static int conv_grid(int B, int T, int F, int nfb = 0) {
+    const long long total = (long long)B * (nfb > 0 ? nfb : geom_nfb(F)) * T;
     const long long g0 = total < 148 ? total : 148;
     const long long per = (total + g0 - 1) / g0;
     return (int)((total + per - 1) / per);
@@ -365,6 +376,246 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(ConvArgs2 a) {
 }
 
 // ====================================================================================================================
+// forward / data-gradient convolution, second formulation: the three kx taps share ONE read of the activation window.
+//
+// conv_tma_kernel issues one instruction group per tap with the A descriptor shifted by kx entries: 9 * KS * 2 instructions of
+// N = 32..96 per tile, each reading its 4 KB A operand from shared memory again -- measured (tools/conv_prof.py, experiments in
+// DESIGN.md): a tile is bound by the operand reads and by the issue overhead of its many small instructions, the tensor pipe is
+// ~35 % busy.  Here A is the UNSHIFTED window (entries e = 0..127) and the B operand of a (ky, k-step) is the three kx filters
+// side by side, N3 = 3 * COUT columns:   E_kx[e][co] = sum_ci a[e][ci] * W[ky][kx][ci][co].   The tap shift moves into the
+// epilogue:   y[o][co] = E_0[o] + E_1[o+1] + E_2[o+2],  o = 0..125   (lane shuffles; the two rows a warp needs from its neighbour
+// travel through shared memory).  3 * KS * 3 instructions per tile of N = 80 / 128, a third of the A reads.  A tile yields
+// 126 outputs, strips advance by 126 positions (geom_nfbc).
+// ====================================================================================================================
+template <int CIN, int COUT>
+struct Conv3Cfg {
+    static constexpr int CINP = (CIN + 15) / 16 * 16, NG = CINP / 8, NGR = (CIN + 7) / 8, KS = CINP / 16;
+    static constexpr int CQ = (COUT + 7) / 8 * 8;                  // filter rows per kx block
+    static constexpr int N3 = (3 * CQ + 15) / 16 * 16;             // instruction N
+    static constexpr int SLOT_BYTES = 2 * NG * PLANE_BYTES;        // hi planes then lo planes
+    static constexpr int WBLK_BYTES = 2 * 2 * N3 * 16;             // one (ky, ks) block: 2 k-groups x [hi rows | lo rows]
+    static constexpr int W_BYTES = 3 * KS * WBLK_BYTES;
+    static constexpr int NW = conv3_nwin(W_BYTES, SLOT_BYTES);
+    static constexpr int SMEM = ((W_BYTES + 127) / 128) * 128 + NW * SLOT_BYTES + 1024;
+    static constexpr int TM_COLS = N3 <= 64 ? 64 : 128;
+};
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(NTHREADS, 1) conv_tma3_kernel(ConvArgs2 a) {
+    using Cfg = Conv3Cfg<CIN, COUT>;
+    constexpr int NG = Cfg::NG, NGR = Cfg::NGR, KS = Cfg::KS, CQ = Cfg::CQ, N3 = Cfg::N3;
+    constexpr int SLOT_BYTES = Cfg::SLOT_BYTES, WBLK_BYTES = Cfg::WBLK_BYTES, W_BYTES = Cfg::W_BYTES, NW = Cfg::NW, TM_COLS = Cfg::TM_COLS;
+    constexpr int COUTP = (COUT + 15) / 16 * 16;                      // rows per block of the packed filter (pa2s_tc_conv_pack)
+    constexpr int NCH = CQ / 8;                                       // 8-channel chunks of the epilogue
+    static_assert(N3 <= TM_COLS && N3 <= 256, "accumulator width");
+
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* wsm = smem;
+    uint8_t* win = smem + ((W_BYTES + 127) / 128) * 128;
+    __shared__ uint64_t full_bar[NW], empty_bar[NW], tfull_bar[2], tempty_bar[2];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(16) float xch[2][4][3][CQ];                  // [tile parity][warp][E1 of lane 0, E2 of lane 0, E2 of lane 1][channel]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int T = a.g.T, F = a.g.F;
+    const int NP = a.g.NP;
+
+    // filter blocks: [ky][ks][kgroup][split][kx * CQ + n] (16-byte units), rows 3*CQ .. N3-1 zero.  Source order (pa2s_tc_conv_pack):
+    // [tap = ky*3+kx][ks][split][kgroup][n < COUTP]
+    for (int i = tid; i < W_BYTES / 16; i += NTHREADS) reinterpret_cast<uint4*>(wsm)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < NW * SLOT_BYTES / 16; i += NTHREADS) reinterpret_cast<uint4*>(win)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    for (int i = tid; i < 9 * KS * 2 * 2 * COUTP; i += NTHREADS) {
+        const int n = i % COUTP;
+        int r = i / COUTP;
+        const int kg = r & 1, split = (r >> 1) & 1;
+        r >>= 2;
+        const int ks = r % KS, tap = r / KS, ky = tap / 3, kx = tap % 3;
+        if (n < CQ) reinterpret_cast<uint4*>(wsm)[((((ky * KS + ks) * 2 + kg) * 2 + split) * N3) + kx * CQ + n] = __ldg(a.Wpack + i);
+    }
+    if (warp == 4) {
+        if (lane == 0) {
+            for (int s = 0; s < NW; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+            for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 128); }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        tmem_alloc(&tmem_base_s, 2 * TM_COLS);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    Walk walk;
+    walk.init(a.g, a.g.nfbc);
+    Chunk ch;
+
+    if (warp < 4) {
+        // ================================================================================= epilogue
+        float ps[COUT], pq[COUT];                                     // BatchNorm batch statistics, per thread over all its tiles
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) { ps[c] = 0.f; pq[c] = 0.f; }
+        const int o = warp * 32 + lane;                               // output index of the tile = window entry of E_0
+        uint32_t it = 0;
+        while (walk.next(ch)) {
+            const int f = ch.fb * OT + o - 1;
+            const bool valid = (o < OT) && (f >= 0) && (f < F);
+            for (int k = 0; k < ch.n; ++k, ++it) {
+                const int acc = it & 1;
+                mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
+                tc_fence_after();
+                float* yrow = a.Y + (((size_t)ch.b * T + ch.t0 + k) * F + f) * COUT;
+                const uint32_t tbase = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * TM_COLS);
+                // pass 1: the rows the previous warp's last two outputs need (E_1 of lane 0, E_2 of lanes 0 and 1), all channels,
+                // into shared memory; ONE barrier per tile (buffers alternate with the tile parity)
+                float (*xw)[3][CQ] = xch[it & 1];
+#pragma unroll
+                for (int c8 = 0; c8 < NCH; ++c8) {
+                    uint32_t r1[8], r2[8];
+                    tc_ld8_nowait(tbase + 1 * CQ + c8 * 8, r1);
+                    tc_ld8_nowait(tbase + 2 * CQ + c8 * 8, r2);
+                    tc_ld_wait();
+                    if (lane < 2) {
+                        float4* d1 = reinterpret_cast<float4*>(&xw[warp][lane == 0 ? 0 : 2][c8 * 8]);      // lane 0: E_1, lane 1: E_2
+                        const uint32_t* s1 = lane == 0 ? r1 : r2;
+                        d1[0] = make_float4(__uint_as_float(s1[0]), __uint_as_float(s1[1]), __uint_as_float(s1[2]), __uint_as_float(s1[3]));
+                        d1[1] = make_float4(__uint_as_float(s1[4]), __uint_as_float(s1[5]), __uint_as_float(s1[6]), __uint_as_float(s1[7]));
+                        if (lane == 0) {
+                            float4* d2 = reinterpret_cast<float4*>(&xw[warp][1][c8 * 8]);
+                            d2[0] = make_float4(__uint_as_float(r2[0]), __uint_as_float(r2[1]), __uint_as_float(r2[2]), __uint_as_float(r2[3]));
+                            d2[1] = make_float4(__uint_as_float(r2[4]), __uint_as_float(r2[5]), __uint_as_float(r2[6]), __uint_as_float(r2[7]));
+                        }
+                    }
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const int wn = (warp + 1) & 3;                        // (warp 3's last two lanes are not outputs)
+                // pass 2: y[o] = E_0[o] + E_1[o+1] + E_2[o+2], branch-free
+#pragma unroll
+                for (int c8 = 0; c8 < NCH; ++c8) {
+                    uint32_t r0[8], r1[8], r2[8];
+                    tc_ld8_nowait(tbase + 0 * CQ + c8 * 8, r0);
+                    tc_ld8_nowait(tbase + 1 * CQ + c8 * 8, r1);
+                    tc_ld8_nowait(tbase + 2 * CQ + c8 * 8, r2);
+                    float x0[8], x1[8], x2[8];                        // neighbour rows (broadcast reads)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const float4 q0 = reinterpret_cast<const float4*>(&xw[wn][0][c8 * 8])[h];
+                        const float4 q1 = reinterpret_cast<const float4*>(&xw[wn][1][c8 * 8])[h];
+                        const float4 q2 = reinterpret_cast<const float4*>(&xw[wn][2][c8 * 8])[h];
+                        x0[4 * h] = q0.x; x0[4 * h + 1] = q0.y; x0[4 * h + 2] = q0.z; x0[4 * h + 3] = q0.w;
+                        x1[4 * h] = q1.x; x1[4 * h + 1] = q1.y; x1[4 * h + 2] = q1.z; x1[4 * h + 3] = q1.w;
+                        x2[4 * h] = q2.x; x2[4 * h + 1] = q2.y; x2[4 * h + 2] = q2.z; x2[4 * h + 3] = q2.w;
+                    }
+                    tc_ld_wait();
+                    float v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        float e1 = __shfl_down_sync(0xffffffffu, __uint_as_float(r1[i]), 1);
+                        float e2 = __shfl_down_sync(0xffffffffu, __uint_as_float(r2[i]), 2);
+                        e1 = lane == 31 ? x0[i] : e1;
+                        e2 = lane == 31 ? x2[i] : (lane == 30 ? x1[i] : e2);
+                        v[i] = __uint_as_float(r0[i]) + e1 + e2;
+                    }
+                    if (valid) {
+                        if (c8 * 8 < COUT) reinterpret_cast<float4*>(yrow + c8 * 8)[0] = make_float4(v[0], v[1], v[2], v[3]);
+                        if (c8 * 8 + 4 < COUT) reinterpret_cast<float4*>(yrow + c8 * 8)[1] = make_float4(v[4], v[5], v[6], v[7]);
+                        if (a.partial != nullptr) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const int c = c8 * 8 + i;
+                                if (c < COUT) { ps[c] += v[i]; pq[c] = fmaf(v[i], v[i], pq[c]); }
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&tempty_bar[acc]);
+            }
+        }
+        if (a.partial != nullptr) {
+            float* pr = a.partial + ((size_t)blockIdx.x * 4 + warp) * 2 * COUT;
+#pragma unroll
+            for (int c = 0; c < COUT; ++c) {
+                const float s1 = warp_sum(ps[c]), s2 = warp_sum(pq[c]);
+                if (lane == 0) { pr[c] = s1; pr[COUT + c] = s2; }
+            }
+        }
+    } else if (warp == 4) {
+        // ================================================================================= MMA issuer (warp-uniform)
+        const uint32_t idesc = make_idesc(BM, N3, 0, 0);
+        const uint32_t w_base = smem_u32(wsm), win_base = smem_u32(win);
+        const uint64_t wdesc0 = make_desc(w_base, 2 * N3 * 16, 128);         // k-group pitch: hi rows + lo rows
+        uint32_t it = 0, wbase = 0;                                   // wbase = ring index of the chunk's first window (row t0-1)
+        while (walk.next(ch)) {
+            for (int k = 0; k < ch.n; ++k, ++it) {
+                const int acc = it & 1;
+                mbar_wait(&tempty_bar[acc], ((it >> 1) & 1) ^ 1);
+                const uint32_t wi0 = wbase + k;                       // windows wi0 + ky = input rows t0 + k + ky - 1
+                if (k == 0) {                                         // the two older windows were awaited by the previous tile
+                    mbar_wait(&full_bar[wi0 % NW], (wi0 / NW) & 1);
+                    mbar_wait(&full_bar[(wi0 + 1) % NW], ((wi0 + 1) / NW) & 1);
+                }
+                mbar_wait(&full_bar[(wi0 + 2) % NW], ((wi0 + 2) / NW) & 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TM_COLS);
+                const bool last = (k == ch.n - 1);
+                uint32_t sl[3];
+                uint64_t dA[3];
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky) {
+                    sl[ky] = (wi0 + ky) % NW;
+                    dA[ky] = make_desc(win_base + sl[ky] * SLOT_BYTES, PLANE_BYTES, 128);
+                }
+                if (elect_one()) {
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+                        for (int ks = 0; ks < KS; ++ks) {
+                            const uint64_t dah = desc_advance(dA[ky], (uint32_t)(2 * ks * PLANE_BYTES));
+                            const uint64_t dal = desc_advance(dah, NG * PLANE_BYTES);
+                            const uint64_t dbh = desc_advance(wdesc0, (uint32_t)((ky * KS + ks) * WBLK_BYTES));
+                            const uint64_t dbl = desc_advance(dbh, N3 * 16);
+                            tc_mma(d_tmem, dah, dbh, idesc, (ky | ks) != 0);             // A_hi * W_hi
+                            if (NP > 1) {
+                                tc_mma(d_tmem, dah, dbl, idesc, 1);                       // A_hi * W_lo
+                                tc_mma(d_tmem, dal, dbh, idesc, 1);                       // A_lo * W_hi
+                            }
+                        }
+                        // a window is free once the last tile that reads it has been issued
+                        if (ky == 0 || last) tc_commit(&empty_bar[sl[ky]]);
+                        if (ky == 2) tc_commit(&tfull_bar[acc]);
+                    }
+                }
+                __syncwarp();
+            }
+            wbase += ch.n + 2;
+        }
+    } else if (lane == 0) {
+        // ================================================================================= copy producer (one thread)
+        const uint32_t win_base = smem_u32(win);
+        uint32_t wi = 0;
+        while (walk.next(ch)) {
+            for (int j = 0; j < ch.n + 2; ++j, ++wi) {                // input rows t0-1 .. t0+n  ->  t' = t0 + j
+                const int slot = wi % NW;
+                mbar_wait(&empty_bar[slot], ((wi / NW) & 1) ^ 1);
+                mbar_expect_tx(&full_bar[slot], (uint32_t)(NP * NGR * PLANE_BYTES));
+                for (int p = 0; p < NP; ++p)
+                    for (int grp = 0; grp < NGR; ++grp)
+                        bulk_g2s(win_base + slot * SLOT_BYTES + (p * NG + grp) * PLANE_BYTES,
+                                 a.P + plane_unit(a.g, NGR, ch.b, ch.t0 + j, p, grp, ch.fb * OT), PLANE_BYTES, &full_bar[slot]);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 2 * TM_COLS);
+    }
+}
+
+// ====================================================================================================================
 // weight gradient:  dW[co][ci][ky][kx] = sum_pixels dy[pixel][co] * a_in[pixel + (ky-1, kx-1)][ci]
 // The reduction runs over pixels, so BOTH operands are MN-major UMMA operands (K = position at a 16-byte pitch):
 //   A = dy   (M = 64 >= COUT)  window of row t,  entries 1..128
@@ -581,6 +832,15 @@ int launch_conv(cudaStream_t st, const ConvArgs2& a) {
     return 0;
 }
 template <int CIN, int COUT>
+int launch_conv3(cudaStream_t st, const ConvArgs2& a) {
+    using Cfg = Conv3Cfg<CIN, COUT>;
+    static_assert(Cfg::SMEM <= 227 * 1024 && Cfg::NW >= 5, "shared memory");
+    PA2S_TRY(cudaFuncSetAttribute(conv_tma3_kernel<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    conv_tma3_kernel<CIN, COUT><<<conv_grid(a.g.B, a.g.T, a.g.F, a.g.nfbc), NTHREADS, Cfg::SMEM, st>>>(a);
+    PA2S_CHECK_LAST();
+    return 0;
+}
+template <int CIN, int COUT>
 int launch_wgrad(cudaStream_t st, const WgradArgs2& a) {
     constexpr int CINP = (CIN + 15) / 16 * 16;
     constexpr int NGB = WgradCat<CIN>::value ? (CIN + 7) / 8 : CINP / 8;
@@ -593,7 +853,7 @@ int launch_wgrad(cudaStream_t st, const WgradArgs2& a) {
 }
 Geom make_geom(int B, int T, int F, int npieces) {
     Geom g;
-    g.B = B; g.T = T; g.F = F; g.nfb = geom_nfb(F); g.FP = geom_fp(F); g.NP = npieces >= 2 ? 2 : 1;
+    g.B = B; g.T = T; g.F = F; g.nfb = geom_nfb(F); g.FP = geom_fp(F); g.NP = npieces >= 2 ? 2 : 1; g.nfbc = geom_nfbc(F);
     return g;
 }
 
@@ -624,7 +884,11 @@ PA2S_API int pa2s_planes_bwd(void* stream, int B, int T, int F, int C, const flo
     if (C == 40) return launch_planes<40, 1>((cudaStream_t)stream, a);
     return -1;
 }
-PA2S_API int pa2s_conv_tma_num_partials(int B, int T, int F) { return conv_grid(B, T, F) * 4; }
+static int g_conv_impl = 1;       // 1: conv_tma3_kernel (kx taps share the A read), 0: conv_tma_kernel (one instruction group per tap)
+PA2S_API int pa2s_conv_tma_set_impl(int impl) { g_conv_impl = impl ? 1 : 0; return 0; }
+PA2S_API int pa2s_conv_tma_num_partials(int B, int T, int F) {
+    return (g_conv_impl ? conv_grid(B, T, F, geom_nfbc(F)) : conv_grid(B, T, F)) * 4;      // every row is written by the kernel
+}
 PA2S_API int pa2s_conv_tma_wgrad_num_partials(int B, int T, int F) { return 2 * conv_grid(B, T, F); }   // two rows per CTA
 // Y (B,T,F,Cout) = conv3x3 of the planes tensor (Cin channels) with Wpack (pa2s_tc_conv_pack: dgrad = 0 the forward filter,
 // dgrad = 1 the flipped / transposed filter, which makes this the data gradient: planes = dy, Cin = channels of dy).
@@ -634,6 +898,13 @@ PA2S_API int pa2s_conv_tma(void* stream, int B, int T, int F, int Cin, int Cout,
     ConvArgs2 a;
     a.P = (const uint4*)planes; a.Wpack = (const uint4*)Wpack; a.Y = Y; a.partial = partial; a.g = make_geom(B, T, F, npieces);
     cudaStream_t st = (cudaStream_t)stream;
+    if (g_conv_impl) {
+        if (Cin == 20 && Cout == 20) return launch_conv3<20, 20>(st, a);
+        if (Cin == 20 && Cout == 40) return launch_conv3<20, 40>(st, a);
+        if (Cin == 40 && Cout == 40) return launch_conv3<40, 40>(st, a);
+        if (Cin == 40 && Cout == 20) return launch_conv3<40, 20>(st, a);
+        return -1;
+    }
     if (Cin == 20 && Cout == 20) return launch_conv<20, 20>(st, a);
     if (Cin == 20 && Cout == 40) return launch_conv<20, 40>(st, a);
     if (Cin == 40 && Cout == 40) return launch_conv<40, 40>(st, a);
