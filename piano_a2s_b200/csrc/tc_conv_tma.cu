@@ -31,8 +31,9 @@ constexpr int WENT = 130;                    // window entries: 128 output posit
 constexpr int PLANE_BYTES = WENT * 16;       // 2080
 constexpr int NWIN = 5;                      // window ring: three rows in use by the MMAs + two in flight
 constexpr int NTHREADS = 192;
+constexpr int NT3 = 320;                     // conv_tma3_kernel: 2 x 4 epilogue warps, MMA warp, copy warp
 __host__ __device__ constexpr int conv3_nwin(int w_bytes, int slot_bytes) {      // window ring of conv_tma3_kernel: what fits, 5..8
-    const int n = (227 * 1024 - 2048 - ((w_bytes + 127) / 128) * 128) / slot_bytes;
+    const int n = (227 * 1024 - 12 * 1024 - ((w_bytes + 127) / 128) * 128) / slot_bytes;      // 12 KB: static shared memory + alignment
     return n > 8 ? 8 : n;
 }
 
@@ -401,7 +402,7 @@ struct Conv3Cfg {
 };
 
 template <int CIN, int COUT>
-__global__ void __launch_bounds__(NTHREADS, 1) conv_tma3_kernel(ConvArgs2 a) {
+__global__ void __launch_bounds__(NT3, 1) conv_tma3_kernel(ConvArgs2 a) {
     using Cfg = Conv3Cfg<CIN, COUT>;
     constexpr int NG = Cfg::NG, NGR = Cfg::NGR, KS = Cfg::KS, CQ = Cfg::CQ, N3 = Cfg::N3;
     constexpr int SLOT_BYTES = Cfg::SLOT_BYTES, WBLK_BYTES = Cfg::WBLK_BYTES, W_BYTES = Cfg::W_BYTES, NW = Cfg::NW, TM_COLS = Cfg::TM_COLS;
@@ -414,17 +415,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma3_kernel(ConvArgs2 a) {
     uint8_t* win = smem + ((W_BYTES + 127) / 128) * 128;
     __shared__ uint64_t full_bar[NW], empty_bar[NW], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_s;
-    __shared__ __align__(16) float xch[2][4][3][CQ];                  // [tile parity][warp][E1 of lane 0, E2 of lane 0, E2 of lane 1][channel]
+    __shared__ __align__(16) float xch[2][2][4][3][CQ];               // [epilogue group][tile parity][warp][E1 of lane 0, E2 of lane 0, E2 of lane 1][channel]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int T = a.g.T, F = a.g.F;
     const int NP = a.g.NP;
 
     // filter blocks: [ky][ks][kgroup][split][kx * CQ + n] (16-byte units), rows 3*CQ .. N3-1 zero.  Source order (pa2s_tc_conv_pack):
     // [tap = ky*3+kx][ks][split][kgroup][n < COUTP]
-    for (int i = tid; i < W_BYTES / 16; i += NTHREADS) reinterpret_cast<uint4*>(wsm)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < NW * SLOT_BYTES / 16; i += NTHREADS) reinterpret_cast<uint4*>(win)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < W_BYTES / 16; i += NT3) reinterpret_cast<uint4*>(wsm)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < NW * SLOT_BYTES / 16; i += NT3) reinterpret_cast<uint4*>(win)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
-    for (int i = tid; i < 9 * KS * 2 * 2 * COUTP; i += NTHREADS) {
+    for (int i = tid; i < 9 * KS * 2 * 2 * COUTP; i += NT3) {
         const int n = i % COUTP;
         int r = i / COUTP;
         const int kg = r & 1, split = (r >> 1) & 1;
@@ -432,7 +433,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma3_kernel(ConvArgs2 a) {
         const int ks = r % KS, tap = r / KS, ky = tap / 3, kx = tap % 3;
         if (n < CQ) reinterpret_cast<uint4*>(wsm)[((((ky * KS + ks) * 2 + kg) * 2 + split) * N3) + kx * CQ + n] = __ldg(a.Wpack + i);
     }
-    if (warp == 4) {
+    if (warp == 8) {
         if (lane == 0) {
             for (int s = 0; s < NW; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
             for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 128); }
@@ -450,25 +451,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma3_kernel(ConvArgs2 a) {
     walk.init(a.g, a.g.nfbc);
     Chunk ch;
 
-    if (warp < 4) {
-        // ================================================================================= epilogue
+    if (warp < 8) {
+        // ================================================================================= epilogue: two groups of four warps, group g
+        // takes the tiles of accumulator g (it & 1 == g), so that a tile's read-out may last two tile periods
+        const int grp = warp >> 2, wq = warp & 3;                     // wq = TMEM lane quarter
         float ps[COUT], pq[COUT];                                     // BatchNorm batch statistics, per thread over all its tiles
 #pragma unroll
         for (int c = 0; c < COUT; ++c) { ps[c] = 0.f; pq[c] = 0.f; }
-        const int o = warp * 32 + lane;                               // output index of the tile = window entry of E_0
+        const int o = wq * 32 + lane;                                 // output index of the tile = window entry of E_0
         uint32_t it = 0;
         while (walk.next(ch)) {
             const int f = ch.fb * OT + o - 1;
             const bool valid = (o < OT) && (f >= 0) && (f < F);
             for (int k = 0; k < ch.n; ++k, ++it) {
                 const int acc = it & 1;
+                if (acc != grp) continue;
                 mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
                 tc_fence_after();
                 float* yrow = a.Y + (((size_t)ch.b * T + ch.t0 + k) * F + f) * COUT;
-                const uint32_t tbase = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * TM_COLS);
+                const uint32_t tbase = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * TM_COLS);
                 // pass 1: the rows the previous warp's last two outputs need (E_1 of lane 0, E_2 of lanes 0 and 1), all channels,
                 // into shared memory; ONE barrier per tile (buffers alternate with the tile parity)
-                float (*xw)[3][CQ] = xch[it & 1];
+                float (*xw)[3][CQ] = xch[grp][(it >> 1) & 1];
 #pragma unroll
                 for (int c8 = 0; c8 < NCH; ++c8) {
                     uint32_t r1[8], r2[8];
@@ -476,19 +480,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma3_kernel(ConvArgs2 a) {
                     tc_ld8_nowait(tbase + 2 * CQ + c8 * 8, r2);
                     tc_ld_wait();
                     if (lane < 2) {
-                        float4* d1 = reinterpret_cast<float4*>(&xw[warp][lane == 0 ? 0 : 2][c8 * 8]);      // lane 0: E_1, lane 1: E_2
+                        float4* d1 = reinterpret_cast<float4*>(&xw[wq][lane == 0 ? 0 : 2][c8 * 8]);      // lane 0: E_1, lane 1: E_2
                         const uint32_t* s1 = lane == 0 ? r1 : r2;
                         d1[0] = make_float4(__uint_as_float(s1[0]), __uint_as_float(s1[1]), __uint_as_float(s1[2]), __uint_as_float(s1[3]));
                         d1[1] = make_float4(__uint_as_float(s1[4]), __uint_as_float(s1[5]), __uint_as_float(s1[6]), __uint_as_float(s1[7]));
                         if (lane == 0) {
-                            float4* d2 = reinterpret_cast<float4*>(&xw[warp][1][c8 * 8]);
+                            float4* d2 = reinterpret_cast<float4*>(&xw[wq][1][c8 * 8]);
                             d2[0] = make_float4(__uint_as_float(r2[0]), __uint_as_float(r2[1]), __uint_as_float(r2[2]), __uint_as_float(r2[3]));
                             d2[1] = make_float4(__uint_as_float(r2[4]), __uint_as_float(r2[5]), __uint_as_float(r2[6]), __uint_as_float(r2[7]));
                         }
                     }
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                const int wn = (warp + 1) & 3;                        // (warp 3's last two lanes are not outputs)
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+                const int wn = (wq + 1) & 3;                        // (warp 3's last two lanes are not outputs)
                 // pass 2: y[o] = E_0[o] + E_1[o+1] + E_2[o+2], branch-free
 #pragma unroll
                 for (int c8 = 0; c8 < NCH; ++c8) {
@@ -533,14 +537,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma3_kernel(ConvArgs2 a) {
             }
         }
         if (a.partial != nullptr) {
-            float* pr = a.partial + ((size_t)blockIdx.x * 4 + warp) * 2 * COUT;
+            float* pr = a.partial + ((size_t)blockIdx.x * 8 + warp) * 2 * COUT;
 #pragma unroll
             for (int c = 0; c < COUT; ++c) {
                 const float s1 = warp_sum(ps[c]), s2 = warp_sum(pq[c]);
                 if (lane == 0) { pr[c] = s1; pr[COUT + c] = s2; }
             }
         }
-    } else if (warp == 4) {
+    } else if (warp == 8) {
         // ================================================================================= MMA issuer (warp-uniform)
         const uint32_t idesc = make_idesc(BM, N3, 0, 0);
         const uint32_t w_base = smem_u32(wsm), win_base = smem_u32(win);
@@ -609,7 +613,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma3_kernel(ConvArgs2 a) {
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == 8) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 2 * TM_COLS);
     }
@@ -836,7 +840,7 @@ int launch_conv3(cudaStream_t st, const ConvArgs2& a) {
     using Cfg = Conv3Cfg<CIN, COUT>;
     static_assert(Cfg::SMEM <= 227 * 1024 && Cfg::NW >= 5, "shared memory");
     PA2S_TRY(cudaFuncSetAttribute(conv_tma3_kernel<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-    conv_tma3_kernel<CIN, COUT><<<conv_grid(a.g.B, a.g.T, a.g.F, a.g.nfbc), NTHREADS, Cfg::SMEM, st>>>(a);
+    conv_tma3_kernel<CIN, COUT><<<conv_grid(a.g.B, a.g.T, a.g.F, a.g.nfbc), NT3, Cfg::SMEM, st>>>(a);
     PA2S_CHECK_LAST();
     return 0;
 }
@@ -887,7 +891,7 @@ PA2S_API int pa2s_planes_bwd(void* stream, int B, int T, int F, int C, const flo
 static int g_conv_impl = 1;       // 1: conv_tma3_kernel (kx taps share the A read), 0: conv_tma_kernel (one instruction group per tap)
 PA2S_API int pa2s_conv_tma_set_impl(int impl) { g_conv_impl = impl ? 1 : 0; return 0; }
 PA2S_API int pa2s_conv_tma_num_partials(int B, int T, int F) {
-    return (g_conv_impl ? conv_grid(B, T, F, geom_nfbc(F)) : conv_grid(B, T, F)) * 4;      // every row is written by the kernel
+    return g_conv_impl ? conv_grid(B, T, F, geom_nfbc(F)) * 8 : conv_grid(B, T, F) * 4;      // every row is written by the kernel
 }
 PA2S_API int pa2s_conv_tma_wgrad_num_partials(int B, int T, int F) { return 2 * conv_grid(B, T, F); }   // two rows per CTA
 // Y (B,T,F,Cout) = conv3x3 of the planes tensor (Cin channels) with Wpack (pa2s_tc_conv_pack: dgrad = 0 the forward filter,
