@@ -182,6 +182,10 @@ struct ConvArgs2 {
     float* Y;              // (B,T,F,COUT) fp32
     float* partial;        // [gridDim.x*4][2*COUT] per-warp [sum y, sum y^2] or null
     Geom g;
+    // conv_tma3_kernel as the data gradient of layer i: with sY = the raw output y of layer i-1 (same shape as Y) the statistics
+    // become those of the BatchNorm/ReLU BACKWARD of layer i-1: [sum g, sum g * xhat], g = Y * (y*zs + zb > 0), xhat = (y - mu) * is
+    // (what pa2s_colstats mode 1 computes in a separate pass over Y and y)
+    const float* sY; const float* szs; const float* szb; const float* smu; const float* sis;
 };
 
 template <int CIN, int COUT>
@@ -415,6 +419,7 @@ __global__ void __launch_bounds__(NT3, 1) conv_tma3_kernel(ConvArgs2 a) {
     uint8_t* win = smem + ((W_BYTES + 127) / 128) * 128;
     __shared__ uint64_t full_bar[NW], empty_bar[NW], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_s;
+    __shared__ float cst[4][CQ];                                      // zs, zb, mu, is of the backward statistics
     __shared__ __align__(16) float xch[2][2][4][3][CQ];               // [epilogue group][tile parity][warp][E1 of lane 0, E2 of lane 0, E2 of lane 1][channel]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int T = a.g.T, F = a.g.F;
@@ -424,6 +429,12 @@ __global__ void __launch_bounds__(NT3, 1) conv_tma3_kernel(ConvArgs2 a) {
     // [tap = ky*3+kx][ks][split][kgroup][n < COUTP]
     for (int i = tid; i < W_BYTES / 16; i += NT3) reinterpret_cast<uint4*>(wsm)[i] = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < NW * SLOT_BYTES / 16; i += NT3) reinterpret_cast<uint4*>(win)[i] = make_uint4(0, 0, 0, 0);
+    const bool dstat = a.sY != nullptr;
+    if (dstat && tid < 4 * CQ) {
+        const int kk = tid / CQ, c = tid % CQ;
+        const float* src = kk == 0 ? a.szs : kk == 1 ? a.szb : kk == 2 ? a.smu : a.sis;
+        cst[kk][c] = c < COUT ? __ldg(src + c) : 0.f;
+    }
     __syncthreads();
     for (int i = tid; i < 9 * KS * 2 * 2 * COUTP; i += NT3) {
         const int n = i % COUTP;
@@ -466,9 +477,16 @@ __global__ void __launch_bounds__(NT3, 1) conv_tma3_kernel(ConvArgs2 a) {
             for (int k = 0; k < ch.n; ++k, ++it) {
                 const int acc = it & 1;
                 if (acc != grp) continue;
+                const size_t yoff = (((size_t)ch.b * T + ch.t0 + k) * F + f) * COUT;
+                float* yrow = a.Y + yoff;
+                // backward statistics: this pixel's row of the layer below, requested before the wait for the accumulator
+                float4 yp[COUT / 4];
+                if (dstat && valid) {
+#pragma unroll
+                    for (int j = 0; j < COUT / 4; ++j) yp[j] = __ldg(reinterpret_cast<const float4*>(a.sY + yoff) + j);
+                }
                 mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
                 tc_fence_after();
-                float* yrow = a.Y + (((size_t)ch.b * T + ch.t0 + k) * F + f) * COUT;
                 const uint32_t tbase = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * TM_COLS);
                 // pass 1: the rows the previous warp's last two outputs need (E_1 of lane 0, E_2 of lanes 0 and 1), all channels,
                 // into shared memory; ONE barrier per tile (buffers alternate with the tile parity)
@@ -523,11 +541,31 @@ __global__ void __launch_bounds__(NT3, 1) conv_tma3_kernel(ConvArgs2 a) {
                     if (valid) {
                         if (c8 * 8 < COUT) reinterpret_cast<float4*>(yrow + c8 * 8)[0] = make_float4(v[0], v[1], v[2], v[3]);
                         if (c8 * 8 + 4 < COUT) reinterpret_cast<float4*>(yrow + c8 * 8)[1] = make_float4(v[4], v[5], v[6], v[7]);
-                        if (a.partial != nullptr) {
+                        if (a.partial != nullptr && !dstat) {
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
                                 const int c = c8 * 8 + i;
                                 if (c < COUT) { ps[c] += v[i]; pq[c] = fmaf(v[i], v[i], pq[c]); }
+                            }
+                        } else if (a.partial != nullptr) {
+                            float yv[8];
+                            const float4 y0 = yp[2 * c8];
+                            yv[0] = y0.x; yv[1] = y0.y; yv[2] = y0.z; yv[3] = y0.w;
+                            if (c8 * 8 + 4 < COUT) {
+                                const float4 y1 = yp[(2 * c8 + 1) < COUT / 4 ? 2 * c8 + 1 : 0];
+                                yv[4] = y1.x; yv[5] = y1.y; yv[6] = y1.z; yv[7] = y1.w;
+                            } else {
+                                yv[4] = yv[5] = yv[6] = yv[7] = 0.f;
+                            }
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const int c = c8 * 8 + i;
+                                if (c < COUT) {
+                                    const float z = fmaf(yv[i], cst[0][c], cst[1][c]);
+                                    const float gj = z > 0.f ? v[i] : 0.f;
+                                    ps[c] += gj;
+                                    pq[c] = fmaf(gj, (yv[i] - cst[2][c]) * cst[3][c], pq[c]);
+                                }
                             }
                         }
                     }
@@ -897,10 +935,27 @@ PA2S_API int pa2s_conv_tma_wgrad_num_partials(int B, int T, int F) { return 2 * 
 // Y (B,T,F,Cout) = conv3x3 of the planes tensor (Cin channels) with Wpack (pa2s_tc_conv_pack: dgrad = 0 the forward filter,
 // dgrad = 1 the flipped / transposed filter, which makes this the data gradient: planes = dy, Cin = channels of dy).
 // partial (or NULL): pa2s_conv_tma_num_partials rows of [sum y, sum y^2].
+static int conv_tma_launch(void* stream, int B, int T, int F, int Cin, int Cout, const ConvArgs2& a);
 PA2S_API int pa2s_conv_tma(void* stream, int B, int T, int F, int Cin, int Cout, const void* planes, int npieces, const void* Wpack,
                            float* Y, float* partial) {
-    ConvArgs2 a;
+    ConvArgs2 a = {};
     a.P = (const uint4*)planes; a.Wpack = (const uint4*)Wpack; a.Y = Y; a.partial = partial; a.g = make_geom(B, T, F, npieces);
+    return conv_tma_launch(stream, B, T, F, Cin, Cout, a);
+}
+// The data gradient of a layer fused with the statistics pass of the BatchNorm/ReLU backward of the layer below (what
+// pa2s_colstats(mode 1, X = Yraw, G = Y) computes): partial = pa2s_conv_tma_num_partials rows of [sum g, sum g * xhat] over Cout
+// channels.  Yraw: raw convolution output of the layer below, (B,T,F,Cout) like Y; zs, zb: its BatchNorm scale / shift (ReLU mask),
+// mean, invstd: its batch statistics.  Only with the conv_tma3 kernel (pa2s_conv_tma_set_impl(1), the default): -2 otherwise.
+PA2S_API int pa2s_conv_tma_dgrad_stats(void* stream, int B, int T, int F, int Cin, int Cout, const void* planes, int npieces,
+                                       const void* Wpack, float* Y, const float* Yraw, const float* zs, const float* zb,
+                                       const float* mean, const float* invstd, float* partial) {
+    if (!g_conv_impl) return -2;
+    ConvArgs2 a = {};
+    a.P = (const uint4*)planes; a.Wpack = (const uint4*)Wpack; a.Y = Y; a.partial = partial; a.g = make_geom(B, T, F, npieces);
+    a.sY = Yraw; a.szs = zs; a.szb = zb; a.smu = mean; a.sis = invstd;
+    return conv_tma_launch(stream, B, T, F, Cin, Cout, a);
+}
+static int conv_tma_launch(void* stream, int B, int T, int F, int Cin, int Cout, const ConvArgs2& a) {
     cudaStream_t st = (cudaStream_t)stream;
     if (g_conv_impl) {
         if (Cin == 20 && Cout == 20) return launch_conv3<20, 20>(st, a);

@@ -540,10 +540,11 @@ class ConvStackFn(torch.autograd.Function):
         nct = 4 * N_SM
         grads = [None] * 15
 
-        def bn_bwd_consts(Y, G, mask, aff, gamma, npix, C):
-            partial = torch.empty(nct, 2 * C, device=dev, dtype=F32)
-            lib.pa2s_colstats(st, 1, ptr(Y), ptr(G), ptr(mask), npix, C, ptr(aff[0]), ptr(aff[1]), ptr(aff[2]), ptr(aff[3]),
-                              ptr(partial), nct)
+        def bn_bwd_consts(Y, G, mask, aff, gamma, npix, C, partial=None):
+            if partial is None:                   # (the data gradient of the layer above may have formed the sums in its epilogue)
+                partial = torch.empty(nct, 2 * C, device=dev, dtype=F32)
+                lib.pa2s_colstats(st, 1, ptr(Y), ptr(G), ptr(mask), npix, C, ptr(aff[0]), ptr(aff[1]), ptr(aff[2]), ptr(aff[3]),
+                                  ptr(partial), nct)
             sums = _bn_sums(partial, C, npix if world > 1 else None)
             local = None
             if world > 1:
@@ -596,12 +597,14 @@ class ConvStackFn(torch.autograd.Function):
                 gemm(dzop, Wop, G, M, Kf, O, ldc=Kf)
         grads[12] = dWp.view(O, Fq, C4).permute(0, 2, 1).reshape(O, Kf).contiguous()
         nw = 8 * N_SM
+        stats_below = None
         for i in (3, 2, 1, 0):
             W = conv_w[i]
             Cout, Cin = W.shape[0], W.shape[1]
             y, aff = ys[i], affs[i]
             npix = B * T * Fq
-            dg, db, k = bn_bwd_consts(y, G, None, aff, gam[i], npix, Cout)
+            dg, db, k = bn_bwd_consts(y, G, None, aff, gam[i], npix, Cout, partial=stats_below)
+            stats_below = None
             grads[3 * i + 1], grads[3 * i + 2] = dg, db
             xin = ys[i - 1] if i > 0 else spec
             isc = affs[i - 1][0] if i > 0 else None
@@ -638,8 +641,12 @@ class ConvStackFn(torch.autograd.Function):
                 Gp = torch.empty(B, T, Fq, Cin, device=dev, dtype=F32)
                 if tc:
                     W2 = _tc_pack(W, Cout, Cin, 1)
+                    # the epilogue also forms the sums of the BatchNorm/ReLU backward of the layer below (sum g, sum g*xhat)
+                    affb = affs[i - 1]
+                    stats_below = torch.empty(lib.pa2s_conv_tma_num_partials(B, T, Fq), 2 * Cin, device=dev, dtype=F32)
                     with ktime(f"conv{i + 1}_dgrad"):
-                        lib.pa2s_conv_tma(st, B, T, Fq, Cout, Cin, ptr(Pdy), npc, ptr(W2), ptr(Gp), None)
+                        lib.pa2s_conv_tma_dgrad_stats(st, B, T, Fq, Cout, Cin, ptr(Pdy), npc, ptr(W2), ptr(Gp), ptr(ys[i - 1]),
+                                                      ptr(affb[0]), ptr(affb[1]), ptr(affb[2]), ptr(affb[3]), ptr(stats_below))
                     del Pdy
                 else:
                     W2 = W.detach().flip(2, 3).permute(2, 3, 0, 1).contiguous()        # [tap][co][ci]

@@ -187,6 +187,23 @@ def test_conv_tma_planes_forward_dgrad_wgrad_match_torch(cuda, Cin, Cout, B, T, 
     d = (dx.double().cpu() - ref_dx).abs()
     print(f"conv_tma dgrad: rel err {e:.2e}  worst at (b,t,f,c) = {tuple(int(i) for i in torch.unravel_index(d.argmax(), d.shape))}")
     assert e < tol
+    # the same data gradient with the fused statistics pass of the layer below: [sum g, sum g*xhat], g = dx * (x*s + b > 0)
+    s2 = torch.rand(Cin, generator=g) + 0.5; b2 = torch.randn(Cin, generator=g) * 0.2
+    mu2 = torch.randn(Cin, generator=g) * 0.1; is2 = torch.rand(Cin, generator=g) + 0.5
+    dx2 = torch.empty(B, T, Fq, Cin, device=cuda)
+    sp = torch.full((lib.pa2s_conv_tma_num_partials(B, T, Fq), 2 * Cin), float("nan"), device=cuda)
+    cs2 = [t.to(cuda) for t in (s2, b2, mu2, is2)]
+    lib.pa2s_conv_tma_dgrad_stats(stream(), B, T, Fq, Cout, Cin, ptr(Pdy), npieces, ptr(W2), ptr(dx2), ptr(xd),
+                                  *[ptr(t) for t in cs2], ptr(sp))
+    assert torch.equal(dx2, dx)
+    gm = torch.where(xraw.double() * s2.double() + b2.double() > 0, ref_dx, torch.zeros_like(ref_dx))
+    ref_s0 = gm.sum((0, 1, 2))
+    ref_s1 = (gm * (xraw.double() - mu2.double()) * is2.double()).sum((0, 1, 2))
+    got = sp.double().sum(0).cpu()
+    scale0 = gm.abs().sum((0, 1, 2)).max()
+    print(f"conv_tma dgrad stats: {float((got[:Cin] - ref_s0).abs().max() / scale0):.2e} {float((got[Cin:] - ref_s1).abs().max() / scale0):.2e}")
+    assert (got[:Cin] - ref_s0).abs().max() < max(tol, 1e-4) * scale0
+    assert (got[Cin:] - ref_s1).abs().max() < max(tol, 1e-4) * scale0 * 2
     ref_dw = torch.nn.grad.conv2d_weight(a_in.permute(0, 3, 1, 2), W.shape, dy.permute(0, 3, 1, 2), 1, 1)
     part = torch.zeros(lib.pa2s_conv_tma_wgrad_num_partials(B, T, Fq), Cout * Cin * 9, device=cuda)
     lib.pa2s_conv_tma_wgrad(stream(), B, T, Fq, Cin, Cout, ptr(Pin), ptr(Pdy), npieces, ptr(part))
