@@ -642,10 +642,11 @@ def algorithmic_work(B, S_total, n_dec_calls, n_dec_bwd_calls=None):
         ci, co = ch[i - 1], ch[i]
         fl = 2.0 * 9 * ci * co * px
         w[f"conv{i}_planes"] = (f"planes_kernel<{ci}> relu(bn(y)) -> bf16 hi/lo planes", 2 * ci * px, px * ci * (4 + 4))
-        w[f"conv{i}_fwd"] = (f"conv_tma_kernel<{ci},{co}> tcgen05 implicit GEMM fwd (+BN sums)", fl, px * 4 * (ci + co))
+        w[f"conv{i}_fwd"] = (f"conv_tma3_kernel<{ci},{co}> tcgen05 implicit GEMM fwd, kx taps share the window read (+BN sums)", fl, px * 4 * (ci + co))
         w[f"conv{i}_dy_planes"] = (f"planes_bwd_kernel<{co}> BN/ReLU backward -> bf16 planes", 8 * co * px, px * co * (4 + 4 + 4))
         w[f"conv{i}_wgrad"] = (f"conv_wgrad_tma_kernel<{ci},{co}> tcgen05 weight gradient", fl, px * 4 * (ci + co))
-        w[f"conv{i}_dgrad"] = (f"conv_tma_kernel<{co},{ci}> tcgen05 data gradient", fl, px * 4 * (ci + co))
+        # (the data gradient also reads y of the layer below: its epilogue forms that layer's BatchNorm-backward sums)
+        w[f"conv{i}_dgrad"] = (f"conv_tma3_kernel<{co},{ci}> tcgen05 data gradient (+BN-backward sums of the layer below)", fl, px * 4 * (ci + co + ci))
     M, K, N = float(B * T), 19200.0, 256.0
     lin = 2 * M * K * N
     # bf16x3 holds an fp32 operand as TWO bf16 pieces (hi, lo): 4 B/element read by the GEMM, 4 B read + 4 B written by the split
@@ -655,7 +656,7 @@ def algorithmic_work(B, S_total, n_dec_calls, n_dec_bwd_calls=None):
     w["out_linear_dgrad"] = ("tc_gemm_tma_kernel out Linear data gradient", lin, (M * N + N * K) * 4 + M * K * 4)
     # encoder BiGRU recurrence, one launch = one layer, both directions: 2 dirs x T steps x B x 2*768*256 FLOP; reads gi, writes out (+gates)
     w["encoder_gru_fwd"] = ("gru_seq_fwd_kernel (cluster-of-8 persistent BiGRU layer)", 2 * T * B * 2.0 * 768 * 256, B * T * 2 * (768 + 256 + 1024) * 4.0)
-    w["encoder_gru_bwd"] = ("gru_seq_bwd_kernel", 2 * 2 * T * B * 2.0 * 768 * 256, B * T * 2 * (768 + 256 + 1024 + 768) * 4.0)
+    w["encoder_gru_bwd"] = ("gru_seq_bwd2_kernel (row-owner reverse recurrence, st.async partial-sum exchange)", 2 * 2 * T * B * 2.0 * 768 * 256, B * T * 2 * (768 + 256 + 1024 + 768) * 4.0)
     # note decoder: per executed step and clip 6.27 MFLOP and 3.69 MB streamed (enc 2.46 MB + Ep 1.23 MB; L2-resident at B=16)
     steps = S_total / max(n_dec_calls, 1)
     steps_bwd = S_total / max(n_dec_bwd_calls or n_dec_calls, 1)
