@@ -662,7 +662,7 @@ def algorithmic_work(B, S_total, n_dec_calls, n_dec_bwd_calls=None):
     steps_bwd = S_total / max(n_dec_bwd_calls or n_dec_calls, 1)
     # (`steps` = executed (bar, step) pairs per launch: a launch of the multi-sequence kernel decodes several bars of a staff)
     w["note_decoder_fwd"] = ("decm_fwd_kernel (all steps of the teacher-forced bars of one staff segment, cooperative)", 6.27e6 * B * steps, 3.69e6 * B * steps)
-    w["note_decoder_bwd"] = ("decm_bwd_kernel (all bars of a staff; +dlogits, out-projection GEMM, deferred dEp/dv)", 2 * 6.27e6 * B * steps_bwd, 3.69e6 * B * steps_bwd)
+    w["note_decoder_bwd"] = ("decm_bwd_kernel (all bars of a staff; +dlogits, out-projection GEMM; the deferred dEp/dv kernel runs on an auxiliary stream, outside this timer)", 2 * 6.27e6 * B * steps_bwd, 3.69e6 * B * steps_bwd)
     return w
 
 

@@ -340,9 +340,10 @@ bool launch_skinny(const GemmArgs& g0, int transA, int transB, cudaStream_t st) 
             // few column blocks (N / 32) and a long K: split K over gridDim.y so that ~150 CTAs share the weight matrix
             const int nblk = ceil_div(g.N, 32);
             int ks = 1;
-            if (!g.atomic && !g.accumulate && g.K >= 512) ks = max(1, min(g.K / 128, 160 / nblk));
+            if (!g.atomic && g.K >= 512) ks = max(1, min(g.K / 128, 160 / nblk));
             if (ks > 1) {
-                if (cudaMemset2DAsync(g.C, (size_t)g.ldc * sizeof(float), 0, (size_t)g.N * sizeof(float), (size_t)g.M, st) != cudaSuccess) ks = 1;
+                // the K slices add into C: zero it first unless the caller accumulates into what is there
+                if (!g.accumulate && cudaMemset2DAsync(g.C, (size_t)g.ldc * sizeof(float), 0, (size_t)g.N * sizeof(float), (size_t)g.M, st) != cudaSuccess) ks = 1;
                 else g.atomic = 1;
             }
             const dim3 grid(nblk, ks);

@@ -381,6 +381,9 @@ class HierarchicalDecoder(nn.Module):
             lins = self.bar_linears(D)
         token = self.get_SOS_token(B)[0].squeeze(1)                      # (B, 4*staff+ts+key)
         h = hidden[0]
+        # one autograd node per bar for the bar-level chain (attention query + attention step + GRU cell), when the Linear maps have
+        # deferred weight gradients (training); otherwise the individual ops
+        chain = ops.BarChain(lins, self.attn.v.weight) if (ops.BAR_CHAIN and all(l.defer for l in lins)) else None
         tok_gt = None
         if tf_bars and any(bar_tf[:nb - 1]):
             # tokens built from the targets (models.py:290-299), for all bars in ONE staff-summariser call per staff: row (b, bar)
@@ -408,7 +411,7 @@ class HierarchicalDecoder(nn.Module):
                     token = torch.cat([us, ls, self.time_sig_emb(ts_pred), self.key_emb(key_pred)], dim=-1)
                 if training:
                     token = token * bar_masks[bar]
-                h, context = self._bar_step(token, h, enc, Ep_bar, lins)
+                h, context = chain.step(token, h, enc, Ep_bar) if chain is not None else self._bar_step(token, h, enc, Ep_bar, lins)
                 seg_h.append(h)
                 seg_ctx.append(context)
             summaries += seg_h

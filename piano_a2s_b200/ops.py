@@ -870,6 +870,114 @@ class AttnStepFn(torch.autograd.Function):
         return dq, dEp, denc, dv
 
 
+BAR_CHAIN = os.environ.get("PA2S_BAR_CHAIN", "1") != "0"          # 0: the bar-level chain as individual autograd ops (round-2 start)
+
+
+class BarChain:
+    """The bar-level chain of one forward pass (models.py:239-247 per bar): attention query, attention step, GRU cell -- one autograd
+    node per bar (BarStepFn) instead of ~15 (Linear x3, cat, attention, gates and the gradient-accumulation adds between them).
+    The gradients that every bar adds to the SAME tensors (d Ep_bar, d enc, d v) are accumulated in place across the bars'
+    backward calls and handed to autograd once, by the node that runs last (bar 0); the weight gradients of the three Linear
+    maps go through their DeferredLinear sinks (one contraction per map at the end of the backward pass)."""
+
+    def __init__(self, lins, v):
+        self.lin_q, self.lin_ih, self.lin_hh = lins
+        self.v = v
+        self.pending = 0
+        self.dEp = self.dv_part = self.zero_dx = None
+        self.attn_rows, self.dctx_rows = [], []
+
+    def step(self, token, h, enc, Ep):
+        lq, li, lh = self.lin_q, self.lin_ih, self.lin_hh
+        return BarStepFn.apply(token, h, enc, Ep, self.v, lq.W, li.W, li.b, lh.W, lh.b, self)
+
+
+class BarStepFn(torch.autograd.Function):
+    """(token, h) -> (h', context) of one bar: q = W_q h;  context = attention(q, Ep, enc);  h' = GRUCell([token | context], h)."""
+
+    @staticmethod
+    def forward(ctx, token, h, enc, Ep, v, Wq, Wih, bih, Whh, bhh, chain):
+        ctx.prec = current_precision()
+        token, h, enc, Ep = _f(token), _f(h), _f(enc), _f(Ep)
+        vv = _f(v).reshape(-1)
+        B, T, D = enc.shape
+        A = Ep.shape[2]
+        H = h.shape[1]
+        K = token.shape[1]
+        assert D == 512 and A == 256, "attention kernels are specialised for hidden_size=256"
+        dev = h.device
+        e = lambda *s_, dt=F32: torch.empty(*s_, device=dev, dtype=dt)
+        qs = e(1, B, A)
+        gemm(h, Wq, qs, B, A, H, transB=True, lda=H, ldb=Wq.stride(0), ldc=A)
+        NS, tile = attn_split(B, T)
+        bufs = dict(attn=e(1, B, T), ctxs=e(1, B, D), xbuf=e(B, 16 + D), hc=e(B, 2 * D), pm=e(B, NS), pl=e(B, NS), pc=e(B, NS, D),
+                    tickets=torch.zeros(B, device=dev, dtype=torch.int32), counters=torch.zeros(2, device=dev, dtype=torch.int32))
+        args = make_dec_args(B=B, T=T, V=0, VP=0, S=1, max_steps=1, NS=NS, tile=tile, inference=0, save=1, enc=enc, Ep=Ep, v=vv, qs=qs,
+                             **bufs)
+        lib.pa2s_attn_step_fwd(stream(), ctypes.byref(args))
+        context = bufs["ctxs"].reshape(B, D)
+        x = torch.cat([token, context], dim=1)
+        gi, gh = e(B, 3 * H), e(B, 3 * H)
+        gemm(x, Wih, gi, B, 3 * H, K + D, transB=True, lda=K + D, ldb=Wih.stride(0), ldc=3 * H, bias=bih)
+        gemm(h, Whh, gh, B, 3 * H, H, transB=True, lda=H, ldb=Whh.stride(0), ldc=3 * H, bias=bhh)
+        hnew = e(B, H)
+        save = e(B, 4 * H)
+        lib.pa2s_gru_gates_fwd(stream(), B, H, ptr(gi), ptr(gh), ptr(h), ptr(hnew), ptr(save))
+        ctx.save_for_backward(x, h, qs, Ep, enc, vv, bufs["attn"], bufs["ctxs"], save, Wq, Wih, Whh)
+        ctx.chain, ctx.split, ctx.vshape, ctx.K = chain, (NS, tile), v.shape, K
+        chain.pending += 1
+        return hnew, context
+
+    @staticmethod
+    @_bwd_precision
+    def backward(ctx, dh, dctx):
+        x, h, qs, Ep, enc, vv, attn, ctxs, save, Wq, Wih, Whh = ctx.saved_tensors
+        chain, (NS, tile), K = ctx.chain, ctx.split, ctx.K
+        B, T, D = enc.shape
+        A = Ep.shape[2]
+        H = h.shape[1]
+        dev = enc.device
+        st = stream()
+        e = lambda *s_: torch.empty(*s_, device=dev, dtype=F32)
+        dgi, dgh, dhp = e(B, 3 * H), e(B, 3 * H), e(B, H)
+        lib.pa2s_gru_gates_bwd(st, B, H, ptr(_f(dh)), ptr(save), ptr(h), ptr(dgi), ptr(dgh), ptr(dhp))
+        dx = e(B, K + D)
+        gemm(dgi, Wih, dx, B, K + D, 3 * H, lda=3 * H, ldb=Wih.stride(0), ldc=K + D)
+        gemm(dgh, Whh, dhp, B, H, 3 * H, lda=3 * H, ldb=Whh.stride(0), ldc=H, accumulate=True)
+        # attention step: d context = (consumers of the context outside the cell) + (GRU input part)
+        d_hc = e(B, 2 * D)
+        torch.add(_f(dctx), dx[:, K:], out=d_hc[:, D:])
+        if chain.dEp is None:
+            chain.dEp = torch.zeros(B, T, A, device=dev, dtype=F32)
+            chain.dv_part = torch.zeros(B * NS, A, device=dev, dtype=F32)
+            chain.zero_dx = torch.zeros(B, 16 + D, device=dev, dtype=F32)
+        dq_part = e(B, NS, A)
+        dctx_all = e(1, B, D)
+        args = make_dec_args(B=B, T=T, V=0, VP=0, S=1, max_steps=1, NS=NS, tile=tile, inference=0, save=1, enc=enc, Ep=Ep, v=vv, qs=qs,
+                             attn=attn, ctxs=ctxs, d_hc=d_hc, dx=chain.zero_dx, dEp=chain.dEp, dq_part=dq_part, dv_part=chain.dv_part,
+                             dctx_all=dctx_all)
+        lib.pa2s_attn_step_bwd(st, ctypes.byref(args))
+        dq = dq_part.sum(1)
+        gemm(dq, Wq, dhp, B, H, A, lda=A, ldb=Wq.stride(0), ldc=H, accumulate=True)
+        # d enc = sum over the bars of attn^T dctx: ONE batched GEMM with K = bars, by the node that runs last
+        chain.attn_rows.append(attn)
+        chain.dctx_rows.append(dctx_all)
+        # weight gradients: rows for the three sinks
+        chain.lin_q.sink.rows.append((h, dq))
+        chain.lin_ih.sink.rows.append((x, dgi))
+        chain.lin_hh.sink.rows.append((h, dgh))
+        chain.pending -= 1
+        dEp = denc = dv = None
+        if chain.pending == 0:
+            dEp = chain.dEp
+            S = len(chain.attn_rows)
+            denc = context_grad_enc(torch.cat(chain.attn_rows), torch.cat(chain.dctx_rows), B, T, D, S)
+            dv = colsum(chain.dv_part).reshape(ctx.vshape)
+            chain.dEp = chain.dv_part = None
+            chain.attn_rows, chain.dctx_rows = [], []
+        return dx[:, :K], dhp, denc, dEp, dv, None, None, None, None, None, None
+
+
 def context_grad_enc(attn, dctx_all, B, T, D, S):
     """d_enc[b] = attn[:, b, :]^T (T x S) @ dctx_all[:, b, :] (S x D): the context read-out's gradient, one GEMM per clip."""
     denc = torch.empty(B, T, D, device=attn.device, dtype=F32)
@@ -1104,7 +1212,8 @@ def decoder_weight_grads(recs, dims):
     d_attn_w = z(A, 2 * D)
     gemm(dq, h_prev, d_attn_w, A, D, SB, transA=True, lda=A, ldb=D, ldc=2 * D, zeroed=True)                  # W_h half only
     dvp = [r["dv_part"] for r in recs]
-    dv = colsum(dvp[0] if len(dvp) == 1 else torch.cat(dvp)).reshape(vshape)
+    # (dv_part None: the caller forms dv itself once the kernel that produces the partial sums has finished on its own stream)
+    dv = None if dvp[0] is None else colsum(dvp[0] if len(dvp) == 1 else torch.cat(dvp)).reshape(vshape)
     # embedding: scatter-add of the (masked) token-input gradients
     d_emb = z(V, E)
     toks = torch.cat([r["toks"][:r["S"]].reshape(-1) for r in recs]).long()
@@ -1228,6 +1337,9 @@ def decm_split(B, T, nq=None):
     ns = max(-(-T // tmax), min(16, max(1, pg // max(B, 1))))
     tile = -(-T // ns)
     return -(-T // tile), tile
+
+
+_AUX_STREAMS = {}          # one auxiliary stream per staff stream (deferred attention gradients of the reverse pass)
 
 
 class StaffRun:
@@ -1367,26 +1479,45 @@ class StaffRun:
                 a0 = gargs(k0, nq)
                 lib.pa2s_decm_dlogits(st, ctypes.byref(a0))
             gemm(bw["dlogits_all"], W_out, dhc_all, S * R, 2 * D, V, lda=VP, ldb=2 * D, ldc=2 * D)
-            dEp, dv_parts = None, []
+            dEps, dv_parts = [], []
             for k0, nq in groups:
                 Rg = nq * B
                 scr = dict(d_hc=e(Rg, 2 * D), dx=e(Rg, E + D), dq_part=e(Rg, NS, A), dh_carry=e(Rg, D), tickets=z(B, dt=torch.int32),
                            sync=z(2, dt=torch.int32), dEp=e(B, T, A), dv_part=e(B * nblk, A))
                 a1 = gargs(k0, nq, dhq=dhq.data_ptr() + k0 * B * D * 4, **scr)
                 lib.pa2s_decm_bwd_chain(st, ctypes.byref(a1))
-                lib.pa2s_decm_bwd_deferred(st, ctypes.byref(a1))
+                # the deferred attention gradients (dEp, dv: 0.7 ms) run on an auxiliary stream, next to the weight-gradient
+                # contractions and the d_enc GEMM below, which only read what the chain kernel left behind
+                aux = self._aux_stream()
+                aux.wait_event(torch.cuda.current_stream().record_event())
+                for t_ in (scr["dEp"], scr["dv_part"]):
+                    t_.record_stream(aux)
+                lib.pa2s_decm_bwd_deferred(ctypes.c_void_p(aux.cuda_stream), ctypes.byref(a1))
                 SYNC_FLAGS.append(scr["sync"])
-                dEp = scr["dEp"] if dEp is None else dEp + scr["dEp"]
+                dEps.append(scr["dEp"])
                 dv_parts.append(scr["dv_part"])
         dxt = bw["dxtok_all"][:S]
         if self.mask is not None:
             dxt = dxt * self.mask[:S]
         rec = dict(S=S, B=R, dlogits=bw["dlogits_all"], hs=sv["hs"], ctxs=sv["ctxs"], dgi=bw["dgi_all"], dgh=bw["dgh_all"], dq=bw["dq_all"],
-                   xtok=sv["xtok"], dv_part=dv_parts[0] if len(dv_parts) == 1 else torch.cat(dv_parts), dxt=dxt, toks=sv["toks"])
-        wg = decoder_weight_grads([rec], (D, A, V, E, VP, attn_v.shape))
+                   xtok=sv["xtok"], dv_part=None, dxt=dxt, toks=sv["toks"])
+        wg = list(decoder_weight_grads([rec], (D, A, V, E, VP, attn_v.shape)))
         # d_enc[b] = sum over (step, bar) of attn^T dctx: rows (s, bar, b) -> one batched GEMM with K = S * bars
         denc = context_grad_enc(sv["attn"], bw["dctx_all"], B, T, D, S * self.bars)
-        return dict(denc=denc, dEp=dEp, dh0=dhq.view(self.bars, B, D), wgrads=list(wg))
+        torch.cuda.current_stream().wait_event(aux.record_event())
+        dEp = dEps[0]
+        for x_ in dEps[1:]:
+            dEp = dEp + x_
+        wg[1] = colsum(dv_parts[0] if len(dv_parts) == 1 else torch.cat(dv_parts)).reshape(attn_v.shape)
+        return dict(denc=denc, dEp=dEp, dh0=dhq.view(self.bars, B, D), wgrads=wg)
+
+    def _aux_stream(self):
+        if getattr(self, "_aux", None) is None:
+            key = self.stream.cuda_stream if self.stream is not None else 0
+            if key not in _AUX_STREAMS:
+                _AUX_STREAMS[key] = torch.cuda.Stream()
+            self._aux = _AUX_STREAMS[key]
+        return self._aux
 
 
 class DecodersFn(torch.autograd.Function):
