@@ -673,6 +673,7 @@ struct WgradArgs2 {
     Geom g;
 };
 
+template <int COUT> struct WgradMComp { static constexpr bool value = 2 * ((COUT + 7) / 8) <= 8 - 2; };
 template <int CIN> struct WgradCat { static constexpr bool value = 2 * ((CIN + 7) / 8) * 8 * 9 <= 512; };
 
 template <int CIN, int COUT>
@@ -686,8 +687,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_wgrad_tma_kernel(WgradArgs2 
     constexpr bool NCATB = WgradCat<CIN>::value;
     constexpr int NGB = NCATB ? NGRB : CINP / 8;
     constexpr int NACC = NCATB ? 2 * NGRB * 8 : CINP;             // accumulator columns per tap
-    constexpr int NGA = 8, NGRA = (COUT + 7) / 8;                 // dy planes: M = 64 per piece
-    constexpr int SLOT_BYTES = 2 * NGB * PLANE_BYTES, ASLOT_BYTES = 2 * NGA * PLANE_BYTES;
+    constexpr int NGRA = (COUT + 7) / 8;
+    // MCOMP (20 output channels): both dy pieces fit ONE M = 64 operand -- rows 0..23 dy_hi, 24..47 dy_lo, 48..63 zero -- half the
+    // A bytes of the M = 128 stacking (2 KB instead of 4 KB per instruction)
+    constexpr bool MCOMP = WgradMComp<COUT>::value;
+    constexpr int NGA = MCOMP ? NGRA : 8;                          // plane pitch between the dy pieces in a slot
+    constexpr int SLOT_BYTES = 2 * NGB * PLANE_BYTES, ASLOT_BYTES = (MCOMP ? 8 : 16) * PLANE_BYTES;
     constexpr int TM_COLS = 512;
     static_assert(9 * NACC <= TM_COLS && COUT <= 64 && NACC % 16 == 0, "accumulators must fit TMEM");
 
@@ -726,18 +731,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_wgrad_tma_kernel(WgradArgs2 
         const bool has_tiles = walk.pos < walk.end;                // a CTA without tiles never initialised its accumulators
         // one piece: M = 64, row r lives in lane (r%16) + 32*(r/16), the second partial row of this CTA is zero.
         // two pieces: M = 128, lane = row; rows 0..63 hold dy_hi * a_in, rows 64..127 dy_lo * a_in -> the two partial rows of this CTA
-        const bool stacked = NP > 1;
-        const int row = 32 * warp + lane;
-        const int co = stacked ? (row & 63) : 16 * warp + lane;
+        // MCOMP: M = 64 with both pieces: row r = 16*warp + lane (lane < 16); rows 0..23 dy_hi channels, 24..47 dy_lo channels
+        const bool stacked = MCOMP || NP > 1;
+        const int row = MCOMP ? 16 * warp + lane : 32 * warp + lane;
+        const int half = MCOMP ? (row >= 8 * NGRA ? 1 : 0) : (stacked ? (row >> 6) : 0);
+        const int co = MCOMP ? (lane < 16 && row < 16 * NGRA ? row - half * 8 * NGRA : COUT) : (stacked ? (row & 63) : 16 * warp + lane);
         const bool writer = stacked ? true : lane < 16;
-        float* out = a.partial + ((size_t)blockIdx.x * 2 + (stacked ? (row >> 6) : 0)) * COUT * CIN * 9;
+        float* out = a.partial + ((size_t)blockIdx.x * 2 + half) * COUT * CIN * 9;
         if (!stacked) {
             float* z = a.partial + ((size_t)blockIdx.x * 2 + 1) * COUT * CIN * 9;
             for (int i = tid; i < COUT * CIN * 9; i += 128) z[i] = 0.f;
         }
 #pragma unroll 1
         for (int tap = 0; tap < 9; ++tap) {
-            if (NCATB && stacked) {                                // columns [0, 24) = x_hi products, [24, 48) = x_lo products
+            if (NCATB && NP > 1) {                                 // columns [0, 24) = x_hi products, [24, 48) = x_lo products
                 float v[NACC];
 #pragma unroll
                 for (int c0 = 0; c0 < NACC; c0 += 16)
@@ -765,7 +772,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_wgrad_tma_kernel(WgradArgs2 
         // two pieces: A = [dy_hi ; dy_lo] stacked along M (the lo planes follow the hi planes in the slot), so that ONE M = 128
         // instruction per a_in piece yields dy_hi * x (rows 0..63) and dy_lo * x (rows 64..127): 2 full-rate MMAs per k-step
         // instead of 3 half-rate M = 64 ones (the lo * lo term comes for free).
-        const uint32_t idesc = make_idesc(NP > 1 ? 128 : 64, (NCATB && NP > 1) ? NACC : CINP, 1, 1);
+        const uint32_t idesc = make_idesc((NP > 1 && !MCOMP) ? 128 : 64, (NCATB && NP > 1) ? NACC : CINP, 1, 1);
         const uint32_t win_base = smem_u32(win), a_base0 = smem_u32(asm_);
         uint32_t it = 0, wbase = 0;                                   // all waits of a tile first, then one elected block (see conv_tma_kernel)
         while (walk.next(ch)) {
@@ -886,7 +893,7 @@ template <int CIN, int COUT>
 int launch_wgrad(cudaStream_t st, const WgradArgs2& a) {
     constexpr int CINP = (CIN + 15) / 16 * 16;
     constexpr int NGB = WgradCat<CIN>::value ? (CIN + 7) / 8 : CINP / 8;
-    constexpr int SMEM = NWIN * (2 * NGB * PLANE_BYTES) + NASLOT * (2 * 8 * PLANE_BYTES) + 1024;
+    constexpr int SMEM = NWIN * (2 * NGB * PLANE_BYTES) + NASLOT * ((WgradMComp<COUT>::value ? 8 : 16) * PLANE_BYTES) + 1024;
     static_assert(SMEM <= 227 * 1024, "shared memory");
     PA2S_TRY(cudaFuncSetAttribute(conv_wgrad_tma_kernel<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     conv_wgrad_tma_kernel<CIN, COUT><<<conv_grid(a.g.B, a.g.T, a.g.F), NTHREADS, SMEM, st>>>(a);

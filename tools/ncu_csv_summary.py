@@ -81,7 +81,7 @@ def traffic(paths):
             n = short(r[ix["Kernel Name"]])
             k = seen[n] = seen.get(n, 0) + 1
             t = None
-            m = re.match(r"conv_tma_kernel<(\d+), (\d+)>", n)
+            m = re.match(r"conv_tma3?_kernel<(\d+), (\d+)>", n)
             if m:                                     # first launch of a shape = forward, second = data gradient (of the layer that has the swapped shape)
                 ci, co = int(m.group(1)), int(m.group(2))
                 layer = {(20, 20): 2, (20, 40): 3, (40, 40): 4, (40, 20): 3}[(ci, co)]

@@ -13,10 +13,10 @@ cap() {   # name regex count
   ncu -i /tmp/ncu/${TAG}_$1.ncu-rep --page raw --csv > gpurun_out/${TAG}_$1_raw.csv 2>/dev/null
   tail -3 gpurun_out/${TAG}_$1.log > gpurun_out/${TAG}_$1.tail; rm -f gpurun_out/${TAG}_$1.log
 }
-cap conv "conv_tma_kernel|conv_wgrad_tma_kernel|planes|conv1_" 17
+cap conv "conv_tma3_kernel|conv_wgrad_tma_kernel|planes|conv1_" 17
 cap decm_fwd decm_fwd_kernel 2
 cap decm_bwd decm_bwd_kernel 2
 cap decm_deferred decm_attn_deferred_kernel 2
-cap gru "gru_seq_fwd_kernel|gru_seq_bwd_kernel" 4
-cap gemm "tc_gemm_tma_kernel" 45
+cap gru "gru_seq_fwd_kernel|gru_seq_bwd2_kernel" 4
+[ "$2" == "nogemm" ] || cap gemm "tc_gemm_tma_kernel" 45
 ls -la gpurun_out | grep ${TAG}; du -sh gpurun_out
