@@ -129,6 +129,7 @@ PA2S_API int pa2s_planes_bwd(void* stream, int B, int T, int F, int C, const flo
 /* 1 (default): conv_tma3_kernel, the three kx taps share one read of the activation window (126 outputs per tile);
  * 0: conv_tma_kernel, one instruction group per tap.  Same results up to fp32 summation order. */
 PA2S_API int pa2s_conv_tma_set_impl(int impl);
+PA2S_API int pa2s_conv_tma_get_impl(void);      /* returns the selection, not a status */
 /* data gradient (planes = dy of layer i, Wpack packed with dgrad = 1) fused with the statistics pass of the BatchNorm/ReLU backward
  * of layer i-1 (reference: autograd of models.py:525-534): partial = pa2s_conv_tma_num_partials rows of [sum g, sum g*xhat],
  * g = Y * (Yraw*zs + zb > 0), xhat = (Yraw - mean) * invstd -- the sums pa2s_colstats(mode 1) forms in a separate pass. */

@@ -58,7 +58,7 @@ class _Lib:
                     "pa2s_tc_conv_pack_bytes", "pa2s_tc_conv_num_partials", "pa2s_gemm_tc_supported",
                     "pa2s_tc_conv_wgrad_num_partials", "pa2s_dec_persist_grid", "pa2s_dec_deferred_blocks", "pa2s_planes_bytes",
                     "pa2s_conv_tma_num_partials", "pa2s_conv_tma_wgrad_num_partials", "pa2s_decm_args_size", "pa2s_decm_max_queries",
-                    "pa2s_decm_tile_max", "pa2s_decm_grid", "pa2s_decm_deferred_blocks"):
+                    "pa2s_decm_tile_max", "pa2s_decm_grid", "pa2s_decm_deferred_blocks", "pa2s_conv_tma_get_impl"):
             return fn
 
         def call(*args):

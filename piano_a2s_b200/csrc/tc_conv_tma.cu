@@ -935,6 +935,7 @@ PA2S_API int pa2s_planes_bwd(void* stream, int B, int T, int F, int C, const flo
 }
 static int g_conv_impl = 1;       // 1: conv_tma3_kernel (kx taps share the A read), 0: conv_tma_kernel (one instruction group per tap)
 PA2S_API int pa2s_conv_tma_set_impl(int impl) { g_conv_impl = impl ? 1 : 0; return 0; }
+PA2S_API int pa2s_conv_tma_get_impl(void) { return g_conv_impl; }
 PA2S_API int pa2s_conv_tma_num_partials(int B, int T, int F) {
     return g_conv_impl ? conv_grid(B, T, F, geom_nfbc(F)) * 8 : conv_grid(B, T, F) * 4;      // every row is written by the kernel
 }

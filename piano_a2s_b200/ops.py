@@ -643,10 +643,13 @@ class ConvStackFn(torch.autograd.Function):
                     W2 = _tc_pack(W, Cout, Cin, 1)
                     # the epilogue also forms the sums of the BatchNorm/ReLU backward of the layer below (sum g, sum g*xhat)
                     affb = affs[i - 1]
-                    stats_below = torch.empty(lib.pa2s_conv_tma_num_partials(B, T, Fq), 2 * Cin, device=dev, dtype=F32)
                     with ktime(f"conv{i + 1}_dgrad"):
-                        lib.pa2s_conv_tma_dgrad_stats(st, B, T, Fq, Cout, Cin, ptr(Pdy), npc, ptr(W2), ptr(Gp), ptr(ys[i - 1]),
-                                                      ptr(affb[0]), ptr(affb[1]), ptr(affb[2]), ptr(affb[3]), ptr(stats_below))
+                        if lib.pa2s_conv_tma_get_impl():
+                            stats_below = torch.empty(lib.pa2s_conv_tma_num_partials(B, T, Fq), 2 * Cin, device=dev, dtype=F32)
+                            lib.pa2s_conv_tma_dgrad_stats(st, B, T, Fq, Cout, Cin, ptr(Pdy), npc, ptr(W2), ptr(Gp), ptr(ys[i - 1]),
+                                                          ptr(affb[0]), ptr(affb[1]), ptr(affb[2]), ptr(affb[3]), ptr(stats_below))
+                        else:                 # the comparator kernel has no statistics epilogue: separate colstats pass
+                            lib.pa2s_conv_tma(st, B, T, Fq, Cout, Cin, ptr(Pdy), npc, ptr(W2), ptr(Gp), None)
                     del Pdy
                 else:
                     W2 = W.detach().flip(2, 3).permute(2, 3, 0, 1).contiguous()        # [tap][co][ci]
