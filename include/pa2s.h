@@ -130,6 +130,15 @@ PA2S_API int pa2s_planes_bwd(void* stream, int B, int T, int F, int C, const flo
  * 0: conv_tma_kernel, one instruction group per tap.  Same results up to fp32 summation order. */
 PA2S_API int pa2s_conv_tma_set_impl(int impl);
 PA2S_API int pa2s_conv_tma_get_impl(void);      /* returns the selection, not a status */
+/* Three-piece (fp32-level) convolution of the eval mode (models.py:526-534 in exact fp32): a = a1 + a2 + a3, W = W1 + W2 + W3 (bf16 pieces);
+ *   pass 1  pa2s_conv_tma      planes (a1, a2) [pa2s_planes_fwd],     pack3 sel 0 (W1, W2)
+ *   pass 2  pa2s_conv_tma_acc  the same planes,                        pack3 sel 1 (W3, 0)
+ *   pass 3  pa2s_conv_tma_acc  planes (a3, a2) [pa2s_planes_fwd_low], pack3 sel 2 (W2, W1)
+ * sums every piece product except a3*W3 (2^-32 relative). */
+PA2S_API int pa2s_planes_fwd_low(void* stream, int B, int T, int F, int C, const float* X, const float* scale, const float* shift, int relu,
+                                 void* planes);
+PA2S_API int pa2s_tc_conv_pack3(void* stream, const float* W, int Cout, int Cin, int dgrad, int sel, void* out);
+PA2S_API int pa2s_conv_tma_acc(void* stream, int B, int T, int F, int Cin, int Cout, const void* planes, const void* Wpack, float* Y);
 /* data gradient (planes = dy of layer i, Wpack packed with dgrad = 1) fused with the statistics pass of the BatchNorm/ReLU backward
  * of layer i-1 (reference: autograd of models.py:525-534): partial = pa2s_conv_tma_num_partials rows of [sum g, sum g*xhat],
  * g = Y * (Yraw*zs + zb > 0), xhat = (Yraw - mean) * invstd -- the sums pa2s_colstats(mode 1) forms in a separate pass. */

@@ -101,6 +101,23 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
     hi = hb;
     lo = *reinterpret_cast<uint32_t*>(&l);
 }
+// three-way split x = p1 + p2 + p3 (3 x 8 mantissa bits: exact for fp32 up to the last bit): returns (p3, p2) = the two LOWER pieces
+__device__ __forceinline__ void split2_low(float a, float b, uint32_t& p3, uint32_t& p2) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    const uint32_t hb = *reinterpret_cast<uint32_t*>(&h);
+    const float ra = a - __uint_as_float(hb << 16), rb = b - __uint_as_float(hb & 0xffff0000u);
+    __nv_bfloat162 m = __floats2bfloat162_rn(ra, rb);
+    const uint32_t mb = *reinterpret_cast<uint32_t*>(&m);
+    __nv_bfloat162 l = __floats2bfloat162_rn(ra - __uint_as_float(mb << 16), rb - __uint_as_float(mb & 0xffff0000u));
+    p2 = mb;
+    p3 = *reinterpret_cast<uint32_t*>(&l);
+}
+__device__ __forceinline__ void split8_packed_low(const float (&x)[8], uint4& p3, uint4& p2) {
+    split2_low(x[0], x[1], p3.x, p2.x);
+    split2_low(x[2], x[3], p3.y, p2.y);
+    split2_low(x[4], x[5], p3.z, p2.z);
+    split2_low(x[6], x[7], p3.w, p2.w);
+}
 __device__ __forceinline__ void split8_packed(const float (&x)[8], uint4& hi, uint4& lo) {
     split2(x[0], x[1], hi.x, lo.x);
     split2(x[2], x[3], hi.y, lo.y);

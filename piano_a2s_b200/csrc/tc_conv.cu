@@ -613,8 +613,9 @@ int launch_tc_wgrad(cudaStream_t st, const TcWgradArgs& a, int* grid_out) {
 //   [tap][ks][split(hi,lo)][kgroup(2)][n (NOUTP)][8]   element k = ks*16 + kgroup*8 + e  (input channel), n = output channel.
 // transpose_flip = 0: forward  (n = co, k = ci, tap = ky*3+kx);
 // transpose_flip = 1: data gradient (n = ci, k = co, tap = (2-ky)*3 + (2-kx)):  conv of dy with the flipped, transposed filter.
+// sel (three-way split W = W1 + W2 + W3 into bf16 pieces): 0 the blocks hold (W1, W2) -- the usual hi/lo --, 1 (W3, 0), 2 (W2, W1)
 __global__ void tc_conv_pack_kernel(const float* __restrict__ W, int Cout, int Cin, int transpose_flip, __nv_bfloat16* __restrict__ out,
-                                    int KIN, int NOUT, int KS, int NOUTP) {
+                                    int KIN, int NOUT, int KS, int NOUTP, int sel) {
     const int total = 9 * KS * 2 * 2 * NOUTP * 8;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
         int e = idx % 8, r = idx / 8;
@@ -629,8 +630,15 @@ __global__ void tc_conv_pack_kernel(const float* __restrict__ W, int Cout, int C
             if (!transpose_flip) w = W[((n * Cin + k) * 3 + ky) * 3 + kx];
             else w = W[((k * Cin + n) * 3 + (2 - ky)) * 3 + (2 - kx)];
         }
-        __nv_bfloat16 h = __float2bfloat16_rn(w);
-        out[idx] = split == 0 ? h : __float2bfloat16_rn(w - __bfloat162float(h));
+        const __nv_bfloat16 w1 = __float2bfloat16_rn(w);
+        const float r1 = w - __bfloat162float(w1);
+        const __nv_bfloat16 w2 = __float2bfloat16_rn(r1);
+        const __nv_bfloat16 w3 = __float2bfloat16_rn(r1 - __bfloat162float(w2));
+        __nv_bfloat16 v;
+        if (sel == 0) v = split == 0 ? w1 : w2;
+        else if (sel == 1) v = split == 0 ? w3 : __float2bfloat16_rn(0.f);
+        else v = split == 0 ? w2 : w1;
+        out[idx] = v;
     }
 }
 
@@ -660,7 +668,16 @@ PA2S_API int pa2s_tc_conv_pack_bytes(int Kin, int Nout) {
 PA2S_API int pa2s_tc_conv_pack(void* stream, const float* W, int Cout, int Cin, int dgrad, void* out) {
     int KIN = dgrad ? Cout : Cin, NOUT = dgrad ? Cin : Cout;
     int KS = (KIN + 15) / 16, NOUTP = (NOUT + 15) / 16 * 16;
-    tc_conv_pack_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(W, Cout, Cin, dgrad, (__nv_bfloat16*)out, KIN, NOUT, KS, NOUTP);
+    tc_conv_pack_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(W, Cout, Cin, dgrad, (__nv_bfloat16*)out, KIN, NOUT, KS, NOUTP, 0);
+    PA2S_CHECK_LAST();
+    return 0;
+}
+// the same layout with other pieces of the three-way split W = W1 + W2 + W3 in the (hi, lo) blocks: sel 0 (W1, W2), 1 (W3, 0), 2 (W2, W1)
+PA2S_API int pa2s_tc_conv_pack3(void* stream, const float* W, int Cout, int Cin, int dgrad, int sel, void* out) {
+    if (sel < 0 || sel > 2) return -1;
+    int KIN = dgrad ? Cout : Cin, NOUT = dgrad ? Cin : Cout;
+    int KS = (KIN + 15) / 16, NOUTP = (NOUT + 15) / 16 * 16;
+    tc_conv_pack_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(W, Cout, Cin, dgrad, (__nv_bfloat16*)out, KIN, NOUT, KS, NOUTP, sel);
     PA2S_CHECK_LAST();
     return 0;
 }

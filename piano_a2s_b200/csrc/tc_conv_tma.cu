@@ -103,6 +103,7 @@ struct PlaneArgs {
     Geom g;
     const float* c0; const float* c1; const float* c2; const float* c3; const float* c4; const float* c5; const float* c6;
     int relu;
+    int low;                   // MODE 0: 1 = write the two LOWER pieces (p3, p2) of the three-way split instead of (p1, p2)
 };
 // MODE 0: a = relu?(x*c0[c] + c1[c])  (c0 null: identity)
 // MODE 1: dy = c4*(gm - c5 - xhat*c6), gm = G*(y*c0+c1 > 0), xhat = (y-c2)*c3      (BatchNorm + ReLU backward, see conv.cu)
@@ -168,7 +169,8 @@ __global__ void __launch_bounds__(128 * ((C + 7) / 8)) planes_kernel(PlaneArgs a
         }
     }
     uint4 hi, lo;
-    split8_packed(x, hi, lo);
+    if (MODE == 0 && a.low) split8_packed_low(x, hi, lo);
+    else split8_packed(x, hi, lo);
     a.P[plane_unit(a.g, NGR, b, tp, 0, grp, q)] = hi;
     if (a.g.NP > 1) a.P[plane_unit(a.g, NGR, b, tp, 1, grp, q)] = lo;
 }
@@ -186,6 +188,7 @@ struct ConvArgs2 {
     // become those of the BatchNorm/ReLU BACKWARD of layer i-1: [sum g, sum g * xhat], g = Y * (y*zs + zb > 0), xhat = (y - mu) * is
     // (what pa2s_colstats mode 1 computes in a separate pass over Y and y)
     const float* sY; const float* szs; const float* szb; const float* smu; const float* sis;
+    int accumulate;        // conv_tma3_kernel: Y += result (passes 2 and 3 of the three-piece convolution)
 };
 
 template <int CIN, int COUT>
@@ -484,6 +487,9 @@ __global__ void __launch_bounds__(NT3, 1) conv_tma3_kernel(ConvArgs2 a) {
                 if (dstat && valid) {
 #pragma unroll
                     for (int j = 0; j < COUT / 4; ++j) yp[j] = __ldg(reinterpret_cast<const float4*>(a.sY + yoff) + j);
+                } else if (a.accumulate && valid) {               // Y += : the row written by the previous pass
+#pragma unroll
+                    for (int j = 0; j < COUT / 4; ++j) yp[j] = *(reinterpret_cast<const float4*>(yrow) + j);
                 }
                 mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
                 tc_fence_after();
@@ -539,6 +545,11 @@ __global__ void __launch_bounds__(NT3, 1) conv_tma3_kernel(ConvArgs2 a) {
                         v[i] = __uint_as_float(r0[i]) + e1 + e2;
                     }
                     if (valid) {
+                        if (a.accumulate) {
+                            const float4 o0 = yp[2 * c8], o1 = yp[(2 * c8 + 1) < COUT / 4 ? 2 * c8 + 1 : 0];
+                            v[0] += o0.x; v[1] += o0.y; v[2] += o0.z; v[3] += o0.w;
+                            v[4] += o1.x; v[5] += o1.y; v[6] += o1.z; v[7] += o1.w;
+                        }
                         if (c8 * 8 < COUT) reinterpret_cast<float4*>(yrow + c8 * 8)[0] = make_float4(v[0], v[1], v[2], v[3]);
                         if (c8 * 8 + 4 < COUT) reinterpret_cast<float4*>(yrow + c8 * 8)[1] = make_float4(v[4], v[5], v[6], v[7]);
                         if (a.partial != nullptr && !dstat) {
@@ -917,7 +928,18 @@ PA2S_API int pa2s_planes_fwd(void* stream, int B, int T, int F, int C, const flo
                              void* planes, int npieces) {
     PlaneArgs a;
     a.X = X; a.Yraw = nullptr; a.P = (uint4*)planes; a.g = make_geom(B, T, F, npieces);
-    a.c0 = scale; a.c1 = shift; a.c2 = a.c3 = a.c4 = a.c5 = a.c6 = nullptr; a.relu = relu;
+    a.c0 = scale; a.c1 = shift; a.c2 = a.c3 = a.c4 = a.c5 = a.c6 = nullptr; a.relu = relu; a.low = 0;
+    if (C == 20) return launch_planes<20, 0>((cudaStream_t)stream, a);
+    if (C == 40) return launch_planes<40, 0>((cudaStream_t)stream, a);
+    return -1;
+}
+// the same activation as its two LOWER bf16 pieces (p3, p2) of the three-way split x = p1 + p2 + p3 (pa2s_planes_fwd writes (p1, p2)):
+// the operand of the third pass of the three-piece convolution of the exact-fp32 (eval) mode, see pa2s_conv_tma_acc
+PA2S_API int pa2s_planes_fwd_low(void* stream, int B, int T, int F, int C, const float* X, const float* scale, const float* shift, int relu,
+                                 void* planes) {
+    PlaneArgs a;
+    a.X = X; a.Yraw = nullptr; a.P = (uint4*)planes; a.g = make_geom(B, T, F, 2);
+    a.c0 = scale; a.c1 = shift; a.c2 = a.c3 = a.c4 = a.c5 = a.c6 = nullptr; a.relu = relu; a.low = 1;
     if (C == 20) return launch_planes<20, 0>((cudaStream_t)stream, a);
     if (C == 40) return launch_planes<40, 0>((cudaStream_t)stream, a);
     return -1;
@@ -927,6 +949,7 @@ PA2S_API int pa2s_planes_bwd(void* stream, int B, int T, int F, int C, const flo
                              const float* mean, const float* invstd, const float* k1, const float* k2, const float* k3,
                              void* planes, int npieces) {
     PlaneArgs a;
+    a.low = 0;
     a.X = G; a.Yraw = Yraw; a.P = (uint4*)planes; a.g = make_geom(B, T, F, npieces);
     a.c0 = zs; a.c1 = zb; a.c2 = mean; a.c3 = invstd; a.c4 = k1; a.c5 = k2; a.c6 = k3; a.relu = 1;
     if (C == 20) return launch_planes<20, 1>((cudaStream_t)stream, a);
@@ -961,6 +984,18 @@ PA2S_API int pa2s_conv_tma_dgrad_stats(void* stream, int B, int T, int F, int Ci
     ConvArgs2 a = {};
     a.P = (const uint4*)planes; a.Wpack = (const uint4*)Wpack; a.Y = Y; a.partial = partial; a.g = make_geom(B, T, F, npieces);
     a.sY = Yraw; a.szs = zs; a.szb = zb; a.smu = mean; a.sis = invstd;
+    return conv_tma_launch(stream, B, T, F, Cin, Cout, a);
+}
+// Y += conv3x3(planes, Wpack): the second and third pass of the three-piece (fp32-level) convolution of the eval mode:
+//   pass 1  pa2s_conv_tma      planes (p1, p2), pack sel 0 (W1, W2):  a1 W1 + a1 W2 + a2 W1
+//   pass 2  pa2s_conv_tma_acc  planes (p1, p2), pack sel 1 (W3, 0):   a1 W3 + a2 W3
+//   pass 3  pa2s_conv_tma_acc  planes (p3, p2) (pa2s_planes_fwd_low), pack sel 2 (W2, W1):  a3 W2 + a3 W1 + a2 W2
+// = every product of the pieces of a = a1 + a2 + a3 and W = W1 + W2 + W3 except a3 W3 (2^-32): the accuracy of an fp32 FMA chain.
+PA2S_API int pa2s_conv_tma_acc(void* stream, int B, int T, int F, int Cin, int Cout, const void* planes, const void* Wpack, float* Y) {
+    if (!g_conv_impl) return -2;
+    ConvArgs2 a = {};
+    a.P = (const uint4*)planes; a.Wpack = (const uint4*)Wpack; a.Y = Y; a.partial = nullptr; a.g = make_geom(B, T, F, 2);
+    a.accumulate = 1;
     return conv_tma_launch(stream, B, T, F, Cin, Cout, a);
 }
 static int conv_tma_launch(void* stream, int B, int T, int F, int Cin, int Cout, const ConvArgs2& a) {

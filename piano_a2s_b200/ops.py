@@ -77,6 +77,7 @@ def _dist_on() -> bool:
 #                        "bf16"   tcgen05, bf16 operands, fp32 accumulation (BASELINE configs[2..3]).
 # Small contractions stay on the FFMA kernel (a 128-row UMMA tile would be mostly padding).
 PRECISION = {"train": "bf16x3", "eval": "fp32"}
+EVAL_CONV = os.environ.get("PA2S_EVAL_CONV", "bf16x6")         # conv2-4 in eval(): "bf16x6" (three tensor-core passes over bf16 pieces, fp32-level) or "fp32" (FFMA)
 EVAL_LINEAR = os.environ.get("PA2S_EVAL_LINEAR", "bf16x6")     # the 19200 -> 256 projection in eval(): "bf16x6" (tensor cores, fp32-level) or "fp32" (FFMA)
 TC_MIN_FLOP = 2.0e8
 _CURRENT = ["bf16x3"]
@@ -431,7 +432,30 @@ class ConvStackFn(torch.autograd.Function):
             Cout, Cin = W.shape[0], W.shape[1]
             y = torch.empty(B, T, Fq, Cout, device=dev, dtype=F32)
             use_tc = ctx.prec != "fp32" and Cin >= 16
-            if use_tc:
+            if (ctx.prec == "fp32" and not training and EVAL_CONV == "bf16x6" and Cin >= 16 and lib.pa2s_conv_tma_get_impl()
+                    and 2.0 * 9 * Cin * Cout * B * T * Fq >= TC_MIN_FLOP):
+                # eval / greedy decode: the exact-fp32 convolution as three tensor-core passes over the bf16 pieces of a = a1 + a2 + a3
+                # and W = W1 + W2 + W3 (every piece product except a3*W3: ~2^-24 relative, the accuracy of an fp32 FMA chain)
+                # instead of 7-27 ms of FFMA per layer at B = 32
+                Wc = W.detach().contiguous()
+
+                def pack3(sel):
+                    buf = torch.empty(lib.pa2s_tc_conv_pack_bytes(Cin, Cout), device=dev, dtype=torch.uint8)
+                    lib.pa2s_tc_conv_pack3(st, ptr(Wc), Cout, Cin, 0, sel, ptr(buf))
+                    return buf
+                P = torch.empty(lib.pa2s_planes_bytes(B, T, Fq, Cin, 2), device=dev, dtype=torch.uint8)
+                with ktime(f"conv{i + 1}_planes"):
+                    lib.pa2s_planes_fwd(st, B, T, Fq, Cin, ptr(xin), ptr(in_scale), ptr(in_shift), 1, ptr(P), 2)
+                with ktime(f"conv{i + 1}_fwd"):
+                    lib.pa2s_conv_tma(st, B, T, Fq, Cin, Cout, ptr(P), 2, ptr(pack3(0)), ptr(y), None)
+                    lib.pa2s_conv_tma_acc(st, B, T, Fq, Cin, Cout, ptr(P), ptr(pack3(1)), ptr(y))
+                with ktime(f"conv{i + 1}_planes"):
+                    lib.pa2s_planes_fwd_low(st, B, T, Fq, Cin, ptr(xin), ptr(in_scale), ptr(in_shift), 1, ptr(P))
+                with ktime(f"conv{i + 1}_fwd"):
+                    lib.pa2s_conv_tma_acc(st, B, T, Fq, Cin, Cout, ptr(P), ptr(pack3(2)), ptr(y))
+                del P
+                partial = None
+            elif use_tc:
                 # a_{i-1} = relu(bn(y_{i-1})) as bf16 planes: written once, read by this convolution and by its weight gradient
                 npc = min(npieces_for(ctx.prec), 2)
                 Pin = torch.empty(lib.pa2s_planes_bytes(B, T, Fq, Cin, npc), device=dev, dtype=torch.uint8)

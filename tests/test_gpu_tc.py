@@ -211,3 +211,36 @@ def test_conv_tma_planes_forward_dgrad_wgrad_match_torch(cuda, Cin, Cout, B, T, 
     e = rel_err(dW, ref_dw)
     print(f"conv_tma wgrad: rel err {e:.2e}")
     assert e < tol
+
+
+@pytest.mark.parametrize("Cin,Cout", [(20, 20), (20, 40), (40, 40)])
+@pytest.mark.parametrize("B,T,Fq", [(2, 9, 30), (1, 70, 481), (2, 33, 480)])
+def test_three_piece_convolution_is_fp32_level(cuda, Cin, Cout, B, T, Fq):
+    """The eval-mode convolution: three tensor-core passes over the bf16 pieces of a = a1+a2+a3 and W = W1+W2+W3 (pa2s_conv_tma,
+    2 x pa2s_conv_tma_acc with pa2s_tc_conv_pack3 / pa2s_planes_fwd_low) vs float64 torch: at least as accurate as an fp32 FFMA conv."""
+    from piano_a2s_b200._lib import lib, ptr, stream
+    g = torch.Generator().manual_seed(Cin * 7 + Cout + T)
+    xraw = torch.randn(B, T, Fq, Cin, generator=g)
+    sc = torch.rand(Cin, generator=g) + 0.5
+    sh = torch.randn(Cin, generator=g) * 0.3
+    W = torch.randn(Cout, Cin, 3, 3, generator=g) * (1.0 / (3 * Cin ** 0.5))
+    a_in = F.relu(xraw.double() * sc.double() + sh.double())
+    ref = F.conv2d(a_in.permute(0, 3, 1, 2), W.double(), None, 1, 1).permute(0, 2, 3, 1)
+    ref32 = F.conv2d(a_in.float().permute(0, 3, 1, 2), W, None, 1, 1).permute(0, 2, 3, 1)          # what plain fp32 gives (CPU)
+    xd, scd, shd, Wd = xraw.to(cuda), sc.to(cuda), sh.to(cuda), W.to(cuda).contiguous()
+    P = torch.empty(lib.pa2s_planes_bytes(B, T, Fq, Cin, 2), device=cuda, dtype=torch.uint8)
+    packs = []
+    for sel in range(3):
+        buf = torch.empty(lib.pa2s_tc_conv_pack_bytes(Cin, Cout), device=cuda, dtype=torch.uint8)
+        lib.pa2s_tc_conv_pack3(stream(), ptr(Wd), Cout, Cin, 0, sel, ptr(buf))
+        packs.append(buf)
+    y = torch.full((B, T, Fq, Cout), float("nan"), device=cuda)
+    lib.pa2s_planes_fwd(stream(), B, T, Fq, Cin, ptr(xd), ptr(scd), ptr(shd), 1, ptr(P), 2)
+    lib.pa2s_conv_tma(stream(), B, T, Fq, Cin, Cout, ptr(P), 2, ptr(packs[0]), ptr(y), None)
+    e2 = rel_err(y, ref)
+    lib.pa2s_conv_tma_acc(stream(), B, T, Fq, Cin, Cout, ptr(P), ptr(packs[1]), ptr(y))
+    lib.pa2s_planes_fwd_low(stream(), B, T, Fq, Cin, ptr(xd), ptr(scd), ptr(shd), 1, ptr(P))
+    lib.pa2s_conv_tma_acc(stream(), B, T, Fq, Cin, Cout, ptr(P), ptr(packs[2]), ptr(y))
+    e3, e32 = rel_err(y, ref), rel_err(ref32, ref)
+    print(f"conv {Cin}->{Cout} B{B} T{T} F{Fq}: two pieces {e2:.2e}, three pieces {e3:.2e}, plain fp32 {e32:.2e}")
+    assert e3 < 1e-6 and e3 <= 3 * e32 and e3 < e2 / 4
