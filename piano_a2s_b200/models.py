@@ -361,9 +361,12 @@ class HierarchicalDecoder(nn.Module):
 
         # step-invariant encoder half of the three attention layers (models.py:458): Ep = enc W_e^T + b
         enc2 = enc.reshape(B * T, D)
-        def ep(att):
-            return ops.linear(enc2, att.attn.weight[:, D:], att.attn.bias).view(B, T, -1)
-        Ep_bar, Ep_up, Ep_lo = ep(self.attn), ep(self.upper_decoder.attn), ep(self.lower_decoder.attn)
+        # (one N = 3*A contraction for the three layers: enc is split into bf16 pieces once, and the backward is one data-gradient
+        # and one weight-gradient GEMM instead of three of each plus the accumulation of three d_enc tensors)
+        atts = (self.attn, self.upper_decoder.attn, self.lower_decoder.attn)
+        W_e = torch.cat([a_.attn.weight[:, D:] for a_ in atts])
+        b_e = torch.cat([a_.attn.bias for a_ in atts])
+        Ep_bar, Ep_up, Ep_lo = (e_.view(B, T, -1) for e_ in ops.SplitColsFn.apply(ops.linear(enc2, W_e, b_e), 3))
 
         grad = torch.is_grad_enabled() and (enc.requires_grad or any(w.requires_grad for d in decs for w in d._weights()))
         main = torch.cuda.current_stream()

@@ -290,6 +290,26 @@ def linear(x, W, b=None):
     return LinearFn.apply(x, W, b)
 
 
+class SplitColsFn(torch.autograd.Function):
+    """(M, n*w) -> n contiguous (M, w) blocks; backward writes the n gradients side by side into ONE (M, n*w) buffer (autograd's own
+    slicing would zero-fill and add a full-size tensor per block)."""
+
+    @staticmethod
+    def forward(ctx, x, n):
+        M, N = x.shape
+        ctx.n = n
+        w = N // n
+        return tuple(x[:, i * w:(i + 1) * w].contiguous() for i in range(n))
+
+    @staticmethod
+    def backward(ctx, *gs):
+        M, w = gs[0].shape
+        out = torch.empty(M, ctx.n * w, device=gs[0].device, dtype=gs[0].dtype)
+        for i, g in enumerate(gs):
+            out[:, i * w:(i + 1) * w].copy_(g)
+        return out, None
+
+
 # ---- Linear layers that are applied once per bar (bar-level GRU cell, attention query): deferred weight gradients ------------------
 class LinearSink:
     """Rows (x, dy) left behind by the backward of every use of one Linear in a forward pass."""
