@@ -172,6 +172,20 @@ class HierarchicalDecoder(nn.Module):
         p = [getattr(g, f"{n}_l0{sfx}") for sfx in ("", "_reverse") for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
         return ops.StaffGRUFn.apply(tokens, lengths, self.note_emb.weight, *p)          # (B, 2*staff_emb)
 
+    def _staff_summary_pair(self, tok_a, len_a, tok_b, len_b):
+        """The summaries of two token matrices (upper / lower staff) in ONE staff-GRU call: the shorter matrix is padded (the lengths
+        bound what the recurrence reads), the rows are stacked, the result is split again -- one launch forward and one backward
+        instead of two latency-bound launches each."""
+        La, Lb = tok_a.shape[1], tok_b.shape[1]
+        L = max(La, Lb)
+        if La < L:
+            tok_a = F.pad(tok_a, (0, L - La), value=PAD)
+        if Lb < L:
+            tok_b = F.pad(tok_b, (0, L - Lb), value=PAD)
+        n = tok_a.shape[0]
+        both = self._staff_summary(torch.cat([tok_a, tok_b]), torch.cat([len_a.reshape(-1), len_b.reshape(-1)]))
+        return both[:n], both[n:]
+
     def get_SOS_token(self, batch_size):
         dev = self.note_emb.weight.device
         # constant index tensors, built once per (device, batch size): `torch.tensor(list, device=cuda)` is a BLOCKING copy that waits
@@ -390,8 +404,9 @@ class HierarchicalDecoder(nn.Module):
         tok_gt = None
         if tf_bars and any(bar_tf[:nb - 1]):
             # tokens built from the targets (models.py:290-299), for all bars in ONE staff-summariser call per staff: row (b, bar)
-            us = self._staff_summary(upper_gt.reshape(B * nb, -1), upper_len_gt.reshape(-1)).view(B, nb, -1)
-            ls = self._staff_summary(lower_gt.reshape(B * nb, -1), lower_len_gt.reshape(-1)).view(B, nb, -1)
+            us, ls = self._staff_summary_pair(upper_gt.reshape(B * nb, -1), upper_len_gt.reshape(-1),
+                                              lower_gt.reshape(B * nb, -1), lower_len_gt.reshape(-1))
+            us, ls = us.view(B, nb, -1), ls.view(B, nb, -1)
             tok_gt = torch.cat([us, ls, self.time_sig_emb(time_sig_gt), self.key_emb(key_gt)], dim=-1)       # [:, k] = token of bar k+1
         summaries, contexts = [], []
         done = []
@@ -405,8 +420,8 @@ class HierarchicalDecoder(nn.Module):
                     for ev in done:
                         main.wait_event(ev)
                     done = []
-                    us = self._staff_summary(torch.argmax(runs[0].logp[:, bar - 1], dim=-1), runs[0].lengths[bar - 1])
-                    ls = self._staff_summary(torch.argmax(runs[1].logp[:, bar - 1], dim=-1), runs[1].lengths[bar - 1])
+                    us, ls = self._staff_summary_pair(torch.argmax(runs[0].logp[:, bar - 1], dim=-1), runs[0].lengths[bar - 1],
+                                                      torch.argmax(runs[1].logp[:, bar - 1], dim=-1), runs[1].lengths[bar - 1])
                     with torch.no_grad():                                # (the differentiable heads of all bars are formed at the end)
                         head_in = torch.cat([summaries[-1], contexts[-1]], dim=1)
                         ts_pred = torch.argmax(self._heads(self.time_sig_out, head_in), dim=-1)

@@ -19,7 +19,8 @@ except Exception as e:
     print("$name FAILED", e)
 PY
 }
+# 4th argument: "short" = bf16x3 + bf16 only, "headline" = bf16x3 + greedy decode only, default all four
 run bf16x3 --steps 8 --warmup 3 --also-steps 0
-run bf16 --steps 8 --warmup 3 --precision bf16
-[ "$4" == "short" ] || run finetune --steps 8 --warmup 3 --workload finetune
+[ "$4" == "headline" ] || run bf16 --steps 8 --warmup 3 --precision bf16
+[ "$4" == "short" ] || [ "$4" == "headline" ] || run finetune --steps 8 --warmup 3 --workload finetune
 [ "$4" == "short" ] || run infer --steps 4 --warmup 3 --workload infer
