@@ -15,8 +15,10 @@
 // descriptor start shifted by kx*16 B; a CTA walks DOWN a strip (b, fb) so consecutive tiles share two of their three windows:
 // every activation byte is copied into shared memory once per strip.
 //
-// Warp roles (192 threads, one persistent CTA per SM): warps 0-3 epilogue (TMEM -> registers -> global, BatchNorm batch
-// statistics of the produced tensor), warp 4 TMEM allocation + single-lane tcgen05.mma issue, warp 5 single-lane copy producer.
+// Warp roles, one persistent CTA per SM.  conv_tma3_kernel (forward / data gradient, the default): 320 threads = warps 0-7 two
+// epilogue groups (one per TMEM accumulator: TMEM -> registers -> tap shift -> global, BatchNorm statistics), warp 8 TMEM
+// allocation + elected-lane tcgen05.mma issue, warp 9 single-lane copy producer.  conv_tma_kernel (the round-1 formulation, kept as
+// comparator) and conv_wgrad_tma_kernel: 192 threads = warps 0-3 epilogue / read-out, warp 4 MMA issue, warp 5 copy producer.
 #include "tc_common.cuh"
 
 #ifndef PA2S_CONV_NCAT
@@ -395,6 +397,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(ConvArgs2 a) {
 // travel through shared memory).  3 * KS * 3 instructions per tile of N = 80 / 128, a third of the A reads.  A tile yields
 // 126 outputs, strips advance by 126 positions (geom_nfbc).
 // ====================================================================================================================
+#ifdef PA2S_CONV_PROF
+// development build only (PA2S_NVCC_DEFS=-DPA2S_CONV_PROF): clock64 stamps of the first 64 tiles of CTA 0 of the conv2 forward
+// launch, read back by tools/conv_prof.py.  Slots: MMA warp 0 before / 1 after the accumulator wait, 2 after the window waits,
+// 3 after issuing the tile; epilogue group of the tile 4 before / 5 after the wait for the accumulator, 6 after its stores.
+__device__ unsigned long long g_conv_prof[64 * 8];
+#define CONV_STAMP(slot_) do { if (PROF_ON && blockIdx.x == 0 && it < 64) g_conv_prof[it * 8 + (slot_)] = clock64(); } while (0)
+#else
+#define CONV_STAMP(slot_) do { } while (0)
+#endif
 template <int CIN, int COUT>
 struct Conv3Cfg {
     static constexpr int CINP = (CIN + 15) / 16 * 16, NG = CINP / 8, NGR = (CIN + 7) / 8, KS = CINP / 16;
@@ -433,6 +444,9 @@ __global__ void __launch_bounds__(NT3, 1) conv_tma3_kernel(ConvArgs2 a) {
     for (int i = tid; i < W_BYTES / 16; i += NT3) reinterpret_cast<uint4*>(wsm)[i] = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < NW * SLOT_BYTES / 16; i += NT3) reinterpret_cast<uint4*>(win)[i] = make_uint4(0, 0, 0, 0);
     const bool dstat = a.sY != nullptr;
+#ifdef PA2S_CONV_PROF
+    const bool PROF_ON = (CIN == 20 && COUT == 20 && a.partial != nullptr && !dstat);
+#endif
     if (dstat && tid < 4 * CQ) {
         const int kk = tid / CQ, c = tid % CQ;
         const float* src = kk == 0 ? a.szs : kk == 1 ? a.szb : kk == 2 ? a.smu : a.sis;
@@ -491,8 +505,10 @@ __global__ void __launch_bounds__(NT3, 1) conv_tma3_kernel(ConvArgs2 a) {
 #pragma unroll
                     for (int j = 0; j < COUT / 4; ++j) yp[j] = *(reinterpret_cast<const float4*>(yrow) + j);
                 }
+                if (lane == 0 && wq == 0) CONV_STAMP(4);
                 mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
                 tc_fence_after();
+                if (lane == 0 && wq == 0) CONV_STAMP(5);
                 const uint32_t tbase = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * TM_COLS);
                 // pass 1: the rows the previous warp's last two outputs need (E_1 of lane 0, E_2 of lanes 0 and 1), all channels,
                 // into shared memory; ONE barrier per tile (buffers alternate with the tile parity)
@@ -583,6 +599,7 @@ __global__ void __launch_bounds__(NT3, 1) conv_tma3_kernel(ConvArgs2 a) {
                 }
                 tc_fence_before();
                 mbar_arrive(&tempty_bar[acc]);
+                if (lane == 0 && wq == 0) CONV_STAMP(6);
             }
         }
         if (a.partial != nullptr) {
@@ -602,7 +619,9 @@ __global__ void __launch_bounds__(NT3, 1) conv_tma3_kernel(ConvArgs2 a) {
         while (walk.next(ch)) {
             for (int k = 0; k < ch.n; ++k, ++it) {
                 const int acc = it & 1;
+                if (lane == 0) CONV_STAMP(0);
                 mbar_wait(&tempty_bar[acc], ((it >> 1) & 1) ^ 1);
+                if (lane == 0) CONV_STAMP(1);
                 const uint32_t wi0 = wbase + k;                       // windows wi0 + ky = input rows t0 + k + ky - 1
                 if (k == 0) {                                         // the two older windows were awaited by the previous tile
                     mbar_wait(&full_bar[wi0 % NW], (wi0 / NW) & 1);
@@ -610,6 +629,7 @@ __global__ void __launch_bounds__(NT3, 1) conv_tma3_kernel(ConvArgs2 a) {
                 }
                 mbar_wait(&full_bar[(wi0 + 2) % NW], ((wi0 + 2) / NW) & 1);
                 tc_fence_after();
+                if (lane == 0) CONV_STAMP(2);
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TM_COLS);
                 const bool last = (k == ch.n - 1);
                 uint32_t sl[3];
@@ -640,6 +660,7 @@ __global__ void __launch_bounds__(NT3, 1) conv_tma3_kernel(ConvArgs2 a) {
                     }
                 }
                 __syncwarp();
+                if (lane == 0) CONV_STAMP(3);
             }
             wbase += ch.n + 2;
         }
@@ -1013,6 +1034,13 @@ static int conv_tma_launch(void* stream, int B, int T, int F, int Cin, int Cout,
     if (Cin == 40 && Cout == 20) return launch_conv<40, 20>(st, a);
     return -1;
 }
+#ifdef PA2S_CONV_PROF
+PA2S_API int pa2s_conv_tma_prof_read(unsigned long long* host_out) {
+    PA2S_TRY(cudaDeviceSynchronize());
+    PA2S_TRY(cudaMemcpyFromSymbol(host_out, g_conv_prof, sizeof(g_conv_prof)));
+    return 0;
+}
+#endif
 // partial: pa2s_conv_tma_wgrad_num_partials rows of Cout*Cin*9 in torch (Cout,Cin,3,3) order.
 PA2S_API int pa2s_conv_tma_wgrad(void* stream, int B, int T, int F, int Cin, int Cout, const void* planes_in, const void* planes_dy,
                                  int npieces, float* partial) {

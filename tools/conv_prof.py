@@ -1,4 +1,5 @@
-"""Development tool: per-tile clock64 stamps of the conv2 forward kernel (library built with PA2S_NVCC_DEFS=-DPA2S_CONV_PROF).
+"""Development tool: per-tile clock64 stamps of the conv2 forward launch of conv_tma3_kernel (library built with
+PA2S_NVCC_DEFS=-DPA2S_CONV_PROF python -m piano_a2s_b200.build --force; rebuild without it afterwards).
 Columns (cycles relative to tile 0): MMA warp [before tempty wait, after, after window waits, after issuing the tile],
 epilogue [before tfull wait, after, after the tile's stores + tempty arrive]."""
 import ctypes
@@ -41,6 +42,5 @@ d = np.diff(a[8:60, 3])
 print("tile period (issue end to issue end): mean", d.mean(), "min", d.min(), "max", d.max())
 print("mean m:tempty wait", (a[8:60, 1] - a[8:60, 0]).mean(), "window wait", (a[8:60, 2] - a[8:60, 1]).mean(), "issue", (a[8:60, 3] - a[8:60, 2]).mean(),
       "loop overhead", (a[9:60, 0] - a[8:59, 3]).mean())
-print("mean e:tfull wait", (a[8:60, 5] - a[8:60, 4]).mean(), "epilogue work", (a[8:60, 6] - a[8:60, 5]).mean(), "e loop", (a[9:60, 4] - a[8:59, 6]).mean())
+print("mean e:tfull wait", (a[8:60, 5] - a[8:60, 4]).mean(), "epilogue work", (a[8:60, 6] - a[8:60, 5]).mean(), "e loop (same group, tile k+2)", (a[10:60, 4] - a[8:58, 6]).mean())
 print("tfull_ok(k) - issued(k)", (a[8:60, 5] - a[8:60, 3]).mean(), " tempty_ok(k+2) - e:done(k)", (a[10:60, 1] - a[8:58, 6]).mean())
-print("m: full_bar wait", (a[8:60, 7] - a[8:60, 1]).mean(), "fence", (a[8:60, 2] - a[8:60, 7]).mean())
