@@ -416,7 +416,7 @@ struct Conv3Cfg {
     static constexpr int W_BYTES = 3 * KS * WBLK_BYTES;
     static constexpr int NW = conv3_nwin(W_BYTES, SLOT_BYTES);
     static constexpr int SMEM = ((W_BYTES + 127) / 128) * 128 + NW * SLOT_BYTES + 1024;
-    static constexpr int TM_COLS = N3 <= 64 ? 64 : 128;
+    static constexpr int TM_COLS = N3 <= 64 ? 64 : 128;            // per accumulator; three accumulators, 4 * TM_COLS allocated (power of two)
 };
 
 template <int CIN, int COUT>
@@ -431,7 +431,8 @@ __global__ void __launch_bounds__(NT3, 1) conv_tma3_kernel(ConvArgs2 a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* wsm = smem;
     uint8_t* win = smem + ((W_BYTES + 127) / 128) * 128;
-    __shared__ uint64_t full_bar[NW], empty_bar[NW], tfull_bar[2], tempty_bar[2];
+    constexpr int NACCB = 3;                                          // TMEM accumulators: the MMA warp may run two tiles ahead of a read-out
+    __shared__ uint64_t full_bar[NW], empty_bar[NW], tfull_bar[NACCB], tempty_bar[NACCB];
     __shared__ uint32_t tmem_base_s;
     __shared__ float cst[4][CQ];                                      // zs, zb, mu, is of the backward statistics
     __shared__ __align__(16) float xch[2][2][4][3][CQ];               // [epilogue group][tile parity][warp][E1 of lane 0, E2 of lane 0, E2 of lane 1][channel]
@@ -464,11 +465,11 @@ __global__ void __launch_bounds__(NT3, 1) conv_tma3_kernel(ConvArgs2 a) {
     if (warp == 8) {
         if (lane == 0) {
             for (int s = 0; s < NW; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-            for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 128); }
+            for (int s = 0; s < NACCB; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 128); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
-        tmem_alloc(&tmem_base_s, 2 * TM_COLS);
+        tmem_alloc(&tmem_base_s, 4 * TM_COLS);
     }
     fence_proxy_async();
     tc_fence_before();
@@ -492,8 +493,8 @@ __global__ void __launch_bounds__(NT3, 1) conv_tma3_kernel(ConvArgs2 a) {
             const int f = ch.fb * OT + o - 1;
             const bool valid = (o < OT) && (f >= 0) && (f < F);
             for (int k = 0; k < ch.n; ++k, ++it) {
-                const int acc = it & 1;
-                if (acc != grp) continue;
+                if ((int)(it & 1) != grp) continue;
+                const int acc = it % NACCB;
                 const size_t yoff = (((size_t)ch.b * T + ch.t0 + k) * F + f) * COUT;
                 float* yrow = a.Y + yoff;
                 // backward statistics: this pixel's row of the layer below, requested before the wait for the accumulator
@@ -506,7 +507,7 @@ __global__ void __launch_bounds__(NT3, 1) conv_tma3_kernel(ConvArgs2 a) {
                     for (int j = 0; j < COUT / 4; ++j) yp[j] = *(reinterpret_cast<const float4*>(yrow) + j);
                 }
                 if (lane == 0 && wq == 0) CONV_STAMP(4);
-                mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
+                mbar_wait(&tfull_bar[acc], (it / NACCB) & 1);
                 tc_fence_after();
                 if (lane == 0 && wq == 0) CONV_STAMP(5);
                 const uint32_t tbase = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * TM_COLS);
@@ -618,9 +619,9 @@ __global__ void __launch_bounds__(NT3, 1) conv_tma3_kernel(ConvArgs2 a) {
         uint32_t it = 0, wbase = 0;                                   // wbase = ring index of the chunk's first window (row t0-1)
         while (walk.next(ch)) {
             for (int k = 0; k < ch.n; ++k, ++it) {
-                const int acc = it & 1;
+                const int acc = it % NACCB;
                 if (lane == 0) CONV_STAMP(0);
-                mbar_wait(&tempty_bar[acc], ((it >> 1) & 1) ^ 1);
+                mbar_wait(&tempty_bar[acc], ((it / NACCB) & 1) ^ 1);
                 if (lane == 0) CONV_STAMP(1);
                 const uint32_t wi0 = wbase + k;                       // windows wi0 + ky = input rows t0 + k + ky - 1
                 if (k == 0) {                                         // the two older windows were awaited by the previous tile
@@ -685,7 +686,7 @@ __global__ void __launch_bounds__(NT3, 1) conv_tma3_kernel(ConvArgs2 a) {
     __syncthreads();
     if (warp == 8) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 2 * TM_COLS);
+        tmem_dealloc(tmem_base, 4 * TM_COLS);
     }
 }
 
