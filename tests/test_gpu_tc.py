@@ -138,7 +138,9 @@ def test_tc_conv_forward_and_dgrad_match_torch(cuda, Cin, Cout, B, T, Fq):
 
 
 @pytest.mark.parametrize("Cin,Cout", [(20, 20), (20, 40), (40, 40)])
-@pytest.mark.parametrize("B,T,Fq,npieces", [(2, 9, 30, 2), (1, 70, 481, 2), (3, 5, 130, 1), (2, 20, 32, 2), (3, 21, 37, 2), (1, 300, 480, 2)])
+# (F = 126, 252: the 126-output strips of conv_tma3_kernel need more strips per row than the 128-position strips of the planes / wgrad)
+@pytest.mark.parametrize("B,T,Fq,npieces", [(2, 9, 30, 2), (1, 70, 481, 2), (3, 5, 130, 1), (2, 20, 32, 2), (3, 21, 37, 2), (1, 300, 480, 2),
+                                            (2, 6, 126, 2), (1, 5, 252, 2), (1, 4, 125, 1)])
 def test_conv_tma_planes_forward_dgrad_wgrad_match_torch(cuda, Cin, Cout, B, T, Fq, npieces):
     """tc_conv_tma.cu: plane producers (BatchNorm-apply+ReLU / BatchNorm-ReLU backward, fused with the bf16 split) feeding the
     bulk-copy-fed tcgen05 convolution (forward with batch-statistics epilogue, data gradient, weight gradient) vs float64 torch."""
