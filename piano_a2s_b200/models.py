@@ -109,6 +109,7 @@ class Encoder(nn.Module):
         g = self.gru
         B = x.shape[0]
         bg = 4 if B >= 4 else (2 if B >= 2 else 1)
+        bg = min(bg, int(os.environ.get("PA2S_GRU_BG", bg)))               # clips per cluster of the recurrence kernels (measurement switch)
         hs = []
         for layer in range(g.num_layers):
             p = [getattr(g, f"{n}_l{layer}{sfx}") for sfx in ("", "_reverse") for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
