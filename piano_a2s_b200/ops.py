@@ -1386,6 +1386,21 @@ def decm_split(B, T, nq=None):
     return -(-T // tile), tile
 
 
+def zeros_multi(dev, **specs):
+    """name -> zero-filled tensor for every name = (shape, dtype) in `specs`, carved out of ONE allocation zeroed by ONE memset (each
+    tensor starts on a 256-byte boundary).  A `torch.zeros` per buffer was ~60 fill launches per training step."""
+    offs, total = {}, 0
+    for k, (shape, dt) in specs.items():
+        n = 1
+        for d in shape:
+            n *= int(d)
+        nbytes = n * torch.empty((), dtype=dt).element_size()
+        offs[k] = (total, nbytes)
+        total += (nbytes + 255) // 256 * 256
+    buf = torch.zeros(max(total, 1), device=dev, dtype=torch.uint8)
+    return {k: buf[o:o + nb].view(specs[k][1]).view(*specs[k][0]) for k, (o, nb) in offs.items()}
+
+
 _AUX_STREAMS = {}          # one auxiliary stream per staff stream (deferred attention gradients of the reverse pass)
 
 
@@ -1422,7 +1437,7 @@ class StaffRun:
         z = lambda *s_, dt=F32: torch.zeros(*s_, device=dev, dtype=dt)
         self.Ee = torch.empty_like(Ep)
         lib.pa2s_exp2x(stream(), ptr(Ep), ptr(self.Ee), Ep.numel())
-        self.logp = z(B, bars, max_steps, V)
+        self.logp = None                                             # (allocated with the saved-state buffers below)
         self.lengths = torch.full((bars, B), max_steps, device=dev, dtype=torch.int64)
         self.gt = gt.contiguous() if gt is not None else None
         if self.gt is not None:
@@ -1437,8 +1452,13 @@ class StaffRun:
         self.sv = None
         if self.save:
             # zero-filled: rows of bars with fewer steps than Smax are never written but are read (times zero) by the contractions
-            self.sv = dict(hs=z(S + 1, R, D), ctxs=z(S, R, D), attn=z(S, R, T), gates=torch.empty(S, R, 4 * D, device=dev, dtype=F32),
-                           qs=z(S + 1, R, A), eqs=z(S, R, A), xtok=z(S + 1, R, E), toks=z(S + 1, R, dt=torch.int32), ml=z(S, R, 2))
+            zb = zeros_multi(dev, logp=((B, bars, max_steps, V), F32), hs=((S + 1, R, D), F32), ctxs=((S, R, D), F32), attn=((S, R, T), F32),
+                             qs=((S + 1, R, A), F32), eqs=((S, R, A), F32), xtok=((S + 1, R, E), F32), toks=((S + 1, R), torch.int32),
+                             ml=((S, R, 2), F32))
+            self.logp = zb.pop("logp")
+            self.sv = dict(gates=torch.empty(S, R, 4 * D, device=dev, dtype=F32), **zb)
+        else:
+            self.logp = z(B, bars, max_steps, V)
         self.counters = []
         self.shared = [self.Ee, self.logp, self.lengths, self.enc] + ([self.gt] if self.gt is not None else []) + \
                       ([self.mask] if self.mask is not None else []) + \
@@ -1473,9 +1493,10 @@ class StaffRun:
             lengths = self.lengths.data_ptr() + k0 * B * 8
             if mask is not None:
                 mask = mask[:, k0 * B:k0 * B + R].contiguous()
-        counters = z(2, dt=torch.int32)
-        scratch = dict(xbuf=e(R, E + D), logits=z(R, VP), pm=e(R, NS), pl=e(R, NS), pc=e(R, NS, D), tickets=z(B, dt=torch.int32),
-                       sync=z(2, dt=torch.int32), eos=z(R, dt=torch.int32), counters=counters)
+        zb = zeros_multi(dev, counters=((2,), torch.int32), logits=((R, VP), F32), tickets=((B,), torch.int32), sync=((2,), torch.int32),
+                         eos=((R,), torch.int32))
+        counters = zb["counters"]
+        scratch = dict(xbuf=e(R, E + D), pm=e(R, NS), pl=e(R, NS), pc=e(R, NS, D), **zb)
         bits = None
         if self.tf_bits is not None:
             bits = 0
@@ -1510,8 +1531,9 @@ class StaffRun:
         groups = [(k0, min(nqmax, self.bars - k0)) for k0 in range(0, self.bars, nqmax)]
         nblk = lib.pa2s_decm_deferred_blocks(T)
         Sa = self.Salloc
-        bw = dict(dlogits_all=e(Sa, R, VP), dgi_all=z(Sa, R, 3 * D), dgh_all=z(Sa, R, 3 * D), dq_all=z(Sa + 1, R, A), dctx_all=z(Sa, R, D),
-                  dxtok_all=z(Sa, R, E), ds_all=z(Sa, R, T))
+        bw = dict(dlogits_all=e(Sa, R, VP),
+                  **zeros_multi(dev, dgi_all=((Sa, R, 3 * D), F32), dgh_all=((Sa, R, 3 * D), F32), dq_all=((Sa + 1, R, A), F32),
+                                dctx_all=((Sa, R, D), F32), dxtok_all=((Sa, R, E), F32), ds_all=((Sa, R, T), F32)))
         dhc_all = e(Sa * R, 2 * D)
         dhq = e(R, D)
         st = stream()
@@ -1529,8 +1551,8 @@ class StaffRun:
             dEps, dv_parts = [], []
             for k0, nq in groups:
                 Rg = nq * B
-                scr = dict(d_hc=e(Rg, 2 * D), dx=e(Rg, E + D), dq_part=e(Rg, NS, A), dh_carry=e(Rg, D), tickets=z(B, dt=torch.int32),
-                           sync=z(2, dt=torch.int32), dEp=e(B, T, A), dv_part=e(B * nblk, A))
+                scr = dict(d_hc=e(Rg, 2 * D), dx=e(Rg, E + D), dq_part=e(Rg, NS, A), dh_carry=e(Rg, D), dEp=e(B, T, A), dv_part=e(B * nblk, A),
+                           **zeros_multi(dev, tickets=((B,), torch.int32), sync=((2,), torch.int32)))
                 a1 = gargs(k0, nq, dhq=dhq.data_ptr() + k0 * B * D * 4, **scr)
                 lib.pa2s_decm_bwd_chain(st, ctypes.byref(a1))
                 # the deferred attention gradients (dEp, dv: 0.7 ms) run on an auxiliary stream, next to the weight-gradient

@@ -45,7 +45,13 @@ def targets_to_device(ground_truth, device):
 
 class FlatAdadelta:
     """All parameters (and their .grad) re-pointed into two flat fp32 buffers; clip_grad_norm_(max_grad_norm) +
-    torch.optim.Adadelta(lr, rho, eps) semantics in two kernels (sum of squares, fused update)."""
+    torch.optim.Adadelta(lr, rho, eps) semantics in two kernels (sum of squares, fused update).
+
+    Gradients: `zero_grad()` zeroes the flat gradient buffer and sets every `p.grad` to None, so that autograd's AccumulateGrad
+    just keeps the tensor a backward node hands it (with `p.grad` pointing into the flat buffer it launched one `add` per
+    parameter: ~100 tiny kernels per step); `gather()` then moves a whole bucket (multi-GPU: as soon as its last gradient has
+    arrived, right before its all-reduce) or everything (single GPU: in `allreduce_mean` / `step`) into the flat buffer with ONE
+    multi-tensor copy and re-points `p.grad` at the flat views."""
 
     def __init__(self, model, lr=1.0, rho=0.95, eps=1e-8, max_grad_norm=5.0, bucket_bytes=24 << 20, overlap=True):
         named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
@@ -66,11 +72,13 @@ class FlatAdadelta:
         self.norm = torch.zeros(1, device=dev, dtype=torch.float32)
         off = 0
         self.offsets = []
+        self.gviews = []
         for p in self.params:
             k = p.numel()
             self.flat[off:off + k].copy_(p.data.reshape(-1))
             p.data = self.flat[off:off + k].view_as(p.data)
-            p.grad = self.grad[off:off + k].view_as(p.data)
+            self.gviews.append(self.grad[off:off + k].view_as(p.data))
+            p.grad = self.gviews[-1]
             self.offsets.append(off)
             off += al(k)
         self.n = n
@@ -115,17 +123,38 @@ class FlatAdadelta:
             b = self.bucket_of[i]
             self._pending[b] -= 1
             if self._pending[b] == 0 and self._works[b] is None:
+                self.gather(self.buckets[b][2])
                 self._reduce_bucket(b)
                 self.launched_early += 1
         return hook
 
+    def gather(self, members=None):
+        """Gradients autograd left in tensors of their own -> their places in the flat buffer (one multi-tensor copy); afterwards
+        `p.grad` is the flat view again.  Parameters without a gradient keep the zeros of `zero_grad()`."""
+        idx = range(len(self.params)) if members is None else members
+        src, dst = [], []
+        for i in idx:
+            p, v = self.params[i], self.gviews[i]
+            g = p.grad
+            if g is None:
+                p.grad = v
+            elif g.data_ptr() != v.data_ptr():
+                src.append(g.detach().reshape(v.shape) if g.shape != v.shape else g.detach())
+                dst.append(v)
+                p.grad = v
+        if src:
+            torch._foreach_copy_(dst, src)
+
     def zero_grad(self):
         self.grad.zero_()
+        for p in self.params:
+            p.grad = None
 
     def allreduce_mean(self):
         """Completes the gradient mean over ranks: buckets not yet started by a hook (parameters without a gradient this
         step, or overlap=False) are reduced now, then the compute stream waits for every bucket."""
         world = self._world()
+        self.gather()
         if world > 1:
             for b in range(len(self.buckets)):
                 if self._works[b] is None:
@@ -139,6 +168,7 @@ class FlatAdadelta:
 
     def step(self):
         st = stream()
+        self.gather()
         lib.pa2s_sumsq(st, ptr(self.grad), self.n, ptr(self.sumsq), 1)
         lib.pa2s_adadelta(st, ptr(self.flat), ptr(self.grad), ptr(self.square_avg), ptr(self.acc_delta), self.n, ptr(self.sumsq),
                           self.max_grad_norm, self.lr, self.rho, self.eps, ptr(self.norm))
