@@ -95,3 +95,32 @@ def test_attention_split_covers_all_frames():
         for T in (1, 7, 24, 1201):
             ns, tile = attn_split(B, T)
             assert ns >= 1 and ns * tile >= T and (ns - 1) * tile < T
+
+
+def test_flat_adadelta_gathers_gradients_with_one_copy():
+    """train.FlatAdadelta: zero_grad() leaves p.grad = None (autograd then keeps the tensors it is handed, no add per parameter);
+    gather() moves them into the flat buffer and re-points p.grad at the flat views; parameters without a gradient read as zeros."""
+    import torch
+    from piano_a2s_b200.train import FlatAdadelta
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Linear(7, 3), torch.nn.Linear(3, 2))
+    opt = FlatAdadelta(net)
+    params = list(net.parameters())
+    assert all(p.grad is not None and p.grad.data_ptr() == v.data_ptr() for p, v in zip(params, opt.gviews))
+    opt.zero_grad()
+    assert all(p.grad is None for p in params) and float(opt.grad.abs().sum()) == 0.0
+    x = torch.randn(4, 5)
+    net[1](net[0](x)).square().sum().backward()               # the last layer gets no gradient
+    want = [None if p.grad is None else p.grad.clone() for p in params]
+    assert want[4] is None and want[5] is None and want[0] is not None
+    assert all(p.grad is None or p.grad.data_ptr() != v.data_ptr() for p, v in zip(params, opt.gviews))
+    opt.gather()
+    for p, v, w, off in zip(params, opt.gviews, want, opt.offsets):
+        assert p.grad.data_ptr() == v.data_ptr()
+        flat = opt.grad[off:off + p.numel()].view_as(p)
+        assert torch.equal(flat, w if w is not None else torch.zeros_like(p))
+    opt.gather()                                               # idempotent
+    assert torch.equal(opt.grad[opt.offsets[0]:opt.offsets[0] + params[0].numel()].view_as(params[0]), want[0])
+    # a second backward without zero_grad accumulates into the flat views, like torch
+    net[1](net[0](x)).square().sum().backward()
+    assert torch.allclose(params[0].grad, 2 * want[0])
