@@ -9,9 +9,10 @@ those exist in this image.  What is built here:
   (humdrum.py:846-858) -- pinned against the reference's own `add_split_token`, `Kern`, `eliminate_duplicate_chords`
   (tests/test_score.py, live in the build container + golden fixture);
 * `kern_pitch_to_midi`: humdrum.py:600-622, pinned the same way;
-* `kern_note_events` + `write_midi`: an OWN reader of that one-spine (optionally two-voice) kern text and a Standard MIDI File
-  writer, so that predictions can be listened to / fed to an evaluator without the external tool chain.  Parity with
-  music21's MIDI export is UNPINNED (music21, hum2xml absent); it is not on the measured path.
+* `kern_note_events` + `write_midi`, `write_musicxml`: an OWN reader of that one-spine (optionally two-voice) kern text, a Standard
+  MIDI File writer and a MusicXML (score-partwise) writer with the predicted key / time signatures, so that predictions can be
+  listened to, engraved or fed to an evaluator without the external tool chain.  Parity with hum2xml / music21's exports is
+  UNPINNED (both absent); none of this is on the measured path.
 """
 from __future__ import annotations
 
@@ -236,4 +237,133 @@ def result_to_midi(pred, path):
     """`pred` of one evaluation record -> a two-track MIDI file (upper staff, lower staff); returns the kern texts used."""
     files = result_kern_files(pred)
     write_midi(path, [kern_note_events(files["upper"]), kern_note_events(files["lower"])])
+    return files
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# MusicXML (score-partwise 3.1) from the same kern text: an OWN writer, where the reference goes through hum2xml + music21
+# (humdrum.py:859-891); unpinned like write_midi.
+# ------------------------------------------------------------------------------------------------------------------
+_DIVISIONS = 10080                                    # per quarter note: divisible by 2^5, 3^2, 5, 7 (all reciprocals of the vocabulary)
+_TYPES = {1: "whole", 2: "half", 4: "quarter", 8: "eighth", 16: "16th", 32: "32nd", 64: "64th", 128: "128th"}
+
+
+def _note_type(recip: int):
+    """kern reciprocal -> (MusicXML type or None, (actual, normal) tuplet ratio or None)."""
+    if recip in _TYPES:
+        return _TYPES[recip], None
+    for actual, normal in ((3, 2), (5, 4), (7, 4)):
+        if recip % actual == 0 and (recip // actual * normal) in _TYPES:
+            return _TYPES[recip // actual * normal], (actual, normal)
+    return None, None
+
+
+def _pitch_xml(name: str, acc: str):
+    step = name[0].upper()
+    octave = 4 + (len(name) - 1) if name[0].islower() else 3 - (len(name) - 1)
+    alter = acc.count("#") - acc.count("-")
+    s = f"<pitch><step>{step}</step>"
+    if alter:
+        s += f"<alter>{alter}</alter>"
+    return s + f"<octave>{octave}</octave></pitch>"
+
+
+def _measure_voices(lines):
+    """kern lines of ONE measure -> list of voices, each a list of (chord note strings, duration in divisions)."""
+    voices = [[], []]
+    for line in lines:
+        if not line or line.startswith(("*", "!")):
+            continue
+        for v, chord in enumerate(line.split("\t")[:2]):
+            notes = [n for n in chord.split(" ") if _NOTE_RE.fullmatch(n)]
+            if not notes:
+                continue
+            dur = min(_duration(*_NOTE_RE.fullmatch(n).group(2, 3)) for n in notes)
+            voices[v].append((notes, int(dur * _DIVISIONS)))
+    return [v for v in voices if v] or [[]]
+
+
+def _part_xml(krn_text, part_id, clef, keys, time_sigs):
+    sign, line = clef
+    measures, cur = [], []
+    for ln in krn_text.splitlines():
+        if ln.startswith("**") or ln.startswith("*-"):
+            continue
+        if ln.startswith("="):
+            measures.append(cur)
+            cur = []
+        else:
+            cur.append(ln)
+    measures = measures[1:] if measures and not measures[0] else measures      # the text starts with a barline
+    out = [f'<part id="{part_id}">']
+    key_now, ts_now = None, None
+    for i, lines in enumerate(measures):
+        out.append(f'<measure number="{i + 1}">')
+        attrs = []
+        if i == 0:
+            attrs.append(f"<divisions>{_DIVISIONS}</divisions>")
+        if i < len(keys) and keys[i] != key_now:
+            key_now = keys[i]
+            attrs.append(f"<key><fifths>{int(key_now)}</fifths></key>")
+        if i < len(time_sigs) and time_sigs[i] != ts_now:
+            ts_now = time_sigs[i]
+            beats, _, beat_type = str(ts_now).partition("/")
+            attrs.append(f"<time><beats>{beats}</beats><beat-type>{beat_type or 4}</beat-type></time>")
+        if i == 0:
+            attrs.append(f"<clef><sign>{sign}</sign><line>{line}</line></clef>")
+        if attrs:
+            out.append("<attributes>" + "".join(attrs) + "</attributes>")
+        voices = _measure_voices(lines)
+        for v, events in enumerate(voices):
+            if v > 0:
+                back = sum(d for _, d in voices[v - 1])
+                if back:
+                    out.append(f"<backup><duration>{back}</duration></backup>")
+            for notes, dur in events:
+                for j, n in enumerate(notes):
+                    m = _NOTE_RE.fullmatch(n)
+                    x = "<note>"
+                    if j > 0:
+                        x += "<chord/>"
+                    x += "<rest/>" if m[4] == "r" else _pitch_xml(m[4], m[5])
+                    x += f"<duration>{dur}</duration>"
+                    if m[4] != "r":
+                        if m[7] in ("]", "_"):
+                            x += '<tie type="stop"/>'
+                        if m[1] == "[" or m[7] == "_":
+                            x += '<tie type="start"/>'
+                    x += f"<voice>{v + 1}</voice>"
+                    typ, tup = _note_type(int(m[2]))
+                    if typ:
+                        x += f"<type>{typ}</type>" + "<dot/>" * len(m[3])
+                        if tup:
+                            x += f"<time-modification><actual-notes>{tup[0]}</actual-notes><normal-notes>{tup[1]}</normal-notes></time-modification>"
+                    nota = ""
+                    if m[4] != "r" and m[7] in ("]", "_"):
+                        nota += '<tied type="stop"/>'
+                    if m[4] != "r" and (m[1] == "[" or m[7] == "_"):
+                        nota += '<tied type="start"/>'
+                    if m[6] == ";":
+                        nota += "<fermata/>"
+                    if nota:
+                        x += f"<notations>{nota}</notations>"
+                    out.append(x + "</note>")
+        out.append("</measure>")
+    out.append("</part>")
+    return "\n".join(out)
+
+
+def write_musicxml(path, pred):
+    """`pred` of one evaluation record -> a two-part MusicXML file (upper staff, treble clef; lower staff, bass clef) with the
+    predicted key and time signatures where they change (what humdrum.py:859-891 assembles with music21).  Returns the kern texts."""
+    files = result_kern_files(pred)
+    body = ['<?xml version="1.0" encoding="UTF-8"?>',
+            '<score-partwise version="3.1">',
+            '<part-list><score-part id="P1"><part-name>Piano</part-name></score-part>'
+            '<score-part id="P2"><part-name>Piano</part-name></score-part></part-list>',
+            _part_xml(files["upper"], "P1", ("G", 2), files["keys"], files["time_sigs"]),
+            _part_xml(files["lower"], "P2", ("F", 4), files["keys"], files["time_sigs"]),
+            "</score-partwise>"]
+    with open(path, "w", encoding="utf-8") as f:
+        f.write("\n".join(body) + "\n")
     return files

@@ -79,3 +79,39 @@ def test_note_events_and_midi_file(tmp_path):
     assert data.count(b"MTrk") == 3
     # every note-on has its note-off
     assert sum(1 for i in range(len(data) - 2) if data[i] == 0x91 and data[i + 2] == 80) == len(lo)
+
+
+def test_musicxml_file(tmp_path):
+    import xml.etree.ElementTree as ET
+    enc = score.encode_kern
+    upper = [enc("4c\t4cc\n4d\t4dd\n2e\t2ee"), enc("[2c [2e\n2c] 2e_"), enc("4e]\n4r\n12g\n12a\n12b\n8.cc#;\n16dd-")]
+    lower = [enc("1C"), enc("2.D\n4r"), enc("1EE-")]
+    pred = [(-1, "4/4", lower[0], upper[0]), (-1, "4/4", lower[1], upper[1]), (2, "3/4", lower[2], upper[2])]
+    path = tmp_path / "pred.xml"
+    score.write_musicxml(str(path), pred)
+    root = ET.parse(str(path)).getroot()
+    assert root.tag == "score-partwise" and [p.get("id") for p in root.findall("part")] == ["P1", "P2"]
+    up, lo = root.findall("part")
+    assert len(up.findall("measure")) == 3 and len(lo.findall("measure")) == 3
+    D = score._DIVISIONS
+    m1 = up.findall("measure")[0]
+    assert m1.find("attributes/key/fifths").text == "-1" and m1.find("attributes/time/beats").text == "4"
+    assert m1.find("attributes/clef/sign").text == "G" and lo.find("measure/attributes/clef/sign").text == "F"
+    assert m1.find("backup/duration").text == str(4 * D)                       # second voice starts over
+    assert [n.find("voice").text for n in m1.findall("note")] == ["1", "1", "1", "2", "2", "2"]
+    assert [int(n.find("duration").text) for n in m1.findall("note")] == [D, D, 2 * D, D, D, 2 * D]
+    m2 = up.findall("measure")[1]
+    assert m2.find("attributes") is None                                       # nothing changed
+    notes = m2.findall("note")
+    assert notes[1].find("chord") is not None and notes[0].find("tie").get("type") == "start"
+    assert [t.get("type") for t in notes[3].findall("tie")] == ["stop", "start"]
+    m3 = up.findall("measure")[2]
+    assert m3.find("attributes/key/fifths").text == "2" and m3.find("attributes/time/beat-type").text == "4"
+    n3 = m3.findall("note")
+    assert n3[1].find("rest") is not None
+    trip = n3[2]
+    assert trip.find("type").text == "eighth" and trip.find("time-modification/actual-notes").text == "3" and int(trip.find("duration").text) == D // 3
+    assert n3[5].find("pitch/alter").text == "1" and n3[5].find("dot") is not None and n3[5].find("notations/fermata") is not None
+    assert n3[6].find("pitch/step").text == "D" and n3[6].find("pitch/alter").text == "-1" and n3[6].find("pitch/octave").text == "5"
+    low3 = lo.findall("measure")[2].find("note/pitch")
+    assert (low3.find("step").text, low3.find("alter").text, low3.find("octave").text) == ("E", "-1", "2")
