@@ -924,26 +924,27 @@ class BarChain:
     """The bar-level chain of one forward pass (models.py:239-247 per bar): attention query, attention step, GRU cell -- one autograd
     node per bar (BarStepFn) instead of ~15 (Linear x3, cat, attention, gates and the gradient-accumulation adds between them).
     The gradients that every bar adds to the SAME tensors (d Ep_bar, d enc, d v) are accumulated in place across the bars'
-    backward calls and handed to autograd once, by the node that runs last (bar 0); the weight gradients of the three Linear
+    backward calls and handed to autograd once, by the node that runs last (the first bar's); the weight gradients of the three Linear
     maps go through their DeferredLinear sinks (one contraction per map at the end of the backward pass)."""
 
     def __init__(self, lins, v):
         self.lin_q, self.lin_ih, self.lin_hh = lins
         self.v = v
-        self.pending = 0
+        self.count = 0
         self.dEp = self.dv_part = self.zero_dx = None
         self.attn_rows, self.dctx_rows = [], []
 
     def step(self, token, h, enc, Ep):
         lq, li, lh = self.lin_q, self.lin_ih, self.lin_hh
-        return BarStepFn.apply(token, h, enc, Ep, self.v, lq.W, li.W, li.b, lh.W, lh.b, self)
+        self.count += 1
+        return BarStepFn.apply(token, h, enc, Ep, self.v, lq.W, li.W, li.b, lh.W, lh.b, self, self.count - 1)
 
 
 class BarStepFn(torch.autograd.Function):
     """(token, h) -> (h', context) of one bar: q = W_q h;  context = attention(q, Ep, enc);  h' = GRUCell([token | context], h)."""
 
     @staticmethod
-    def forward(ctx, token, h, enc, Ep, v, Wq, Wih, bih, Whh, bhh, chain):
+    def forward(ctx, token, h, enc, Ep, v, Wq, Wih, bih, Whh, bhh, chain, index):
         ctx.prec = current_precision()
         token, h, enc, Ep = _f(token), _f(h), _f(enc), _f(Ep)
         vv = _f(v).reshape(-1)
@@ -971,8 +972,7 @@ class BarStepFn(torch.autograd.Function):
         save = e(B, 4 * H)
         lib.pa2s_gru_gates_fwd(stream(), B, H, ptr(gi), ptr(gh), ptr(h), ptr(hnew), ptr(save))
         ctx.save_for_backward(x, h, qs, Ep, enc, vv, bufs["attn"], bufs["ctxs"], save, Wq, Wih, Whh)
-        ctx.chain, ctx.split, ctx.vshape, ctx.K = chain, (NS, tile), v.shape, K
-        chain.pending += 1
+        ctx.chain, ctx.split, ctx.vshape, ctx.K, ctx.index = chain, (NS, tile), v.shape, K, index
         return hnew, context
 
     @staticmethod
@@ -1013,16 +1013,17 @@ class BarStepFn(torch.autograd.Function):
         chain.lin_q.sink.rows.append((h, dq))
         chain.lin_ih.sink.rows.append((x, dgi))
         chain.lin_hh.sink.rows.append((h, dgh))
-        chain.pending -= 1
+        # every later bar's state derives from this bar's (h is chained), so of the nodes that run at all the one of the FIRST bar
+        # runs last: it hands the accumulated gradients to autograd (also when the loss does not reach some later bars)
         dEp = denc = dv = None
-        if chain.pending == 0:
+        if ctx.index == 0:
             dEp = chain.dEp
             S = len(chain.attn_rows)
             denc = context_grad_enc(torch.cat(chain.attn_rows), torch.cat(chain.dctx_rows), B, T, D, S)
             dv = colsum(chain.dv_part).reshape(ctx.vshape)
             chain.dEp = chain.dv_part = None
             chain.attn_rows, chain.dctx_rows = [], []
-        return dx[:, :K], dhp, denc, dEp, dv, None, None, None, None, None, None
+        return dx[:, :K], dhp, denc, dEp, dv, None, None, None, None, None, None, None
 
 
 def context_grad_enc(attn, dctx_all, B, T, D, S):
